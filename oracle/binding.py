@@ -1,0 +1,238 @@
+"""ctypes bindings for the parity checkers (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import this module.  The product package ``scrooge_b200`` never does.
+
+* ``Oracle``   -- our plain-C restatement (oracle/genasm_oracle.c -> oracle/libsgoracle.so)
+* ``RefCpu``   -- the UNMODIFIED reference genasm_cpu.cpp behind oracle/ref_shim.cpp
+                  (oracle/_ref/libscrooge_ref_w{64,32}.so), when it has been built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "libsgoracle.so")
+REF_DIR = os.path.join(HERE, "_ref")
+
+# (W, O) pairs the reference is used with: in-file default (src/genasm_cpu.cpp:7-9) and the
+# short-read setting (README.md:208, scripts/profile.py:78: O = min(W//2+1, W-1)).
+CONFIGS = {64: 33, 32: 17}
+
+
+def build(force: bool = False) -> None:
+    """Compile the C restatement, and the reference shim when /root/reference is present."""
+    if force or not os.path.exists(ORACLE_SO) or (
+        os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(HERE, "genasm_oracle.c"))
+    ):
+        subprocess.check_call(["make", "-s", "-C", HERE, "all"])
+    subprocess.check_call(["make", "-s", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
+
+
+def _blob(strings: Sequence[str | bytes]) -> Tuple[bytes, np.ndarray]:
+    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in strings]
+    off = np.zeros(len(bs) + 1, dtype=np.uint64)
+    if bs:
+        off[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+    return b"".join(bs), off
+
+
+def _u64p(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_uint64))
+
+
+def _i64p(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+class AlignResult:
+    """edit distances, CIGAR strings, consumed reference prefix lengths, work counters."""
+
+    def __init__(self, edit, cigars, ref_consumed=None, stats=None, core_ns=0):
+        self.edit = edit
+        self.cigars = cigars
+        self.ref_consumed = ref_consumed
+        self.stats = stats  # dict(windows, dc_entries, tb_steps) or None
+        self.core_ns = core_ns
+
+
+def cigar_ref_consumed(cigar: str) -> int:
+    """#(=, X, D) characters: the consumed reference prefix implied by a CIGAR (src/tests.cu:62-86)."""
+    total, num = 0, 0
+    for ch in cigar:
+        if ch.isdigit():
+            num = num * 10 + ord(ch) - 48
+        else:
+            if ch in "=XDM":
+                total += num
+            num = 0
+    return total
+
+
+class Oracle:
+    def __init__(self):
+        if not os.path.exists(ORACLE_SO):
+            build()
+        self.lib = C.CDLL(ORACLE_SO)
+        self.lib.sgo_align_pairs.restype = C.c_int
+        self.lib.sgo_align_candidates.restype = C.c_int
+        self.lib.sgo_validate_cigar.restype = C.c_int
+        self.lib.sgo_ascii_to_twobit_ref_layout.restype = C.c_int
+        self.lib.sgo_max_threads.restype = C.c_int
+
+    def max_threads(self) -> int:
+        return int(self.lib.sgo_max_threads())
+
+    def align_pairs_blob(self, tblob: bytes, toff: np.ndarray, qblob: bytes, qoff: np.ndarray,
+                         W: int = 64, O: Optional[int] = None, threads: int = 1,
+                         want_cigars: bool = True) -> AlignResult:
+        O = CONFIGS[W] if O is None else O
+        n = len(toff) - 1
+        edit = np.zeros(n, dtype=np.int64)
+        refc = np.zeros(n, dtype=np.uint64)
+        stats = np.zeros(3, dtype=np.uint64)
+        cig = C.create_string_buffer(int(4 * int(qoff[-1]) + n + 1))
+        ns = C.c_int64(0)
+        rc = self.lib.sgo_align_pairs(C.c_int(W), C.c_int(O), tblob, _u64p(toff), qblob, _u64p(qoff),
+                                      C.c_uint64(n), C.c_int(threads), _i64p(edit), _u64p(refc), cig,
+                                      _u64p(stats), C.byref(ns))
+        if rc != 0:
+            raise ValueError(f"oracle: sgo_align_pairs failed with {rc}")
+        cigars: List[str] = []
+        if want_cigars:
+            raw = cig.raw
+            for p in range(n):
+                s = 4 * int(qoff[p]) + p
+                e = raw.index(b"\0", s)
+                cigars.append(raw[s:e].decode())
+        return AlignResult(edit, cigars, refc,
+                           dict(windows=int(stats[0]), dc_entries=int(stats[1]), tb_steps=int(stats[2])),
+                           int(ns.value))
+
+    def align_pairs(self, texts: Sequence[str], queries: Sequence[str], W: int = 64,
+                    O: Optional[int] = None, threads: int = 1) -> AlignResult:
+        assert len(texts) == len(queries)
+        tblob, toff = _blob(texts)
+        qblob, qoff = _blob(queries)
+        return self.align_pairs_blob(tblob, toff, qblob, qoff, W, O, threads)
+
+    def align_candidates(self, genome: str | bytes, reads: Sequence[str], cand_start: Sequence[int],
+                         cand_read: Sequence[int], W: int = 64, O: Optional[int] = None,
+                         threads: int = 1) -> AlignResult:
+        O = CONFIGS[W] if O is None else O
+        g = genome.encode() if isinstance(genome, str) else bytes(genome)
+        rblob, roff = _blob(reads)
+        cs = np.asarray(cand_start, dtype=np.uint64)
+        cr = np.asarray(cand_read, dtype=np.uint32)
+        n = len(cs)
+        lens = (roff[1:] - roff[:-1])[cr] if n else np.zeros(0, dtype=np.uint64)
+        coff = np.zeros(n + 1, dtype=np.uint64)
+        if n:
+            coff[1:] = np.cumsum(4 * lens + 1, dtype=np.uint64)
+        edit = np.zeros(n, dtype=np.int64)
+        refc = np.zeros(n, dtype=np.uint64)
+        stats = np.zeros(3, dtype=np.uint64)
+        cig = C.create_string_buffer(int(coff[-1]) + 1)
+        ns = C.c_int64(0)
+        rc = self.lib.sgo_align_candidates(C.c_int(W), C.c_int(O), g, C.c_uint64(len(g)), rblob, _u64p(roff),
+                                           C.c_uint64(len(reads)), _u64p(cs),
+                                           cr.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint64(n),
+                                           C.c_int(threads), _i64p(edit), _u64p(refc), cig, _u64p(coff),
+                                           _u64p(stats), C.byref(ns))
+        if rc != 0:
+            raise ValueError(f"oracle: sgo_align_candidates failed with {rc}")
+        raw = cig.raw
+        cigars = []
+        for c in range(n):
+            s = int(coff[c])
+            cigars.append(raw[s:raw.index(b"\0", s)].decode())
+        return AlignResult(edit, cigars, refc,
+                           dict(windows=int(stats[0]), dc_entries=int(stats[1]), tb_steps=int(stats[2])),
+                           int(ns.value))
+
+    def validate_cigar(self, cigar: str, ref: str, read: str, edit_distance: int, ref_start: int = 0) -> int:
+        r, q = ref.encode(), read.encode()
+        return int(self.lib.sgo_validate_cigar(cigar.encode(), r, C.c_uint64(len(r)), C.c_uint64(ref_start),
+                                               q, C.c_uint64(len(q)), C.c_int64(edit_distance)))
+
+    def twobit_ref_layout(self, ascii_str: str) -> bytes:
+        a = ascii_str.encode()
+        out = C.create_string_buffer((len(a) + 3) // 4 + 1)
+        rc = self.lib.sgo_ascii_to_twobit_ref_layout(a, C.c_size_t(len(a)), out)
+        if rc != 0:
+            raise ValueError("non-ACGT character")
+        return out.raw[: (len(a) + 3) // 4]
+
+
+class RefCpu:
+    """The unmodified reference CPU aligner (genasm_cpu::align_all) for one (W, O) build."""
+
+    def __init__(self, W: int = 64):
+        path = os.path.join(REF_DIR, f"libscrooge_ref_w{W}.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.W = W
+        self.lib = C.CDLL(path)
+        for f in ("ref_align_pairs", "ref_align_mapping", "ref_config_w", "ref_config_o", "ref_max_threads"):
+            getattr(self.lib, f).restype = C.c_int
+        assert self.lib.ref_config_w() == W and self.lib.ref_config_o() == CONFIGS[W]
+
+    @staticmethod
+    def available(W: int = 64) -> bool:
+        return os.path.exists(os.path.join(REF_DIR, f"libscrooge_ref_w{W}.so"))
+
+    def max_threads(self) -> int:
+        return int(self.lib.ref_max_threads())
+
+    def align_pairs_blob(self, tblob: bytes, toff: np.ndarray, qblob: bytes, qoff: np.ndarray,
+                         threads: int = 1, want_cigars: bool = True) -> AlignResult:
+        n = len(toff) - 1
+        edit = np.zeros(n, dtype=np.int64)
+        cig = C.create_string_buffer(int(4 * int(qoff[-1]) + n + 1))
+        ns = C.c_int64(0)
+        rc = self.lib.ref_align_pairs(tblob, _u64p(toff), qblob, _u64p(qoff), C.c_uint64(n), C.c_int(threads),
+                                      _i64p(edit), cig, C.byref(ns))
+        if rc != 0:
+            raise RuntimeError(f"reference align_all returned {rc}")
+        cigars = []
+        if want_cigars:
+            raw = cig.raw
+            for p in range(n):
+                s = 4 * int(qoff[p]) + p
+                cigars.append(raw[s:raw.index(b"\0", s)].decode())
+        return AlignResult(edit, cigars, None, None, int(ns.value))
+
+    def align_pairs(self, texts: Sequence[str], queries: Sequence[str], threads: int = 1) -> AlignResult:
+        tblob, toff = _blob(texts)
+        qblob, qoff = _blob(queries)
+        return self.align_pairs_blob(tblob, toff, qblob, qoff, threads)
+
+    def align_mapping(self, genome: str, reads: Sequence[str], locations: Sequence[Sequence[int]],
+                      threads: int = 1) -> AlignResult:
+        """locations[r] = candidate start positions of read r (read-major output order)."""
+        g = genome.encode()
+        rblob, roff = _blob(reads)
+        begin = np.zeros(len(reads) + 1, dtype=np.uint64)
+        begin[1:] = np.cumsum([len(l) for l in locations], dtype=np.uint64)
+        starts = np.asarray([s for l in locations for s in l], dtype=np.uint64)
+        n = len(starts)
+        lens = np.repeat(roff[1:] - roff[:-1], [len(l) for l in locations]).astype(np.uint64)
+        coff = np.zeros(n + 1, dtype=np.uint64)
+        if n:
+            coff[1:] = np.cumsum(4 * lens + 1, dtype=np.uint64)
+        edit = np.zeros(n, dtype=np.int64)
+        cig = C.create_string_buffer(int(coff[-1]) + 1)
+        ns = C.c_int64(0)
+        rc = self.lib.ref_align_mapping(g, C.c_uint64(len(g)), rblob, _u64p(roff), C.c_uint64(len(reads)),
+                                        _u64p(begin), _u64p(starts), C.c_int(threads), _i64p(edit), cig,
+                                        _u64p(coff), C.byref(ns))
+        if rc != 0:
+            raise RuntimeError(f"reference align_all (mapping) returned {rc}")
+        raw = cig.raw
+        cigars = [raw[int(coff[c]):raw.index(b"\0", int(coff[c]))].decode() for c in range(n)]
+        return AlignResult(edit, cigars, None, None, int(ns.value))
