@@ -1,0 +1,35 @@
+# Builds the product library (sm_100a only) in-tree:
+#   scrooge_b200/lib/libscrooge_b200.so   C ABI of include/scrooge_b200.h + C++ drop-in genasm_gpu::align_all
+#   build/library_example, build/sg_tests  (C++ programs mirroring the reference's library_example / tests)
+# The oracle (test infrastructure) is built by oracle/Makefile.
+NVCC ?= /usr/local/cuda/bin/nvcc
+CCBIN ?= /usr/bin/g++
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -ccbin $(CCBIN) -Xcompiler -fPIC,-fopenmp,-Wall,-Wno-unknown-pragmas \
+           -Xptxas -v -Iinclude
+SRC := scrooge_b200/csrc
+LIB := scrooge_b200/lib/libscrooge_b200.so
+OBJS := build/sg_device_api.o build/sg_host_api.o build/genasm_gpu.o
+HDRS := $(wildcard $(SRC)/*.cuh $(SRC)/*.h include/*.h include/*.hpp)
+
+all: $(LIB) build/library_example
+
+build/%.o: $(SRC)/%.cu $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
+
+build/%.o: $(SRC)/%.cpp $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -x cu -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
+
+$(LIB): $(OBJS)
+	@mkdir -p scrooge_b200/lib
+	$(NVCC) $(ARCH) -shared -ccbin $(CCBIN) -Xcompiler -fopenmp -o $@ $(OBJS) -lcudart -lgomp
+
+build/library_example: examples/library_example.cpp $(LIB) $(HDRS)
+	$(CCBIN) -O2 -std=c++17 -Iinclude -o $@ $< -Lscrooge_b200/lib -lscrooge_b200 -Wl,-rpath,'$$ORIGIN/../scrooge_b200/lib'
+
+clean:
+	rm -rf build scrooge_b200/lib
+
+.PHONY: all clean

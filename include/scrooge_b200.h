@@ -1,0 +1,176 @@
+/*
+ * scrooge_b200.h -- C ABI of the B200-native (sm_100a) Scrooge/GenASM aligner.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.  It replaces the
+ * reference's GPU library interface
+ *     genasm_gpu::align_all(std::vector<std::string>& texts, std::vector<std::string>& queries, long long*)
+ *                                                                  (reference src/genasm_gpu.hpp:8)
+ *     genasm_gpu::align_all(Genome_t& reference, std::vector<Read_t>& reads, long long*)
+ *                                                                  (reference src/genasm_gpu.hpp:7)
+ * The C++ overloads with the reference's exact signatures live in include/genasm_gpu.hpp and are thin
+ * wrappers over the sg_* functions below.
+ *
+ * Two layers:
+ *   1. host API  (sg_ctx_*, sg_align_pairs, sg_set_reference, sg_align_candidates, sg_result_*):
+ *      HOST buffers in, HOST results out; owns devices, streams, pinned staging and the per-GPU replicated
+ *      packed reference.  Work is scattered over the context's GPUs with no inter-GPU exchange.
+ *   2. device API (sg_dev_*): DEVICE pointers and an explicit cudaStream_t (passed as void*), current
+ *      device, asynchronous.  This is what layer 1 is built from; benchmarks and tests call it directly
+ *      to time the kernels with inputs resident in HBM.
+ *
+ * There is no CPU fallback anywhere: every entry point that computes needs a CUDA device and fails with
+ * SG_ERR_CUDA (and a message in sg_last_error) when there is none.
+ *
+ * Semantics (bit-exact with reference src/genasm_cpu.cpp): semi-global edit distance of the whole query
+ * against a prefix of the text, computed over a chain of W x W windows with overlap O (W=64,O=33 or
+ * W=32,O=17; K=W); traceback priority I > D > X > '='; CIGAR runs are run-length encoded within a window
+ * and never merged across windows.
+ */
+#ifndef SCROOGE_B200_H
+#define SCROOGE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------ */
+/* status codes (the reference exit()s / assert()s instead: src/cuda_util.hpp:3-10,                   */
+/* src/genasm_gpu.cu:636,931-934,984)                                                               */
+#define SG_OK                 0
+#define SG_ERR_CUDA           1  /* CUDA runtime error or no device */
+#define SG_ERR_BAD_BASE       2  /* a character outside ACGTacgt (sg_last_error names the position) */
+#define SG_ERR_BAD_ARG        3
+#define SG_ERR_OOM            4
+#define SG_ERR_CIGAR_OVERFLOW 5  /* an alignment produced more runs than its slab capacity */
+#define SG_ERR_NO_REFERENCE   6  /* sg_align_candidates before sg_set_reference */
+
+/* flags */
+#define SG_FLAG_DISTANCE_ONLY 1u /* skip CIGAR storage and writeback (traceback still runs) */
+
+/* A CIGAR run as the kernels store it: one byte, (op << 6) | count, count in 1..W-O.
+ * op: 0 '=', 1 'X', 2 'I', 3 'D'.  sg_cigar_entry is the reference's CigarEntry_t (src/util.hpp:43-46). */
+#define SG_RUN_OP(b)    ((unsigned)(b) >> 6)
+#define SG_RUN_COUNT(b) ((unsigned)(b) & 63u)
+typedef struct sg_cigar_entry { uint8_t edit_count; char edit_type; } sg_cigar_entry;
+
+typedef struct sg_ctx sg_ctx;
+typedef struct sg_result sg_result;
+
+/* Message for the last failing call on this thread ("" when none). */
+const char *sg_last_error(void);
+/* ABI version, bumped on incompatible change. */
+int sg_version(void);
+/* Number of CUDA devices visible (0 when there is no driver/device). */
+int sg_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* 1. host API                                                                                      */
+
+/* Create a context over n_devices GPUs (device_ids == NULL: devices 0..n_devices-1; n_devices == 0: all).
+ * W is 64 (O=33) or 32 (O=17).  Replaces the reference's hard-wired GPU_ID 0 (src/genasm_gpu.cu:67). */
+int sg_ctx_create(sg_ctx **out, const int *device_ids, int n_devices, int W);
+void sg_ctx_destroy(sg_ctx *ctx);
+int sg_ctx_num_devices(const sg_ctx *ctx);
+
+/* Unstructured interface (reference src/genasm_gpu.cu:982-1065).  Blobs are ASCII, strings concatenated
+ * without separators; *_off have n_pairs+1 entries.  Pair p aligns query p against text p.
+ * Results come back in input order in *out (release with sg_result_free). */
+int sg_align_pairs(sg_ctx *ctx, const char *text_blob, const uint64_t *text_off, const char *query_blob,
+                   const uint64_t *query_off, uint64_t n_pairs, uint32_t flags, sg_result **out);
+
+/* Read-mapping interface (reference src/genasm_gpu.cu:890-980).  sg_set_reference packs the genome to
+ * 2 bit/base once and replicates it into every GPU's HBM (reference twobit_reference, :692-748).
+ * Candidate c aligns read cand_read[c] against the genome suffix starting at cand_start[c]
+ * (src/genasm_gpu.cu:716-726); reads are packed once and shared by their candidates (:784-796).
+ * Results are in candidate order. */
+int sg_set_reference(sg_ctx *ctx, const char *genome_ascii, uint64_t genome_len);
+int sg_align_candidates(sg_ctx *ctx, const char *read_blob, const uint64_t *read_off, uint64_t n_reads,
+                        const uint64_t *cand_start, const uint32_t *cand_read, uint64_t n_cand,
+                        uint32_t flags, sg_result **out);
+
+/* Result accessors.  All pointers stay valid until sg_result_free. */
+uint64_t sg_result_count(const sg_result *r);
+const int64_t *sg_result_edit_distances(const sg_result *r);   /* [count] */
+const uint64_t *sg_result_ref_consumed(const sg_result *r);    /* [count] consumed text prefix = #(=,X,D) */
+const uint64_t *sg_result_run_offsets(const sg_result *r);     /* [count+1] into runs; NULL if distance-only */
+const uint8_t *sg_result_runs(const sg_result *r);             /* packed runs, see SG_RUN_OP/COUNT */
+/* device time of the alignment kernels only, max over GPUs: the reference's core_algorithm_ns
+ * (src/genasm_gpu.cu:940-948) */
+int64_t sg_result_kernel_ns(const sg_result *r);
+/* wall time of the whole call */
+int64_t sg_result_total_ns(const sg_result *r);
+/* Length of alignment idx's CIGAR text ("%d%c" per run, reference src/genasm_gpu.cu:881-888). */
+uint64_t sg_result_cigar_len(const sg_result *r, uint64_t idx);
+/* Render alignment idx's CIGAR text into buf (cap bytes incl. NUL).  Returns the length, or -1 if cap is
+ * too small. */
+int64_t sg_result_render_cigar(const sg_result *r, uint64_t idx, char *buf, uint64_t cap);
+/* Expand alignment idx's runs into CigarEntry_t-shaped entries; returns the number written, -1 if cap is
+ * too small. */
+int64_t sg_result_entries(const sg_result *r, uint64_t idx, sg_cigar_entry *out, uint64_t cap);
+void sg_result_free(sg_result *r);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* 2. device API: device pointers, current device, asynchronous on `stream` (a cudaStream_t).        */
+
+/* ASCII -> 2 bit/base, 16 bases per little-endian 32-bit word, base k of a word in bits 2k+1:2k,
+ * A=0 C=1 G=2 T=3, case-insensitive (codes as reference src/genasm_cpu.cpp:87-90).  d_packed must hold
+ * sg_packed_words(n_bases) words.  *d_bad_pos (device uint64, initialise to UINT64_MAX) receives the
+ * smallest offending position if any character is outside ACGTacgt.
+ * Replaces single_ascii_to_twobit_string (reference src/genasm_gpu.cu:640-685). */
+uint64_t sg_packed_words(uint64_t n_bases);
+int sg_dev_pack_2bit(const char *d_ascii, uint64_t n_bases, uint32_t *d_packed, uint64_t *d_bad_pos,
+                     void *stream);
+
+/* The alignment kernel (DC + TB + per-window RLE), one launch over n alignments.
+ *   d_text / d_query    packed blobs (may be the same blob)
+ *   d_text_start/len    per alignment: first base and number of bases of the text in d_text
+ *   d_query_start/len   same for the query
+ *   d_slab, d_slab_off  run slab and n+1 byte offsets into it: alignment a may write at most
+ *                       d_slab_off[a+1]-d_slab_off[a] runs (ignored with SG_FLAG_DISTANCE_ONLY)
+ *   d_counter           device uint64 work-queue head; the call zeroes it on `stream`
+ * outputs per alignment: d_edit (int64), d_ref_consumed (uint64), d_nruns (uint32),
+ *   d_status (uint8: SG_OK or SG_ERR_CIGAR_OVERFLOW)
+ * Replaces genasm_kernel (reference src/genasm_gpu.cu:583-629).  W is 64 or 32. */
+int sg_dev_align(int W, const uint32_t *d_text, const uint64_t *d_text_start, const uint64_t *d_text_len,
+                 const uint32_t *d_query, const uint64_t *d_query_start, const uint64_t *d_query_len,
+                 uint64_t n, uint32_t flags, uint8_t *d_slab, const uint64_t *d_slab_off,
+                 uint64_t *d_counter, int64_t *d_edit, uint64_t *d_ref_consumed, uint32_t *d_nruns,
+                 uint8_t *d_status, void *stream);
+
+/* CIGAR compaction: exclusive scan of d_nruns into d_run_off[n+1] (d_scan_tmp: sg_scan_tmp_bytes(n)
+ * bytes), then gather every alignment's runs from its slab slot into one dense array.
+ * Replaces the reference's linked-list walk (src/cuda_list.hpp, src/genasm_gpu.cu:881-888). */
+uint64_t sg_scan_tmp_bytes(uint64_t n);
+int sg_dev_scan_runs(const uint32_t *d_nruns, uint64_t n, uint64_t *d_run_off, void *d_scan_tmp, void *stream);
+int sg_dev_gather_runs(const uint8_t *d_slab, const uint64_t *d_slab_off, const uint32_t *d_nruns,
+                       const uint64_t *d_run_off, uint64_t n, uint8_t *d_runs, void *stream);
+
+/* Launch geometry of sg_dev_align on the current device: persistent warps per SM and shared memory per
+ * warp (for reports). */
+int sg_dev_align_geometry(int W, int *warps_per_sm, int *smem_per_warp, int *num_sms);
+
+/* Sustained 32-bit integer ALU throughput probe (LOP3 + SHF mix, the instruction mix of the DC
+ * recurrence): runs for roughly `ms` milliseconds and returns giga-ops/s through *gops.  kind: 0 LOP3 only,
+ * 1 SHF only, 2 LOP3+SHF 2:1, 3 LOP3+IMAD 1:1.  This is the denominator of the integer roofline. */
+int sg_dev_int32_peak(int kind, double ms, double *gops);
+
+/* Synthetic pair generator (deterministic in (seed, pair index); identical on host and device).
+ * The text is i.i.d. uniform ACGT; the read walks the text applying, with probability err per text base,
+ * a substitution / insertion / deletion chosen with weights w_sub:w_ins:w_del, until it holds read_len
+ * bases; `slack` random bases are then appended to the text.  Pair p's text occupies
+ * [p*text_stride, p*text_stride + text_len[p]) and its read [p*read_len, (p+1)*read_len).
+ * text_stride must be >= sg_synth_text_stride(read_len, slack). */
+uint64_t sg_synth_text_stride(uint32_t read_len, uint32_t slack);
+int sg_synth_pairs_host(uint64_t seed, uint64_t first_pair, uint64_t n_pairs, uint32_t read_len, double err,
+                        uint32_t w_sub, uint32_t w_ins, uint32_t w_del, uint32_t slack, char *text,
+                        uint64_t text_stride, uint64_t *text_len, char *reads);
+int sg_dev_synth_pairs(uint64_t seed, uint64_t first_pair, uint64_t n_pairs, uint32_t read_len, double err,
+                       uint32_t w_sub, uint32_t w_ins, uint32_t w_del, uint32_t slack, char *d_text,
+                       uint64_t text_stride, uint64_t *d_text_len, char *d_reads, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCROOGE_B200_H */

@@ -1,0 +1,95 @@
+"""ctypes binding of libscrooge_b200.so (the C ABI declared in include/scrooge_b200.h).
+
+The library is built in-tree by the repository Makefile (``__graft_entry__.build()``).  There is no
+Python or CPU fallback: if the shared library is missing, importing this module's ``lib()`` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(ROOT, "scrooge_b200", "lib", "libscrooge_b200.so")
+
+SG_OK = 0
+SG_ERR_CUDA = 1
+SG_ERR_BAD_BASE = 2
+SG_ERR_BAD_ARG = 3
+SG_ERR_OOM = 4
+SG_ERR_CIGAR_OVERFLOW = 5
+SG_ERR_NO_REFERENCE = 6
+SG_FLAG_DISTANCE_ONLY = 1
+
+u64, i64, u32, i32, vp, cp = C.c_uint64, C.c_int64, C.c_uint32, C.c_int, C.c_void_p, C.c_char_p
+dbl = C.c_double
+
+# name -> (restype, argtypes); every symbol include/scrooge_b200.h declares
+SIGNATURES = {
+    "sg_last_error": (cp, []),
+    "sg_version": (i32, []),
+    "sg_device_count": (i32, []),
+    "sg_ctx_create": (i32, [C.POINTER(vp), C.POINTER(i32), i32, i32]),
+    "sg_ctx_destroy": (None, [vp]),
+    "sg_ctx_num_devices": (i32, [vp]),
+    "sg_align_pairs": (i32, [vp, vp, vp, vp, vp, u64, u32, C.POINTER(vp)]),
+    "sg_set_reference": (i32, [vp, vp, u64]),
+    "sg_align_candidates": (i32, [vp, vp, vp, u64, vp, vp, u64, u32, C.POINTER(vp)]),
+    "sg_result_count": (u64, [vp]),
+    "sg_result_edit_distances": (vp, [vp]),
+    "sg_result_ref_consumed": (vp, [vp]),
+    "sg_result_run_offsets": (vp, [vp]),
+    "sg_result_runs": (vp, [vp]),
+    "sg_result_kernel_ns": (i64, [vp]),
+    "sg_result_total_ns": (i64, [vp]),
+    "sg_result_cigar_len": (u64, [vp, u64]),
+    "sg_result_render_cigar": (i64, [vp, u64, vp, u64]),
+    "sg_result_entries": (i64, [vp, u64, vp, u64]),
+    "sg_result_free": (None, [vp]),
+    "sg_packed_words": (u64, [u64]),
+    "sg_dev_pack_2bit": (i32, [vp, u64, vp, vp, vp]),
+    "sg_dev_align": (i32, [i32, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "sg_scan_tmp_bytes": (u64, [u64]),
+    "sg_dev_scan_runs": (i32, [vp, u64, vp, vp, vp]),
+    "sg_dev_gather_runs": (i32, [vp, vp, vp, vp, u64, vp, vp]),
+    "sg_dev_align_geometry": (i32, [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+    "sg_dev_int32_peak": (i32, [i32, dbl, C.POINTER(dbl)]),
+    "sg_synth_text_stride": (u64, [u32, u32]),
+    "sg_synth_pairs_host": (i32, [u64, u64, u64, u32, dbl, u32, u32, u32, u32, vp, u64, vp, vp]),
+    "sg_dev_synth_pairs": (i32, [u64, u64, u64, u32, dbl, u32, u32, u32, u32, vp, u64, vp, vp, vp]),
+}
+
+_lib = None
+
+
+class ScroogeError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"scrooge_b200 error {code}: {message}")
+        self.code = code
+
+
+def build() -> None:
+    """Compile libscrooge_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    subprocess.check_call(["make", "-s", "-C", ROOT, "all"])
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: run `make` (or __graft_entry__.build()). "
+                "scrooge_b200 has no Python/CPU fallback for the alignment path."
+            )
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != SG_OK:
+        raise ScroogeError(rc, lib().sg_last_error().decode(errors="replace"))

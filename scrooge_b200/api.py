@@ -1,0 +1,227 @@
+"""Host-side mirror of the reference's library interface on top of the C ABI.
+
+``align_all(texts, queries)`` and ``align_all(reference, reads)`` keep the names, argument order and result
+order of the reference's ``genasm_gpu::align_all`` overloads (reference src/genasm_gpu.hpp:7-8,
+src/library_example.cu:25-88); ``Aligner`` is the persistent context underneath (one per process is enough,
+it owns the GPUs, streams and the replicated packed reference).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _lib
+from ._lib import SG_FLAG_DISTANCE_ONLY, ScroogeError, check, lib
+
+OPS = "=XID"
+
+
+@dataclass
+class Alignment:
+    """reference Alignment_t (src/util.hpp:38-41) plus the consumed reference prefix."""
+    cigar: str
+    edit_distance: int
+    ref_consumed: int = 0
+
+
+@dataclass
+class CandidateLocation:
+    """reference CandidateLocation_t (src/util.hpp:22-30); only start_in_reference is used by the aligner."""
+    start_in_reference: int
+    strand: bool = True
+    chromosome: str = ""
+    start_in_chromosome: int = 0
+
+
+@dataclass
+class Read:
+    """reference Read_t (src/util.hpp:32-36)."""
+    description: str
+    content: str
+    locations: List[CandidateLocation] = field(default_factory=list)
+
+
+@dataclass
+class Genome:
+    """reference Genome_t (src/util.hpp:16-19)."""
+    content: str
+    chromosome_starts: dict = field(default_factory=dict)
+
+
+def _blob(strings: Sequence[Union[str, bytes]]) -> Tuple[bytes, np.ndarray]:
+    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in strings]
+    off = np.zeros(len(bs) + 1, dtype=np.uint64)
+    if bs:
+        off[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+    return b"".join(bs), off
+
+
+class Result:
+    """Owns an sg_result; arrays are copied out on access."""
+
+    def __init__(self, handle: C.c_void_p):
+        self._h = handle
+        l = lib()
+        self.count = int(l.sg_result_count(handle))
+        self.kernel_ns = int(l.sg_result_kernel_ns(handle))
+        self.total_ns = int(l.sg_result_total_ns(handle))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().sg_result_free(self._h)
+            self._h = None
+
+    def _arr(self, ptr, n, dtype):
+        if not ptr or n == 0:
+            return np.zeros(0, dtype=dtype)
+        buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype).copy()
+
+    @property
+    def edit_distances(self) -> np.ndarray:
+        return self._arr(lib().sg_result_edit_distances(self._h), self.count, np.int64)
+
+    @property
+    def ref_consumed(self) -> np.ndarray:
+        return self._arr(lib().sg_result_ref_consumed(self._h), self.count, np.uint64)
+
+    @property
+    def run_offsets(self) -> np.ndarray:
+        return self._arr(lib().sg_result_run_offsets(self._h), self.count + 1, np.uint64)
+
+    @property
+    def runs(self) -> np.ndarray:
+        off = self.run_offsets
+        total = int(off[-1]) if len(off) else 0
+        return self._arr(lib().sg_result_runs(self._h), total, np.uint8)
+
+    def cigar(self, idx: int) -> str:
+        l = lib()
+        n = int(l.sg_result_cigar_len(self._h, idx))
+        buf = C.create_string_buffer(n + 1)
+        got = l.sg_result_render_cigar(self._h, idx, buf, n + 1)
+        if got < 0:
+            raise ScroogeError(_lib.SG_ERR_BAD_ARG, "render_cigar failed")
+        return buf.value.decode()
+
+    def cigars(self) -> List[str]:
+        """All CIGAR strings, rendered with numpy from the packed runs ("%d%c" per run)."""
+        off = self.run_offsets
+        if len(off) == 0:
+            return [""] * self.count
+        runs = self.runs
+        cnt = (runs & 63).astype(np.int64)
+        op = np.frombuffer(OPS.encode(), dtype=np.uint8)[runs >> 6]
+        width = np.where(cnt >= 10, 3, 2)
+        pos = np.zeros(len(runs) + 1, dtype=np.int64)
+        np.cumsum(width, out=pos[1:])
+        text = np.zeros(int(pos[-1]), dtype=np.uint8)
+        two = cnt >= 10
+        text[pos[:-1][two]] = 48 + cnt[two] // 10
+        text[pos[1:] - 2] = 48 + cnt % 10
+        text[pos[1:] - 1] = op
+        raw = text.tobytes()
+        bounds = pos[off.astype(np.int64)]
+        return [raw[bounds[i]:bounds[i + 1]].decode() for i in range(self.count)]
+
+    def alignments(self) -> List[Alignment]:
+        ed, rc, cg = self.edit_distances, self.ref_consumed, self.cigars()
+        return [Alignment(cg[i], int(ed[i]), int(rc[i])) for i in range(self.count)]
+
+
+class Aligner:
+    """sg_ctx wrapper.  W=64 -> O=33 (reference default), W=32 -> O=17 (reference short-read setting)."""
+
+    def __init__(self, W: int = 64, n_gpus: int = 0, device_ids: Optional[Sequence[int]] = None):
+        h = C.c_void_p()
+        if device_ids is not None:
+            ids = (C.c_int * len(device_ids))(*device_ids)
+            check(lib().sg_ctx_create(C.byref(h), ids, len(device_ids), W))
+        else:
+            check(lib().sg_ctx_create(C.byref(h), None, n_gpus, W))
+        self._h = h
+        self.W = W
+        self._genome_keepalive = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().sg_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    @property
+    def num_devices(self) -> int:
+        return int(lib().sg_ctx_num_devices(self._h))
+
+    def align_pairs_blob(self, tblob, toff: np.ndarray, qblob, qoff: np.ndarray, distance_only: bool = False) -> Result:
+        """tblob/qblob: bytes or a uint8 numpy array (may be pinned); offsets: uint64 arrays with n+1 entries."""
+        n = len(toff) - 1
+        assert len(qoff) - 1 == n
+        toff = np.ascontiguousarray(toff, dtype=np.uint64)
+        qoff = np.ascontiguousarray(qoff, dtype=np.uint64)
+        out = C.c_void_p()
+        check(lib().sg_align_pairs(self._h, _ptr(tblob), toff.ctypes.data, _ptr(qblob), qoff.ctypes.data, n,
+                                   SG_FLAG_DISTANCE_ONLY if distance_only else 0, C.byref(out)))
+        return Result(out)
+
+    def align_pairs(self, texts: Sequence[str], queries: Sequence[str], distance_only: bool = False) -> Result:
+        if len(texts) != len(queries):
+            raise ValueError("texts and queries differ in size")  # reference asserts, src/genasm_gpu.cu:984
+        tblob, toff = _blob(texts)
+        qblob, qoff = _blob(queries)
+        return self.align_pairs_blob(tblob, toff, qblob, qoff, distance_only)
+
+    def set_reference(self, genome: Union[str, bytes, np.ndarray]) -> None:
+        g = genome.encode() if isinstance(genome, str) else genome
+        check(lib().sg_set_reference(self._h, _ptr(g), len(g)))
+
+    def align_candidates(self, reads: Sequence[str], cand_start: Sequence[int], cand_read: Sequence[int],
+                         distance_only: bool = False) -> Result:
+        rblob, roff = _blob(reads)
+        cs = np.ascontiguousarray(cand_start, dtype=np.uint64)
+        cr = np.ascontiguousarray(cand_read, dtype=np.uint32)
+        out = C.c_void_p()
+        check(lib().sg_align_candidates(self._h, _ptr(rblob), roff.ctypes.data, len(reads), cs.ctypes.data, cr.ctypes.data,
+                                        len(cs), SG_FLAG_DISTANCE_ONLY if distance_only else 0, C.byref(out)))
+        return Result(out)
+
+
+def _ptr(buf) -> int:
+    if isinstance(buf, np.ndarray):
+        return buf.ctypes.data
+    if isinstance(buf, (bytes, bytearray)):
+        return C.cast(C.c_char_p(bytes(buf)) if isinstance(buf, bytearray) else C.c_char_p(buf), C.c_void_p).value or 0
+    if hasattr(buf, "data_ptr"):  # a (pinned) torch tensor
+        return int(buf.data_ptr())
+    raise TypeError(type(buf))
+
+
+_default: dict = {}
+
+
+def _aligner(W: int) -> Aligner:
+    if W not in _default:
+        _default[W] = Aligner(W=W)
+    return _default[W]
+
+
+def align_all(a, b, W: int = 64) -> List[Alignment]:
+    """The reference's two overloads in one function.
+
+    ``align_all(texts, queries)``   -- unstructured interface (src/genasm_gpu.hpp:8): lists of strings.
+    ``align_all(reference, reads)`` -- read-mapping interface (src/genasm_gpu.hpp:7): a ``Genome`` and a list of
+    ``Read``; one result per (read, location), read-major.
+    """
+    al = _aligner(W)
+    if isinstance(a, Genome):
+        reads: Sequence[Read] = b
+        al.set_reference(a.content)
+        cs = [loc.start_in_reference for r in reads for loc in r.locations]
+        cr = [i for i, r in enumerate(reads) for _ in r.locations]
+        return al.align_candidates([r.content for r in reads], cs, cr).alignments()
+    return al.align_pairs(a, b).alignments()

@@ -1,0 +1,168 @@
+// genasm_gpu.cpp -- the reference's two C++ library overloads (src/genasm_gpu.hpp:7-8) on top of the C ABI.
+//
+// Host side of the drop-in: flattens the caller's containers into blobs + offsets, calls sg_align_pairs /
+// sg_set_reference + sg_align_candidates, renders the packed runs to CIGAR text with all host threads
+// (the reference renders serially through a stringstream per alignment, src/genasm_gpu.cu:881-888,
+// 1049-1053 -- 20x its kernel time in its own README transcript, README.md:103-108).
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/genasm_gpu.hpp"
+#include "../../include/scrooge_b200.h"
+
+namespace genasm_gpu {
+
+bool enabled_algorithm_log = true;
+
+namespace {
+
+struct Holder {
+    sg_ctx *ctx = nullptr;
+    int W = 0, n_gpus = 0;
+    ~Holder() { if (ctx) sg_ctx_destroy(ctx); }
+};
+
+std::mutex g_mutex;  // calls are serialised per process (the reference is not re-entrant either)
+Holder g_holder;
+
+int env_int(const char *name, int dflt)
+{
+    const char *v = std::getenv(name);
+    return v && *v ? std::atoi(v) : dflt;
+}
+
+sg_ctx *context()
+{
+    const int W = env_int("SG_WINDOW", 64);
+    const int n = env_int("SG_NUM_GPUS", 0);
+    if (g_holder.ctx && (g_holder.W != W || g_holder.n_gpus != n)) {
+        sg_ctx_destroy(g_holder.ctx);
+        g_holder.ctx = nullptr;
+    }
+    if (!g_holder.ctx) {
+        if (sg_ctx_create(&g_holder.ctx, nullptr, n, W) != SG_OK)
+            throw std::runtime_error(std::string("scrooge_b200: ") + sg_last_error());
+        g_holder.W = W;
+        g_holder.n_gpus = n;
+    }
+    return g_holder.ctx;
+}
+
+void check(int rc)
+{
+    if (rc != SG_OK) throw std::runtime_error(std::string("scrooge_b200: ") + sg_last_error());
+}
+
+std::vector<Alignment_t> collect(sg_result *res, Extra *extra, long long *core_algorithm_ns)
+{
+    const uint64_t n = sg_result_count(res);
+    std::vector<Alignment_t> out(n);
+    const int64_t *ed = sg_result_edit_distances(res);
+    const uint64_t *rc = sg_result_ref_consumed(res);
+    if (extra) extra->ref_consumed.resize(n);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long long i = 0; i < (long long)n; i++) {
+        const uint64_t len = sg_result_cigar_len(res, (uint64_t)i);
+        out[i].cigar.resize(len);
+        if (len) {
+            // render straight into the string's buffer (cap counts the NUL the string already owns)
+            sg_result_render_cigar(res, (uint64_t)i, &out[i].cigar[0], len + 1);
+        }
+        out[i].edit_distance = ed[i];
+        if (extra) extra->ref_consumed[i] = rc[i];
+    }
+    const long long ns = sg_result_kernel_ns(res);
+    if (core_algorithm_ns) *core_algorithm_ns = ns;
+    if (extra) extra->total_ns = sg_result_total_ns(res);
+    if (enabled_algorithm_log && ns > 0)  // same line the reference prints (src/genasm_gpu.cu:950-951)
+        std::cerr << "core algorithm ran at " << (long long)((double)n * 1e9 / (double)ns) << " aligns/second" << std::endl;
+    sg_result_free(res);
+    return out;
+}
+
+void flatten(const std::vector<std::string> &v, std::string &blob, std::vector<uint64_t> &off)
+{
+    off.resize(v.size() + 1);
+    uint64_t total = 0;
+    for (size_t i = 0; i < v.size(); i++) { off[i] = total; total += v[i].size(); }
+    off[v.size()] = total;
+    blob.resize(total);
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)v.size(); i++)
+        if (!v[i].empty()) std::memcpy(&blob[off[i]], v[i].data(), v[i].size());
+}
+
+std::vector<Alignment_t> pairs_impl(std::vector<std::string> &texts, std::vector<std::string> &queries, Extra *extra,
+                                    long long *core_algorithm_ns)
+{
+    if (texts.size() != queries.size())  // the reference asserts (src/genasm_gpu.cu:984)
+        throw std::runtime_error("scrooge_b200: texts and queries differ in size");
+    std::lock_guard<std::mutex> lock(g_mutex);
+    sg_ctx *ctx = context();
+    if (enabled_algorithm_log) std::cerr << "Preparing data..." << std::endl;
+    std::string tblob, qblob;
+    std::vector<uint64_t> toff, qoff;
+    flatten(texts, tblob, toff);
+    flatten(queries, qblob, qoff);
+    sg_result *res = nullptr;
+    check(sg_align_pairs(ctx, tblob.data(), toff.data(), qblob.data(), qoff.data(), texts.size(), 0, &res));
+    return collect(res, extra, core_algorithm_ns);
+}
+
+std::vector<Alignment_t> mapping_impl(Genome_t &reference, std::vector<Read_t> &reads, Extra *extra, long long *core_algorithm_ns)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    sg_ctx *ctx = context();
+    if (enabled_algorithm_log) std::cerr << "Preparing data..." << std::endl;
+    check(sg_set_reference(ctx, reference.content.data(), reference.content.size()));
+    std::vector<uint64_t> roff(reads.size() + 1);
+    uint64_t total = 0, n_cand = 0;
+    for (size_t r = 0; r < reads.size(); r++) { roff[r] = total; total += reads[r].content.size(); n_cand += reads[r].locations.size(); }
+    roff[reads.size()] = total;
+    std::string rblob(total, '\0');
+    std::vector<uint64_t> cstart;
+    std::vector<uint32_t> cread;
+    cstart.reserve(n_cand);
+    cread.reserve(n_cand);
+    for (size_t r = 0; r < reads.size(); r++) {
+        if (!reads[r].content.empty()) std::memcpy(&rblob[roff[r]], reads[r].content.data(), reads[r].content.size());
+        for (const CandidateLocation_t &loc : reads[r].locations) {  // read-major, then location order (src/genasm_gpu.cu:961-967)
+            if (loc.start_in_reference < 0) throw std::runtime_error("scrooge_b200: negative start_in_reference");
+            cstart.push_back((uint64_t)loc.start_in_reference);
+            cread.push_back((uint32_t)r);
+        }
+    }
+    sg_result *res = nullptr;
+    check(sg_align_candidates(ctx, rblob.data(), roff.data(), reads.size(), cstart.data(), cread.data(), n_cand, 0, &res));
+    return collect(res, extra, core_algorithm_ns);
+}
+
+}  // namespace
+
+std::vector<Alignment_t> align_all(Genome_t &reference, std::vector<Read_t> &reads, long long *core_algorithm_ns)
+{
+    return mapping_impl(reference, reads, nullptr, core_algorithm_ns);
+}
+
+std::vector<Alignment_t> align_all(std::vector<std::string> &texts, std::vector<std::string> &queries, long long *core_algorithm_ns)
+{
+    return pairs_impl(texts, queries, nullptr, core_algorithm_ns);
+}
+
+std::vector<Alignment_t> align_all_ex(Genome_t &reference, std::vector<Read_t> &reads, Extra &extra, long long *core_algorithm_ns)
+{
+    return mapping_impl(reference, reads, &extra, core_algorithm_ns);
+}
+
+std::vector<Alignment_t> align_all_ex(std::vector<std::string> &texts, std::vector<std::string> &queries, Extra &extra,
+                                      long long *core_algorithm_ns)
+{
+    return pairs_impl(texts, queries, &extra, core_algorithm_ns);
+}
+
+}  // namespace genasm_gpu

@@ -1,0 +1,236 @@
+// sg_aux.cuh -- the kernels around the aligner: sequence ingest (ASCII -> 2 bit), CIGAR run compaction
+// (scan + gather), the synthetic-pair generator and the integer-ALU peak probe.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "sg_synth.h"
+
+namespace sg {
+
+// ---- ingest -----------------------------------------------------------------------------------------
+// Replaces reference single_ascii_to_twobit_string (src/genasm_gpu.cu:640-685), where every block
+// redundantly converts the whole blob with 32 threads and byte loads.  Here a thread converts 16 bases:
+// one 16-byte load, SWAR conversion of 4 bases per 32-bit register, one 4-byte store; a warp reads 512
+// contiguous bytes and writes 128.  HBM-bound: 1 B read + 0.25 B written per base.
+//
+// code = ((c >> 1) ^ (c >> 2)) & 3 maps A,C,G,T (either case) to 0,1,2,3 (src/genasm_cpu.cpp:87-90);
+// validity is checked by mapping the code back to its letter with a byte permute and comparing.
+__device__ __forceinline__ uint32_t pack4(uint32_t w, uint32_t &bad)
+{
+    const uint32_t u = w & 0xDFDFDFDFu;                         // fold case
+    const uint32_t x = ((u >> 1) ^ (u >> 2)) & 0x03030303u;     // 2-bit code in each byte
+    // every byte of x is 0x0k, so the low 16 bits of x are a PRMT selector (k0, 0, k1, 0): the permute
+    // returns (letter[k0], 'A', letter[k1], 'A'); same for the upper two bytes.  Compare with the input
+    // bytes spread the same way.
+    const uint32_t letters = 0x54474341u;  // "ACGT"
+    const uint32_t e_lo = __byte_perm(letters, 0u, x);
+    const uint32_t e_hi = __byte_perm(letters, 0u, x >> 16);
+    const uint32_t u_lo = __byte_perm(u, 0x41414141u, 0x4140u);  // (b0, 'A', b1, 'A')
+    const uint32_t u_hi = __byte_perm(u, 0x41414141u, 0x4342u);  // (b2, 'A', b3, 'A')
+    bad |= (e_lo ^ u_lo) | (e_hi ^ u_hi);
+    return (x * 0x01041040u) >> 24;                             // 4 codes -> 8 bits, base k at bits 2k+1:2k
+}
+
+__global__ void __launch_bounds__(256) pack_2bit_kernel(const char *__restrict__ ascii, uint64_t n_bases,
+                                                         uint32_t *__restrict__ packed, uint64_t n_words,
+                                                         unsigned long long *__restrict__ bad_pos)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < n_words; wi += stride) {
+        const uint64_t base = wi * 16ull;
+        uint32_t bad = 0, out;
+        if (base + 16ull <= n_bases) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(ascii + base));
+            out = pack4(v.x, bad) | (pack4(v.y, bad) << 8) | (pack4(v.z, bad) << 16) | (pack4(v.w, bad) << 24);
+        } else {  // tail (or padding) word: byte by byte, missing bases are zero
+            out = 0;
+            for (int k = 0; k < 16; k++) {
+                if (base + k < n_bases) {
+                    uint32_t b1 = 0;
+                    uint32_t code = pack4((uint32_t)(uint8_t)ascii[base + k] | 0x41414100u, b1);
+                    bad |= b1 ? 1u : 0u;
+                    out |= (code & 3u) << (2 * k);
+                }
+            }
+        }
+        packed[wi] = out;
+        if (bad) {  // rare: find the first offending base of this word
+            for (int k = 0; k < 16 && base + k < n_bases; k++) {
+                const uint32_t c = (uint32_t)(uint8_t)ascii[base + k] & 0xDFu;
+                if (c != 'A' && c != 'C' && c != 'G' && c != 'T') {
+                    atomicMin(bad_pos, (unsigned long long)(base + k));
+                    break;
+                }
+            }
+        }
+    }
+}
+
+// ---- CIGAR run compaction -----------------------------------------------------------------------------
+// The aligner writes each alignment's runs into its own slab slot (capacity known in advance, no device
+// allocator, no linked list: cf. reference src/cuda_list.hpp).  Compaction = exclusive scan of the run
+// counts, then a gather into one dense byte array that is copied to the host in a single transfer.
+
+constexpr int kScanBlock = 256;
+constexpr int kScanItems = 8;  // elements per thread
+constexpr int kScanTile = kScanBlock * kScanItems;
+
+__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t *total)
+{
+    __shared__ uint64_t warp_sums[kScanBlock / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint64_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint64_t s = lane < kScanBlock / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < kScanBlock / 32; o <<= 1) {
+            uint64_t y = __shfl_up_sync(0xFFFFFFFFu, s, o);
+            if (lane >= o) s += y;
+        }
+        if (lane < kScanBlock / 32) warp_sums[lane] = s;
+    }
+    __syncthreads();
+    const uint64_t warp_off = wid ? warp_sums[wid - 1] : 0;
+    if (total) *total = warp_sums[kScanBlock / 32 - 1];
+    const uint64_t res = warp_off + x - v;
+    __syncthreads();
+    return res;
+}
+
+// pass 1: per-tile totals
+__global__ void __launch_bounds__(kScanBlock) scan_tile_sums_kernel(const uint32_t *__restrict__ in, uint64_t n,
+                                                                     uint64_t *__restrict__ tile_sums)
+{
+    const uint64_t base = (uint64_t)blockIdx.x * kScanTile;
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        const uint64_t idx = base + (uint64_t)k * kScanBlock + threadIdx.x;
+        if (idx < n) s += in[idx];
+    }
+    uint64_t total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// pass 2: exclusive scan of the tile totals in one block (n_tiles is small: n / 2048)
+__global__ void __launch_bounds__(kScanBlock) scan_tile_offsets_kernel(uint64_t *__restrict__ tile_sums, uint64_t n_tiles)
+{
+    uint64_t carry = 0;
+    for (uint64_t base = 0; base < n_tiles; base += kScanBlock) {
+        const uint64_t idx = base + threadIdx.x;
+        const uint64_t v = idx < n_tiles ? tile_sums[idx] : 0;
+        uint64_t total;
+        const uint64_t ex = block_exclusive_scan(v, &total);
+        if (idx < n_tiles) tile_sums[idx] = carry + ex;
+        carry += total;
+    }
+}
+
+// pass 3: final offsets; out[n] = grand total
+__global__ void __launch_bounds__(kScanBlock) scan_finish_kernel(const uint32_t *__restrict__ in, uint64_t n,
+                                                                  const uint64_t *__restrict__ tile_offs,
+                                                                  uint64_t *__restrict__ out)
+{
+    const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        v[k] = base + k < n ? in[base + k] : 0u;
+        s += v[k];
+    }
+    uint64_t ex = block_exclusive_scan(s, nullptr) + tile_offs[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        if (base + k < n) out[base + k] = ex;
+        ex += v[k];
+        if (base + k == n - 1) out[n] = ex;
+    }
+}
+
+// gather: GROUP lanes per alignment copy its runs from the slab slot to the dense array
+template <int GROUP>
+__global__ void __launch_bounds__(256) gather_runs_kernel(const uint8_t *__restrict__ slab, const uint64_t *__restrict__ slab_off,
+                                                           const uint32_t *__restrict__ nruns, const uint64_t *__restrict__ run_off,
+                                                           uint64_t n, uint8_t *__restrict__ runs)
+{
+    const uint64_t gid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
+    const uint32_t sub = threadIdx.x % GROUP;
+    const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) / GROUP;
+    for (uint64_t a = gid; a < n; a += ngroups) {
+        const uint8_t *src = slab + slab_off[a];
+        uint8_t *dst = runs + run_off[a];
+        const uint32_t cnt = nruns[a];
+        for (uint32_t k = sub; k < cnt; k += GROUP) dst[k] = src[k];
+    }
+}
+
+// ---- synthetic pairs ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) synth_pairs_kernel(SgSynthParams p, uint64_t first_pair, uint64_t n_pairs,
+                                                           char *__restrict__ text, uint64_t text_stride,
+                                                           uint64_t *__restrict__ text_len, char *__restrict__ reads)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_pairs) return;
+    char *t = text + k * text_stride;
+    const uint64_t tl = sg_synth_pair(p, first_pair + k, t, reads + k * (uint64_t)p.read_len);
+    text_len[k] = tl;
+    for (uint64_t x = tl; x < text_stride; x++) t[x] = 'A';  // keep the whole slot packable
+}
+
+// ---- integer-ALU peak probe -----------------------------------------------------------------------------
+// Independent chains of the DC recurrence's own instructions.  kind 0: LOP3 only; 1: SHF (funnel shift) only;
+// 2: two LOP3 per SHF (the DC mix); 3: LOP3 + IMAD alternating (alu pipe + fma pipe).
+template <int KIND>
+__global__ void __launch_bounds__(256) int32_peak_kernel(uint32_t *__restrict__ sink, int iters, uint32_t seed)
+{
+    constexpr int CH = 8;
+    uint32_t a[CH], b[CH], c[CH];
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+        a[k] = seed + threadIdx.x * 2654435761u + k;
+        b[k] = a[k] * 40503u + 17u;
+        c[k] = b[k] ^ 0x9E3779B9u;
+    }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int rep = 0; rep < 4; rep++) {
+#pragma unroll
+            for (int k = 0; k < CH; k++) {
+                if (KIND == 0) {
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[k]) : "r"(b[k]), "r"(c[k]));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(b[k]) : "r"(c[k]), "r"(a[k]));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0xCA;" : "+r"(c[k]) : "r"(a[k]), "r"(b[k]));
+                } else if (KIND == 1) {
+                    asm volatile("shf.l.wrap.b32 %0, %1, %0, 1;" : "+r"(a[k]) : "r"(b[k]));
+                    asm volatile("shf.l.wrap.b32 %0, %1, %0, 1;" : "+r"(b[k]) : "r"(c[k]));
+                    asm volatile("shf.l.wrap.b32 %0, %1, %0, 1;" : "+r"(c[k]) : "r"(a[k]));
+                } else if (KIND == 2) {
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[k]) : "r"(b[k]), "r"(c[k]));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(b[k]) : "r"(c[k]), "r"(a[k]));
+                    asm volatile("shf.l.wrap.b32 %0, %1, %0, 1;" : "+r"(c[k]) : "r"(a[k]));
+                } else {
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[k]) : "r"(b[k]), "r"(c[k]));
+                    asm volatile("mad.lo.u32 %0, %0, 3, %1;" : "+r"(b[k]) : "r"(c[k]));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0xCA;" : "+r"(c[k]) : "r"(a[k]), "r"(b[k]));
+                    asm volatile("mad.lo.u32 %0, %0, 5, %1;" : "+r"(a[k]) : "r"(b[k]));
+                }
+            }
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < CH; k++) acc ^= a[k] ^ b[k] ^ c[k];
+    if (acc == 0x12345678u) sink[0] = acc;  // keep the chains alive
+}
+constexpr int kPeakOpsPerIter[4] = {8 * 4 * 3, 8 * 4 * 3, 8 * 4 * 3, 8 * 4 * 4};
+
+}  // namespace sg

@@ -1,0 +1,283 @@
+// sg_device_api.cu -- layer 2 of include/scrooge_b200.h: launches of the sm_100a kernels on device
+// pointers and an explicit stream.  No CPU fallback: every function needs a CUDA device.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cuda_runtime.h>
+
+#include "../../include/scrooge_b200.h"
+#include "sg_internal.h"
+#include "sg_align.cuh"
+#include "sg_aux.cuh"
+
+namespace sg {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    return fail(SG_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+struct DeviceInfo {
+    int sms = 0;
+    int warps_per_sm[2] = {0, 0};  // [0]: W=64, [1]: W=32
+    bool ready = false;
+};
+static DeviceInfo g_dev_info[64];
+
+template <int W> static int setup_kernel(int *blocks_per_sm)
+{
+    auto kern = genasm_align_kernel<W>;
+    const int smem = SmemLayout<W>::BYTES_PER_WARP;
+    SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, 32, smem));
+    if (*blocks_per_sm < 1) return fail(SG_ERR_CUDA, "alignment kernel does not fit on this device");
+    return SG_OK;
+}
+
+static int device_info(DeviceInfo **out)
+{
+    int dev = 0;
+    SG_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(SG_ERR_BAD_ARG, "device index out of range");
+    DeviceInfo &di = g_dev_info[dev];
+    if (!di.ready) {
+        SG_CUDA(cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, dev));
+        int rc = setup_kernel<64>(&di.warps_per_sm[0]);
+        if (rc) return rc;
+        rc = setup_kernel<32>(&di.warps_per_sm[1]);
+        if (rc) return rc;
+        di.ready = true;
+    }
+    *out = &di;
+    return SG_OK;
+}
+
+}  // namespace sg
+
+using namespace sg;
+
+extern "C" {
+
+const char *sg_last_error(void) { return g_last_error.c_str(); }
+
+int sg_version(void) { return 1; }
+
+int sg_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+uint64_t sg_packed_words(uint64_t n_bases) { return (n_bases + 15ull) / 16ull + 8ull; }
+
+int sg_dev_pack_2bit(const char *d_ascii, uint64_t n_bases, uint32_t *d_packed, uint64_t *d_bad_pos, void *stream)
+{
+    if (!d_packed || !d_bad_pos || (!d_ascii && n_bases)) return fail(SG_ERR_BAD_ARG, "sg_dev_pack_2bit: null pointer");
+    if (((uintptr_t)d_ascii & 15u) != 0) return fail(SG_ERR_BAD_ARG, "sg_dev_pack_2bit: d_ascii must be 16-byte aligned");
+    DeviceInfo *di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    const uint64_t n_words = sg_packed_words(n_bases);  // includes zeroed padding words the aligner may read
+    const uint64_t want = (n_words + 255ull) / 256ull;
+    const int blocks = (int)std::min<uint64_t>(want, (uint64_t)di->sms * 16ull);
+    pack_2bit_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_ascii, n_bases, d_packed, n_words,
+                                                              (unsigned long long *)d_bad_pos);
+    SG_CUDA(cudaGetLastError());
+    return SG_OK;
+}
+
+int sg_dev_align_geometry(int W, int *warps_per_sm, int *smem_per_warp, int *num_sms)
+{
+    if (W != 64 && W != 32) return fail(SG_ERR_BAD_ARG, "W must be 64 or 32");
+    DeviceInfo *di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    if (warps_per_sm) *warps_per_sm = di->warps_per_sm[W == 64 ? 0 : 1];
+    if (smem_per_warp) *smem_per_warp = W == 64 ? SmemLayout<64>::BYTES_PER_WARP : SmemLayout<32>::BYTES_PER_WARP;
+    if (num_sms) *num_sms = di->sms;
+    return SG_OK;
+}
+
+int sg_dev_align(int W, const uint32_t *d_text, const uint64_t *d_text_start, const uint64_t *d_text_len,
+                 const uint32_t *d_query, const uint64_t *d_query_start, const uint64_t *d_query_len,
+                 uint64_t n, uint32_t flags, uint8_t *d_slab, const uint64_t *d_slab_off,
+                 uint64_t *d_counter, int64_t *d_edit, uint64_t *d_ref_consumed, uint32_t *d_nruns,
+                 uint8_t *d_status, void *stream)
+{
+    if (W != 64 && W != 32) return fail(SG_ERR_BAD_ARG, "W must be 64 or 32");
+    if (n == 0) return SG_OK;
+    if (!d_text || !d_text_start || !d_text_len || !d_query || !d_query_start || !d_query_len || !d_counter ||
+        !d_edit || !d_ref_consumed || !d_nruns || !d_status)
+        return fail(SG_ERR_BAD_ARG, "sg_dev_align: null pointer");
+    if (!(flags & SG_FLAG_DISTANCE_ONLY) && (!d_slab || !d_slab_off))
+        return fail(SG_ERR_BAD_ARG, "sg_dev_align: CIGAR output needs d_slab and d_slab_off");
+    DeviceInfo *di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    SG_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(uint64_t), st));
+    AlignParams P;
+    P.text = d_text; P.text_start = d_text_start; P.text_len = d_text_len;
+    P.query = d_query; P.query_start = d_query_start; P.query_len = d_query_len;
+    P.n = n; P.flags = flags; P.slab = d_slab; P.slab_off = d_slab_off;
+    P.counter = (unsigned long long *)d_counter;
+    P.edit = d_edit; P.ref_consumed = d_ref_consumed; P.nruns = d_nruns; P.status = d_status;
+    const int wps = di->warps_per_sm[W == 64 ? 0 : 1];
+    // persistent warps: one CTA of one warp each, a multiple of the SM count, never more lanes than work
+    uint64_t warps = (uint64_t)di->sms * (uint64_t)wps;
+    const uint64_t needed = (n + 31ull) / 32ull;
+    if (warps > needed) warps = needed;
+    if (W == 64)
+        genasm_align_kernel<64><<<(unsigned)warps, 32, SmemLayout<64>::BYTES_PER_WARP, st>>>(P);
+    else
+        genasm_align_kernel<32><<<(unsigned)warps, 32, SmemLayout<32>::BYTES_PER_WARP, st>>>(P);
+    SG_CUDA(cudaGetLastError());
+    return SG_OK;
+}
+
+uint64_t sg_scan_tmp_bytes(uint64_t n) { return ((n + kScanTile - 1) / kScanTile + 1) * sizeof(uint64_t); }
+
+int sg_dev_scan_runs(const uint32_t *d_nruns, uint64_t n, uint64_t *d_run_off, void *d_scan_tmp, void *stream)
+{
+    if (!d_run_off) return fail(SG_ERR_BAD_ARG, "sg_dev_scan_runs: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) {
+        SG_CUDA(cudaMemsetAsync(d_run_off, 0, sizeof(uint64_t), st));
+        return SG_OK;
+    }
+    if (!d_nruns || !d_scan_tmp) return fail(SG_ERR_BAD_ARG, "sg_dev_scan_runs: null pointer");
+    const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
+    uint64_t *tmp = (uint64_t *)d_scan_tmp;
+    scan_tile_sums_kernel<<<(unsigned)tiles, kScanBlock, 0, st>>>(d_nruns, n, tmp);
+    scan_tile_offsets_kernel<<<1, kScanBlock, 0, st>>>(tmp, tiles);
+    scan_finish_kernel<<<(unsigned)tiles, kScanBlock, 0, st>>>(d_nruns, n, tmp, d_run_off);
+    SG_CUDA(cudaGetLastError());
+    return SG_OK;
+}
+
+int sg_dev_gather_runs(const uint8_t *d_slab, const uint64_t *d_slab_off, const uint32_t *d_nruns,
+                       const uint64_t *d_run_off, uint64_t n, uint8_t *d_runs, void *stream)
+{
+    if (n == 0) return SG_OK;
+    if (!d_slab || !d_slab_off || !d_nruns || !d_run_off || !d_runs)
+        return fail(SG_ERR_BAD_ARG, "sg_dev_gather_runs: null pointer");
+    DeviceInfo *di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    // a warp per alignment (long reads have thousands of runs; short reads a handful, where the gather is
+    // a negligible part of the step either way)
+    const uint64_t want = (n * 32ull + 255ull) / 256ull;
+    const unsigned blocks = (unsigned)std::min<uint64_t>(want, (uint64_t)di->sms * 32ull);
+    gather_runs_kernel<32><<<blocks, 256, 0, st>>>(d_slab, d_slab_off, d_nruns, d_run_off, n, d_runs);
+    SG_CUDA(cudaGetLastError());
+    return SG_OK;
+}
+
+int sg_dev_int32_peak(int kind, double ms, double *gops)
+{
+    if (kind < 0 || kind > 3 || !gops) return fail(SG_ERR_BAD_ARG, "sg_dev_int32_peak: bad argument");
+    DeviceInfo *di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    uint32_t *sink = nullptr;
+    SG_CUDA(cudaMalloc(&sink, 64));
+    cudaEvent_t e0, e1;
+    SG_CUDA(cudaEventCreate(&e0));
+    SG_CUDA(cudaEventCreate(&e1));
+    const int blocks = di->sms * 8, threads = 256;
+    auto launch = [&](int iters) {
+        switch (kind) {
+            case 0: int32_peak_kernel<0><<<blocks, threads>>>(sink, iters, 1u); break;
+            case 1: int32_peak_kernel<1><<<blocks, threads>>>(sink, iters, 1u); break;
+            case 2: int32_peak_kernel<2><<<blocks, threads>>>(sink, iters, 1u); break;
+            default: int32_peak_kernel<3><<<blocks, threads>>>(sink, iters, 1u); break;
+        }
+    };
+    int iters = 2048;
+    float t = 0.f;
+    for (int round = 0; round < 6; round++) {  // grow until the launch lasts about `ms`
+        launch(iters);  // warm-up at this size
+        cudaEventRecord(e0);
+        launch(iters);
+        cudaEventRecord(e1);
+        SG_CUDA(cudaEventSynchronize(e1));
+        SG_CUDA(cudaEventElapsedTime(&t, e0, e1));
+        if (t >= ms * 0.5 || iters >= (1 << 24)) break;
+        double scale = ms / (t > 1e-3 ? t : 1e-3);
+        iters = (int)std::min<double>((double)iters * std::min(scale, 16.0), (double)(1 << 24));
+    }
+    const double ops = (double)blocks * threads * (double)iters * (double)kPeakOpsPerIter[kind];
+    *gops = ops / ((double)t * 1e-3) / 1e9;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return SG_OK;
+}
+
+uint64_t sg_synth_text_stride(uint32_t read_len, uint32_t slack)
+{
+    uint64_t s = sg_synth_stride(read_len, slack);
+    return (s + 15ull) & ~15ull;
+}
+
+static SgSynthParams make_synth(uint64_t seed, uint32_t read_len, double err, uint32_t w_sub, uint32_t w_ins,
+                                uint32_t w_del, uint32_t slack)
+{
+    SgSynthParams p;
+    p.seed = seed;
+    p.read_len = read_len;
+    double e = err < 0 ? 0 : (err > 1 ? 1 : err);
+    double thr = e * 4294967296.0;
+    p.err_threshold = thr >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)thr;
+    p.w_sub = w_sub; p.w_ins = w_ins; p.w_del = w_del;
+    p.slack = slack;
+    return p;
+}
+
+int sg_synth_pairs_host(uint64_t seed, uint64_t first_pair, uint64_t n_pairs, uint32_t read_len, double err,
+                        uint32_t w_sub, uint32_t w_ins, uint32_t w_del, uint32_t slack, char *text,
+                        uint64_t text_stride, uint64_t *text_len, char *reads)
+{
+    if (text_stride < sg_synth_stride(read_len, slack)) return fail(SG_ERR_BAD_ARG, "text_stride too small");
+    const SgSynthParams p = make_synth(seed, read_len, err, w_sub, w_ins, w_del, slack);
+#pragma omp parallel for schedule(static)
+    for (long long k = 0; k < (long long)n_pairs; k++) {
+        char *t = text + (uint64_t)k * text_stride;
+        const uint64_t tl = sg_synth_pair(p, first_pair + (uint64_t)k, t, reads + (uint64_t)k * read_len);
+        text_len[k] = tl;
+        memset(t + tl, 'A', text_stride - tl);  // keep the whole slot packable
+    }
+    return SG_OK;
+}
+
+int sg_dev_synth_pairs(uint64_t seed, uint64_t first_pair, uint64_t n_pairs, uint32_t read_len, double err,
+                       uint32_t w_sub, uint32_t w_ins, uint32_t w_del, uint32_t slack, char *d_text,
+                       uint64_t text_stride, uint64_t *d_text_len, char *d_reads, void *stream)
+{
+    if (text_stride < sg_synth_stride(read_len, slack)) return fail(SG_ERR_BAD_ARG, "text_stride too small");
+    if (n_pairs == 0) return SG_OK;
+    const SgSynthParams p = make_synth(seed, read_len, err, w_sub, w_ins, w_del, slack);
+    const unsigned blocks = (unsigned)((n_pairs + 127ull) / 128ull);
+    synth_pairs_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(p, first_pair, n_pairs, d_text, text_stride,
+                                                                d_text_len, d_reads);
+    SG_CUDA(cudaGetLastError());
+    return SG_OK;
+}
+
+}  // extern "C"

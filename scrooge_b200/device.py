@@ -1,0 +1,106 @@
+"""Device-level entry points (sg_dev_*) on torch tensors.
+
+torch is used only as plumbing: device memory, the current stream and CUDA events.  Every function here
+launches the library's own sm_100a kernels on ``torch.cuda.current_stream()`` so that ``torch.cuda.Event``
+timing brackets them.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from ._lib import SG_FLAG_DISTANCE_ONLY, check, lib
+
+U64_MAX = (1 << 64) - 1
+
+
+def _stream() -> int:
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else int(t.data_ptr())
+
+
+def pack_2bit(ascii_dev: torch.Tensor, n_bases: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """ASCII bytes (uint8, device) -> packed 2-bit words (int32 storage, device) and the first-bad-position cell
+    (int64 storage; -1 == none).  Replaces reference single_ascii_to_twobit_string (src/genasm_gpu.cu:640-685)."""
+    assert ascii_dev.is_cuda and ascii_dev.dtype == torch.uint8 and ascii_dev.is_contiguous()
+    n = ascii_dev.numel() if n_bases is None else n_bases
+    words = int(lib().sg_packed_words(n))
+    packed = torch.empty(words, dtype=torch.int32, device=ascii_dev.device)
+    bad = torch.full((1,), -1, dtype=torch.int64, device=ascii_dev.device)  # == UINT64_MAX
+    check(lib().sg_dev_pack_2bit(_p(ascii_dev), n, _p(packed), _p(bad), _stream()))
+    return packed, bad
+
+
+@dataclass
+class AlignOut:
+    edit: torch.Tensor          # int64 [n]
+    ref_consumed: torch.Tensor  # int64 storage of uint64 [n]
+    nruns: torch.Tensor         # int32 storage of uint32 [n]
+    status: torch.Tensor        # uint8 [n]
+
+
+class DeviceAligner:
+    """Preallocated outputs + one sg_dev_align launch per call (inputs resident in HBM)."""
+
+    def __init__(self, W: int, n: int, device: torch.device, slab_bytes: int = 0):
+        self.W, self.n, self.device = W, n, device
+        self.counter = torch.zeros(1, dtype=torch.int64, device=device)
+        self.out = AlignOut(
+            edit=torch.empty(n, dtype=torch.int64, device=device),
+            ref_consumed=torch.empty(n, dtype=torch.int64, device=device),
+            nruns=torch.empty(n, dtype=torch.int32, device=device),
+            status=torch.empty(n, dtype=torch.uint8, device=device),
+        )
+        self.slab = torch.empty(max(slab_bytes, 16), dtype=torch.uint8, device=device) if slab_bytes else None
+        self.run_off = torch.empty(n + 1, dtype=torch.int64, device=device)
+        self.scan_tmp = torch.empty(int(lib().sg_scan_tmp_bytes(n)), dtype=torch.uint8, device=device)
+
+    def align(self, text: torch.Tensor, text_start: torch.Tensor, text_len: torch.Tensor, query: torch.Tensor,
+              query_start: torch.Tensor, query_len: torch.Tensor, slab_off: Optional[torch.Tensor] = None,
+              distance_only: bool = False) -> AlignOut:
+        flags = SG_FLAG_DISTANCE_ONLY if distance_only else 0
+        o = self.out
+        check(lib().sg_dev_align(self.W, _p(text), _p(text_start), _p(text_len), _p(query), _p(query_start), _p(query_len),
+                                 self.n, flags, _p(self.slab), _p(slab_off), _p(self.counter), _p(o.edit),
+                                 _p(o.ref_consumed), _p(o.nruns), _p(o.status), _stream()))
+        return o
+
+    def compact(self, slab_off: torch.Tensor, runs: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """scan + gather; returns (run_off [n+1], dense runs).  `runs` may be a preallocated buffer."""
+        o = self.out
+        check(lib().sg_dev_scan_runs(_p(o.nruns), self.n, _p(self.run_off), _p(self.scan_tmp), _stream()))
+        if runs is None:
+            total = int(self.run_off[-1].item())
+            runs = torch.empty(max(total, 1), dtype=torch.uint8, device=self.device)
+        check(lib().sg_dev_gather_runs(_p(self.slab), _p(slab_off), _p(o.nruns), _p(self.run_off), self.n, _p(runs), _stream()))
+        return self.run_off, runs
+
+
+def align_geometry(W: int) -> Tuple[int, int, int]:
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    check(lib().sg_dev_align_geometry(W, C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value  # warps per SM, smem bytes per warp, SMs
+
+
+def int32_peak(kind: int = 2, ms: float = 50.0) -> float:
+    g = C.c_double()
+    check(lib().sg_dev_int32_peak(kind, ms, C.byref(g)))
+    return g.value
+
+
+def synth_pairs_device(seed: int, first_pair: int, n_pairs: int, read_len: int, err: float, ratio: Tuple[int, int, int],
+                       slack: int, device: torch.device):
+    """Generates pairs on the device.  Returns (text uint8 [n, stride], text_len int64 [n], reads uint8 [n, L])."""
+    stride = int(lib().sg_synth_text_stride(read_len, slack))
+    text = torch.empty((n_pairs, stride), dtype=torch.uint8, device=device)
+    tlen = torch.empty(n_pairs, dtype=torch.int64, device=device)
+    reads = torch.empty((n_pairs, read_len), dtype=torch.uint8, device=device)
+    check(lib().sg_dev_synth_pairs(seed, first_pair, n_pairs, read_len, float(err), ratio[0], ratio[1], ratio[2], slack,
+                                   _p(text), stride, _p(tlen), _p(reads), _stream()))
+    return text, tlen, reads

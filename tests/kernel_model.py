@@ -1,0 +1,107 @@
+"""Pure-Python model of the CUDA kernel's algorithm (scrooge_b200/csrc/sg_align.cuh): left-aligned vectors,
+G-row chunks with a forefront, V/H/E edge words instead of stored R rows, traceback over the edge words.
+It exists so that the algorithmic identities the kernel relies on can be checked against the oracle on a
+machine without a GPU (tests/test_kernel_model.py); it is not used by the product."""
+from typing import List, Tuple
+
+OPS = "=XID"
+CODE = {"A": 0, "C": 1, "G": 2, "T": 3, "a": 0, "c": 1, "g": 2, "t": 3}
+
+
+def align(text: str, read: str, W: int = 64, O: int = 33, G: int = 8) -> Tuple[int, str, int]:
+    MASK = (1 << W) - 1
+    TBL = W - O
+    TOP_SHIFT = W - 32
+    t = [CODE[c] for c in text]
+    q = [CODE[c] for c in read]
+    t_pos = q_pos = 0
+    ed = 0
+    out: List[str] = []
+    while q_pos < len(q):
+        n = min(W, len(t) - t_pos)
+        m = min(W, len(q) - q_pos)
+        hm = (MASK << (W - m)) & MASK
+        pm = [0, 0, 0, 0]
+        for c in range(4):
+            v = 0
+            for J in range(m):
+                if q[q_pos + J] != c:
+                    v |= 1 << (W - 1 - J)
+            pm[c] = v & hm
+        FF = [0] * (W + 1)
+        V = [0] * (TBL + 1)
+        H = [0] * (TBL + 1)
+        E = [0] * (TBL + 1)
+        d0 = 0
+        while True:
+            first = d0 == 0
+            C = [0] * G
+            S = [0] * G
+            XFp = MASK
+            for i in range(n, -1, -1):
+                F = MASK if first else FF[i]
+                sF = (F << 1) & MASK
+                v = h = e = 0
+                if i == n:
+                    for r in range(G):
+                        s = W - m + d0 + r
+                        C[r] = (MASK << s) & MASK if s < W else 0
+                        S[r] = (C[r] << 1) & MASK
+                        v |= C[r] & ~S[r]
+                else:
+                    p = pm[t[t_pos + i]]
+                    e = p
+                    aboveS = MASK if first else sF
+                    aboveX = XFp
+                    for r in range(G):
+                        Xr = C[r] & S[r]
+                        newC = ((S[r] | p) & aboveX) & aboveS
+                        h |= newC & ~C[r]
+                        C[r] = newC
+                        aboveX = Xr
+                        S[r] = (C[r] << 1) & MASK
+                        v |= C[r] & ~S[r]
+                        aboveS = S[r]
+                XFp = MASK if first else (F & sF)
+                FF[i] = C[G - 1]
+                if i <= TBL:
+                    top = lambda x: (x & MASK) >> TOP_SHIFT
+                    V[i] = top(v) if first else V[i] | top(v)
+                    H[i] = top(h) if first else H[i] | top(h)
+                    if first:
+                        E[i] = top(e)
+            above = sum((C[r] >> (W - 1)) & 1 for r in range(G))
+            if above == G:
+                d0 += G
+                continue
+            break
+        i = j = 0
+        mask = 1 << 31
+        cur_op, cur_cnt = None, 0
+        while j < m and i < TBL and j < TBL:
+            if V[i] & mask:
+                op = 2
+            elif H[i] & mask:
+                op = 3
+            elif E[i] & mask:
+                op = 1
+            else:
+                op = 0
+            if op != 2:
+                i += 1
+            if op != 3:
+                j += 1
+                mask >>= 1
+            if op != 0:
+                ed += 1
+            if op != cur_op:
+                if cur_cnt:
+                    out.append(f"{cur_cnt}{OPS[cur_op]}")
+                cur_op, cur_cnt = op, 1
+            else:
+                cur_cnt += 1
+        if cur_cnt:
+            out.append(f"{cur_cnt}{OPS[cur_op]}")
+        t_pos += i
+        q_pos += j
+    return ed, "".join(out), t_pos

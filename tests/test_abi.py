@@ -1,0 +1,75 @@
+"""The C-ABI library on a machine without a GPU: it loads, exports every symbol include/scrooge_b200.h
+declares, fails loudly (no CPU fallback) and its host-only helpers work."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "scrooge_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported_and_bound(sglib):
+    from scrooge_b200._lib import SIGNATURES
+    names = declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(sglib, n), f"{n} declared in the header but not exported"
+        assert n in SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(SIGNATURES) == names
+
+
+def test_no_cpu_fallback(sglib):
+    import scrooge_b200
+    if sglib.sg_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(scrooge_b200.ScroogeError) as e:
+        scrooge_b200.Aligner()
+    assert e.value.code == 1 and "no CPU fallback" in str(e.value)
+    with pytest.raises(scrooge_b200.ScroogeError):
+        scrooge_b200.align_all(["ACGT"], ["ACG"])
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under scrooge_b200/ or include/ may import, load or link it."""
+    for top in ("scrooge_b200", "include"):
+        for d, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                    text = open(os.path.join(d, f)).read()
+                    for needle in ("oracle/", "libsgoracle", "import oracle", "from oracle", "sgo_", "libscrooge_ref"):
+                        assert needle not in text, (f, needle)
+    mk = open(os.path.join(ROOT, "Makefile")).read()
+    assert "libsgoracle" not in mk and "genasm_oracle" not in mk
+
+
+def test_synth_generator_is_deterministic_and_shaped(sglib):
+    from scrooge_b200 import synth
+    wl = synth.WORKLOADS["long_10kbp"]
+    t1, l1, r1 = synth.pairs_host(wl, 5, 6)
+    t2, l2, r2 = synth.pairs_host(wl, 7, 2)
+    assert np.array_equal(t1[2], t2[0]) and np.array_equal(r1[3], r2[1]) and l1[2] == l2[0]
+    assert set(np.unique(r1)) <= set(b"ACGT")
+    assert all(10000 * 0.9 < x < 10000 * 1.1 + 64 for x in l1)
+    assert t1.shape[1] % 16 == 0 and t1.shape[1] >= 2 * 10000 + 64
+    # padding after the text is packable
+    assert set(np.unique(t1[0, int(l1[0]):])) == {ord("A")}
+
+
+def test_synth_error_rate(sglib, oracle):
+    from scrooge_b200 import synth
+    wl = synth.Workload("t", 2000, 0.10, synth.PACBIO, 64, 99)
+    text, tlen, reads = synth.pairs_host(wl, 0, 20)
+    T, Q = synth.pairs_as_strings(text, tlen, reads)
+    res = oracle.align_pairs(T, Q)
+    rate = float(np.mean(res.edit)) / 2000
+    assert 0.07 < rate < 0.12  # observed distance is a little under e*L (adjacent edits cancel)
+    tb, toff, qb, qoff = synth.pairs_as_blobs(text, tlen, reads)
+    assert bytes(tb[int(toff[3]):int(toff[4])]).decode() == T[3] and bytes(qb[int(qoff[3]):int(qoff[4])]).decode() == Q[3]

@@ -1,0 +1,206 @@
+"""Parity of the CUDA path with the oracle, through the C ABI (host API and device API).  Bit-exact:
+edit distance, CIGAR string, consumed reference prefix."""
+import numpy as np
+import pytest
+
+from conftest import mutate, rand_seq, random_pairs
+from oracle.binding import cigar_ref_consumed
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def aligners(sglib):
+    import scrooge_b200
+    assert sglib.sg_device_count() > 0, "GPU tests need a CUDA device"
+    return {64: scrooge_b200.Aligner(W=64, n_gpus=1), 32: scrooge_b200.Aligner(W=32, n_gpus=1)}
+
+
+def check_against_oracle(oracle, aligner, T, Q, W):
+    want = oracle.align_pairs(T, Q, W=W, threads=4)
+    got = aligner.align_pairs(T, Q)
+    ed, rc, cg = got.edit_distances, got.ref_consumed, got.cigars()
+    assert got.count == len(T)
+    for k in range(len(T)):
+        assert int(ed[k]) == int(want.edit[k]), (k, T[k], Q[k])
+        assert cg[k] == want.cigars[k], (k, T[k], Q[k])
+        assert int(rc[k]) == int(want.ref_consumed[k]) == cigar_ref_consumed(cg[k]), k
+    return got
+
+
+@pytest.mark.parametrize("W", [64, 32])
+def test_golden_groups(aligners, golden, W):
+    for name, g in golden[W]["groups"].items():
+        got = aligners[W].align_pairs([x["text"] for x in g], [x["query"] for x in g])
+        ed, cg = got.edit_distances, got.cigars()
+        for k, x in enumerate(g):
+            assert int(ed[k]) == x["edit"], (name, k)
+            assert cg[k] == x["cigar"], (name, k)
+            assert got.cigar(k) == x["cigar"]
+
+
+@pytest.mark.parametrize("W", [64, 32])
+def test_golden_mapping(aligners, golden, W):
+    m = golden[W]["mapping"]
+    cs = [s for l in m["locations"] for s in l]
+    cr = [r for r, l in enumerate(m["locations"]) for _ in l]
+    al = aligners[W]
+    al.set_reference(m["genome"])
+    got = al.align_candidates(m["reads"], cs, cr)
+    assert [int(x) for x in got.edit_distances] == m["edit"]
+    assert got.cigars() == m["cigar"]
+    assert [int(x) for x in got.ref_consumed] == [cigar_ref_consumed(c) for c in m["cigar"]]
+
+
+def test_reference_interface_mirror(aligners, golden):
+    """align_all(texts, queries) and align_all(Genome, reads) give the same strings (reference
+    src/tests.cu:273-333: all entry points must agree)."""
+    import scrooge_b200 as sb
+    for x in golden[64]["groups"]["differential_tests_cu"]:
+        a = sb.align_all([x["text"]], [x["query"]])
+        b = sb.align_all(sb.Genome(x["text"]), [sb.Read("test", x["query"], [sb.CandidateLocation(0)])])
+        assert a[0].cigar == b[0].cigar == x["cigar"] and a[0].edit_distance == b[0].edit_distance == x["edit"]
+
+
+@pytest.mark.parametrize("W", [64, 32])
+def test_random_mixed(oracle, aligners, W):
+    T, Q = random_pairs(100 + W, 6000, [0, 1, 2, 3, 4, 5, 15, 16, 17, 31, 32, 33, 63, 64, 65, 100, 150, 151, 400, 1000],
+                        [0.0, 0.02, 0.05, 0.1, 0.15, 0.3, 0.6])
+    check_against_oracle(oracle, aligners[W], T, Q, W)
+
+
+def test_long_reads_config3_shape(oracle, aligners):
+    """10 kbp / 10 % PacBio-like pairs from the benchmark generator (BASELINE.json configs[2])."""
+    from scrooge_b200 import synth
+    wl = synth.WORKLOADS["long_10kbp"]
+    text, tlen, reads = synth.pairs_host(wl, 0, 300)
+    T, Q = synth.pairs_as_strings(text, tlen, reads)
+    got = check_against_oracle(oracle, aligners[64], T, Q, 64)
+    assert got.kernel_ns > 0
+
+
+def test_short_reads_config2_shape(oracle, aligners):
+    from scrooge_b200 import synth
+    wl = synth.WORKLOADS["short_150bp"]
+    text, tlen, reads = synth.pairs_host(wl, 0, 20000)
+    T, Q = synth.pairs_as_strings(text, tlen, reads)
+    check_against_oracle(oracle, aligners[64], T, Q, 64)
+    check_against_oracle(oracle, aligners[32], T, Q, 32)
+
+
+def test_very_long_and_unrelated(oracle, aligners):
+    rng = __import__("random").Random(9)
+    t = rand_seq(rng, 120000)
+    T = [t, rand_seq(rng, 30000), t[:50000], "ACGT" * 5000]
+    Q = [mutate(rng, t, 100000, 0.15), rand_seq(rng, 20000), mutate(rng, t, 60000, 0.05), "ACGT" * 4000 + "TTTT"]
+    check_against_oracle(oracle, aligners[64], T, Q, 64)
+
+
+def test_distance_only(oracle, aligners):
+    T, Q = random_pairs(3, 500, [100, 150, 1000], [0.05, 0.1])
+    want = oracle.align_pairs(T, Q)
+    got = aligners[64].align_pairs(T, Q, distance_only=True)
+    assert list(got.edit_distances) == list(want.edit)
+    assert list(got.ref_consumed) == list(want.ref_consumed)
+    assert len(got.run_offsets) == 0
+
+
+def test_bad_base_reports_pair(aligners):
+    import scrooge_b200
+    with pytest.raises(scrooge_b200.ScroogeError) as e:
+        aligners[64].align_pairs(["ACGT", "ACGTACGTNACGT", "AC"], ["ACG", "ACGT", "A"])
+    assert e.value.code == 2 and "pair 1" in str(e.value) and "position 8" in str(e.value)
+    with pytest.raises(scrooge_b200.ScroogeError):
+        aligners[64].set_reference("ACGTXACGT")
+
+
+def test_size_mismatch_and_missing_reference(aligners):
+    import scrooge_b200
+    with pytest.raises(ValueError):
+        aligners[64].align_pairs(["A"], [])
+    fresh = scrooge_b200.Aligner(W=64, n_gpus=1)
+    with pytest.raises(scrooge_b200.ScroogeError) as e:
+        fresh.align_candidates(["ACGT"], [0], [0])
+    assert e.value.code == 6
+
+
+def test_empty_batch(aligners):
+    got = aligners[64].align_pairs([], [])
+    assert got.count == 0 and got.cigars() == []
+
+
+def test_pack_kernel_matches_numpy(sglib):
+    import torch
+    from scrooge_b200 import device
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 15, 16, 17, 4097, 1_000_003):
+        codes = rng.integers(0, 4, size=n, dtype=np.uint8)
+        letters = np.frombuffer(b"ACGTacgt", dtype=np.uint8)
+        ascii_np = letters[codes + 4 * rng.integers(0, 2, size=n, dtype=np.uint8)]
+        a = torch.from_numpy(ascii_np.copy()).cuda() if n else torch.empty(0, dtype=torch.uint8, device="cuda")
+        packed, bad = device.pack_2bit(a)
+        torch.cuda.synchronize()
+        assert int(bad.item()) == -1
+        words = packed.cpu().numpy().view(np.uint32)
+        pad = np.zeros((len(words)) * 16, dtype=np.uint64)
+        pad[:n] = codes
+        expect = (pad.reshape(-1, 16) << (2 * np.arange(16, dtype=np.uint64))).sum(axis=1).astype(np.uint32)
+        assert np.array_equal(words, expect), n
+    a = torch.from_numpy(np.frombuffer(b"ACGT" * 10 + b"ACNT", dtype=np.uint8).copy()).cuda()
+    _, bad = device.pack_2bit(a)
+    assert int(bad.item()) == 42
+
+
+def test_device_api_resident_inputs(oracle, sglib):
+    """The path bench.py times: generator, ingest, aligner and compaction all on device-resident buffers."""
+    import torch
+    from scrooge_b200 import device, synth
+    wl = synth.Workload("t", 1000, 0.10, synth.PACBIO, 64, 4242)
+    n = 4096
+    dev = torch.device("cuda:0")
+    text, tlen, reads = device.synth_pairs_device(wl.seed, 0, n, wl.read_len, wl.err, wl.ratio, wl.slack, dev)
+    h_text, h_tlen, h_reads = synth.pairs_host(wl, 0, n)
+    assert np.array_equal(text.cpu().numpy(), h_text) and np.array_equal(tlen.cpu().numpy().astype(np.uint64), h_tlen)
+    assert np.array_equal(reads.cpu().numpy(), h_reads)
+    stride, L = text.shape[1], wl.read_len
+    ptext, bad_t = device.pack_2bit(text.view(-1))
+    pquery, bad_q = device.pack_2bit(reads.view(-1))
+    idx = torch.arange(n, dtype=torch.int64, device=dev)
+    cap = 2 * L + 8
+    slab_off = torch.arange(n + 1, dtype=torch.int64, device=dev) * cap
+    da = device.DeviceAligner(64, n, dev, slab_bytes=n * cap)
+    out = da.align(ptext, idx * stride, tlen, pquery, idx * L, torch.full((n,), L, dtype=torch.int64, device=dev), slab_off)
+    run_off, runs = da.compact(slab_off)
+    torch.cuda.synchronize()
+    assert int(bad_t.item()) == -1 and int(bad_q.item()) == -1 and int(out.status.max().item()) == 0
+    T, Q = synth.pairs_as_strings(h_text, h_tlen, h_reads)
+    want = oracle.align_pairs(T, Q, threads=4)
+    assert np.array_equal(out.edit.cpu().numpy(), want.edit)
+    assert np.array_equal(out.ref_consumed.cpu().numpy().astype(np.uint64), want.ref_consumed)
+    ro, rr = run_off.cpu().numpy(), runs.cpu().numpy()
+    ops = "=XID"
+    for k in (0, 1, 17, n - 1):
+        seg = rr[ro[k]:ro[k + 1]]
+        assert "".join(f"{int(b) & 63}{ops[int(b) >> 6]}" for b in seg) == want.cigars[k]
+    # distance-only gives the same distances without a slab
+    da2 = device.DeviceAligner(64, n, dev)
+    out2 = da2.align(ptext, idx * stride, tlen, pquery, idx * L, torch.full((n,), L, dtype=torch.int64, device=dev),
+                     None, distance_only=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(out2.edit.cpu().numpy(), want.edit)
+
+
+def test_cigar_properties_at_scale(oracle, aligners):
+    """Size-independent property (reference validateCigarString, src/tests.cu:106-169) on a batch too large for
+    string-by-string oracle comparison to be the only check: every CIGAR is a valid transformation whose edit
+    count equals the reported distance."""
+    from scrooge_b200 import synth
+    wl = synth.WORKLOADS["long_10kbp"]
+    text, tlen, reads = synth.pairs_host(wl, 1000, 2000)
+    tb, toff, qb, qoff = synth.pairs_as_blobs(text, tlen, reads)
+    got = aligners[64].align_pairs_blob(tb, toff, qb, qoff)
+    ed, cg = got.edit_distances, got.cigars()
+    T, Q = synth.pairs_as_strings(text, tlen, reads)
+    for k in range(0, 2000, 7):
+        assert oracle.validate_cigar(cg[k], T[k], Q[k], int(ed[k])) == 0, k
+    assert 800 < float(np.mean(ed)) < 1100

@@ -1,0 +1,21 @@
+"""The algorithmic identities the CUDA kernel relies on (left-aligned vectors, G-row chunks, V/H/E edge words
+replacing stored R rows -- see scrooge_b200/csrc/sg_align.cuh) checked on the CPU against the oracle."""
+import pytest
+
+from conftest import random_pairs
+from kernel_model import align
+
+
+@pytest.mark.parametrize("W,O", [(64, 33), (32, 17)])
+def test_model_matches_oracle(oracle, W, O):
+    T, Q = random_pairs(11 + W, 150, [0, 1, 2, 15, 16, 17, 31, 32, 33, 63, 64, 65, 100, 200], [0, 0.05, 0.15, 0.4, 0.8])
+    res = oracle.align_pairs(T, Q, W=W)
+    for k in range(len(T)):
+        ed, cg, rc = align(T[k], Q[k], W, O)
+        assert (ed, cg, rc) == (int(res.edit[k]), res.cigars[k], int(res.ref_consumed[k])), (T[k], Q[k])
+
+
+def test_model_golden_kats(golden):
+    for x in golden[64]["groups"]["kat_tests_cu"] + golden[64]["groups"]["differential_tests_cu"]:
+        ed, cg, _ = align(x["text"], x["query"])
+        assert ed == x["edit"] and cg == x["cigar"]
