@@ -594,7 +594,7 @@ int64_t sg_result_render_cigar(const sg_result *r, uint64_t idx, char *buf, uint
     uint64_t len = 0;
     for (uint64_t k = 0; k < cnt; k++) {
         const unsigned c = SG_RUN_COUNT(p[k]);
-        if (len + 4 > cap) return -1;
+        if (len + (c >= 10 ? 3u : 2u) + 1u > cap) return -1;
         if (c >= 10) buf[len++] = (char)('0' + c / 10);
         buf[len++] = (char)('0' + c % 10);
         buf[len++] = ops[SG_RUN_OP(p[k])];
