@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark: alignments/s (and GCUPS) on BASELINE.json configs[2],
+"long reads: 1M synthetic 10 kbp PacBio-like pairs at 10% error, W=64/O=33 windows, full CIGAR".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]               (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                              (the reference's CPU path on the host cores)
+
+A step is one pass of the hot path over one batch of `--pairs` synthetic pairs per GPU:
+ingest (ASCII -> 2 bit) -> alignment kernel (DC + TB + RLE) -> CIGAR compaction (scan + gather), with the
+ASCII inputs already resident in HBM.  Alignments are independent, so N GPUs run N shards of the same
+shape with no data-path collective (weak scaling); torch.distributed is used only for the barrier and the
+max-over-ranks of the device time.
+
+One JSON line on stdout (rank 0).  `value` = alignments/s over all GPUs, device-timed.  `e2e` = the same metric
+through the host C ABI (sg_align_pairs on pinned HOST buffers: H2D, ingest, alignment, compaction, D2H of
+distances + runs all inside the timed region).  `roofline` = the alignment kernel against the INT32-ALU peak
+measured live by the LOP3/SHF probe (the path is integer-issue bound, not HBM or tensor bound; the HBM figures
+are reported beside it).  `cpu_baseline` = the unmodified reference genasm_cpu (oracle/_ref) on a bounded
+sample of the same pairs on this box's host cores; the same sample doubles as a parity check of the GPU
+results (edit distance + CIGAR string).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OPS_PER_ENTRY = 14  # 7 W-bit ops per R[d][i] entry (reference src/genasm_cpu.cpp:247-251, scripts/plot.py:2346) x 2 words
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="long_10kbp")
+    ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU per step")
+    ap.add_argument("--e2e-pairs", type=int, default=131_072, help="pairs per GPU per end-to-end step (host buffers)")
+    ap.add_argument("--cpu-sample", type=int, default=32_768, help="pairs of the CPU baseline / parity sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix="sg_clocks_", suffix=".csv")
+        self.f = open(self.path, "w")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.p.kill()
+        self.f.close()
+        sm, mx, reasons, power = [], [], set(), []
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 8:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power)}
+
+
+def cpu_reference_run(wl, first_pair, n_pairs, threads=None):
+    """Times the reference's own CPU implementation (oracle/_ref when built, else the plain-C oracle port) on
+    pairs [first_pair, first_pair+n_pairs) of the workload.  Returns (info dict, result) -- the result is used as
+    the parity checker by the caller."""
+    from oracle.binding import Oracle, RefCpu
+    from scrooge_b200 import synth
+    text, tlen, reads = synth.pairs_host(wl, first_pair, n_pairs)
+    tb, toff, qb, qoff = synth.pairs_as_blobs(text, tlen, reads)
+    tb, qb = tb.tobytes(), qb.tobytes()
+    if RefCpu.available(wl.W):
+        impl, kind = RefCpu(wl.W), "reference"
+        threads = threads or impl.max_threads()
+        res = impl.align_pairs_blob(tb, toff, qb, qoff, threads=threads)
+    else:
+        impl, kind = Oracle(), "port"
+        threads = threads or impl.max_threads()
+        res = impl.align_pairs_blob(tb, toff, qb, qoff, W=wl.W, threads=threads)
+    secs = res.core_ns / 1e9  # the OpenMP alignment region only, like core_algorithm_ns (src/genasm_cpu.cpp:589-594)
+    info = {"value": n_pairs / secs, "unit": "alignments/s", "cores": threads, "kind": kind,
+            "sample": f"{n_pairs} pairs of {wl.name} (pairs {first_pair}..{first_pair + n_pairs - 1} of rank 0's shard), "
+                      f"{secs:.2f} s in the OpenMP region",
+            "gcups": n_pairs / secs * wl.read_len ** 2 / 1e9}
+    return info, res
+
+
+def run_reference_arm(args):
+    from scrooge_b200 import synth
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = synth.WORKLOADS[args.workload]
+    n = args.cpu_sample
+    times = []
+    info = None
+    for s in range(args.warmup + args.steps):
+        t0 = time.time()
+        info, _ = cpu_reference_run(wl, 0, n)
+        if s >= args.warmup:
+            times.append(n / info["value"])
+    per_step = sum(times) / len(times)
+    value = n / per_step
+    info["value"] = value
+    info["gcups"] = value * wl.read_len ** 2 / 1e9
+    line = {"impl": "reference", "metric": "alignments_per_second", "value": value, "unit": "alignments/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": wl.name, "read_len": wl.read_len, "error_rate": wl.err, "W": wl.W,
+                       "pairs_per_step": n, "note": "reference genasm_cpu::align_all on the host cores; each step is a bounded "
+                                                    "sample of the workload"},
+            "gcups": info["gcups"], "cpu_baseline": info,
+            "e2e": {"value": value, "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import scrooge_b200
+    from scrooge_b200 import device, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with torchrun: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N")
+    lib = scrooge_b200.lib()  # raises if the CUDA library is missing: there is no fallback
+    if lib.sg_device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = synth.WORKLOADS[args.workload]
+    W, L = wl.W, wl.read_len
+    n = args.pairs
+    first_pair = rank * n  # weak scaling: every rank aligns its own n pairs of the same shape
+
+    # ---- inputs resident in HBM (ASCII, as they arrive from the host) ---------------------------------
+    text, tlen, reads = device.synth_pairs_device(wl.seed, first_pair, n, L, wl.err, wl.ratio, wl.slack, dev)
+    stride = text.shape[1]
+    idx = torch.arange(n, dtype=torch.int64, device=dev)
+    tstart, qstart = idx * stride, idx * L
+    qlen = torch.full((n,), L, dtype=torch.int64, device=dev)
+    cap = 2 * L + 8  # runs per alignment (reference: 2*|query| entries, src/genasm_gpu.cu:995-1001)
+    slab_off = torch.arange(n + 1, dtype=torch.int64, device=dev) * cap
+    da = device.DeviceAligner(W, n, dev, slab_bytes=n * cap)
+    words_t, words_q = int(lib.sg_packed_words(n * stride)), int(lib.sg_packed_words(n * L))
+    ptext = torch.empty(words_t, dtype=torch.int32, device=dev)
+    pquery = torch.empty(words_q, dtype=torch.int32, device=dev)
+    bad = torch.full((2,), -1, dtype=torch.int64, device=dev)
+    runs = None  # dense run array, sized exactly by the first (untimed) step: the batch is the same every step
+    stream = int(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: int(t.data_ptr())
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+
+    def step(k=None):
+        scrooge_b200._lib.check(lib.sg_dev_pack_2bit(p(text), n * stride, p(ptext), p(bad), stream))
+        scrooge_b200._lib.check(lib.sg_dev_pack_2bit(p(reads), n * L, p(pquery), p(bad) + 8, stream))
+        if k is not None:
+            ev[k][0].record()
+        da.align(ptext, tstart, tlen, pquery, qstart, qlen, slab_off)
+        if k is not None:
+            ev[k][1].record()
+        return da.compact(slab_off, runs)[1]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    runs = step()  # untimed: also allocates the dense run array
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin.record()
+    for k in range(args.steps):
+        step(k)
+    t_end.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_total = t_begin.elapsed_time(t_end)
+    ms_kernel = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    if world > 1:
+        tt = torch.tensor([ms_total, ms_kernel], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total, ms_kernel = float(tt[0]), float(tt[1])
+    ms_step = ms_total / args.steps
+    value = world * n / (ms_step / 1e3)
+
+    assert int(bad[0]) == -1 and int(bad[1]) == -1, "ingest flagged a non-ACGT base"
+    assert int(da.out.status.max()) == 0, "a CIGAR slab overflowed"
+    entries = int(da.out.dc_entries.sum())   # algorithmic DC work of this rank's batch (oracle-checked below)
+    total_runs = int(da.run_off[-1])
+    mean_ed = float(da.out.edit.double().mean())
+
+    # ---- end to end through the host C ABI (host buffers, copies inside the timed region) ----------
+    e2e = None
+    if not args.no_e2e:
+        ne = min(args.e2e_pairs, n)
+        h_text, h_tlen, h_reads = synth.pairs_host(wl, first_pair, ne)
+        tb, toff, qb, qoff = synth.pairs_as_blobs(h_text, h_tlen, h_reads)
+        del h_text
+        tb_pin = torch.from_numpy(tb).pin_memory()
+        qb_pin = torch.from_numpy(qb).pin_memory()
+        al = scrooge_b200.Aligner(W=W, device_ids=[local_rank])
+        res = None
+        for _ in range(max(args.warmup, 1)):
+            res = al.align_pairs_blob(tb_pin, toff, qb_pin, qoff)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = al.align_pairs_blob(tb_pin, toff, qb_pin, qoff)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_s = float(tt[0])
+        d2h = ne * 16 + (ne + 1) * 8 + int(res.run_offsets[-1]) + ne
+        e2e = {"value": world * ne * args.steps / e2e_s, "unit": "alignments/s",
+               "h2d_bytes_per_step": int(tb.nbytes + qb.nbytes + 2 * (ne + 1) * 8), "d2h_bytes_per_step": int(d2h),
+               "pairs_per_step": ne, "ms_per_step": e2e_s / args.steps * 1e3,
+               "api": "sg_align_pairs (C ABI, pinned host ASCII blobs in, distances + packed CIGAR runs out)"}
+        del tb_pin, qb_pin
+        al.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the alignment kernel) --------------------------------------
+    peak_gops = device.int32_peak(2, 60.0)  # LOP3+SHF 2:1, measured now, same clocks as the run
+    achieved_gops = entries * OPS_PER_ENTRY / (ms_kernel / 1e3) / 1e9
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"
+    # algorithmic HBM bytes of the alignment kernel per launch: packed text+query read once, runs + 28 B results written
+    algo_bytes = int(tlen.sum()) / 4 + n * L / 4 + total_runs + n * (8 + 8 + 4 + 1 + 8) + n * 40
+    wps, smem_warp, sms = device.align_geometry(W)
+    roofline = {"bound": "int32_alu", "kernel": f"genasm_align_kernel<{W}>", "achieved": achieved_gops / 1e3,
+                "peak": peak_gops / 1e3, "unit": "TIOP/s", "frac": achieved_gops / peak_gops, "traffic": None,
+                "peak_source": "sg_dev_int32_peak (LOP3+SHF 2:1 probe) measured in this run",
+                "algorithmic_ops_per_launch": entries * OPS_PER_ENTRY, "dc_entries_per_alignment": entries / n,
+                "kernel_ms": ms_kernel, "kernel_share_of_step": ms_kernel / ms_step,
+                "hbm": {"achieved": algo_bytes / (ms_kernel / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": algo_bytes / (ms_kernel / 1e3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                        "algorithmic_bytes_per_launch": int(algo_bytes)},
+                "geometry": {"sms": sms, "warps_per_sm": wps, "smem_bytes_per_warp": smem_warp}}
+
+    # ---- CPU baseline on a bounded sample + parity of the GPU results on that sample ------------------
+    cpu = None
+    parity = None
+    if not args.no_cpu_baseline:
+        ns = min(args.cpu_sample, n)
+        cpu, ref = cpu_reference_run(wl, first_pair, ns)
+        ro = da.run_off[: ns + 1].cpu().numpy()
+        rr = runs[: int(ro[-1])].cpu().numpy()
+        ed = da.out.edit[:ns].cpu().numpy()
+        ops = np.frombuffer(b"=XID", dtype=np.uint8)
+        ok = bool(np.array_equal(ed, ref.edit))
+        for k in range(ns):
+            seg = rr[ro[k]:ro[k + 1]]
+            s = "".join(f"{int(b) & 63}{chr(ops[int(b) >> 6])}" for b in seg) if k % 16 == 0 else None
+            if s is not None and s != ref.cigars[k]:
+                ok = False
+                break
+        parity = {"pairs": ns, "cigars_compared": (ns + 15) // 16, "bit_exact": ok, "against": cpu["kind"]}
+        if not ok:
+            raise SystemExit("PARITY FAILURE against the CPU reference on the benchmark sample")
+
+    line = {"metric": "alignments_per_second", "value": value, "unit": "alignments/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": wl.name, "read_len": L, "error_rate": wl.err, "sub_ins_del": list(wl.ratio), "W": W,
+                       "O": 33 if W == 64 else 17, "pairs_per_gpu_per_step": n, "cigar": "full", "seed": wl.seed,
+                       "l2": "inputs larger than L2 (ASCII %.1f GB + packed %.1f GB per step)" % (
+                           (n * stride + n * L) / 1e9, (words_t + words_q) * 4 / 1e9),
+                       "step": "ingest(ASCII->2bit) + align(DC+TB+RLE) + compaction(scan+gather), inputs resident in HBM"},
+            "gcups": value * L * L / 1e9, "mean_edit_distance": mean_ed, "runs_per_alignment": total_runs / n,
+            "gpu_launches": args.steps * 7, "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+            "parity": parity}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -80,6 +80,7 @@ struct AlignParams {
     uint64_t *ref_consumed;
     uint32_t *nruns;
     uint8_t *status;
+    uint64_t *dc_entries;  // optional: sum over windows of (d_w+1)*(n+1), the early-termination-minimal DC work
 };
 
 // ---- small helpers -------------------------------------------------------------------------------
@@ -188,6 +189,7 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
     int64_t ed = 0;
     uint8_t *out = nullptr, *out_end = nullptr;
     uint32_t nruns = 0;
+    uint64_t entries = 0;
     bool overflow = false;
     int d0 = 0, n = -1, m = 0;
     uint32_t tw[NWIN];
@@ -206,6 +208,7 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
                     P.ref_consumed[idx] = 0;
                     P.nruns[idx] = 0;
                     P.status[idx] = 0;
+                    if (P.dc_entries) P.dc_entries[idx] = 0;
                     continue;
                 }
                 pair = idx;
@@ -215,6 +218,7 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
                 q_end = q_pos + ql;
                 ed = 0;
                 nruns = 0;
+                entries = 0;
                 overflow = false;
                 if (want_cigar) {
                     out = P.slab + P.slab_off[idx];
@@ -339,6 +343,7 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
             d0 += G;
             continue;
         }
+        entries += (uint64_t)(d0 + above + 1) * (uint64_t)(n + 1);  // d_w = d0 + above
         d0 = 0;
 
         // ---- TB: walk the V/H/E words from (0,0) ------------------------------------------------------
@@ -384,6 +389,7 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
             P.ref_consumed[pair] = t_pos - t_begin;
             P.nruns[pair] = nruns;
             P.status[pair] = overflow ? 5 : 0;
+            if (P.dc_entries) P.dc_entries[pair] = entries;
             have = false;
         }
     }

@@ -193,7 +193,7 @@ int run_pairs_batch(sg_ctx *ctx, Device &d, const char *tb, const uint64_t *toff
     R(sg_dev_align(ctx->W, d.packed_t.as<uint32_t>(), d.tstart.as<uint64_t>(), d.tlen.as<uint64_t>(),
                    d.packed_q.as<uint32_t>(), d.qstart.as<uint64_t>(), d.qlen.as<uint64_t>(), n, flags,
                    d.slab.as<uint8_t>(), d.slab_off.as<uint64_t>(), d.counter.as<uint64_t>(), d.edit.as<int64_t>(),
-                   d.refc.as<uint64_t>(), d.nruns.as<uint32_t>(), d.status.as<uint8_t>(), st));
+                   d.refc.as<uint64_t>(), d.nruns.as<uint32_t>(), d.status.as<uint8_t>(), nullptr, st));
     SG_CUDA(cudaEventRecord(d.ev1, st));
     uint64_t *h = d.h_small.as<uint64_t>();
     SG_CUDA(cudaMemcpyAsync(h, d.bad.p, 16, cudaMemcpyDeviceToHost, st));
@@ -456,7 +456,7 @@ int run_cand_batch(sg_ctx *ctx, Device &d, const char *rb, const uint64_t *roff,
     R(sg_dev_align(ctx->W, d.genome.as<uint32_t>(), d.tstart.as<uint64_t>(), d.tlen.as<uint64_t>(), d.packed_q.as<uint32_t>(),
                    d.qstart.as<uint64_t>(), d.qlen.as<uint64_t>(), n, flags, d.slab.as<uint8_t>(), d.slab_off.as<uint64_t>(),
                    d.counter.as<uint64_t>(), d.edit.as<int64_t>(), d.refc.as<uint64_t>(), d.nruns.as<uint32_t>(),
-                   d.status.as<uint8_t>(), st));
+                   d.status.as<uint8_t>(), nullptr, st));
     SG_CUDA(cudaEventRecord(d.ev1, st));
     uint64_t *h = d.h_small.as<uint64_t>();
     SG_CUDA(cudaMemcpyAsync(h, d.bad.p, 16, cudaMemcpyDeviceToHost, st));
