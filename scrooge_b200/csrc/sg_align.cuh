@@ -12,10 +12,12 @@
 //  * DC order: column-major in chunks of G rows.  The reference walks d outer / i inner and keeps a
 //    W+1-entry forefront in memory.  Here the G entries R[d0..d0+G-1][i+1] of the previous column live
 //    in registers (multi-word, one 32-bit register per word) together with their <<1 copies, and a
-//    column step is, per 32-bit word and row: one funnel shift, one AND, two LOP3
-//        X[r]   = P[r] & sP[r]                          (P = previous column, sP = P << 1)
-//        C[r]   = ((sP[r] | pm) & X[r-1]) & sC[r-1]      (= mat & del & sub & ins of src/genasm_cpu.cpp:247-251)
+//    column step is, per 32-bit word and row: one shift and two LOP3
+//        u      = (sP[r] | pm) & P[r-1]                  (P = previous column, sP = P << 1; off the critical path)
+//        C[r]   = u & sP[r-1] & sC[r-1]                  (= mat & del & sub & ins of src/genasm_cpu.cpp:247-251)
 //        sC[r]  = C[r] << 1
+//    Two register sets alternate between "previous" and "current" column (the column loop is unrolled by
+//    two), so no register is ever copied.
 //    The last row of a chunk is kept as a forefront in shared memory so that a lane whose window needs
 //    more than G rows continues with rows d0+G.. in its next phase (early termination at chunk
 //    granularity; the reported distance is exact).
@@ -28,9 +30,9 @@
 //    two words over all rows
 //        V_i = OR_d ( R[d][i] & ~(R[d][i] << 1) )   bit J set <=> D(i,J+1) = D(i,J) - 1   (insertion edge)
 //        H_i = OR_d ( R[d][i] & ~R[d][i+1] )        bit J set <=> D(i+1,J) = D(i,J) - 1   (deletion edge)
-//    where D(i,J) = min{d : bit J of R[d][i] is 0} is the edit-distance matrix the R rows encode.  With
-//    E_i = pm[text[i]] (mismatch bits) this is 12 bytes per column, 384 B per alignment, independent
-//    of the window distance.  The traceback's tests (src/genasm_cpu.cpp:321-343)
+//    where D(i,J) = min{d : bit J of R[d][i] is 0} is the edit-distance matrix the R rows encode.  That is
+//    8 bytes per column, 256 B per alignment, independent of the window distance; the mismatch bits
+//    E_i = pm[text[i]] are read back from the pattern-mask table.  The traceback's tests (src/genasm_cpu.cpp:321-343)
 //        can_ins = d>0 && zero(R[d-1][i],   J+1)  <=> D(i,J+1)   <= d-1
 //        can_del = d>0 && zero(R[d-1][i+1], J)    <=> D(i+1,J)   <= d-1
 //        can_sub = d>0 && zero(R[d-1][i+1], J+1)  <=> D(i+1,J+1) <= d-1
@@ -38,9 +40,9 @@
 //    can_del <=> H_i(J), and when neither holds can_sub <=> text[i] != pattern[J] <=> E_i(J) by the DP
 //    recurrence.  The j == m-1 special case and the i >= n limit fall out of the same bits.
 //
-// Per-warp shared memory (W=64): pattern masks 1 KB + forefront 16.25 KB + V/H/E 12 KB = 29.25 KB,
-// every array laid out [column][lane] so that all accesses are bank-conflict free whatever column each
-// lane is at.
+// Per-warp shared memory (W=64): pattern masks 1 KB + forefront 16.25 KB + V/H 8 KB = 25.25 KB (8 warps
+// per SM), every array laid out [column][lane] so that all accesses are bank-conflict free whatever
+// column each lane is at.
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
@@ -57,9 +59,9 @@ template <int W> struct SmemLayout {
     static constexpr int NW = W / 32;               // 32-bit words per bitvector
     static constexpr int TBL = W - WinCfg<W>::O;    // TB_LIMIT (src/genasm_cpu.cpp:50)
     static constexpr int TBCOLS = TBL + 1;          // traceback columns kept (0..TBL)
-    static constexpr int PM_WORDS = 4 * NW * 32;
-    static constexpr int FF_WORDS = (W + 1) * NW * 32;
-    static constexpr int TB_WORDS = 3 * TBCOLS * 32;
+    static constexpr int PM_WORDS = 4 * NW * 32;    // [base code][lane][NW]
+    static constexpr int FF_WORDS = (W + 1) * NW * 32;  // [column][lane][NW]
+    static constexpr int TB_WORDS = TBCOLS * 2 * 32;    // [column][lane][V,H]
     static constexpr int WORDS_PER_WARP = PM_WORDS + FF_WORDS + TB_WORDS;
     static constexpr int BYTES_PER_WARP = WORDS_PER_WARP * 4;
 };
@@ -159,6 +161,67 @@ template <> __device__ __forceinline__ void sts_vec<2>(uint32_t *p, const uint32
     *reinterpret_cast<uint2 *>(p) = make_uint2(v[0], v[1]);
 }
 
+// G rows of one column: entries and their << 1
+template <int NW> struct RowSet {
+    uint32_t C[kRowsPerChunk][NW];
+    uint32_t S[kRowsPerChunk][NW];
+};
+
+// Boundary column R[d][n] = ones << d (src/genasm_cpu.cpp:225-231,239-245), left-aligned: row r of the chunk is
+// ~0 << (W - m + d0 + r), and each row is the previous one shifted by one.
+template <int W, int NW>
+__device__ __forceinline__ void dc_boundary(RowSet<NW> &N, int m, int d0, uint32_t &V)
+{
+    ones_shl<NW>(W - m + d0, N.C[0]);
+#pragma unroll
+    for (int r = 0; r < kRowsPerChunk; r++) {
+        shl1<NW>(N.C[r], N.S[r]);
+        V |= N.C[r][NW - 1] & ~N.S[r][NW - 1];
+        if (r + 1 < kRowsPerChunk) {
+#pragma unroll
+            for (int k = 0; k < NW; k++) N.C[r + 1][k] = N.S[r][k];
+        }
+    }
+}
+
+// One DC column: P holds column i+1, N receives column i.  F is row d0-1 of column i (the forefront left
+// by the previous chunk; ignored when fm == ~0, i.e. in the first chunk of a window), XF carries
+// (F & F<<1) | fm from column i+1 in and from column i out.  With TBCOL the insertion/deletion edge words
+// of the column are OR-accumulated into V/H (top word only: the first W-O pattern positions).
+template <int NW, bool TBCOL>
+__device__ __forceinline__ void dc_column(const RowSet<NW> &P, RowSet<NW> &N, const uint32_t (&pm)[NW],
+                                          const uint32_t (&F)[NW], const uint32_t fm, uint32_t (&XF)[NW], uint32_t &V,
+                                          uint32_t &H)
+{
+    constexpr int G = kRowsPerChunk;
+    constexpr int TOP = NW - 1;
+    uint32_t sF[NW];
+    shl1<NW>(F, sF);
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        const uint32_t u = (P.S[0][k] | pm[k]) & XF[k];
+        N.C[0][k] = u & (sF[k] | fm);
+        XF[k] = (F[k] & sF[k]) | fm;
+    }
+    shl1<NW>(N.C[0], N.S[0]);
+#pragma unroll
+    for (int r = 1; r < G; r++) {
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            const uint32_t u = (P.S[r][k] | pm[k]) & P.C[r - 1][k];
+            N.C[r][k] = u & P.S[r - 1][k] & N.S[r - 1][k];
+        }
+        shl1<NW>(N.C[r], N.S[r]);
+    }
+    if (TBCOL) {
+#pragma unroll
+        for (int r = 0; r < G; r++) {
+            H |= N.C[r][TOP] & ~P.C[r][TOP];
+            V |= N.C[r][TOP] & ~N.S[r][TOP];
+        }
+    }
+}
+
 // ---- the kernel ------------------------------------------------------------------------------------
 
 template <int W>
@@ -171,15 +234,15 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
     constexpr int TBCOLS = L::TBCOLS;
     constexpr int G = kRowsPerChunk;
     constexpr int TOP = NW - 1;
+    constexpr int PMS = NW * 32;   // words between the masks of consecutive base codes
+    constexpr int FFS = NW * 32;   // words between forefront columns
+    constexpr int TBS = 2 * 32;    // words between traceback columns
 
-    extern __shared__ uint32_t smem[];
+    extern __shared__ __align__(16) uint32_t smem[];
     const int lane = threadIdx.x;
-    // [c][lane][NW], [col][lane][NW], [3][col][lane]
     uint32_t *pm_s = smem + lane * NW;
     uint32_t *ff_s = smem + L::PM_WORDS + lane * NW;
-    uint32_t *tbv_s = smem + L::PM_WORDS + L::FF_WORDS + lane;
-    uint32_t *tbh_s = tbv_s + TBCOLS * 32;
-    uint32_t *tbe_s = tbh_s + TBCOLS * 32;
+    uint32_t *tb_s = smem + L::PM_WORDS + L::FF_WORDS + lane * 2;
 
     const bool want_cigar = !(P.flags & 1u);
 
@@ -244,92 +307,95 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
             ones_shl<NW>(W - m, hm);
             // pm[c] = ((p1 ^ C1) | (p0 ^ C0)) & hm : zero where pattern[J] == c (src/genasm_cpu.cpp:178-198),
             // low W-m bits zero (left-aligned representation)
+            uint32_t m0[NW], m1[NW], m2[NW], m3[NW];
 #pragma unroll
             for (int k = 0; k < NW; k++) {
-                pm_s[0 * NW * 32 + k] = (p1[k] | p0[k]) & hm[k];
-                pm_s[1 * NW * 32 + k] = (p1[k] | ~p0[k]) & hm[k];
-                pm_s[2 * NW * 32 + k] = (~p1[k] | p0[k]) & hm[k];
-                pm_s[3 * NW * 32 + k] = (~p1[k] | ~p0[k]) & hm[k];
+                m0[k] = (p1[k] | p0[k]) & hm[k];
+                m1[k] = (p1[k] | ~p0[k]) & hm[k];
+                m2[k] = (~p1[k] | p0[k]) & hm[k];
+                m3[k] = (~p1[k] | ~p0[k]) & hm[k];
             }
+            sts_vec<NW>(pm_s + 0 * PMS, m0);
+            sts_vec<NW>(pm_s + 1 * PMS, m1);
+            sts_vec<NW>(pm_s + 2 * PMS, m2);
+            sts_vec<NW>(pm_s + 3 * PMS, m3);
         }
         const int nn = have ? n : -1;
         const uint32_t fm = d0 == 0 ? 0xFFFFFFFFu : 0u;  // "no row above this chunk"
 
         // ---- DC: one chunk of G rows, columns n .. 0 -------------------------------------------------
-        uint32_t C[G][NW], S[G][NW];   // previous column entries and their << 1
-        uint32_t XFp[NW];               // F & (F << 1) of row d0-1 at the previous column
-#pragma unroll
-        for (int k = 0; k < NW; k++) XFp[k] = 0xFFFFFFFFu;
-#pragma unroll
-        for (int r = 0; r < G; r++)
-#pragma unroll
-            for (int k = 0; k < NW; k++) { C[r][k] = 0; S[r][k] = 0; }
+        RowSet<NW> A, B;
+        uint32_t XF[NW];  // (F & F << 1) | fm of row d0-1 at the previous column
+        const bool uniform = __all_sync(0xFFFFFFFFu, nn == W);
 
-        // One column step.  i is the text column, c the base code of text[i] (unused on the boundary column),
-        // TBCOL says at compile time whether the column can be visited by the traceback.
-        auto column = [&](const int i, const uint32_t c, const bool TBCOL) {
-            uint32_t *ffp = ff_s + i * (NW * 32);
+        // boundary column: forefront in, chunk's last row out, insertion edges of the column if it is a TB column
+        auto boundary_column = [&](const int i) {
             uint32_t F[NW], sF[NW];
+            uint32_t *ffp = ff_s + i * FFS;
             lds_vec<NW>(ffp, F);
-#pragma unroll
-            for (int k = 0; k < NW; k++) F[k] |= fm;
             shl1<NW>(F, sF);
-            uint32_t V = 0, H = 0, E = 0;
-            if (i == nn) {
-                // boundary column: R[d][n] = ones << d  (src/genasm_cpu.cpp:225-231,239-245), left-aligned
 #pragma unroll
-                for (int r = 0; r < G; r++) {
-                    ones_shl<NW>(W - m + d0 + r, C[r]);
-                    shl1<NW>(C[r], S[r]);
-                    V |= C[r][TOP] & ~S[r][TOP];
-                }
-            } else {
-                uint32_t pm[NW];
-                lds_vec<NW>(pm_s + c * (NW * 32), pm);
-                E = pm[TOP];
-                uint32_t aboveS[NW], aboveX[NW];
-#pragma unroll
-                for (int k = 0; k < NW; k++) { aboveS[k] = sF[k] | fm; aboveX[k] = XFp[k]; }
-#pragma unroll
-                for (int r = 0; r < G; r++) {
-                    uint32_t Xr[NW], newC[NW];
-#pragma unroll
-                    for (int k = 0; k < NW; k++) {
-                        Xr[k] = C[r][k] & S[r][k];
-                        newC[k] = ((S[r][k] | pm[k]) & aboveX[k]) & aboveS[k];
-                    }
-                    if (TBCOL) H |= newC[TOP] & ~C[r][TOP];
-#pragma unroll
-                    for (int k = 0; k < NW; k++) { C[r][k] = newC[k]; aboveX[k] = Xr[k]; }
-                    shl1<NW>(C[r], S[r]);
-                    if (TBCOL) V |= C[r][TOP] & ~S[r][TOP];
-#pragma unroll
-                    for (int k = 0; k < NW; k++) aboveS[k] = S[r][k];
-                }
+            for (int k = 0; k < NW; k++) XF[k] = (F[k] & sF[k]) | fm;
+            uint32_t V = 0;
+            dc_boundary<W, NW>(A, m, d0, V);
+            sts_vec<NW>(ffp, A.C[G - 1]);
+            if (i < TBCOLS) {
+                uint32_t vh[2];
+                lds_vec<2>(tb_s + i * TBS, vh);
+                vh[0] = (vh[0] & ~fm) | V;
+                vh[1] = vh[1] & ~fm;
+                sts_vec<2>(tb_s + i * TBS, vh);
             }
-            // row d0-1 of this column is "topright" for the next column
-#pragma unroll
-            for (int k = 0; k < NW; k++) XFp[k] = (F[k] & sF[k]) | fm;
-            sts_vec<NW>(ffp, C[G - 1]);
+        };
+        // text column i with base code at bits 31:30 of cw: Pv (column i+1) -> Nv (column i)
+        auto text_column = [&](const RowSet<NW> &Pv, RowSet<NW> &Nv, const int i, const uint32_t cw, const bool TBCOL) {
+            uint32_t pm[NW], F[NW];
+            // (cw >> 30) * PMS words == ((cw >> 30) << (5 + log2 NW + 2)) bytes
+            const uint32_t *pmp = pm_s + (cw >> 30) * PMS;
+            lds_vec<NW>(pmp, pm);
+            uint32_t *ffp = ff_s + i * FFS;
+            lds_vec<NW>(ffp, F);
+            uint32_t V = 0, H = 0;
+            if (TBCOL) dc_column<NW, true>(Pv, Nv, pm, F, fm, XF, V, H);
+            else dc_column<NW, false>(Pv, Nv, pm, F, fm, XF, V, H);
+            sts_vec<NW>(ffp, Nv.C[G - 1]);
             if (TBCOL) {
-                const int o = i * 32;
-                tbv_s[o] = (tbv_s[o] & ~fm) | V;
-                tbh_s[o] = (tbh_s[o] & ~fm) | H;
-                if (fm) tbe_s[o] = E;
+                uint32_t vh[2];
+                lds_vec<2>(tb_s + i * TBS, vh);
+                vh[0] = (vh[0] & ~fm) | V;
+                vh[1] = (vh[1] & ~fm) | H;
+                sts_vec<2>(tb_s + i * TBS, vh);
             }
         };
 
-        if (nn == W) column(W, 0u, false);
+        if (uniform) {
+            // fast path: every lane of the warp has a full text window; no per-column tests
+            boundary_column(W);
 #pragma unroll
-        for (int blk = NWIN - 1; blk >= 0; blk--) {
-            const uint32_t word = tw[blk];
-            const bool TBCOL = (blk * 16 + 15) < TBCOLS;
+            for (int blk = NWIN - 1; blk >= 0; blk--) {
+                uint32_t cw = tw[blk];
+                const bool TBCOL = blk * 16 < TBCOLS;  // W=64: blocks 0,1 (columns 0..31); W=32: block 0
 #pragma unroll 2
-            for (int ii = 15; ii >= 0; ii--) {
-                const int i = blk * 16 + ii;
+                for (int ii = 15; ii >= 1; ii -= 2) {
+                    const int i = blk * 16 + ii;
+                    text_column(A, B, i, cw, TBCOL);
+                    cw <<= 2;
+                    text_column(B, A, i - 1, cw, TBCOL);
+                    cw <<= 2;
+                }
+            }
+        } else {
+            // generic path (some lane's text is running out, n < W): per-lane start column
+            for (int i = W; i >= 0; i--) {
                 if (i > nn) continue;
-                const uint32_t c = (word >> (ii * 2)) & 3u;
-                column(i, c, TBCOL);
+                if (i == nn) {
+                    boundary_column(i);
+                } else {
+                    const uint32_t word = i >= 48 ? tw[NWIN - 1] : (i >= 32 ? tw[NWIN > 2 ? 2 : 0] : (i >= 16 ? tw[1] : tw[0]));
+                    const uint32_t cw = word << (30 - 2 * (i & 15));
+                    text_column(A, B, i, cw, i < TBCOLS);
+                    A = B;
+                }
             }
         }
 
@@ -338,7 +404,7 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
         // ---- early termination: first row of the chunk whose sign bit is clear ------------------------
         int above = 0;  // rows of this chunk with the sign bit still set (monotone in r)
 #pragma unroll
-        for (int r = 0; r < G; r++) above += (int)(C[r][TOP] >> 31);
+        for (int r = 0; r < G; r++) above += (int)(A.C[r][TOP] >> 31);
         if (above == G) {  // not within this chunk: continue with rows d0+G.. next phase
             d0 += G;
             continue;
@@ -346,37 +412,49 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
         entries += (uint64_t)(d0 + above + 1) * (uint64_t)(n + 1);  // d_w = d0 + above
         d0 = 0;
 
-        // ---- TB: walk the V/H/E words from (0,0) ------------------------------------------------------
+        // ---- TB: walk the V/H words and the mismatch bits from (0,0) ----------------------------------
+        // can_ins <=> V_i(J), can_del <=> H_i(J), else can_sub <=> pm[text[i]](J); priority I > D > X > '='
+        // (src/genasm_cpu.cpp:321-370).  Branch-free per step: all lanes of the warp walk in lock step.
         int i = 0, j = 0;
+        const int jmax = m < TBL ? m : TBL;
         uint32_t mask = 0x80000000u;
-        uint32_t cur_op = 4u, cur_cnt = 0u, edits = 0u;
-        while (j < m && i < TBL && j < TBL) {
-            const uint32_t v = tbv_s[i * 32], h = tbh_s[i * 32], e = tbe_s[i * 32];
-            uint32_t op;  // 0 '=', 1 'X', 2 'I', 3 'D'; priority I > D > X > '=' (src/genasm_cpu.cpp:346-370)
-            if (v & mask) op = 2u;
-            else if (h & mask) op = 3u;
-            else if (e & mask) op = 1u;
-            else op = 0u;
-            if (op != 2u) i++;
-            if (op != 3u) { j++; mask >>= 1; }
-            if (op != 0u) edits++;
-            if (op != cur_op) {
-                if (cur_cnt) {
+        uint32_t tlo = tw[0], thi = tw[1];  // shifting text window, current base code = tlo & 3
+        uint32_t cur = 0;                   // current run: (op << 6) | count, 0 = none
+        uint32_t edits = 0;
+        uint32_t vh[2], e;
+        lds_vec<2>(tb_s, vh);
+        e = pm_s[(tlo & 3u) * PMS + TOP];
+        while (j < jmax && i < TBL) {
+            const bool is_i = (vh[0] & mask) != 0;
+            const bool is_d = !is_i && (vh[1] & mask) != 0;
+            const bool is_x = !is_i && !is_d && (e & mask) != 0;
+            const uint32_t op = is_i ? 2u : (is_d ? 3u : (is_x ? 1u : 0u));  // 0 '=', 1 'X', 2 'I', 3 'D'
+            if (!is_i) {
+                i++;
+                tlo = __funnelshift_r(tlo, thi, 2);
+                thi >>= 2;
+            }
+            if (!is_d) { j++; mask >>= 1; }
+            edits += op != 0u;
+            // next column's words (reloaded even when i did not move: keeps the step branch-free)
+            lds_vec<2>(tb_s + i * TBS, vh);
+            e = pm_s[(tlo & 3u) * PMS + TOP];
+            if ((cur >> 6) == op && cur != 0u) {
+                cur++;
+            } else {
+                if (cur != 0u) {
                     if (want_cigar) {
-                        if (out < out_end) *out++ = (uint8_t)((cur_op << 6) | cur_cnt);
+                        if (out < out_end) *out++ = (uint8_t)cur;
                         else overflow = true;
                     }
                     nruns++;
                 }
-                cur_op = op;
-                cur_cnt = 1u;
-            } else {
-                cur_cnt++;
+                cur = (op << 6) | 1u;
             }
         }
-        if (cur_cnt) {  // runs are flushed at window end, never merged across windows (quirk Q2)
+        if (cur != 0u) {  // runs are flushed at window end, never merged across windows (quirk Q2)
             if (want_cigar) {
-                if (out < out_end) *out++ = (uint8_t)((cur_op << 6) | cur_cnt);
+                if (out < out_end) *out++ = (uint8_t)cur;
                 else overflow = true;
             }
             nruns++;
