@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
         const bool uniform = __all_sync(0xFFFFFFFFu, nn == W);
 
         // boundary column: forefront in, chunk's last row out, insertion edges of the column if it is a TB column
-        auto boundary_column = [&](const int i) {
+        auto boundary_column = [&](RowSet<NW> &Nv, const int i) {
             uint32_t F[NW], sF[NW];
             uint32_t *ffp = ff_s + i * FFS;
             lds_vec<NW>(ffp, F);
@@ -337,8 +337,8 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
 #pragma unroll
             for (int k = 0; k < NW; k++) XF[k] = (F[k] & sF[k]) | fm;
             uint32_t V = 0;
-            dc_boundary<W, NW>(A, m, d0, V);
-            sts_vec<NW>(ffp, A.C[G - 1]);
+            dc_boundary<W, NW>(Nv, m, d0, V);
+            sts_vec<NW>(ffp, Nv.C[G - 1]);
             if (i < TBCOLS) {
                 uint32_t vh[2];
                 lds_vec<2>(tb_s + i * TBS, vh);
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
 
         if (uniform) {
             // fast path: every lane of the warp has a full text window; no per-column tests
-            boundary_column(W);
+            boundary_column(A, W);
 #pragma unroll
             for (int blk = NWIN - 1; blk >= 0; blk--) {
                 uint32_t cw = tw[blk];
@@ -385,17 +385,22 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
                 }
             }
         } else {
-            // generic path (some lane's text is running out, n < W): per-lane start column
-            for (int i = W; i >= 0; i--) {
-                if (i > nn) continue;
+            // generic path (some lane's text is running out, n < W): per-lane start column.  Column i lives in
+            // set A when i is even and in set B when it is odd, exactly as in the fast path, so a lane that
+            // starts at its own boundary column n joins the alternation without any register copies.
+            auto generic_column = [&](const RowSet<NW> &Pv, RowSet<NW> &Nv, const int i) {
+                if (i > nn) return;
                 if (i == nn) {
-                    boundary_column(i);
+                    boundary_column(Nv, i);
                 } else {
                     const uint32_t word = i >= 48 ? tw[NWIN - 1] : (i >= 32 ? tw[NWIN > 2 ? 2 : 0] : (i >= 16 ? tw[1] : tw[0]));
-                    const uint32_t cw = word << (30 - 2 * (i & 15));
-                    text_column(A, B, i, cw, i < TBCOLS);
-                    A = B;
+                    text_column(Pv, Nv, i, word << (30 - 2 * (i & 15)), i < TBCOLS);
                 }
+            };
+            generic_column(B, A, W);
+            for (int i = W - 1; i >= 1; i -= 2) {
+                generic_column(A, B, i);
+                generic_column(B, A, i - 1);
             }
         }
 
@@ -414,51 +419,55 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
 
         // ---- TB: walk the V/H words and the mismatch bits from (0,0) ----------------------------------
         // can_ins <=> V_i(J), can_del <=> H_i(J), else can_sub <=> pm[text[i]](J); priority I > D > X > '='
-        // (src/genasm_cpu.cpp:321-370).  Branch-free per step: all lanes of the warp walk in lock step.
-        int i = 0, j = 0;
+        // (src/genasm_cpu.cpp:321-370).  Branch-free per step: all lanes of the warp walk in lock step.  The
+        // text position is carried by the column pointer, the pattern position by the one-hot mask; finished
+        // runs are staged in this lane's (now dead) forefront slots, one word per run.
         const int jmax = m < TBL ? m : TBL;
+        const uint32_t mask_end = 0x80000000u >> jmax;   // jmax <= W-O <= 31
+        const uint32_t *tbp = tb_s;
+        const uint32_t *const tbp_end = tb_s + TBL * TBS;
         uint32_t mask = 0x80000000u;
         uint32_t tlo = tw[0], thi = tw[1];  // shifting text window, current base code = tlo & 3
-        uint32_t cur = 0;                   // current run: (op << 6) | count, 0 = none
-        uint32_t edits = 0;
+        uint32_t prev = 0u, cnt = 0u, nb = 0u, edits = 0u;
         uint32_t vh[2], e;
-        lds_vec<2>(tb_s, vh);
+        lds_vec<2>(tbp, vh);
         e = pm_s[(tlo & 3u) * PMS + TOP];
-        while (j < jmax && i < TBL) {
+        while (mask != mask_end && tbp != tbp_end) {
             const bool is_i = (vh[0] & mask) != 0;
             const bool is_d = !is_i && (vh[1] & mask) != 0;
             const bool is_x = !is_i && !is_d && (e & mask) != 0;
             const uint32_t op = is_i ? 2u : (is_d ? 3u : (is_x ? 1u : 0u));  // 0 '=', 1 'X', 2 'I', 3 'D'
+            const bool brk = op != prev && cnt != 0u;
+            if (brk) ff_s[nb * FFS] = (prev << 6) | cnt;
+            nb += brk ? 1u : 0u;
+            cnt = op != prev ? 1u : cnt + 1u;
+            prev = op;
+            edits += op != 0u ? 1u : 0u;
             if (!is_i) {
-                i++;
+                tbp += TBS;
                 tlo = __funnelshift_r(tlo, thi, 2);
                 thi >>= 2;
             }
-            if (!is_d) { j++; mask >>= 1; }
-            edits += op != 0u;
-            // next column's words (reloaded even when i did not move: keeps the step branch-free)
-            lds_vec<2>(tb_s + i * TBS, vh);
+            mask >>= is_d ? 0u : 1u;
+            // next column's words (reloaded even when the column did not move: keeps the step branch-free)
+            lds_vec<2>(tbp, vh);
             e = pm_s[(tlo & 3u) * PMS + TOP];
-            if ((cur >> 6) == op && cur != 0u) {
-                cur++;
+        }
+        if (cnt != 0u) {  // runs are flushed at window end, never merged across windows (quirk Q2)
+            ff_s[nb * FFS] = (prev << 6) | cnt;
+            nb++;
+        }
+        const int i = (int)(tbp - tb_s) / TBS;
+        const int j = __clz(mask);
+        if (want_cigar) {
+            if ((uint64_t)(out_end - out) >= (uint64_t)nb) {
+                for (uint32_t k = 0; k < nb; k++) out[k] = (uint8_t)ff_s[k * FFS];
+                out += nb;
             } else {
-                if (cur != 0u) {
-                    if (want_cigar) {
-                        if (out < out_end) *out++ = (uint8_t)cur;
-                        else overflow = true;
-                    }
-                    nruns++;
-                }
-                cur = (op << 6) | 1u;
+                overflow = true;
             }
         }
-        if (cur != 0u) {  // runs are flushed at window end, never merged across windows (quirk Q2)
-            if (want_cigar) {
-                if (out < out_end) *out++ = (uint8_t)cur;
-                else overflow = true;
-            }
-            nruns++;
-        }
+        nruns += nb;
         ed += edits;
         t_pos += (uint64_t)i;
         q_pos += (uint64_t)j;
