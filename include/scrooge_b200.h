@@ -155,7 +155,8 @@ int sg_dev_align_geometry(int W, int *warps_per_sm, int *smem_per_warp, int *num
 
 /* Sustained 32-bit integer ALU throughput probe (LOP3 + SHF mix, the instruction mix of the DC
  * recurrence): runs for roughly `ms` milliseconds and returns giga-ops/s through *gops.  kind: 0 LOP3 only,
- * 1 SHF only, 2 LOP3+SHF 2:1, 3 LOP3+IMAD 1:1.  This is the denominator of the integer roofline. */
+ * 1 SHF only, 2 LOP3+SHF 2:1 (the roofline denominator), 3 LOP3+IMAD 1:1, 4-6 one DC entry (4 LOP3 + a 64-bit
+ * shift) with the shift as IMAD+SHF / IMAD.SHL+IMAD.WIDE / IMAD.HI+IMAD+SHL (counted as 6 ops per entry). */
 int sg_dev_int32_peak(int kind, double ms, double *gops);
 
 /* Synthetic pair generator (deterministic in (seed, pair index); identical on host and device).

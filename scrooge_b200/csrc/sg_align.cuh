@@ -424,49 +424,53 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
         // runs are staged in this lane's (now dead) forefront slots, one word per run.
         const int jmax = m < TBL ? m : TBL;
         const uint32_t mask_end = 0x80000000u >> jmax;   // jmax <= W-O <= 31
-        const uint32_t *tbp = tb_s;
-        const uint32_t *const tbp_end = tb_s + TBL * TBS;
+        int tcol = 0;                                    // word offset of column i in the V/H array
+        int stage = 0;                                   // word offset of the next staged run
         uint32_t mask = 0x80000000u;
         uint32_t tlo = tw[0], thi = tw[1];  // shifting text window, current base code = tlo & 3
-        uint32_t prev = 0u, cnt = 0u, nb = 0u, edits = 0u;
+        uint32_t prev = 0u, cnt = 0u;
         uint32_t vh[2], e;
-        lds_vec<2>(tbp, vh);
+        lds_vec<2>(tb_s, vh);
         e = pm_s[(tlo & 3u) * PMS + TOP];
-        while (mask != mask_end && tbp != tbp_end) {
+        while (mask != mask_end && tcol != TBL * TBS) {
             const bool is_i = (vh[0] & mask) != 0;
-            const bool is_d = !is_i && (vh[1] & mask) != 0;
-            const bool is_x = !is_i && !is_d && (e & mask) != 0;
-            const uint32_t op = is_i ? 2u : (is_d ? 3u : (is_x ? 1u : 0u));  // 0 '=', 1 'X', 2 'I', 3 'D'
-            const bool brk = op != prev && cnt != 0u;
-            if (brk) ff_s[nb * FFS] = (prev << 6) | cnt;
-            nb += brk ? 1u : 0u;
-            cnt = op != prev ? 1u : cnt + 1u;
+            const bool has_d = (vh[1] & mask) != 0;
+            const bool has_x = (e & mask) != 0;
+            uint32_t op = has_x ? 1u : 0u;  // 0 '=', 1 'X', 2 'I', 3 'D'
+            op = has_d ? 3u : op;
+            op = is_i ? 2u : op;
+            const bool brk = op != prev;
+            if (brk && cnt != 0u) {
+                ff_s[stage] = prev * 64u + cnt;
+                stage += FFS;
+            }
+            cnt = brk ? 1u : cnt + 1u;
             prev = op;
-            edits += op != 0u ? 1u : 0u;
             if (!is_i) {
-                tbp += TBS;
+                tcol += TBS;
                 tlo = __funnelshift_r(tlo, thi, 2);
                 thi >>= 2;
             }
-            mask >>= is_d ? 0u : 1u;
+            if (is_i || !has_d) mask >>= 1;
             // next column's words (reloaded even when the column did not move: keeps the step branch-free)
-            lds_vec<2>(tbp, vh);
+            lds_vec<2>(tb_s + tcol, vh);
             e = pm_s[(tlo & 3u) * PMS + TOP];
         }
         if (cnt != 0u) {  // runs are flushed at window end, never merged across windows (quirk Q2)
-            ff_s[nb * FFS] = (prev << 6) | cnt;
-            nb++;
+            ff_s[stage] = prev * 64u + cnt;
+            stage += FFS;
         }
-        const int i = (int)(tbp - tb_s) / TBS;
+        const int i = tcol / TBS;
         const int j = __clz(mask);
-        if (want_cigar) {
-            if ((uint64_t)(out_end - out) >= (uint64_t)nb) {
-                for (uint32_t k = 0; k < nb; k++) out[k] = (uint8_t)ff_s[k * FFS];
-                out += nb;
-            } else {
-                overflow = true;
-            }
+        const uint32_t nb = (uint32_t)(stage / FFS);
+        uint32_t edits = 0u;
+        const bool fits = !want_cigar || (uint64_t)(out_end - out) >= (uint64_t)nb;
+        for (int k = 0; k < stage; k += FFS) {
+            const uint32_t run = ff_s[k];
+            edits += run >= 64u ? (run & 63u) : 0u;   // every op but '=' is an edit
+            if (want_cigar && fits) *out++ = (uint8_t)run;
         }
+        if (!fits) overflow = true;
         nruns += nb;
         ed += edits;
         t_pos += (uint64_t)i;

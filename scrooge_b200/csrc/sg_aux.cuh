@@ -188,7 +188,8 @@ __global__ void __launch_bounds__(128) synth_pairs_kernel(SgSynthParams p, uint6
 
 // ---- integer-ALU peak probe -----------------------------------------------------------------------------
 // Independent chains of the DC recurrence's own instructions.  kind 0: LOP3 only; 1: SHF (funnel shift) only;
-// 2: two LOP3 per SHF (the DC mix); 3: LOP3 + IMAD alternating (alu pipe + fma pipe).
+// 2: two LOP3 per SHF (the DC mix); 3: LOP3 + IMAD alternating (alu pipe + fma pipe); 4-6: one DC entry
+// (4 LOP3 + a 64-bit shift left by one) with the shift done as IMAD+SHF, IMAD.SHL+IMAD.WIDE, or IMAD.HI+IMAD+SHL.
 template <int KIND>
 __global__ void __launch_bounds__(256) int32_peak_kernel(uint32_t *__restrict__ sink, int iters, uint32_t seed)
 {
@@ -217,11 +218,35 @@ __global__ void __launch_bounds__(256) int32_peak_kernel(uint32_t *__restrict__ 
                     asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[k]) : "r"(b[k]), "r"(c[k]));
                     asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(b[k]) : "r"(c[k]), "r"(a[k]));
                     asm volatile("shf.l.wrap.b32 %0, %1, %0, 1;" : "+r"(c[k]) : "r"(a[k]));
-                } else {
+                } else if (KIND == 3) {
                     asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[k]) : "r"(b[k]), "r"(c[k]));
                     asm volatile("mad.lo.u32 %0, %0, 3, %1;" : "+r"(b[k]) : "r"(c[k]));
                     asm volatile("lop3.b32 %0, %0, %1, %2, 0xCA;" : "+r"(c[k]) : "r"(a[k]), "r"(b[k]));
                     asm volatile("mad.lo.u32 %0, %0, 5, %1;" : "+r"(a[k]) : "r"(b[k]));
+                } else if (KIND == 4) {
+                    // one DC entry as the kernel issues it today: 4 LOP3 + lo shift on the fma pipe + funnel shift
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[k]) : "r"(b[k]), "r"(c[k]));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(b[k]) : "r"(c[k]), "r"(a[k]));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0xCA;" : "+r"(c[k]) : "r"(a[k]), "r"(b[k]));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x1E;" : "+r"(a[k]) : "r"(b[k]), "r"(c[k]));
+                    asm volatile("shf.l.wrap.b32 %0, %1, %0, 1;" : "+r"(b[k]) : "r"(a[k]));
+                    asm volatile("mad.lo.u32 %0, %0, 2, %1;" : "+r"(c[k]) : "r"(b[k]));
+                } else if (KIND == 5) {
+                    // 4 LOP3 + 64-bit shift entirely on the fma pipe: hi*2 then mad.wide(lo, 2, {0, hi*2})
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[k]) : "r"(b[k]), "r"(c[k]));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(b[k]) : "r"(c[k]), "r"(a[k]));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0xCA;" : "+r"(c[k]) : "r"(a[k]), "r"(b[k]));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x1E;" : "+r"(a[k]) : "r"(b[k]), "r"(c[k]));
+                    asm volatile("{ .reg .b64 t, u; .reg .b32 z; shl.b32 z, %1, 1; mov.b64 t, {0, z}; mad.wide.u32 u, %0, 2, t; mov.b64 {%0, %1}, u; }"
+                                 : "+r"(b[k]), "+r"(c[k]));
+                } else {
+                    // 4 LOP3 + 64-bit shift on the fma pipe through the carry: lo*2, mulhi(lo,2), hi*2+carry
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[k]) : "r"(b[k]), "r"(c[k]));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(b[k]) : "r"(c[k]), "r"(a[k]));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0xCA;" : "+r"(c[k]) : "r"(a[k]), "r"(b[k]));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x1E;" : "+r"(a[k]) : "r"(b[k]), "r"(c[k]));
+                    asm volatile("{ .reg .b32 cy; mul.hi.u32 cy, %0, 2; mad.lo.u32 %1, %1, 2, cy; shl.b32 %0, %0, 1; }"
+                                 : "+r"(b[k]), "+r"(c[k]));
                 }
             }
         }
@@ -231,6 +256,7 @@ __global__ void __launch_bounds__(256) int32_peak_kernel(uint32_t *__restrict__ 
     for (int k = 0; k < CH; k++) acc ^= a[k] ^ b[k] ^ c[k];
     if (acc == 0x12345678u) sink[0] = acc;  // keep the chains alive
 }
-constexpr int kPeakOpsPerIter[4] = {8 * 4 * 3, 8 * 4 * 3, 8 * 4 * 3, 8 * 4 * 4};
+// ops per loop iteration; kinds 4-6 count one "DC entry" (4 LOP3 + a 64-bit shift) as 6 ops
+constexpr int kPeakOpsPerIter[7] = {8 * 4 * 3, 8 * 4 * 3, 8 * 4 * 3, 8 * 4 * 4, 8 * 4 * 6, 8 * 4 * 6, 8 * 4 * 6};
 
 }  // namespace sg

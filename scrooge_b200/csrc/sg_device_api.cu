@@ -191,7 +191,7 @@ int sg_dev_gather_runs(const uint8_t *d_slab, const uint64_t *d_slab_off, const 
 
 int sg_dev_int32_peak(int kind, double ms, double *gops)
 {
-    if (kind < 0 || kind > 3 || !gops) return fail(SG_ERR_BAD_ARG, "sg_dev_int32_peak: bad argument");
+    if (kind < 0 || kind > 6 || !gops) return fail(SG_ERR_BAD_ARG, "sg_dev_int32_peak: bad argument");
     DeviceInfo *di;
     int rc = device_info(&di);
     if (rc) return rc;
@@ -206,7 +206,10 @@ int sg_dev_int32_peak(int kind, double ms, double *gops)
             case 0: int32_peak_kernel<0><<<blocks, threads>>>(sink, iters, 1u); break;
             case 1: int32_peak_kernel<1><<<blocks, threads>>>(sink, iters, 1u); break;
             case 2: int32_peak_kernel<2><<<blocks, threads>>>(sink, iters, 1u); break;
-            default: int32_peak_kernel<3><<<blocks, threads>>>(sink, iters, 1u); break;
+            case 3: int32_peak_kernel<3><<<blocks, threads>>>(sink, iters, 1u); break;
+            case 4: int32_peak_kernel<4><<<blocks, threads>>>(sink, iters, 1u); break;
+            case 5: int32_peak_kernel<5><<<blocks, threads>>>(sink, iters, 1u); break;
+            default: int32_peak_kernel<6><<<blocks, threads>>>(sink, iters, 1u); break;
         }
     };
     int iters = 2048;
