@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="long_10kbp")
     ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU per step")
-    ap.add_argument("--e2e-pairs", type=int, default=131_072, help="pairs per GPU per end-to-end step (host buffers)")
+    ap.add_argument("--e2e-pairs", type=int, default=524_288, help="pairs per GPU per end-to-end step (host buffers)")
     ap.add_argument("--cpu-sample", type=int, default=32_768, help="pairs of the CPU baseline / parity sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

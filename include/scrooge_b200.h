@@ -111,6 +111,11 @@ int64_t sg_result_render_cigar(const sg_result *r, uint64_t idx, char *buf, uint
 int64_t sg_result_entries(const sg_result *r, uint64_t idx, sg_cigar_entry *out, uint64_t cap);
 void sg_result_free(sg_result *r);
 
+/* Page-locked host memory for input blobs: uploads from it run at full PCIe speed and overlap with compute
+ * (pageable memory works too, but the driver then stages every copy).  NULL on failure. */
+void *sg_host_alloc(uint64_t bytes);
+void sg_host_free(void *p);
+
 /* ------------------------------------------------------------------------------------------------ */
 /* 2. device API: device pointers, current device, asynchronous on `stream` (a cudaStream_t).        */
 

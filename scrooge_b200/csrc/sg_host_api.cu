@@ -1,20 +1,23 @@
 // sg_host_api.cu -- layer 1 of include/scrooge_b200.h: host buffers in, host results out.
 //
 // Replaces the host side of the reference GPU library (src/genasm_gpu.cu:692-1065): cudaMallocManaged
-// blobs, per-string descriptor loops and a linked-list walk per alignment become
-//   * one contiguous ASCII upload per batch, packed to 2 bit/base on the device,
-//   * descriptors derived on the device from the offset arrays,
-//   * a run slab with per-alignment capacity 2*|query|+8 (reference: 2*|query| entries,
-//     src/genasm_gpu.cu:995-1001), compacted on the device and downloaded in one transfer,
+// blobs, per-string descriptor loops, one synchronous kernel over everything and a linked-list walk per
+// alignment become
 //   * a host-side scatter over the context's GPUs: alignments are independent
 //     (src/genasm_cpu.cpp:451-455), so each GPU gets a contiguous share balanced by query bases and there
-//     is no inter-GPU exchange of any kind.  In mapping mode every GPU holds its own packed reference.
+//     is no inter-GPU exchange of any kind.  In mapping mode every GPU holds its own packed reference;
+//   * per GPU, a three-slot software pipeline over sub-batches: while batch k is being aligned, batch
+//     k+1's ASCII is on its way over PCIe (one contiguous copy, packed to 2 bit/base on the device) and
+//     batch k-1's distances and compacted CIGAR runs are on their way back into pinned host memory;
+//   * descriptors derived on the device from the offset arrays, a run slab with per-alignment capacity
+//     2*|query|+8 (reference: 2*|query| entries, src/genasm_gpu.cu:995-1001) compacted on the device.
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
 #include <string>
 #include <vector>
 #include <thread>
+#include <mutex>
 #include <chrono>
 #include <algorithm>
 #include <memory>
@@ -25,7 +28,7 @@
 
 namespace sg {
 
-// ---- tiny RAII device / pinned buffers that only grow ----------------------------------------------
+// ---- device / pinned buffers that only grow ----------------------------------------------------------
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -38,9 +41,13 @@ struct DevBuf {
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) {
             cudaGetLastError();
-            e = cudaMalloc(&p, bytes);
             want = bytes;
-            if (e != cudaSuccess) { cudaGetLastError(); p = nullptr; return fail(SG_ERR_OOM, "cudaMalloc failed for " + std::to_string(bytes) + " bytes"); }
+            e = cudaMalloc(&p, want);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                p = nullptr;
+                return fail(SG_ERR_OOM, "cudaMalloc failed for " + std::to_string(bytes) + " bytes");
+            }
         }
         cap = want;
         return SG_OK;
@@ -58,7 +65,11 @@ struct PinBuf {
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 8 + 256;
-        if (cudaMallocHost(&p, want) != cudaSuccess) { cudaGetLastError(); p = nullptr; return fail(SG_ERR_OOM, "cudaMallocHost failed"); }
+        if (cudaMallocHost(&p, want) != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            return fail(SG_ERR_OOM, "cudaMallocHost failed for " + std::to_string(bytes) + " bytes");
+        }
         cap = want;
         return SG_OK;
     }
@@ -66,7 +77,64 @@ struct PinBuf {
     template <class T> T *as() const { return (T *)p; }
 };
 
-// descriptors from offset arrays: start[a] = off[a] - off[0] + base, len[a] = off[a+1]-off[a], slab_off
+// Pinned blocks for result pieces are expensive to create (page pinning) and cheap to reuse: a process-wide
+// pool hands them to results and takes them back in sg_result_free.
+struct PinnedPool {
+    struct Block { uint8_t *p; size_t cap; };
+    std::mutex mu;
+    std::vector<Block> free_blocks;
+    size_t cached = 0;
+    static constexpr size_t kMaxCached = 16ull << 30;
+
+    int acquire(size_t bytes, Block *out)
+    {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            size_t best = free_blocks.size();
+            for (size_t k = 0; k < free_blocks.size(); k++)
+                if (free_blocks[k].cap >= bytes && (best == free_blocks.size() || free_blocks[k].cap < free_blocks[best].cap)) best = k;
+            if (best != free_blocks.size()) {
+                *out = free_blocks[best];
+                cached -= out->cap;
+                free_blocks.erase(free_blocks.begin() + best);
+                return SG_OK;
+            }
+        }
+        size_t want = std::max<size_t>(bytes + bytes / 16, 4096);
+        void *p = nullptr;
+        if (cudaMallocHost(&p, want) != cudaSuccess) {
+            cudaGetLastError();
+            trim(0);
+            if (cudaMallocHost(&p, want) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(SG_ERR_OOM, "cudaMallocHost failed for " + std::to_string(want) + " bytes");
+            }
+        }
+        out->p = (uint8_t *)p;
+        out->cap = want;
+        return SG_OK;
+    }
+    void release(Block b)
+    {
+        if (!b.p) return;
+        std::lock_guard<std::mutex> g(mu);
+        if (cached + b.cap > kMaxCached) { cudaFreeHost(b.p); return; }
+        free_blocks.push_back(b);
+        cached += b.cap;
+    }
+    void trim(size_t keep)
+    {
+        std::lock_guard<std::mutex> g(mu);
+        while (!free_blocks.empty() && cached > keep) {
+            cached -= free_blocks.back().cap;
+            cudaFreeHost(free_blocks.back().p);
+            free_blocks.pop_back();
+        }
+    }
+};
+static PinnedPool g_pool;
+
+// descriptors from offset arrays: start[a] = off[a] - off[0], len[a] = off[a+1]-off[a], slab offsets
 __global__ void __launch_bounds__(256) pair_descriptors_kernel(const uint64_t *__restrict__ toff, const uint64_t *__restrict__ qoff,
                                                                 uint64_t n, uint64_t *__restrict__ tstart, uint64_t *__restrict__ tlen,
                                                                 uint64_t *__restrict__ qstart, uint64_t *__restrict__ qlen,
@@ -88,7 +156,7 @@ __global__ void __launch_bounds__(256) cand_descriptors_kernel(const uint64_t *_
                                                                 const uint64_t *__restrict__ roff, uint32_t read_base, uint64_t genome_len, uint64_t n,
                                                                 uint64_t *__restrict__ tstart, uint64_t *__restrict__ tlen,
                                                                 uint64_t *__restrict__ qstart, uint64_t *__restrict__ qlen,
-                                                                uint32_t *__restrict__ qlen32)
+                                                                uint32_t *__restrict__ cap32)
 {
     const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
@@ -99,27 +167,53 @@ __global__ void __launch_bounds__(256) cand_descriptors_kernel(const uint64_t *_
     qstart[c] = roff[r] - roff[0];
     const uint64_t ql = roff[r + 1] - roff[r];
     qlen[c] = ql;
-    qlen32[c] = (uint32_t)(2ull * ql + 8ull);  // slab capacity; scanned into slab offsets
+    cap32[c] = (uint32_t)(2ull * ql + 8ull);  // slab capacity; scanned into slab offsets
 }
+
+constexpr int kSlots = 3;
+
+// One pipeline stage's worth of buffers: a sub-batch lives in a slot from upload to download.
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_mid = nullptr, ev_end = nullptr;
+    DevBuf ascii_t, ascii_q, packed_t, packed_q, toff, qoff, tstart, tlen, qstart, qlen, slab_off, slab, counter, edit,
+        refc, nruns, status, run_off, scan_tmp, runs, bad, cstart, cread, cap32;
+    PinBuf h_small, h_edit, h_refc, h_runoff, h_status;
+    PinnedPool::Block piece{nullptr, 0};
+    // the batch in flight
+    bool busy = false, mid_done = false;
+    uint64_t a0 = 0, a1 = 0, total_runs = 0;
+    int create()
+    {
+        SG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        SG_CUDA(cudaEventCreate(&ev_k0));
+        SG_CUDA(cudaEventCreate(&ev_k1));
+        SG_CUDA(cudaEventCreateWithFlags(&ev_mid, cudaEventDisableTiming));
+        SG_CUDA(cudaEventCreateWithFlags(&ev_end, cudaEventDisableTiming));
+        return SG_OK;
+    }
+    void destroy()
+    {
+        for (DevBuf *b : {&ascii_t, &ascii_q, &packed_t, &packed_q, &toff, &qoff, &tstart, &tlen, &qstart, &qlen, &slab_off,
+                          &slab, &counter, &edit, &refc, &nruns, &status, &run_off, &scan_tmp, &runs, &bad, &cstart, &cread, &cap32})
+            b->release();
+        for (PinBuf *b : {&h_small, &h_edit, &h_refc, &h_runoff, &h_status}) b->release();
+        g_pool.release(piece);
+        piece = {nullptr, 0};
+        if (ev_k0) cudaEventDestroy(ev_k0);
+        if (ev_k1) cudaEventDestroy(ev_k1);
+        if (ev_mid) cudaEventDestroy(ev_mid);
+        if (ev_end) cudaEventDestroy(ev_end);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
 
 struct Device {
     int id = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf ascii_t, ascii_q, packed_t, packed_q, toff, qoff, tstart, tlen, qstart, qlen, slab_off, slab, counter, edit,
-        refc, nruns, status, run_off, scan_tmp, runs, bad, cstart, cread, cap32;
+    Slot slots[kSlots];
     DevBuf genome;  // packed reference, resident across calls
     uint64_t genome_len = 0;
     bool has_genome = false;
-    PinBuf h_small;
-    void release_all()
-    {
-        for (DevBuf *b : {&ascii_t, &ascii_q, &packed_t, &packed_q, &toff, &qoff, &tstart, &tlen, &qstart, &qlen, &slab_off,
-                          &slab, &counter, &edit, &refc, &nruns, &status, &run_off, &scan_tmp, &runs, &bad, &cstart, &cread,
-                          &cap32, &genome})
-            b->release();
-        h_small.release();
-    }
 };
 
 }  // namespace sg
@@ -129,7 +223,13 @@ using namespace sg;
 struct sg_ctx {
     int W = 64;
     std::vector<Device> devs;
-    uint64_t max_batch_query_bases = 1ull << 31;  // bounds the per-batch slab (2 B per query base)
+    // sub-batch rule: at least batch_bytes of ASCII AND at least min_batch_units alignments (one alignment
+    // occupies one lane for its whole life -- 2.4 ms for a 10 kbp read -- so a launch needs a couple of
+    // alignments per lane to fill the device), but never more than max_batch_bytes (per-slot buffers)
+    uint64_t batch_bytes = 256ull << 20;
+    uint64_t max_batch_bytes = 3ull << 30;
+    uint64_t min_batch_units = 65536;
+    std::mutex mu;  // calls on one context are serialised
 };
 
 struct sg_result {
@@ -138,12 +238,14 @@ struct sg_result {
     std::vector<int64_t> edit;
     std::vector<uint64_t> refc;
     std::vector<uint64_t> run_off;  // n+1
-    // runs of the alignments, one contiguous piece per processed batch; piece_of[a] gives the piece
-    std::vector<std::vector<uint8_t>> pieces;
+    // packed runs, one pinned piece per processed sub-batch, in alignment order
+    std::vector<PinnedPool::Block> pieces;
     std::vector<uint64_t> piece_first;   // first alignment of each piece
     std::vector<uint64_t> piece_run0;    // global run offset of each piece's first run
+    std::vector<uint64_t> piece_runs;    // runs in each piece
     std::vector<uint8_t> flat;           // lazily flattened view for sg_result_runs
     int64_t kernel_ns = 0, total_ns = 0;
+    ~sg_result() { for (auto &b : pieces) g_pool.release(b); }
 };
 
 namespace {
@@ -152,89 +254,204 @@ struct ShardOut {
     int rc = SG_OK;
     std::string err;
     double kernel_ms = 0;
-    std::vector<std::vector<uint8_t>> pieces;
-    std::vector<uint64_t> piece_first;
+    std::vector<PinnedPool::Block> pieces;
+    std::vector<uint64_t> piece_first, piece_runs;
+    ~ShardOut() { for (auto &b : pieces) g_pool.release(b); }
 };
 
-// Runs one batch [a0, a1) of the unstructured interface on device d.
-int run_pairs_batch(sg_ctx *ctx, Device &d, const char *tb, const uint64_t *toff, const char *qb, const uint64_t *qoff,
-                    uint64_t a0, uint64_t a1, uint32_t flags, sg_result *res, ShardOut &so)
+// What differs between the two interfaces: how a sub-batch's inputs get to the device.
+struct Workload {
+    bool mapping = false;
+    // pairs
+    const char *tb = nullptr; const uint64_t *toff = nullptr; const char *qb = nullptr; const uint64_t *qoff = nullptr;
+    // mapping
+    const char *rb = nullptr; const uint64_t *roff = nullptr; const uint64_t *cand_start = nullptr; const uint32_t *cand_read = nullptr;
+    const uint64_t *woff = nullptr;  // per-candidate query-length prefix sums
+    uint32_t flags = 0;
+};
+
+#define R(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
+
+// stage A: uploads, ingest, descriptors, alignment kernel, run-count scan; ends with ev_mid
+int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uint64_t a1)
 {
     const uint64_t n = a1 - a0;
-    const uint64_t tbytes = toff[a1] - toff[a0], qbytes = qoff[a1] - qoff[a0];
-    const bool want_cigar = !(flags & SG_FLAG_DISTANCE_ONLY);
-    cudaStream_t st = d.stream;
-    int rc;
-#define R(x) do { rc = (x); if (rc) return rc; } while (0)
-    R(d.ascii_t.reserve(tbytes + 64)); R(d.ascii_q.reserve(qbytes + 64));
-    R(d.packed_t.reserve(sg_packed_words(tbytes) * 4)); R(d.packed_q.reserve(sg_packed_words(qbytes) * 4));
-    R(d.toff.reserve((n + 1) * 8)); R(d.qoff.reserve((n + 1) * 8));
-    R(d.tstart.reserve(n * 8)); R(d.tlen.reserve(n * 8)); R(d.qstart.reserve(n * 8)); R(d.qlen.reserve(n * 8));
-    R(d.slab_off.reserve((n + 1) * 8));
-    const uint64_t slab_bytes = 2ull * qbytes + 8ull * n;
-    if (want_cigar) R(d.slab.reserve(slab_bytes + 16));
-    R(d.counter.reserve(8)); R(d.edit.reserve(n * 8)); R(d.refc.reserve(n * 8)); R(d.nruns.reserve(n * 4));
-    R(d.status.reserve(n)); R(d.run_off.reserve((n + 1) * 8)); R(d.scan_tmp.reserve(sg_scan_tmp_bytes(n)));
-    R(d.bad.reserve(16));
-    R(d.h_small.reserve(64));
-
-    SG_CUDA(cudaMemcpyAsync(d.ascii_t.p, tb + toff[a0], tbytes, cudaMemcpyHostToDevice, st));
-    SG_CUDA(cudaMemcpyAsync(d.ascii_q.p, qb + qoff[a0], qbytes, cudaMemcpyHostToDevice, st));
-    SG_CUDA(cudaMemcpyAsync(d.toff.p, toff + a0, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-    SG_CUDA(cudaMemcpyAsync(d.qoff.p, qoff + a0, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-    SG_CUDA(cudaMemsetAsync(d.bad.p, 0xFF, 16, st));
-    R(sg_dev_pack_2bit(d.ascii_t.as<char>(), tbytes, d.packed_t.as<uint32_t>(), d.bad.as<uint64_t>(), st));
-    R(sg_dev_pack_2bit(d.ascii_q.as<char>(), qbytes, d.packed_q.as<uint32_t>(), d.bad.as<uint64_t>() + 1, st));
-    pair_descriptors_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(
-        d.toff.as<uint64_t>(), d.qoff.as<uint64_t>(), n, d.tstart.as<uint64_t>(), d.tlen.as<uint64_t>(),
-        d.qstart.as<uint64_t>(), d.qlen.as<uint64_t>(), d.slab_off.as<uint64_t>());
-    SG_CUDA(cudaGetLastError());
-    SG_CUDA(cudaEventRecord(d.ev0, st));
-    R(sg_dev_align(ctx->W, d.packed_t.as<uint32_t>(), d.tstart.as<uint64_t>(), d.tlen.as<uint64_t>(),
-                   d.packed_q.as<uint32_t>(), d.qstart.as<uint64_t>(), d.qlen.as<uint64_t>(), n, flags,
-                   d.slab.as<uint8_t>(), d.slab_off.as<uint64_t>(), d.counter.as<uint64_t>(), d.edit.as<int64_t>(),
-                   d.refc.as<uint64_t>(), d.nruns.as<uint32_t>(), d.status.as<uint8_t>(), nullptr, st));
-    SG_CUDA(cudaEventRecord(d.ev1, st));
-    uint64_t *h = d.h_small.as<uint64_t>();
-    SG_CUDA(cudaMemcpyAsync(h, d.bad.p, 16, cudaMemcpyDeviceToHost, st));
+    const bool want_cigar = !(w.flags & SG_FLAG_DISTANCE_ONLY);
+    cudaStream_t st = s.stream;
+    s.a0 = a0; s.a1 = a1; s.busy = true; s.mid_done = false; s.total_runs = 0;
+    R(s.tstart.reserve(n * 8)); R(s.tlen.reserve(n * 8)); R(s.qstart.reserve(n * 8)); R(s.qlen.reserve(n * 8));
+    R(s.slab_off.reserve((n + 1) * 8)); R(s.counter.reserve(8)); R(s.edit.reserve(n * 8)); R(s.refc.reserve(n * 8));
+    R(s.nruns.reserve(n * 4)); R(s.status.reserve(n)); R(s.run_off.reserve((n + 1) * 8));
+    R(s.scan_tmp.reserve(sg_scan_tmp_bytes(n))); R(s.bad.reserve(16)); R(s.h_small.reserve(64));
+    R(s.h_edit.reserve(n * 8)); R(s.h_refc.reserve(n * 8)); R(s.h_runoff.reserve((n + 1) * 8)); R(s.h_status.reserve(n));
+    SG_CUDA(cudaMemsetAsync(s.bad.p, 0xFF, 16, st));
+    const uint32_t *d_text, *d_query;
+    uint64_t slab_bytes;
+    if (!w.mapping) {
+        const uint64_t tbytes = w.toff[a1] - w.toff[a0], qbytes = w.qoff[a1] - w.qoff[a0];
+        R(s.ascii_t.reserve(tbytes + 64)); R(s.ascii_q.reserve(qbytes + 64));
+        R(s.packed_t.reserve(sg_packed_words(tbytes) * 4)); R(s.packed_q.reserve(sg_packed_words(qbytes) * 4));
+        R(s.toff.reserve((n + 1) * 8)); R(s.qoff.reserve((n + 1) * 8));
+        slab_bytes = 2ull * qbytes + 8ull * n;
+        SG_CUDA(cudaMemcpyAsync(s.ascii_t.p, w.tb + w.toff[a0], tbytes, cudaMemcpyHostToDevice, st));
+        SG_CUDA(cudaMemcpyAsync(s.ascii_q.p, w.qb + w.qoff[a0], qbytes, cudaMemcpyHostToDevice, st));
+        SG_CUDA(cudaMemcpyAsync(s.toff.p, w.toff + a0, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+        SG_CUDA(cudaMemcpyAsync(s.qoff.p, w.qoff + a0, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+        R(sg_dev_pack_2bit(s.ascii_t.as<char>(), tbytes, s.packed_t.as<uint32_t>(), s.bad.as<uint64_t>(), st));
+        R(sg_dev_pack_2bit(s.ascii_q.as<char>(), qbytes, s.packed_q.as<uint32_t>(), s.bad.as<uint64_t>() + 1, st));
+        pair_descriptors_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(
+            s.toff.as<uint64_t>(), s.qoff.as<uint64_t>(), n, s.tstart.as<uint64_t>(), s.tlen.as<uint64_t>(),
+            s.qstart.as<uint64_t>(), s.qlen.as<uint64_t>(), s.slab_off.as<uint64_t>());
+        SG_CUDA(cudaGetLastError());
+        d_text = s.packed_t.as<uint32_t>();
+        d_query = s.packed_q.as<uint32_t>();
+    } else {
+        // reads referenced by this sub-batch: the contiguous index range [r0, r1] (candidates arrive read-major,
+        // so the range is tight; each read is uploaded and packed once and shared by its candidates,
+        // cf. reference twobit_reads, src/genasm_gpu.cu:784-796)
+        uint32_t r0 = w.cand_read[a0], r1 = w.cand_read[a0];
+        for (uint64_t c = a0; c < a1; c++) { r0 = std::min(r0, w.cand_read[c]); r1 = std::max(r1, w.cand_read[c]); }
+        const uint64_t nr = (uint64_t)r1 - r0 + 1, rbytes = w.roff[r1 + 1] - w.roff[r0];
+        slab_bytes = 2ull * (w.woff[a1] - w.woff[a0]) + 8ull * n;
+        R(s.ascii_q.reserve(rbytes + 64)); R(s.packed_q.reserve(sg_packed_words(rbytes) * 4));
+        R(s.qoff.reserve((nr + 1) * 8)); R(s.cstart.reserve(n * 8)); R(s.cread.reserve(n * 4)); R(s.cap32.reserve(n * 4));
+        SG_CUDA(cudaMemcpyAsync(s.ascii_q.p, w.rb + w.roff[r0], rbytes, cudaMemcpyHostToDevice, st));
+        SG_CUDA(cudaMemcpyAsync(s.qoff.p, w.roff + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, st));
+        SG_CUDA(cudaMemcpyAsync(s.cstart.p, w.cand_start + a0, n * 8, cudaMemcpyHostToDevice, st));
+        SG_CUDA(cudaMemcpyAsync(s.cread.p, w.cand_read + a0, n * 4, cudaMemcpyHostToDevice, st));
+        R(sg_dev_pack_2bit(s.ascii_q.as<char>(), rbytes, s.packed_q.as<uint32_t>(), s.bad.as<uint64_t>() + 1, st));
+        cand_descriptors_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+            s.cstart.as<uint64_t>(), s.cread.as<uint32_t>(), s.qoff.as<uint64_t>(), r0, d.genome_len, n, s.tstart.as<uint64_t>(),
+            s.tlen.as<uint64_t>(), s.qstart.as<uint64_t>(), s.qlen.as<uint64_t>(), s.cap32.as<uint32_t>());
+        SG_CUDA(cudaGetLastError());
+        R(sg_dev_scan_runs(s.cap32.as<uint32_t>(), n, s.slab_off.as<uint64_t>(), s.scan_tmp.p, st));
+        d_text = d.genome.as<uint32_t>();
+        d_query = s.packed_q.as<uint32_t>();
+    }
+    if (want_cigar) R(s.slab.reserve(slab_bytes + 16));
+    SG_CUDA(cudaEventRecord(s.ev_k0, st));
+    R(sg_dev_align(ctx->W, d_text, s.tstart.as<uint64_t>(), s.tlen.as<uint64_t>(), d_query, s.qstart.as<uint64_t>(),
+                   s.qlen.as<uint64_t>(), n, w.flags, s.slab.as<uint8_t>(), s.slab_off.as<uint64_t>(), s.counter.as<uint64_t>(),
+                   s.edit.as<int64_t>(), s.refc.as<uint64_t>(), s.nruns.as<uint32_t>(), s.status.as<uint8_t>(), nullptr, st));
+    SG_CUDA(cudaEventRecord(s.ev_k1, st));
+    uint64_t *h = s.h_small.as<uint64_t>();
+    SG_CUDA(cudaMemcpyAsync(h, s.bad.p, 16, cudaMemcpyDeviceToHost, st));
     if (want_cigar) {
-        R(sg_dev_scan_runs(d.nruns.as<uint32_t>(), n, d.run_off.as<uint64_t>(), d.scan_tmp.p, st));
-        SG_CUDA(cudaMemcpyAsync(h + 2, d.run_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+        R(sg_dev_scan_runs(s.nruns.as<uint32_t>(), n, s.run_off.as<uint64_t>(), s.scan_tmp.p, st));
+        SG_CUDA(cudaMemcpyAsync(h + 2, s.run_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
     }
-    SG_CUDA(cudaMemcpyAsync(res->edit.data() + a0, d.edit.p, n * 8, cudaMemcpyDeviceToHost, st));
-    SG_CUDA(cudaMemcpyAsync(res->refc.data() + a0, d.refc.p, n * 8, cudaMemcpyDeviceToHost, st));
-    SG_CUDA(cudaStreamSynchronize(st));
+    SG_CUDA(cudaMemcpyAsync(s.h_edit.p, s.edit.p, n * 8, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(s.h_refc.p, s.refc.p, n * 8, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(s.h_status.p, s.status.p, n, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaEventRecord(s.ev_mid, st));
+    return SG_OK;
+}
+
+// stage B: once the run total is known, gather the runs and send everything home; ends with ev_end
+int stage_b(Slot &s, const Workload &w)
+{
+    if (!s.busy || s.mid_done) return SG_OK;
+    const uint64_t n = s.a1 - s.a0;
+    const bool want_cigar = !(w.flags & SG_FLAG_DISTANCE_ONLY);
+    cudaStream_t st = s.stream;
+    SG_CUDA(cudaEventSynchronize(s.ev_mid));
+    s.mid_done = true;
+    const uint64_t *h = s.h_small.as<uint64_t>();
     if (h[0] != ~0ull || h[1] != ~0ull) {
-        // name the pair like the reference's assert would have stopped on it (src/genasm_gpu.cu:636)
-        const bool in_text = h[0] != ~0ull;
-        const uint64_t pos = (in_text ? h[0] + toff[a0] : h[1] + qoff[a0]);
-        const uint64_t *off = in_text ? toff : qoff;
-        uint64_t p = (uint64_t)(std::upper_bound(off + a0, off + a1 + 1, pos) - off) - 1;
-        return fail(SG_ERR_BAD_BASE, std::string("non-ACGT character in ") + (in_text ? "text" : "query") + " of pair " +
-                                         std::to_string(p) + " at position " + std::to_string(pos - off[p]));
+        // name the offender like the reference's assert would have stopped on it (src/genasm_gpu.cu:636)
+        if (!w.mapping) {
+            const bool in_text = h[0] != ~0ull;
+            const uint64_t *off = in_text ? w.toff : w.qoff;
+            const uint64_t pos = (in_text ? h[0] : h[1]) + off[s.a0];
+            const uint64_t p = (uint64_t)(std::upper_bound(off + s.a0, off + s.a1 + 1, pos) - off) - 1;
+            return fail(SG_ERR_BAD_BASE, std::string("non-ACGT character in ") + (in_text ? "text" : "query") + " of pair " +
+                                             std::to_string(p) + " at position " + std::to_string(pos - off[p]));
+        }
+        uint32_t r0 = w.cand_read[s.a0], r1 = r0;
+        for (uint64_t c = s.a0; c < s.a1; c++) { r0 = std::min(r0, w.cand_read[c]); r1 = std::max(r1, w.cand_read[c]); }
+        const uint64_t pos = h[1] + w.roff[r0];
+        const uint64_t r = (uint64_t)(std::upper_bound(w.roff + r0, w.roff + r1 + 2, pos) - w.roff) - 1;
+        return fail(SG_ERR_BAD_BASE, "non-ACGT character in read " + std::to_string(r) + " at position " + std::to_string(pos - w.roff[r]));
     }
+    if (want_cigar) {
+        s.total_runs = h[2];
+        R(s.runs.reserve(s.total_runs + 16));
+        g_pool.release(s.piece);
+        s.piece = {nullptr, 0};
+        R(g_pool.acquire(s.total_runs + 16, &s.piece));
+        R(sg_dev_gather_runs(s.slab.as<uint8_t>(), s.slab_off.as<uint64_t>(), s.nruns.as<uint32_t>(), s.run_off.as<uint64_t>(), n,
+                             s.runs.as<uint8_t>(), st));
+        SG_CUDA(cudaMemcpyAsync(s.piece.p, s.runs.p, s.total_runs, cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaMemcpyAsync(s.h_runoff.p, s.run_off.p, n * 8, cudaMemcpyDeviceToHost, st));
+    }
+    SG_CUDA(cudaEventRecord(s.ev_end, st));
+    return SG_OK;
+}
+
+// stage C: results of the slot's sub-batch into the caller-visible result; frees the slot
+int stage_c(Slot &s, const Workload &w, sg_result *res, ShardOut &so)
+{
+    if (!s.busy) return SG_OK;
+    const uint64_t n = s.a1 - s.a0;
+    const bool want_cigar = !(w.flags & SG_FLAG_DISTANCE_ONLY);
+    R(stage_b(s, w));
+    SG_CUDA(cudaEventSynchronize(s.ev_end));
+    s.busy = false;
+    const uint8_t *status = s.h_status.as<uint8_t>();
+    for (uint64_t k = 0; k < n; k++)
+        if (status[k]) return fail(SG_ERR_CIGAR_OVERFLOW, "alignment " + std::to_string(s.a0 + k) + " exceeded its run capacity");
+    memcpy(res->edit.data() + s.a0, s.h_edit.p, n * 8);
+    memcpy(res->refc.data() + s.a0, s.h_refc.p, n * 8);
     float ms = 0;
-    SG_CUDA(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+    SG_CUDA(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
     so.kernel_ms += ms;
     if (want_cigar) {
-        const uint64_t total_runs = h[2];
-        R(d.runs.reserve(total_runs + 16));
-        R(sg_dev_gather_runs(d.slab.as<uint8_t>(), d.slab_off.as<uint64_t>(), d.nruns.as<uint32_t>(), d.run_off.as<uint64_t>(),
-                             n, d.runs.as<uint8_t>(), st));
-        std::vector<uint8_t> piece(total_runs);
-        std::vector<uint8_t> status(n);
-        SG_CUDA(cudaMemcpyAsync(piece.data(), d.runs.p, total_runs, cudaMemcpyDeviceToHost, st));
-        // per-batch run offsets land in the result's global array; rebased by the caller after all shards finish
-        SG_CUDA(cudaMemcpyAsync(res->run_off.data() + a0, d.run_off.p, n * 8, cudaMemcpyDeviceToHost, st));
-        SG_CUDA(cudaMemcpyAsync(status.data(), d.status.p, n, cudaMemcpyDeviceToHost, st));
-        SG_CUDA(cudaStreamSynchronize(st));
-        for (uint64_t k = 0; k < n; k++)
-            if (status[k]) return fail(SG_ERR_CIGAR_OVERFLOW, "alignment " + std::to_string(a0 + k) + " exceeded its run capacity");
-        so.pieces.push_back(std::move(piece));
-        so.piece_first.push_back(a0);
+        memcpy(res->run_off.data() + s.a0, s.h_runoff.p, n * 8);  // sub-batch-local offsets, rebased in finalize()
+        so.pieces.push_back(s.piece);
+        so.piece_first.push_back(s.a0);
+        so.piece_runs.push_back(s.total_runs);
+        s.piece = {nullptr, 0};
     }
-#undef R
     return SG_OK;
+}
+
+// The pipeline over one device's share [c0, c1): weight prefix `woff` decides the sub-batch cuts.
+void run_shard(sg_ctx *ctx, Device &d, const Workload &w, const uint64_t *woff, uint64_t per_unit_extra, uint64_t c0, uint64_t c1,
+               sg_result *res, ShardOut &so)
+{
+    auto bail = [&](int rc) {
+        so.rc = rc;
+        so.err = g_last_error;
+        for (Slot &s : d.slots) {  // let the device drain before the buffers are reused
+            if (s.stream) cudaStreamSynchronize(s.stream);
+            s.busy = false;
+        }
+        cudaGetLastError();
+    };
+    if (cudaSetDevice(d.id) != cudaSuccess) { cudaGetLastError(); fail(SG_ERR_CUDA, "cudaSetDevice failed"); bail(SG_ERR_CUDA); return; }
+    std::vector<uint64_t> cuts{c0};
+    while (cuts.back() < c1) {
+        uint64_t a = cuts.back(), b = a + 1;
+        while (b < c1) {
+            const uint64_t bytes = (woff[b + 1] - woff[a]) + per_unit_extra * (b + 1 - a);
+            if (bytes > ctx->max_batch_bytes) break;
+            if (bytes > ctx->batch_bytes && b - a >= ctx->min_batch_units) break;
+            b++;
+        }
+        cuts.push_back(b);
+    }
+    const int nb = (int)cuts.size() - 1;
+    for (int k = 0; k < nb; k++) {
+        Slot &s = d.slots[k % kSlots];
+        int rc = stage_c(s, w, res, so);                       // frees the slot used by batch k - kSlots
+        if (!rc) rc = stage_a(ctx, d, s, w, cuts[k], cuts[k + 1]);
+        if (!rc && k >= 1) rc = stage_b(d.slots[(k - 1) % kSlots], w);
+        if (rc) { bail(rc); return; }
+    }
+    for (int k = std::max(0, nb - kSlots); k < nb; k++) {
+        int rc = stage_c(d.slots[k % kSlots], w, res, so);
+        if (rc) { bail(rc); return; }
+    }
 }
 
 // splits [0,n) into contiguous parts with about equal weight, weight prefix given by off (n+1 entries)
@@ -255,22 +472,30 @@ std::vector<uint64_t> split_by_weight(const uint64_t *off, uint64_t n, int parts
     return cut;
 }
 
-void finalize_runs(sg_result *res, std::vector<ShardOut> &shards)
+void finalize(sg_result *res, std::vector<ShardOut> &shards)
 {
-    // pieces are in alignment order once shards are concatenated; rebase per-piece offsets to global ones
+    double kms = 0;
+    for (ShardOut &so : shards) kms = std::max(kms, so.kernel_ms);
+    res->kernel_ns = (int64_t)(kms * 1e6);
+    if (!res->has_cigar) return;
+    // pieces are in alignment order once the shards are concatenated; rebase per-piece offsets to global ones
     uint64_t run0 = 0;
     for (ShardOut &so : shards) {
         for (size_t k = 0; k < so.pieces.size(); k++) {
             res->piece_first.push_back(so.piece_first[k]);
             res->piece_run0.push_back(run0);
-            run0 += so.pieces[k].size();
-            res->pieces.push_back(std::move(so.pieces[k]));
+            res->piece_runs.push_back(so.piece_runs[k]);
+            run0 += so.piece_runs[k];
+            res->pieces.push_back(so.pieces[k]);
         }
+        so.pieces.clear();
     }
     for (size_t k = 0; k < res->pieces.size(); k++) {
         const uint64_t a0 = res->piece_first[k];
         const uint64_t a1 = k + 1 < res->pieces.size() ? res->piece_first[k + 1] : res->n;
-        for (uint64_t a = a0; a < a1; a++) res->run_off[a] += res->piece_run0[k];
+        const uint64_t base = res->piece_run0[k];
+        if (base)
+            for (uint64_t a = a0; a < a1; a++) res->run_off[a] += base;
     }
     res->run_off[res->n] = run0;
 }
@@ -278,8 +503,39 @@ void finalize_runs(sg_result *res, std::vector<ShardOut> &shards)
 const uint8_t *runs_of(const sg_result *r, uint64_t idx, uint64_t *count)
 {
     *count = r->run_off[idx + 1] - r->run_off[idx];
+    if (*count == 0) return nullptr;
     size_t k = (size_t)(std::upper_bound(r->piece_first.begin(), r->piece_first.end(), idx) - r->piece_first.begin()) - 1;
-    return r->pieces[k].data() + (r->run_off[idx] - r->piece_run0[k]);
+    return r->pieces[k].p + (r->run_off[idx] - r->piece_run0[k]);
+}
+
+int run_all(sg_ctx *ctx, const Workload &w, const uint64_t *woff, uint64_t per_unit_extra, uint64_t n, sg_result **out)
+{
+    auto t_begin = std::chrono::steady_clock::now();
+    std::unique_ptr<sg_result> res(new sg_result);
+    res->n = n;
+    res->has_cigar = !(w.flags & SG_FLAG_DISTANCE_ONLY);
+    res->edit.resize(n);
+    res->refc.resize(n);
+    res->run_off.assign(res->has_cigar ? n + 1 : 1, 0);
+    const int nd = (int)ctx->devs.size();
+    std::vector<ShardOut> shards(nd);
+    if (n) {
+        const std::vector<uint64_t> cut = split_by_weight(woff, n, nd);
+        if (nd == 1) {
+            run_shard(ctx, ctx->devs[0], w, woff, per_unit_extra, cut[0], cut[1], res.get(), shards[0]);
+        } else {
+            std::vector<std::thread> th;
+            for (int k = 0; k < nd; k++)
+                th.emplace_back([&, k]() { run_shard(ctx, ctx->devs[k], w, woff, per_unit_extra, cut[k], cut[k + 1], res.get(), shards[k]); });
+            for (auto &t : th) t.join();
+        }
+        for (ShardOut &so : shards)
+            if (so.rc) return fail(so.rc, so.err);
+    }
+    finalize(res.get(), shards);
+    res->total_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_begin).count();
+    *out = res.release();
+    return SG_OK;
 }
 
 }  // namespace
@@ -293,20 +549,27 @@ int sg_ctx_create(sg_ctx **out, const int *device_ids, int n_devices, int W)
     const int avail = sg_device_count();
     if (avail == 0) return fail(SG_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
     if (n_devices <= 0) n_devices = avail;
-    std::unique_ptr<sg_ctx> ctx(new sg_ctx);
+    std::unique_ptr<sg_ctx, void (*)(sg_ctx *)> ctx(new sg_ctx, sg_ctx_destroy);
     ctx->W = W;
     ctx->devs.resize(n_devices);
+    ctx->min_batch_units = 0;
+    if (const char *v = std::getenv("SG_BATCH_MB")) {  // tuning knobs for experiments
+        const long mb = std::atol(v);
+        if (mb > 0) ctx->batch_bytes = (uint64_t)mb << 20;
+    }
+    if (const char *v = std::getenv("SG_MAX_BATCH_MB")) {
+        const long mb = std::atol(v);
+        if (mb > 0) ctx->max_batch_bytes = (uint64_t)mb << 20;
+    }
     for (int k = 0; k < n_devices; k++) {
         Device &d = ctx->devs[k];
         d.id = device_ids ? device_ids[k] : k;
         if (d.id < 0 || d.id >= avail) return fail(SG_ERR_BAD_ARG, "device id out of range");
         SG_CUDA(cudaSetDevice(d.id));
-        SG_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
-        SG_CUDA(cudaEventCreate(&d.ev0));
-        SG_CUDA(cudaEventCreate(&d.ev1));
-        int wps = 0;
-        int rc = sg_dev_align_geometry(W, &wps, nullptr, nullptr);
-        if (rc) return rc;
+        for (Slot &s : d.slots) R(s.create());
+        int wps = 0, sms = 0;
+        R(sg_dev_align_geometry(W, &wps, nullptr, &sms));
+        ctx->min_batch_units = std::max<uint64_t>(ctx->min_batch_units, 2ull * 32ull * (uint64_t)wps * (uint64_t)sms);
     }
     *out = ctx.release();
     return SG_OK;
@@ -317,10 +580,8 @@ void sg_ctx_destroy(sg_ctx *ctx)
     if (!ctx) return;
     for (Device &d : ctx->devs) {
         cudaSetDevice(d.id);
-        d.release_all();
-        if (d.ev0) cudaEventDestroy(d.ev0);
-        if (d.ev1) cudaEventDestroy(d.ev1);
-        if (d.stream) cudaStreamDestroy(d.stream);
+        for (Slot &s : d.slots) s.destroy();
+        d.genome.release();
     }
     delete ctx;
 }
@@ -331,76 +592,51 @@ int sg_align_pairs(sg_ctx *ctx, const char *text_blob, const uint64_t *text_off,
                    const uint64_t *query_off, uint64_t n_pairs, uint32_t flags, sg_result **out)
 {
     if (!ctx || !out || !text_off || !query_off) return fail(SG_ERR_BAD_ARG, "sg_align_pairs: null argument");
-    auto t_begin = std::chrono::steady_clock::now();
-    std::unique_ptr<sg_result> res(new sg_result);
-    res->n = n_pairs;
-    res->has_cigar = !(flags & SG_FLAG_DISTANCE_ONLY);
-    res->edit.assign(n_pairs, 0);
-    res->refc.assign(n_pairs, 0);
-    res->run_off.assign(n_pairs + 1, 0);
-    const int nd = (int)ctx->devs.size();
-    std::vector<ShardOut> shards(nd);
-    if (n_pairs) {
-        const std::vector<uint64_t> cut = split_by_weight(query_off, n_pairs, nd);
-        auto work = [&](int k) {
-            Device &d = ctx->devs[k];
-            ShardOut &so = shards[k];
-            if (cudaSetDevice(d.id) != cudaSuccess) { so.rc = SG_ERR_CUDA; so.err = "cudaSetDevice failed"; return; }
-            uint64_t a = cut[k];
-            while (a < cut[k + 1]) {  // batches bounded by query bases (slab size)
-                uint64_t b = a + 1;
-                while (b < cut[k + 1] && query_off[b + 1] - query_off[a] <= ctx->max_batch_query_bases) b++;
-                so.rc = run_pairs_batch(ctx, d, text_blob, text_off, query_blob, query_off, a, b, flags, res.get(), so);
-                if (so.rc) { so.err = g_last_error; return; }
-                a = b;
-            }
-        };
-        if (nd == 1) work(0);
-        else {
-            std::vector<std::thread> th;
-            for (int k = 0; k < nd; k++) th.emplace_back(work, k);
-            for (auto &t : th) t.join();
-        }
-        for (ShardOut &so : shards) if (so.rc) return fail(so.rc, so.err);
-        if (res->has_cigar) finalize_runs(res.get(), shards);
-    }
-    double kms = 0;
-    for (ShardOut &so : shards) kms = std::max(kms, so.kernel_ms);
-    res->kernel_ns = (int64_t)(kms * 1e6);
-    res->total_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_begin).count();
-    *out = res.release();
-    return SG_OK;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    Workload w;
+    w.tb = text_blob; w.toff = text_off; w.qb = query_blob; w.qoff = query_off; w.flags = flags;
+    // sub-batches are cut by uploaded bytes (text + query), shards by the same weight
+    std::vector<uint64_t> woff(n_pairs + 1);
+    for (uint64_t p = 0; p <= n_pairs; p++) woff[p] = (text_off[p] - text_off[0]) + (query_off[p] - query_off[0]);
+    return run_all(ctx, w, woff.data(), 48, n_pairs, out);
 }
 
 int sg_set_reference(sg_ctx *ctx, const char *genome_ascii, uint64_t genome_len)
 {
     if (!ctx || (!genome_ascii && genome_len)) return fail(SG_ERR_BAD_ARG, "sg_set_reference: null argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
     const int nd = (int)ctx->devs.size();
     std::vector<int> rcs(nd, SG_OK);
     std::vector<std::string> errs(nd);
     auto work = [&](int k) -> int {
         Device &d = ctx->devs[k];
+        Slot &s = d.slots[0];
         SG_CUDA(cudaSetDevice(d.id));
         d.has_genome = false;
-        int rc = d.genome.reserve(sg_packed_words(genome_len) * 4 + 64);
-        if (rc) return rc;
-        rc = d.bad.reserve(16); if (rc) return rc;
-        rc = d.h_small.reserve(64); if (rc) return rc;
-        SG_CUDA(cudaMemsetAsync(d.bad.p, 0xFF, 16, d.stream));
-        // upload in 256 Mbase pieces (a multiple of 16 bases, so every piece packs to whole words)
+        R(d.genome.reserve(sg_packed_words(genome_len) * 4 + 64));
+        R(s.bad.reserve(16));
+        R(s.h_small.reserve(64));
+        SG_CUDA(cudaMemsetAsync(s.bad.p, 0xFF, 16, s.stream));
+        // upload in 256 Mbase pieces (a multiple of 16 bases, so every piece packs to whole words), alternating
+        // between two staging buffers so that the copy of piece k+1 can overlap the packing of piece k
         const uint64_t piece = 256ull << 20;
-        rc = d.ascii_t.reserve(std::min<uint64_t>(piece, genome_len) + 64); if (rc) return rc;
-        for (uint64_t pos = 0; pos < genome_len || pos == 0; pos += piece) {
+        DevBuf *stage[2] = {&s.ascii_t, &s.ascii_q};
+        R(stage[0]->reserve(std::min<uint64_t>(piece, genome_len) + 64));
+        if (genome_len > piece) R(stage[1]->reserve(std::min<uint64_t>(piece, genome_len - piece) + 64));
+        uint64_t pos = 0, first_bad = ~0ull;
+        uint64_t *h = s.h_small.as<uint64_t>();
+        int k2 = 0;
+        do {
             const uint64_t len = std::min<uint64_t>(piece, genome_len - pos);
-            SG_CUDA(cudaMemcpyAsync(d.ascii_t.p, genome_ascii + pos, len, cudaMemcpyHostToDevice, d.stream));
-            rc = sg_dev_pack_2bit(d.ascii_t.as<char>(), len, d.genome.as<uint32_t>() + pos / 16, d.bad.as<uint64_t>(), d.stream);
-            if (rc) return rc;
-            uint64_t *h = d.h_small.as<uint64_t>();
-            SG_CUDA(cudaMemcpyAsync(h, d.bad.p, 8, cudaMemcpyDeviceToHost, d.stream));
-            SG_CUDA(cudaStreamSynchronize(d.stream));
-            if (h[0] != ~0ull) return fail(SG_ERR_BAD_BASE, "non-ACGT character in reference at position " + std::to_string(pos + h[0]));
-            if (genome_len == 0) break;
-        }
+            SG_CUDA(cudaMemcpyAsync(stage[k2]->p, genome_ascii + pos, len, cudaMemcpyHostToDevice, s.stream));
+            R(sg_dev_pack_2bit(stage[k2]->as<char>(), len, d.genome.as<uint32_t>() + pos / 16, s.bad.as<uint64_t>(), s.stream));
+            SG_CUDA(cudaMemcpyAsync(h, s.bad.p, 8, cudaMemcpyDeviceToHost, s.stream));
+            SG_CUDA(cudaStreamSynchronize(s.stream));
+            if (h[0] != ~0ull) { first_bad = pos + h[0]; break; }
+            pos += len;
+            k2 ^= 1;
+        } while (pos < genome_len);
+        if (first_bad != ~0ull) return fail(SG_ERR_BAD_BASE, "non-ACGT character in reference at position " + std::to_string(first_bad));
         d.genome_len = genome_len;
         d.has_genome = true;
         return SG_OK;
@@ -412,147 +648,26 @@ int sg_set_reference(sg_ctx *ctx, const char *genome_ascii, uint64_t genome_len)
     return SG_OK;
 }
 
-}  // extern "C"
-
-namespace {
-
-int run_cand_batch(sg_ctx *ctx, Device &d, const char *rb, const uint64_t *roff, const uint64_t *cand_start,
-                   const uint32_t *cand_read, uint64_t c0, uint64_t c1, uint32_t flags, sg_result *res, ShardOut &so)
-{
-    const uint64_t n = c1 - c0;
-    const bool want_cigar = !(flags & SG_FLAG_DISTANCE_ONLY);
-    cudaStream_t st = d.stream;
-    // reads referenced by this batch: the contiguous index range [r0, r1]
-    uint32_t r0 = cand_read[c0], r1 = cand_read[c0];
-    for (uint64_t c = c0; c < c1; c++) { r0 = std::min(r0, cand_read[c]); r1 = std::max(r1, cand_read[c]); }
-    const uint64_t nr = (uint64_t)r1 - r0 + 1;
-    const uint64_t rbytes = roff[r1 + 1] - roff[r0];
-    uint64_t slab_bytes = 0;
-    if (want_cigar) for (uint64_t c = c0; c < c1; c++) slab_bytes += 2ull * (roff[cand_read[c] + 1] - roff[cand_read[c]]) + 8ull;
-    int rc;
-#define R(x) do { rc = (x); if (rc) return rc; } while (0)
-    R(d.ascii_q.reserve(rbytes + 64)); R(d.packed_q.reserve(sg_packed_words(rbytes) * 4));
-    R(d.qoff.reserve((nr + 1) * 8)); R(d.cstart.reserve(n * 8)); R(d.cread.reserve(n * 4)); R(d.cap32.reserve(n * 4));
-    R(d.tstart.reserve(n * 8)); R(d.tlen.reserve(n * 8)); R(d.qstart.reserve(n * 8)); R(d.qlen.reserve(n * 8));
-    R(d.slab_off.reserve((n + 1) * 8));
-    if (want_cigar) R(d.slab.reserve(slab_bytes + 16));
-    R(d.counter.reserve(8)); R(d.edit.reserve(n * 8)); R(d.refc.reserve(n * 8)); R(d.nruns.reserve(n * 4));
-    R(d.status.reserve(n)); R(d.run_off.reserve((n + 1) * 8)); R(d.scan_tmp.reserve(sg_scan_tmp_bytes(n)));
-    R(d.bad.reserve(16)); R(d.h_small.reserve(64));
-
-    SG_CUDA(cudaMemcpyAsync(d.ascii_q.p, rb + roff[r0], rbytes, cudaMemcpyHostToDevice, st));
-    SG_CUDA(cudaMemcpyAsync(d.qoff.p, roff + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, st));
-    SG_CUDA(cudaMemcpyAsync(d.cstart.p, cand_start + c0, n * 8, cudaMemcpyHostToDevice, st));
-    SG_CUDA(cudaMemcpyAsync(d.cread.p, cand_read + c0, n * 4, cudaMemcpyHostToDevice, st));
-    SG_CUDA(cudaMemsetAsync(d.bad.p, 0xFF, 16, st));
-    R(sg_dev_pack_2bit(d.ascii_q.as<char>(), rbytes, d.packed_q.as<uint32_t>(), d.bad.as<uint64_t>() + 1, st));
-    cand_descriptors_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-        d.cstart.as<uint64_t>(), d.cread.as<uint32_t>(), d.qoff.as<uint64_t>(), r0, d.genome_len, n, d.tstart.as<uint64_t>(),
-        d.tlen.as<uint64_t>(), d.qstart.as<uint64_t>(), d.qlen.as<uint64_t>(), d.cap32.as<uint32_t>());
-    SG_CUDA(cudaGetLastError());
-    // slab offsets = exclusive scan of the capacities
-    R(sg_dev_scan_runs(d.cap32.as<uint32_t>(), n, d.slab_off.as<uint64_t>(), d.scan_tmp.p, st));
-    SG_CUDA(cudaEventRecord(d.ev0, st));
-    R(sg_dev_align(ctx->W, d.genome.as<uint32_t>(), d.tstart.as<uint64_t>(), d.tlen.as<uint64_t>(), d.packed_q.as<uint32_t>(),
-                   d.qstart.as<uint64_t>(), d.qlen.as<uint64_t>(), n, flags, d.slab.as<uint8_t>(), d.slab_off.as<uint64_t>(),
-                   d.counter.as<uint64_t>(), d.edit.as<int64_t>(), d.refc.as<uint64_t>(), d.nruns.as<uint32_t>(),
-                   d.status.as<uint8_t>(), nullptr, st));
-    SG_CUDA(cudaEventRecord(d.ev1, st));
-    uint64_t *h = d.h_small.as<uint64_t>();
-    SG_CUDA(cudaMemcpyAsync(h, d.bad.p, 16, cudaMemcpyDeviceToHost, st));
-    if (want_cigar) {
-        R(sg_dev_scan_runs(d.nruns.as<uint32_t>(), n, d.run_off.as<uint64_t>(), d.scan_tmp.p, st));
-        SG_CUDA(cudaMemcpyAsync(h + 2, d.run_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
-    }
-    SG_CUDA(cudaMemcpyAsync(res->edit.data() + c0, d.edit.p, n * 8, cudaMemcpyDeviceToHost, st));
-    SG_CUDA(cudaMemcpyAsync(res->refc.data() + c0, d.refc.p, n * 8, cudaMemcpyDeviceToHost, st));
-    SG_CUDA(cudaStreamSynchronize(st));
-    if (h[1] != ~0ull) {
-        const uint64_t pos = h[1] + roff[r0];
-        uint64_t r = (uint64_t)(std::upper_bound(roff + r0, roff + r1 + 2, pos) - roff) - 1;
-        return fail(SG_ERR_BAD_BASE, "non-ACGT character in read " + std::to_string(r) + " at position " + std::to_string(pos - roff[r]));
-    }
-    float ms = 0;
-    SG_CUDA(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
-    so.kernel_ms += ms;
-    if (want_cigar) {
-        const uint64_t total_runs = h[2];
-        R(d.runs.reserve(total_runs + 16));
-        R(sg_dev_gather_runs(d.slab.as<uint8_t>(), d.slab_off.as<uint64_t>(), d.nruns.as<uint32_t>(), d.run_off.as<uint64_t>(),
-                             n, d.runs.as<uint8_t>(), st));
-        std::vector<uint8_t> piece(total_runs), status(n);
-        SG_CUDA(cudaMemcpyAsync(piece.data(), d.runs.p, total_runs, cudaMemcpyDeviceToHost, st));
-        SG_CUDA(cudaMemcpyAsync(res->run_off.data() + c0, d.run_off.p, n * 8, cudaMemcpyDeviceToHost, st));
-        SG_CUDA(cudaMemcpyAsync(status.data(), d.status.p, n, cudaMemcpyDeviceToHost, st));
-        SG_CUDA(cudaStreamSynchronize(st));
-        for (uint64_t k = 0; k < n; k++)
-            if (status[k]) return fail(SG_ERR_CIGAR_OVERFLOW, "alignment " + std::to_string(c0 + k) + " exceeded its run capacity");
-        so.pieces.push_back(std::move(piece));
-        so.piece_first.push_back(c0);
-    }
-#undef R
-    return SG_OK;
-}
-
-}  // namespace
-
-extern "C" {
-
 int sg_align_candidates(sg_ctx *ctx, const char *read_blob, const uint64_t *read_off, uint64_t n_reads,
                         const uint64_t *cand_start, const uint32_t *cand_read, uint64_t n_cand, uint32_t flags,
                         sg_result **out)
 {
     if (!ctx || !out || !read_off || (n_cand && (!cand_start || !cand_read)))
         return fail(SG_ERR_BAD_ARG, "sg_align_candidates: null argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
     for (Device &d : ctx->devs)
         if (!d.has_genome) return fail(SG_ERR_NO_REFERENCE, "sg_align_candidates: call sg_set_reference first");
     const uint64_t genome_len = ctx->devs[0].genome_len;
+    std::vector<uint64_t> woff(n_cand + 1, 0);  // weight of a candidate = its read's length
     for (uint64_t c = 0; c < n_cand; c++) {
         if (cand_read[c] >= n_reads) return fail(SG_ERR_BAD_ARG, "candidate " + std::to_string(c) + ": read index out of range");
         if (cand_start[c] > genome_len) return fail(SG_ERR_BAD_ARG, "candidate " + std::to_string(c) + ": start beyond the reference");
+        woff[c + 1] = woff[c] + (read_off[cand_read[c] + 1] - read_off[cand_read[c]]);
     }
-    auto t_begin = std::chrono::steady_clock::now();
-    std::unique_ptr<sg_result> res(new sg_result);
-    res->n = n_cand;
-    res->has_cigar = !(flags & SG_FLAG_DISTANCE_ONLY);
-    res->edit.assign(n_cand, 0);
-    res->refc.assign(n_cand, 0);
-    res->run_off.assign(n_cand + 1, 0);
-    const int nd = (int)ctx->devs.size();
-    std::vector<ShardOut> shards(nd);
-    if (n_cand) {
-        // weight of a candidate = its read's length
-        std::vector<uint64_t> woff(n_cand + 1, 0);
-        for (uint64_t c = 0; c < n_cand; c++) woff[c + 1] = woff[c] + (read_off[cand_read[c] + 1] - read_off[cand_read[c]]);
-        const std::vector<uint64_t> cut = split_by_weight(woff.data(), n_cand, nd);
-        auto work = [&](int k) {
-            Device &d = ctx->devs[k];
-            ShardOut &so = shards[k];
-            if (cudaSetDevice(d.id) != cudaSuccess) { so.rc = SG_ERR_CUDA; so.err = "cudaSetDevice failed"; return; }
-            uint64_t a = cut[k];
-            while (a < cut[k + 1]) {
-                uint64_t b = a + 1;
-                while (b < cut[k + 1] && woff[b + 1] - woff[a] <= ctx->max_batch_query_bases) b++;
-                so.rc = run_cand_batch(ctx, d, read_blob, read_off, cand_start, cand_read, a, b, flags, res.get(), so);
-                if (so.rc) { so.err = g_last_error; return; }
-                a = b;
-            }
-        };
-        if (nd == 1) work(0);
-        else {
-            std::vector<std::thread> th;
-            for (int k = 0; k < nd; k++) th.emplace_back(work, k);
-            for (auto &t : th) t.join();
-        }
-        for (ShardOut &so : shards) if (so.rc) return fail(so.rc, so.err);
-        if (res->has_cigar) finalize_runs(res.get(), shards);
-    }
-    double kms = 0;
-    for (ShardOut &so : shards) kms = std::max(kms, so.kernel_ms);
-    res->kernel_ns = (int64_t)(kms * 1e6);
-    res->total_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_begin).count();
-    *out = res.release();
-    return SG_OK;
+    Workload w;
+    w.mapping = true;
+    w.rb = read_blob; w.roff = read_off; w.cand_start = cand_start; w.cand_read = cand_read; w.woff = woff.data(); w.flags = flags;
+    return run_all(ctx, w, woff.data(), 64, n_cand, out);
 }
 
 uint64_t sg_result_count(const sg_result *r) { return r ? r->n : 0; }
@@ -563,11 +678,11 @@ const uint64_t *sg_result_run_offsets(const sg_result *r) { return r && r->has_c
 const uint8_t *sg_result_runs(const sg_result *r)
 {
     if (!r || !r->has_cigar) return nullptr;
-    if (r->pieces.size() == 1) return r->pieces[0].data();
+    if (r->pieces.size() == 1) return r->pieces[0].p;
     sg_result *m = const_cast<sg_result *>(r);
     if (m->flat.empty() && r->run_off[r->n]) {
-        m->flat.reserve(r->run_off[r->n]);
-        for (const auto &p : r->pieces) m->flat.insert(m->flat.end(), p.begin(), p.end());
+        m->flat.resize(r->run_off[r->n]);
+        for (size_t k = 0; k < r->pieces.size(); k++) memcpy(m->flat.data() + r->piece_run0[k], r->pieces[k].p, r->piece_runs[k]);
     }
     return m->flat.data();
 }
@@ -619,5 +734,21 @@ int64_t sg_result_entries(const sg_result *r, uint64_t idx, sg_cigar_entry *out,
 }
 
 void sg_result_free(sg_result *r) { delete r; }
+
+void *sg_host_alloc(uint64_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        fail(SG_ERR_OOM, "cudaMallocHost failed for " + std::to_string(bytes) + " bytes");
+        return nullptr;
+    }
+    return p;
+}
+
+void sg_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
 
 }  // extern "C"
