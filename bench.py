@@ -160,7 +160,7 @@ def main():
     import torch.distributed as dist
 
     import scrooge_b200
-    from scrooge_b200 import device, synth
+    from scrooge_b200 import device, sharding, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -179,7 +179,7 @@ def main():
     wl = synth.WORKLOADS[args.workload]
     W, L = wl.W, wl.read_len
     n = args.pairs
-    first_pair = rank * n  # weak scaling: every rank aligns its own n pairs of the same shape
+    first_pair, _ = sharding.rank_shard(rank, world, n)  # weak scaling: every rank aligns its own n pairs
 
     # ---- inputs resident in HBM (ASCII, as they arrive from the host) ---------------------------------
     text, tlen, reads = device.synth_pairs_device(wl.seed, first_pair, n, L, wl.err, wl.ratio, wl.slack, dev)
@@ -228,10 +228,8 @@ def main():
     clocks = sampler.stop() if sampler else None
     ms_total = t_begin.elapsed_time(t_end)
     ms_kernel = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
-    if world > 1:
-        tt = torch.tensor([ms_total, ms_kernel], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_total, ms_kernel = float(tt[0]), float(tt[1])
+    ms_total = sharding.max_over_ranks(ms_total, dev)   # multi-GPU time = the slowest rank's device time
+    ms_kernel = sharding.max_over_ranks(ms_kernel, dev)
     ms_step = ms_total / args.steps
     value = world * n / (ms_step / 1e3)
 
@@ -260,10 +258,7 @@ def main():
             res = al.align_pairs_blob(tb_pin, toff, qb_pin, qoff)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
-        if world > 1:
-            tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e_s = float(tt[0])
+        e2e_s = sharding.max_over_ranks(e2e_s, dev)
         d2h = ne * 16 + (ne + 1) * 8 + int(res.run_offsets[-1]) + ne
         e2e = {"value": world * ne * args.steps / e2e_s, "unit": "alignments/s",
                "h2d_bytes_per_step": int(tb.nbytes + qb.nbytes + 2 * (ne + 1) * 8), "d2h_bytes_per_step": int(d2h),

@@ -205,3 +205,33 @@ def test_cigar_properties_at_scale(oracle, aligners):
     for k in range(0, 2000, 7):
         assert oracle.validate_cigar(cg[k], T[k], Q[k], int(ed[k])) == 0, k
     assert 800 < float(np.mean(ed)) < 1100
+
+
+def test_multi_gpu_context_matches_single(oracle, sglib):
+    """Host-side scatter over several GPUs (no collective): identical results for any GPU count."""
+    import scrooge_b200
+    if sglib.sg_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    T, Q = random_pairs(31, 3000, [0, 50, 150, 1000, 3000], [0.02, 0.1, 0.2])
+    one = scrooge_b200.Aligner(W=64, n_gpus=1).align_pairs(T, Q)
+    al = scrooge_b200.Aligner(W=64, n_gpus=2)
+    assert al.num_devices == 2
+    two = al.align_pairs(T, Q)
+    assert list(one.edit_distances) == list(two.edit_distances)
+    assert one.cigars() == two.cigars()
+    assert list(one.ref_consumed) == list(two.ref_consumed)
+    want = oracle.align_pairs(T, Q, threads=4)
+    assert two.cigars() == want.cigars
+    # mapping mode: the packed reference is replicated per GPU
+    rng = __import__("random").Random(5)
+    genome = rand_seq(rng, 20000)
+    reads, cs, cr = [], [], []
+    for r in range(200):
+        s = rng.randrange(0, 19000)
+        reads.append(mutate(rng, genome[s:], 500, 0.1))
+        for d in (0, 3):
+            cs.append(max(0, s - d)); cr.append(r)
+    al.set_reference(genome)
+    got = al.align_candidates(reads, cs, cr)
+    want = oracle.align_candidates(genome, reads, cs, cr, threads=4)
+    assert list(got.edit_distances) == list(want.edit) and got.cigars() == want.cigars
