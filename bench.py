@@ -8,8 +8,8 @@
 A step is one pass of the hot path over one batch of `--pairs` synthetic pairs per GPU:
 ingest (ASCII -> 2 bit) -> alignment kernel (DC + TB + RLE) -> CIGAR compaction (scan + gather), with the
 ASCII inputs already resident in HBM.  Alignments are independent, so N GPUs run N shards of the same
-shape with no data-path collective (weak scaling); torch.distributed is used only for the barrier and the
-max-over-ranks of the device time.
+shape with no data-path collective (weak scaling); torch.distributed (gloo) is used only for the barrier and the
+max-over-ranks of the device time -- NCCL is used nowhere.
 
 One JSON line on stdout (rank 0).  `value` = alignments/s over all GPUs, device-timed.  `e2e` = the same metric
 through the host C ABI (sg_align_pairs on pinned HOST buffers: H2D, ingest, alignment, compaction, D2H of
@@ -174,7 +174,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # Plumbing only: a barrier and a max of the elapsed device time.  The data path has no exchange step
+        # (alignments are independent), so no NCCL communicator is ever created -- gloo over 127.0.0.1.
+        dist.init_process_group("gloo")
 
     wl = synth.WORKLOADS[args.workload]
     W, L = wl.W, wl.read_len
@@ -228,8 +230,8 @@ def main():
     clocks = sampler.stop() if sampler else None
     ms_total = t_begin.elapsed_time(t_end)
     ms_kernel = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
-    ms_total = sharding.max_over_ranks(ms_total, dev)   # multi-GPU time = the slowest rank's device time
-    ms_kernel = sharding.max_over_ranks(ms_kernel, dev)
+    ms_total = sharding.max_over_ranks(ms_total)   # multi-GPU time = the slowest rank's device time
+    ms_kernel = sharding.max_over_ranks(ms_kernel)
     ms_step = ms_total / args.steps
     value = world * n / (ms_step / 1e3)
 
@@ -258,7 +260,7 @@ def main():
             res = al.align_pairs_blob(tb_pin, toff, qb_pin, qoff)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
-        e2e_s = sharding.max_over_ranks(e2e_s, dev)
+        e2e_s = sharding.max_over_ranks(e2e_s)
         d2h = ne * 16 + (ne + 1) * 8 + int(res.run_offsets[-1]) + ne
         e2e = {"value": world * ne * args.steps / e2e_s, "unit": "alignments/s",
                "h2d_bytes_per_step": int(tb.nbytes + qb.nbytes + 2 * (ne + 1) * 8), "d2h_bytes_per_step": int(d2h),
