@@ -31,7 +31,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-OPS_PER_ENTRY = 14  # 7 W-bit ops per R[d][i] entry (reference src/genasm_cpu.cpp:247-251, scripts/plot.py:2346) x 2 words
+# 7 W-bit ops per R[d][i] entry (reference src/genasm_cpu.cpp:247-251, scripts/plot.py:2346): 14 INT32 ops at W=64, 7 at W=32
+OPS_PER_ENTRY = {64: 14, 32: 7}
 
 
 def parse_args():
@@ -276,7 +277,7 @@ def main():
 
     # ---- roofline of the dominant kernel (the alignment kernel) --------------------------------------
     peak_gops = device.int32_peak(2, 60.0)  # LOP3+SHF 2:1, measured now, same clocks as the run
-    achieved_gops = entries * OPS_PER_ENTRY / (ms_kernel / 1e3) / 1e9
+    achieved_gops = entries * OPS_PER_ENTRY[W] / (ms_kernel / 1e3) / 1e9
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -290,7 +291,7 @@ def main():
     roofline = {"bound": "int32_alu", "kernel": f"genasm_align_kernel<{W}>", "achieved": achieved_gops / 1e3,
                 "peak": peak_gops / 1e3, "unit": "TIOP/s", "frac": achieved_gops / peak_gops, "traffic": None,
                 "peak_source": "sg_dev_int32_peak (LOP3+SHF 2:1 probe) measured in this run",
-                "algorithmic_ops_per_launch": entries * OPS_PER_ENTRY, "dc_entries_per_alignment": entries / n,
+                "algorithmic_ops_per_launch": entries * OPS_PER_ENTRY[W], "dc_entries_per_alignment": entries / n,
                 "kernel_ms": ms_kernel, "kernel_share_of_step": ms_kernel / ms_step,
                 "hbm": {"achieved": algo_bytes / (ms_kernel / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": algo_bytes / (ms_kernel / 1e3) / 1e9 / hbm_peak, "peak_source": hbm_src,

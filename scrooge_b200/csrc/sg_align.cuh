@@ -55,16 +55,46 @@ template <int W> struct WinCfg;
 template <> struct WinCfg<64> { static constexpr int O = 33; };
 template <> struct WinCfg<32> { static constexpr int O = 17; };
 
-template <int W> struct SmemLayout {
+// Per-warp shared memory.  TMEM = false: the forefront lives in shared memory (one-warp CTAs, 8 per SM at W=64).
+// TMEM = true: the forefront lives in tensor memory -- W columns x NW words per lane, private to the lane, addressed
+// with a warp-uniform column: exactly the access shape of tcgen05.ld/st.32x32b -- which frees 16 KB of shared
+// memory per warp (four-warp CTAs owning 128 TMEM columns each at W=64, 4 CTAs = 16 warps per SM).
+template <int W, bool TMEM = false> struct SmemLayout {
     static constexpr int NW = W / 32;               // 32-bit words per bitvector
     static constexpr int TBL = W - WinCfg<W>::O;    // TB_LIMIT (src/genasm_cpu.cpp:50)
     static constexpr int TBCOLS = TBL + 1;          // traceback columns kept (0..TBL)
     static constexpr int PM_WORDS = 4 * NW * 32;    // [base code][lane][NW]
-    static constexpr int FF_WORDS = (W + 1) * NW * 32;  // [column][lane][NW]
+    static constexpr int FF_WORDS = TMEM ? 0 : (W + 1) * NW * 32;  // [column][lane][NW]
     static constexpr int TB_WORDS = TBCOLS * 2 * 32;    // [column][lane][V,H]
-    static constexpr int WORDS_PER_WARP = PM_WORDS + FF_WORDS + TB_WORDS;
+    static constexpr int STAGE_WORDS = TMEM ? W * 32 / 4 : 0;  // [run][lane] bytes (smem variant stages runs in FF)
+    static constexpr int WORDS_PER_WARP = PM_WORDS + FF_WORDS + TB_WORDS + STAGE_WORDS;
     static constexpr int BYTES_PER_WARP = WORDS_PER_WARP * 4;
+    static constexpr int WARPS_PER_CTA = TMEM ? 4 : 1;
+    static constexpr int TMEM_COLS = W * NW < 32 ? 32 : W * NW;   // power of two >= 32: 128 (W=64), 32 (W=32)
+    static constexpr int BYTES_PER_CTA = BYTES_PER_WARP * WARPS_PER_CTA + (TMEM ? 16 : 0);
 };
+
+// ---- tensor memory as per-lane scratch (sm_100a tcgen05) ----------------------------------------------
+template <int NW> __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[NW]);
+template <> __device__ __forceinline__ void tmem_ld<1>(uint32_t taddr, uint32_t (&v)[1])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[0]) : "r"(taddr));
+}
+template <> __device__ __forceinline__ void tmem_ld<2>(uint32_t taddr, uint32_t (&v)[2])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr));
+}
+template <int NW> __device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t (&v)[NW]);
+template <> __device__ __forceinline__ void tmem_st<1>(uint32_t taddr, const uint32_t (&v)[1])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v[0]));
+}
+template <> __device__ __forceinline__ void tmem_st<2>(uint32_t taddr, const uint32_t (&v)[2])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(v[0]), "r"(v[1]));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 struct AlignParams {
     const uint32_t *text;
@@ -224,10 +254,10 @@ __device__ __forceinline__ void dc_column(const RowSet<NW> &P, RowSet<NW> &N, co
 
 // ---- the kernel ------------------------------------------------------------------------------------
 
-template <int W>
-__global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
+template <int W, bool TMEM>
+__global__ void __launch_bounds__(SmemLayout<W, TMEM>::WARPS_PER_CTA * 32, TMEM ? 4 : 1) genasm_align_kernel(const AlignParams P)
 {
-    using L = SmemLayout<W>;
+    using L = SmemLayout<W, TMEM>;
     constexpr int NW = L::NW;
     constexpr int NWIN = 2 * NW;  // words of a 2-bit window
     constexpr int TBL = L::TBL;
@@ -238,11 +268,39 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
     constexpr int FFS = NW * 32;   // words between forefront columns
     constexpr int TBS = 2 * 32;    // words between traceback columns
 
-    extern __shared__ __align__(16) uint32_t smem[];
-    const int lane = threadIdx.x;
+    extern __shared__ __align__(16) uint32_t smem_all[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint32_t *smem = smem_all + warp * L::WORDS_PER_WARP;
     uint32_t *pm_s = smem + lane * NW;
-    uint32_t *ff_s = smem + L::PM_WORDS + lane * NW;
+    uint32_t *ff_s = smem + L::PM_WORDS + lane * NW;                      // forefront (smem variant only)
     uint32_t *tb_s = smem + L::PM_WORDS + L::FF_WORDS + lane * 2;
+    uint8_t *stage_s = reinterpret_cast<uint8_t *>(smem + L::PM_WORDS + L::FF_WORDS + L::TB_WORDS) + lane;  // TMEM variant
+    (void)ff_s; (void)stage_s;
+
+    // tensor-memory forefront: one allocation per CTA, lanes 32*warp.. belong to this warp
+    uint32_t tff = 0;
+    if constexpr (TMEM) {
+        uint32_t *tmem_addr_s = smem_all + L::WARPS_PER_CTA * L::WORDS_PER_WARP;
+        if (warp == 0) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tmem_addr_s);
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"((uint32_t)L::TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tff = *tmem_addr_s + ((uint32_t)(warp * 32) << 16);
+    }
+    auto ff_load = [&](const int i, uint32_t (&F)[NW]) {   // TMEM: asynchronous, ff_wait() before F is read
+        if constexpr (TMEM) tmem_ld<NW>(tff + (uint32_t)(i * NW), F);
+        else lds_vec<NW>(ff_s + i * FFS, F);
+    };
+    auto ff_wait = [&]() { if constexpr (TMEM) tmem_wait_ld(); };
+    auto ff_store = [&](const int i, const uint32_t (&v)[NW]) {
+        if constexpr (TMEM) tmem_st<NW>(tff + (uint32_t)(i * NW), v);
+        else sts_vec<NW>(ff_s + i * FFS, v);
+    };
 
     const bool want_cigar = !(P.flags & 1u);
 
@@ -330,15 +388,14 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
 
         // boundary column: forefront in, chunk's last row out, insertion edges of the column if it is a TB column
         auto boundary_column = [&](RowSet<NW> &Nv, const int i) {
+            // row d0-1 of a boundary column is itself a boundary value, ones << (d0-1): no forefront access
             uint32_t F[NW], sF[NW];
-            uint32_t *ffp = ff_s + i * FFS;
-            lds_vec<NW>(ffp, F);
+            ones_shl<NW>(W - m + d0 - 1, F);
             shl1<NW>(F, sF);
 #pragma unroll
             for (int k = 0; k < NW; k++) XF[k] = (F[k] & sF[k]) | fm;
             uint32_t V = 0;
             dc_boundary<W, NW>(Nv, m, d0, V);
-            sts_vec<NW>(ffp, Nv.C[G - 1]);
             if (i < TBCOLS) {
                 uint32_t vh[2];
                 lds_vec<2>(tb_s + i * TBS, vh);
@@ -348,17 +405,14 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
             }
         };
         // text column i with base code at bits 31:30 of cw: Pv (column i+1) -> Nv (column i)
-        auto text_column = [&](const RowSet<NW> &Pv, RowSet<NW> &Nv, const int i, const uint32_t cw, const bool TBCOL) {
-            uint32_t pm[NW], F[NW];
-            // (cw >> 30) * PMS words == ((cw >> 30) << (5 + log2 NW + 2)) bytes
+        auto text_column = [&](const RowSet<NW> &Pv, RowSet<NW> &Nv, const int i, const uint32_t cw, const bool TBCOL,
+                               const uint32_t (&F)[NW]) {
+            uint32_t pm[NW];
             const uint32_t *pmp = pm_s + (cw >> 30) * PMS;
             lds_vec<NW>(pmp, pm);
-            uint32_t *ffp = ff_s + i * FFS;
-            lds_vec<NW>(ffp, F);
             uint32_t V = 0, H = 0;
             if (TBCOL) dc_column<NW, true>(Pv, Nv, pm, F, fm, XF, V, H);
             else dc_column<NW, false>(Pv, Nv, pm, F, fm, XF, V, H);
-            sts_vec<NW>(ffp, Nv.C[G - 1]);
             if (TBCOL) {
                 uint32_t vh[2];
                 lds_vec<2>(tb_s + i * TBS, vh);
@@ -368,9 +422,12 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
             }
         };
 
+        if constexpr (TMEM) __syncwarp();  // tcgen05.ld/st are warp-collective: reconverge after the per-lane setup
         if (uniform) {
             // fast path: every lane of the warp has a full text window; no per-column tests
             boundary_column(A, W);
+            uint32_t Fa[NW], Fb[NW];
+            ff_load(W - 1, Fa);
 #pragma unroll
             for (int blk = NWIN - 1; blk >= 0; blk--) {
                 uint32_t cw = tw[blk];
@@ -378,24 +435,41 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
 #pragma unroll 2
                 for (int ii = 15; ii >= 1; ii -= 2) {
                     const int i = blk * 16 + ii;
-                    text_column(A, B, i, cw, TBCOL);
+                    ff_wait();
+                    ff_load(i - 1, Fb);              // forefront of the next column is in flight during this one
+                    text_column(A, B, i, cw, TBCOL, Fa);
+                    ff_store(i, B.C[G - 1]);
                     cw <<= 2;
-                    text_column(B, A, i - 1, cw, TBCOL);
+                    ff_wait();
+                    ff_load(i >= 2 ? i - 2 : 0, Fa);
+                    text_column(B, A, i - 1, cw, TBCOL, Fb);
+                    ff_store(i - 1, A.C[G - 1]);
                     cw <<= 2;
                 }
             }
+            ff_wait();
         } else {
             // generic path (some lane's text is running out, n < W): per-lane start column.  Column i lives in
             // set A when i is even and in set B when it is odd, exactly as in the fast path, so a lane that
             // starts at its own boundary column n joins the alternation without any register copies.
             auto generic_column = [&](const RowSet<NW> &Pv, RowSet<NW> &Nv, const int i) {
-                if (i > nn) return;
-                if (i == nn) {
-                    boundary_column(Nv, i);
-                } else {
-                    const uint32_t word = i >= 48 ? tw[NWIN - 1] : (i >= 32 ? tw[NWIN > 2 ? 2 : 0] : (i >= 16 ? tw[1] : tw[0]));
-                    text_column(Pv, Nv, i, word << (30 - 2 * (i & 15)), i < TBCOLS);
+                uint32_t F[NW];
+#pragma unroll
+                for (int k = 0; k < NW; k++) F[k] = 0;
+                if (i < W) {  // forefront access is warp-uniform (tcgen05.ld/st are collective), use of it is per lane
+                    ff_load(i, F);
+                    ff_wait();
                 }
+                if (i <= nn) {
+                    if (i == nn) {
+                        boundary_column(Nv, i);
+                    } else {
+                        const uint32_t word = i >= 48 ? tw[NWIN - 1] : (i >= 32 ? tw[NWIN > 2 ? 2 : 0] : (i >= 16 ? tw[1] : tw[0]));
+                        text_column(Pv, Nv, i, word << (30 - 2 * (i & 15)), i < TBCOLS, F);
+                    }
+                }
+                if constexpr (TMEM) __syncwarp();
+                if (i < W) ff_store(i, Nv.C[G - 1]);
             };
             generic_column(B, A, W);
             for (int i = W - 1; i >= 1; i -= 2) {
@@ -403,6 +477,7 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
                 generic_column(B, A, i - 1);
             }
         }
+        if constexpr (TMEM) tmem_wait_st();  // the next phase reads this forefront back
 
         if (!have) continue;
 
@@ -422,6 +497,16 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
         // (src/genasm_cpu.cpp:321-370).  Branch-free per step: all lanes of the warp walk in lock step.  The
         // text position is carried by the column pointer, the pattern position by the one-hot mask; finished
         // runs are staged in this lane's (now dead) forefront slots, one word per run.
+        // finished runs are staged per lane: in the dead forefront slots (smem variant) or in a byte array (TMEM variant);
+        // `stage` advances by FFS per run in both
+        auto stage_put = [&](const int at, const uint32_t run) {
+            if constexpr (TMEM) stage_s[(at / FFS) * 32] = (uint8_t)run;
+            else ff_s[at] = run;
+        };
+        auto stage_get = [&](const int at) -> uint32_t {
+            if constexpr (TMEM) return stage_s[(at / FFS) * 32];
+            else return ff_s[at];
+        };
         const int jmax = m < TBL ? m : TBL;
         const uint32_t mask_end = 0x80000000u >> jmax;   // jmax <= W-O <= 31
         int tcol = 0;                                    // word offset of column i in the V/H array
@@ -441,7 +526,7 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
             op = is_i ? 2u : op;
             const bool brk = op != prev;
             if (brk && cnt != 0u) {
-                ff_s[stage] = prev * 64u + cnt;
+                stage_put(stage, prev * 64u + cnt);
                 stage += FFS;
             }
             cnt = brk ? 1u : cnt + 1u;
@@ -457,7 +542,7 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
             e = pm_s[(tlo & 3u) * PMS + TOP];
         }
         if (cnt != 0u) {  // runs are flushed at window end, never merged across windows (quirk Q2)
-            ff_s[stage] = prev * 64u + cnt;
+            stage_put(stage, prev * 64u + cnt);
             stage += FFS;
         }
         const int i = tcol / TBS;
@@ -466,7 +551,7 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
         uint32_t edits = 0u;
         const bool fits = !want_cigar || (uint64_t)(out_end - out) >= (uint64_t)nb;
         for (int k = 0; k < stage; k += FFS) {
-            const uint32_t run = ff_s[k];
+            const uint32_t run = stage_get(k);
             edits += run >= 64u ? (run & 63u) : 0u;   // every op but '=' is an edit
             if (want_cigar && fits) *out++ = (uint8_t)run;
         }
@@ -482,6 +567,16 @@ __global__ void __launch_bounds__(32) genasm_align_kernel(const AlignParams P)
             P.status[pair] = overflow ? 5 : 0;
             if (P.dc_entries) P.dc_entries[pair] = entries;
             have = false;
+        }
+    }
+    if constexpr (TMEM) {
+        __syncwarp();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t base = tff & 0x0000FFFFu;  // warp 0: lane field is zero
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tff), "r"((uint32_t)L::TMEM_COLS));
+            (void)base;
         }
     }
 }

@@ -1,6 +1,7 @@
 // sg_device_api.cu -- layer 2 of include/scrooge_b200.h: launches of the sm_100a kernels on device
 // pointers and an explicit stream.  No CPU fallback: every function needs a CUDA device.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -29,19 +30,58 @@ int cuda_fail(cudaError_t e, const char *what)
 
 struct DeviceInfo {
     int sms = 0;
-    int warps_per_sm[2] = {0, 0};  // [0]: W=64, [1]: W=32
+    int ctas_per_sm[2][2] = {{0, 0}, {0, 0}};  // [W=64 | W=32][smem forefront | TMEM forefront]
     bool ready = false;
 };
 static DeviceInfo g_dev_info[64];
 
-template <int W> static int setup_kernel(int *blocks_per_sm)
+// Which kernel variant sg_dev_align launches.  W=64: forefront in tensor memory (16 warps per SM, alu pipe 89 %
+// busy) unless SG_FOREFRONT=smem; W=32: forefront in shared memory (it is only 4 KB per warp there, 20 warps per SM)
+// unless SG_FOREFRONT=tmem.  All variants are bit-identical; see SmemLayout in sg_align.cuh.
+static bool use_tmem(int W)
 {
-    auto kern = genasm_align_kernel<W>;
-    const int smem = SmemLayout<W>::BYTES_PER_WARP;
-    SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    static const int forced = [] {
+        const char *e = std::getenv("SG_FOREFRONT");
+        if (e && std::string(e) == "smem") return 0;
+        if (e && std::string(e) == "tmem") return 1;
+        return -1;
+    }();
+    return forced >= 0 ? forced == 1 : W == 64;
+}
+
+template <int W, bool TMEM> static int setup_kernel(int *ctas_per_sm)
+{
+    using L = SmemLayout<W, TMEM>;
+    auto kern = genasm_align_kernel<W, TMEM>;
+    SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES_PER_CTA));
     SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, 32, smem));
-    if (*blocks_per_sm < 1) return fail(SG_ERR_CUDA, "alignment kernel does not fit on this device");
+    SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kern, L::WARPS_PER_CTA * 32, L::BYTES_PER_CTA));
+    if (std::getenv("SG_DEBUG")) {
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, kern);
+        fprintf(stderr, "[sg] W=%d tmem=%d: occupancy %d CTAs/SM, %d regs, %zu static smem, %d dyn smem, %d threads/CTA\n", W, (int)TMEM,
+                *ctas_per_sm, fa.numRegs, fa.sharedSizeBytes, L::BYTES_PER_CTA, L::WARPS_PER_CTA * 32);
+    }
+    if (TMEM) {
+        // cudaOccupancyMaxActiveBlocksPerMultiprocessor reports 1 for any kernel that allocates tensor memory, but the
+        // hardware co-schedules CTAs as long as their tcgen05.alloc requests fit in the SM's 512 columns (measured:
+        // sm__warps_active shows 16 resident warps with 4 CTAs).  Compute the residency from the real limits.
+        cudaFuncAttributes fa;
+        SG_CUDA(cudaFuncGetAttributes(&fa, kern));
+        int dev = 0, smem_sm = 0, regs_sm = 0;
+        SG_CUDA(cudaGetDevice(&dev));
+        SG_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+        SG_CUDA(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
+        const int threads = L::WARPS_PER_CTA * 32;
+        const int regs_cta = ((fa.numRegs + 7) / 8 * 8) * threads;
+        int lim = 512 / L::TMEM_COLS;
+        lim = std::min(lim, smem_sm / (L::BYTES_PER_CTA + (int)fa.sharedSizeBytes + 1024));
+        lim = std::min(lim, regs_sm / std::max(regs_cta, 1));
+        lim = std::min(lim, 2048 / threads);
+        if (const char *e = std::getenv("SG_TMEM_CTAS")) lim = std::min(lim, std::max(1, atoi(e)));  // experiment knob
+        *ctas_per_sm = std::max(*ctas_per_sm, lim);
+    }
+    if (*ctas_per_sm < 1) return fail(SG_ERR_CUDA, "alignment kernel does not fit on this device");
     return SG_OK;
 }
 
@@ -53,13 +93,26 @@ static int device_info(DeviceInfo **out)
     DeviceInfo &di = g_dev_info[dev];
     if (!di.ready) {
         SG_CUDA(cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, dev));
-        int rc = setup_kernel<64>(&di.warps_per_sm[0]);
-        if (rc) return rc;
-        rc = setup_kernel<32>(&di.warps_per_sm[1]);
+        int rc = setup_kernel<64, false>(&di.ctas_per_sm[0][0]);
+        if (!rc) rc = setup_kernel<64, true>(&di.ctas_per_sm[0][1]);
+        if (!rc) rc = setup_kernel<32, false>(&di.ctas_per_sm[1][0]);
+        if (!rc) rc = setup_kernel<32, true>(&di.ctas_per_sm[1][1]);
         if (rc) return rc;
         di.ready = true;
     }
     *out = &di;
+    return SG_OK;
+}
+
+template <int W, bool TMEM> static int launch_align(const DeviceInfo &di, const AlignParams &P, cudaStream_t st)
+{
+    using L = SmemLayout<W, TMEM>;
+    // persistent CTAs: a multiple of the SM count, never more lanes than work
+    uint64_t ctas = (uint64_t)di.sms * (uint64_t)di.ctas_per_sm[W == 64 ? 0 : 1][TMEM ? 1 : 0];
+    const uint64_t needed = (P.n + 32ull * L::WARPS_PER_CTA - 1) / (32ull * L::WARPS_PER_CTA);
+    if (ctas > needed) ctas = needed;
+    genasm_align_kernel<W, TMEM><<<(unsigned)ctas, L::WARPS_PER_CTA * 32, L::BYTES_PER_CTA, st>>>(P);
+    SG_CUDA(cudaGetLastError());
     return SG_OK;
 }
 
@@ -107,8 +160,11 @@ int sg_dev_align_geometry(int W, int *warps_per_sm, int *smem_per_warp, int *num
     DeviceInfo *di;
     int rc = device_info(&di);
     if (rc) return rc;
-    if (warps_per_sm) *warps_per_sm = di->warps_per_sm[W == 64 ? 0 : 1];
-    if (smem_per_warp) *smem_per_warp = W == 64 ? SmemLayout<64>::BYTES_PER_WARP : SmemLayout<32>::BYTES_PER_WARP;
+    const bool t = use_tmem(W);
+    if (warps_per_sm) *warps_per_sm = di->ctas_per_sm[W == 64 ? 0 : 1][t ? 1 : 0] * (t ? 4 : 1);
+    if (smem_per_warp)
+        *smem_per_warp = W == 64 ? (t ? SmemLayout<64, true>::BYTES_PER_WARP : SmemLayout<64, false>::BYTES_PER_WARP)
+                                 : (t ? SmemLayout<32, true>::BYTES_PER_WARP : SmemLayout<32, false>::BYTES_PER_WARP);
     if (num_sms) *num_sms = di->sms;
     return SG_OK;
 }
@@ -137,17 +193,8 @@ int sg_dev_align(int W, const uint32_t *d_text, const uint64_t *d_text_start, co
     P.n = n; P.flags = flags; P.slab = d_slab; P.slab_off = d_slab_off;
     P.counter = (unsigned long long *)d_counter;
     P.edit = d_edit; P.ref_consumed = d_ref_consumed; P.nruns = d_nruns; P.status = d_status; P.dc_entries = d_dc_entries;
-    const int wps = di->warps_per_sm[W == 64 ? 0 : 1];
-    // persistent warps: one CTA of one warp each, a multiple of the SM count, never more lanes than work
-    uint64_t warps = (uint64_t)di->sms * (uint64_t)wps;
-    const uint64_t needed = (n + 31ull) / 32ull;
-    if (warps > needed) warps = needed;
-    if (W == 64)
-        genasm_align_kernel<64><<<(unsigned)warps, 32, SmemLayout<64>::BYTES_PER_WARP, st>>>(P);
-    else
-        genasm_align_kernel<32><<<(unsigned)warps, 32, SmemLayout<32>::BYTES_PER_WARP, st>>>(P);
-    SG_CUDA(cudaGetLastError());
-    return SG_OK;
+    if (use_tmem(W)) return W == 64 ? launch_align<64, true>(*di, P, st) : launch_align<32, true>(*di, P, st);
+    return W == 64 ? launch_align<64, false>(*di, P, st) : launch_align<32, false>(*di, P, st);
 }
 
 uint64_t sg_scan_tmp_bytes(uint64_t n) { return ((n + kScanTile - 1) / kScanTile + 1) * sizeof(uint64_t); }

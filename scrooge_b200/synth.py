@@ -30,6 +30,14 @@ WORKLOADS = {
     "library_example_100bp": Workload("library_example_100bp", 100, 0.05, UNIFORM, 64, BASE_SEED + 1),
     "short_150bp": Workload("short_150bp", 150, 0.05, ILLUMINA, 64, BASE_SEED + 2),
     "long_10kbp": Workload("long_10kbp", 10000, 0.10, PACBIO, 64, BASE_SEED + 3),
+    # the reference's short-read window setting (README.md:208: W=32, O=17) on the same pairs as short_150bp
+    "short_150bp_w32": Workload("short_150bp_w32", 150, 0.05, ILLUMINA, 32, BASE_SEED + 2),
+    # BASELINE.json configs[4] sweep points (1-100 kbp at 5/10/15 %)
+    "sweep_1kbp_5": Workload("sweep_1kbp_5", 1000, 0.05, PACBIO, 64, BASE_SEED + 5),
+    "sweep_1kbp_15": Workload("sweep_1kbp_15", 1000, 0.15, PACBIO, 64, BASE_SEED + 5),
+    "sweep_10kbp_5": Workload("sweep_10kbp_5", 10000, 0.05, PACBIO, 64, BASE_SEED + 5),
+    "sweep_10kbp_15": Workload("sweep_10kbp_15", 10000, 0.15, PACBIO, 64, BASE_SEED + 5),
+    "sweep_100kbp_10": Workload("sweep_100kbp_10", 100000, 0.10, PACBIO, 64, BASE_SEED + 5),
 }
 
 

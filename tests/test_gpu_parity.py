@@ -235,3 +235,33 @@ def test_multi_gpu_context_matches_single(oracle, sglib):
     got = al.align_candidates(reads, cs, cr)
     want = oracle.align_candidates(genome, reads, cs, cr, threads=4)
     assert list(got.edit_distances) == list(want.edit) and got.cigars() == want.cigars
+
+
+@pytest.mark.parametrize("forefront", ["smem", "tmem"])
+def test_both_forefront_variants(forefront):
+    """The kernel has two bit-identical variants (forefront in shared memory or in tensor memory); the default is
+    picked per W, so run the non-default ones too, in a fresh process (the choice is made once per process)."""
+    import subprocess
+    import sys
+    code = (
+        "import json, sys; sys.path.insert(0, '.'); sys.path.insert(0, 'tests')\n"
+        "import scrooge_b200\n"
+        "from oracle.binding import Oracle\n"
+        "from conftest import random_pairs\n"
+        "o = Oracle()\n"
+        "for W in (64, 32):\n"
+        "    g = json.load(open(f'tests/golden/golden_w{W}.json'))['groups']\n"
+        "    T = [x['text'] for v in g.values() for x in v]; Q = [x['query'] for v in g.values() for x in v]\n"
+        "    T2, Q2 = random_pairs(7 + W, 3000, [0, 1, 31, 32, 33, 64, 65, 150, 400, 2000], [0, 0.05, 0.1, 0.3])\n"
+        "    T += T2; Q += Q2\n"
+        "    got = scrooge_b200.Aligner(W=W, n_gpus=1).align_pairs(T, Q)\n"
+        "    want = o.align_pairs(T, Q, W=W, threads=4)\n"
+        "    assert list(got.edit_distances) == list(want.edit) and got.cigars() == want.cigars, W\n"
+        "    assert list(got.ref_consumed) == list(want.ref_consumed)\n"
+        "print('variant ok')\n"
+    )
+    import os
+    env = dict(os.environ, SG_FOREFRONT=forefront)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "variant ok" in r.stdout, r.stderr[-2000:]
