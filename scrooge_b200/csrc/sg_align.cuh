@@ -49,11 +49,12 @@
 
 namespace sg {
 
-constexpr int kRowsPerChunk = 8;  // G
 
 template <int W> struct WinCfg;
-template <> struct WinCfg<64> { static constexpr int O = 33; };
-template <> struct WinCfg<32> { static constexpr int O = 17; };
+// O: window overlap; G: rows per DC chunk (about the typical window distance + 1: 10 kbp reads at 10 % need 7.9 rows
+// per 64-column window on average, 150 bp reads at 5 % need 2.6 rows per 32-column window)
+template <> struct WinCfg<64> { static constexpr int O = 33; static constexpr int G = 8; };
+template <> struct WinCfg<32> { static constexpr int O = 17; static constexpr int G = 4; };
 
 // Per-warp shared memory.  TMEM = false: the forefront lives in shared memory (one-warp CTAs, 8 per SM at W=64).
 // TMEM = true: the forefront lives in tensor memory -- W columns x NW words per lane, private to the lane, addressed
@@ -193,8 +194,9 @@ template <> __device__ __forceinline__ void sts_vec<2>(uint32_t *p, const uint32
 
 // G rows of one column: entries and their << 1
 template <int NW> struct RowSet {
-    uint32_t C[kRowsPerChunk][NW];
-    uint32_t S[kRowsPerChunk][NW];
+    static constexpr int G = WinCfg<NW * 32>::G;
+    uint32_t C[G][NW];
+    uint32_t S[G][NW];
 };
 
 // Boundary column R[d][n] = ones << d (src/genasm_cpu.cpp:225-231,239-245), left-aligned: row r of the chunk is
@@ -204,10 +206,10 @@ __device__ __forceinline__ void dc_boundary(RowSet<NW> &N, int m, int d0, uint32
 {
     ones_shl<NW>(W - m + d0, N.C[0]);
 #pragma unroll
-    for (int r = 0; r < kRowsPerChunk; r++) {
+    for (int r = 0; r < RowSet<NW>::G; r++) {
         shl1<NW>(N.C[r], N.S[r]);
         V |= N.C[r][NW - 1] & ~N.S[r][NW - 1];
-        if (r + 1 < kRowsPerChunk) {
+        if (r + 1 < RowSet<NW>::G) {
 #pragma unroll
             for (int k = 0; k < NW; k++) N.C[r + 1][k] = N.S[r][k];
         }
@@ -223,7 +225,7 @@ __device__ __forceinline__ void dc_column(const RowSet<NW> &P, RowSet<NW> &N, co
                                           const uint32_t (&F)[NW], const uint32_t fm, uint32_t (&XF)[NW], uint32_t &V,
                                           uint32_t &H)
 {
-    constexpr int G = kRowsPerChunk;
+    constexpr int G = RowSet<NW>::G;
     constexpr int TOP = NW - 1;
     uint32_t sF[NW];
     shl1<NW>(F, sF);
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(SmemLayout<W, TMEM>::WARPS_PER_CTA * 32, TMEM 
     constexpr int NWIN = 2 * NW;  // words of a 2-bit window
     constexpr int TBL = L::TBL;
     constexpr int TBCOLS = L::TBCOLS;
-    constexpr int G = kRowsPerChunk;
+    constexpr int G = WinCfg<W>::G;
     constexpr int TOP = NW - 1;
     constexpr int PMS = NW * 32;   // words between the masks of consecutive base codes
     constexpr int FFS = NW * 32;   // words between forefront columns
@@ -384,7 +386,9 @@ __global__ void __launch_bounds__(SmemLayout<W, TMEM>::WARPS_PER_CTA * 32, TMEM 
         // ---- DC: one chunk of G rows, columns n .. 0 -------------------------------------------------
         RowSet<NW> A, B;
         uint32_t XF[NW];  // (F & F << 1) | fm of row d0-1 at the previous column
-        const bool uniform = __all_sync(0xFFFFFFFFu, nn == W);
+        // lanes without work (queue drained) ride along in the fast path: whatever they compute stays in their own
+        // scratch and is never read
+        const bool uniform = __all_sync(0xFFFFFFFFu, !have || n == W);
 
         // boundary column: forefront in, chunk's last row out, insertion edges of the column if it is a TB column
         auto boundary_column = [&](RowSet<NW> &Nv, const int i) {
