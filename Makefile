@@ -9,7 +9,7 @@ NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -ccbin $(CCBIN) -Xcompiler -fPIC,-fo
            -Xptxas -v -Iinclude
 SRC := scrooge_b200/csrc
 LIB := scrooge_b200/lib/libscrooge_b200.so
-OBJS := build/sg_device_api.o build/sg_host_api.o build/genasm_gpu.o
+OBJS := build/sg_device_api.o build/sg_host_api.o build/genasm_gpu.o build/sg_host_pack.o
 HDRS := $(wildcard $(SRC)/*.cuh $(SRC)/*.h include/*.h include/*.hpp)
 
 all: $(LIB) build/library_example
@@ -17,6 +17,11 @@ all: $(LIB) build/library_example
 build/%.o: $(SRC)/%.cu $(HDRS)
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
+
+# host-only code with ISA-specific function versions: plain g++
+build/sg_host_pack.o: $(SRC)/sg_host_pack.cpp
+	@mkdir -p build
+	$(CCBIN) -O3 -std=c++17 -fPIC -fopenmp -Wall -c $< -o $@
 
 build/%.o: $(SRC)/%.cpp $(HDRS)
 	@mkdir -p build

@@ -251,6 +251,8 @@ def main():
         del h_text
         tb_pin = torch.from_numpy(tb).pin_memory()
         qb_pin = torch.from_numpy(qb).pin_memory()
+        # every rank is its own process with its own context: share the host's threads between the ranks of this box
+        os.environ.setdefault("SG_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
         al = scrooge_b200.Aligner(W=W, device_ids=[local_rank])
         res = None
         for _ in range(max(args.warmup, 1)):
@@ -266,7 +268,9 @@ def main():
         e2e = {"value": world * ne * args.steps / e2e_s, "unit": "alignments/s",
                "h2d_bytes_per_step": int(tb.nbytes + qb.nbytes + 2 * (ne + 1) * 8), "d2h_bytes_per_step": int(d2h),
                "pairs_per_step": ne, "ms_per_step": e2e_s / args.steps * 1e3,
-               "api": "sg_align_pairs (C ABI, pinned host ASCII blobs in, distances + packed CIGAR runs out)"}
+               "host_threads_per_gpu": int(os.environ["SG_HOST_THREADS"]),
+               "api": "sg_align_pairs (C ABI, pinned host ASCII blobs in, distances + packed CIGAR runs out); ingest on the "
+                      "host (AVX-512, 2 bit/base before the upload) when a GPU has >= 10 host threads, else on the device"}
         del tb_pin, qb_pin
         al.close()
 

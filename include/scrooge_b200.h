@@ -116,6 +116,12 @@ void sg_result_free(sg_result *r);
 void *sg_host_alloc(uint64_t bytes);
 void sg_host_free(void *p);
 
+/* Host-side ingest: the same packing as sg_dev_pack_2bit done by `threads` host threads (0 = all), AVX-512 / AVX2 when
+ * the CPU has them.  packed must hold ceil(n_bases/16) words.  Returns the smallest offending position or UINT64_MAX.
+ * sg_host_pack_isa: 2 AVX-512, 1 AVX2, 0 scalar. */
+uint64_t sg_host_pack_2bit(const char *ascii, uint64_t n_bases, uint32_t *packed, int threads);
+int sg_host_pack_isa(void);
+
 /* ------------------------------------------------------------------------------------------------ */
 /* 2. device API: device pointers, current device, asynchronous on `stream` (a cudaStream_t).        */
 

@@ -48,6 +48,8 @@ SIGNATURES = {
     "sg_result_free": (None, [vp]),
     "sg_host_alloc": (vp, [u64]),
     "sg_host_free": (None, [vp]),
+    "sg_host_pack_2bit": (u64, [vp, u64, vp, i32]),
+    "sg_host_pack_isa": (i32, []),
     "sg_packed_words": (u64, [u64]),
     "sg_dev_pack_2bit": (i32, [vp, u64, vp, vp, vp]),
     "sg_dev_align": (i32, [i32, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

@@ -178,7 +178,7 @@ struct Slot {
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_mid = nullptr, ev_end = nullptr;
     DevBuf ascii_t, ascii_q, packed_t, packed_q, toff, qoff, tstart, tlen, qstart, qlen, slab_off, slab, counter, edit,
         refc, nruns, status, run_off, scan_tmp, runs, bad, cstart, cread, cap32;
-    PinBuf h_small, h_edit, h_refc, h_runoff, h_status;
+    PinBuf h_small, h_edit, h_refc, h_runoff, h_status, h_packed_t, h_packed_q;
     PinnedPool::Block piece{nullptr, 0};
     // the batch in flight
     bool busy = false, mid_done = false;
@@ -197,7 +197,7 @@ struct Slot {
         for (DevBuf *b : {&ascii_t, &ascii_q, &packed_t, &packed_q, &toff, &qoff, &tstart, &tlen, &qstart, &qlen, &slab_off,
                           &slab, &counter, &edit, &refc, &nruns, &status, &run_off, &scan_tmp, &runs, &bad, &cstart, &cread, &cap32})
             b->release();
-        for (PinBuf *b : {&h_small, &h_edit, &h_refc, &h_runoff, &h_status}) b->release();
+        for (PinBuf *b : {&h_small, &h_edit, &h_refc, &h_runoff, &h_status, &h_packed_t, &h_packed_q}) b->release();
         g_pool.release(piece);
         piece = {nullptr, 0};
         if (ev_k0) cudaEventDestroy(ev_k0);
@@ -224,11 +224,16 @@ struct sg_ctx {
     int W = 64;
     std::vector<Device> devs;
     // sub-batch rule: at least batch_bytes of ASCII AND at least min_batch_units alignments (one alignment
-    // occupies one lane for its whole life -- 2.4 ms for a 10 kbp read -- so a launch needs a couple of
-    // alignments per lane to fill the device), but never more than max_batch_bytes (per-slot buffers)
+    // occupies one lane for its whole life -- 11 ms for a 10 kbp read with every lane busy -- so a launch needs an
+    // alignment per lane to fill the device), but never more than max_batch_bytes (per-slot buffers)
     uint64_t batch_bytes = 256ull << 20;
     uint64_t max_batch_bytes = 3ull << 30;
     uint64_t min_batch_units = 65536;
+    // ingest policy: pack to 2 bit/base on the host (all host threads, AVX-512) and upload a quarter of the bytes, or
+    // upload ASCII and pack on the device.  Host packing wins when the upload is the bottleneck and there are enough
+    // host threads per GPU (measured on the B200 box: 101 GB/s of ASCII on 16 threads vs 47 GB/s over PCIe).
+    bool host_pack = false;
+    int host_threads = 1;
     std::mutex mu;  // calls on one context are serialised
 };
 
@@ -272,6 +277,37 @@ struct Workload {
 
 #define R(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
 
+// One ASCII blob -> packed words on the device, through the device ingest kernel or through the host packer.
+// *bad_pos receives the first offending position when the host packer finds one (the device path reports through
+// d_bad after the fact).
+int upload_packed(sg_ctx *ctx, cudaStream_t st, const char *ascii, uint64_t nbytes, DevBuf &d_ascii, DevBuf &d_packed, PinBuf &h_packed,
+                  uint64_t *d_bad, uint64_t *bad_pos)
+{
+    const uint64_t words = sg_packed_words(nbytes);
+    R(d_packed.reserve(words * 4));
+    if (ctx->host_pack) {
+        R(h_packed.reserve(words * 4));
+        uint32_t *hp = h_packed.as<uint32_t>();
+        const uint64_t used = (nbytes + 15) / 16;
+        const uint64_t bad = sg_host_pack_2bit(ascii, nbytes, hp, ctx->host_threads);
+        memset(hp + used, 0, (words - used) * 4);  // padding words the aligner may read
+        if (bad != ~0ull) { *bad_pos = bad; return SG_OK; }
+        SG_CUDA(cudaMemcpyAsync(d_packed.p, hp, words * 4, cudaMemcpyHostToDevice, st));
+        return SG_OK;
+    }
+    R(d_ascii.reserve(nbytes + 64));
+    SG_CUDA(cudaMemcpyAsync(d_ascii.p, ascii, nbytes, cudaMemcpyHostToDevice, st));
+    return sg_dev_pack_2bit(d_ascii.as<char>(), nbytes, d_packed.as<uint32_t>(), d_bad, st);
+}
+
+// error text for an offending base at `pos` of a blob whose strings start at off[first..last]
+int bad_base_error(const char *what, const char *unit, const uint64_t *off, uint64_t first, uint64_t last, uint64_t pos)
+{
+    const uint64_t p = (uint64_t)(std::upper_bound(off + first, off + last + 1, pos) - off) - 1;
+    return fail(SG_ERR_BAD_BASE, std::string("non-ACGT character in ") + what + " of " + unit + " " + std::to_string(p) + " at position " +
+                                     std::to_string(pos - off[p]));
+}
+
 // stage A: uploads, ingest, descriptors, alignment kernel, run-count scan; ends with ev_mid
 int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uint64_t a1)
 {
@@ -289,16 +325,15 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
     uint64_t slab_bytes;
     if (!w.mapping) {
         const uint64_t tbytes = w.toff[a1] - w.toff[a0], qbytes = w.qoff[a1] - w.qoff[a0];
-        R(s.ascii_t.reserve(tbytes + 64)); R(s.ascii_q.reserve(qbytes + 64));
-        R(s.packed_t.reserve(sg_packed_words(tbytes) * 4)); R(s.packed_q.reserve(sg_packed_words(qbytes) * 4));
         R(s.toff.reserve((n + 1) * 8)); R(s.qoff.reserve((n + 1) * 8));
         slab_bytes = 2ull * qbytes + 8ull * n;
-        SG_CUDA(cudaMemcpyAsync(s.ascii_t.p, w.tb + w.toff[a0], tbytes, cudaMemcpyHostToDevice, st));
-        SG_CUDA(cudaMemcpyAsync(s.ascii_q.p, w.qb + w.qoff[a0], qbytes, cudaMemcpyHostToDevice, st));
+        uint64_t bad_t = ~0ull, bad_q = ~0ull;
+        R(upload_packed(ctx, st, w.tb + w.toff[a0], tbytes, s.ascii_t, s.packed_t, s.h_packed_t, s.bad.as<uint64_t>(), &bad_t));
+        if (bad_t != ~0ull) return bad_base_error("text", "pair", w.toff, a0, a1, bad_t + w.toff[a0]);
+        R(upload_packed(ctx, st, w.qb + w.qoff[a0], qbytes, s.ascii_q, s.packed_q, s.h_packed_q, s.bad.as<uint64_t>() + 1, &bad_q));
+        if (bad_q != ~0ull) return bad_base_error("query", "pair", w.qoff, a0, a1, bad_q + w.qoff[a0]);
         SG_CUDA(cudaMemcpyAsync(s.toff.p, w.toff + a0, (n + 1) * 8, cudaMemcpyHostToDevice, st));
         SG_CUDA(cudaMemcpyAsync(s.qoff.p, w.qoff + a0, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-        R(sg_dev_pack_2bit(s.ascii_t.as<char>(), tbytes, s.packed_t.as<uint32_t>(), s.bad.as<uint64_t>(), st));
-        R(sg_dev_pack_2bit(s.ascii_q.as<char>(), qbytes, s.packed_q.as<uint32_t>(), s.bad.as<uint64_t>() + 1, st));
         pair_descriptors_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(
             s.toff.as<uint64_t>(), s.qoff.as<uint64_t>(), n, s.tstart.as<uint64_t>(), s.tlen.as<uint64_t>(),
             s.qstart.as<uint64_t>(), s.qlen.as<uint64_t>(), s.slab_off.as<uint64_t>());
@@ -313,13 +348,13 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
         for (uint64_t c = a0; c < a1; c++) { r0 = std::min(r0, w.cand_read[c]); r1 = std::max(r1, w.cand_read[c]); }
         const uint64_t nr = (uint64_t)r1 - r0 + 1, rbytes = w.roff[r1 + 1] - w.roff[r0];
         slab_bytes = 2ull * (w.woff[a1] - w.woff[a0]) + 8ull * n;
-        R(s.ascii_q.reserve(rbytes + 64)); R(s.packed_q.reserve(sg_packed_words(rbytes) * 4));
         R(s.qoff.reserve((nr + 1) * 8)); R(s.cstart.reserve(n * 8)); R(s.cread.reserve(n * 4)); R(s.cap32.reserve(n * 4));
-        SG_CUDA(cudaMemcpyAsync(s.ascii_q.p, w.rb + w.roff[r0], rbytes, cudaMemcpyHostToDevice, st));
+        uint64_t bad_q = ~0ull;
+        R(upload_packed(ctx, st, w.rb + w.roff[r0], rbytes, s.ascii_q, s.packed_q, s.h_packed_q, s.bad.as<uint64_t>() + 1, &bad_q));
+        if (bad_q != ~0ull) return bad_base_error("content", "read", w.roff, r0, (uint64_t)r1 + 1, bad_q + w.roff[r0]);
         SG_CUDA(cudaMemcpyAsync(s.qoff.p, w.roff + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, st));
         SG_CUDA(cudaMemcpyAsync(s.cstart.p, w.cand_start + a0, n * 8, cudaMemcpyHostToDevice, st));
         SG_CUDA(cudaMemcpyAsync(s.cread.p, w.cand_read + a0, n * 4, cudaMemcpyHostToDevice, st));
-        R(sg_dev_pack_2bit(s.ascii_q.as<char>(), rbytes, s.packed_q.as<uint32_t>(), s.bad.as<uint64_t>() + 1, st));
         cand_descriptors_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
             s.cstart.as<uint64_t>(), s.cread.as<uint32_t>(), s.qoff.as<uint64_t>(), r0, d.genome_len, n, s.tstart.as<uint64_t>(),
             s.tlen.as<uint64_t>(), s.qstart.as<uint64_t>(), s.qlen.as<uint64_t>(), s.cap32.as<uint32_t>());
@@ -362,16 +397,11 @@ int stage_b(Slot &s, const Workload &w)
         if (!w.mapping) {
             const bool in_text = h[0] != ~0ull;
             const uint64_t *off = in_text ? w.toff : w.qoff;
-            const uint64_t pos = (in_text ? h[0] : h[1]) + off[s.a0];
-            const uint64_t p = (uint64_t)(std::upper_bound(off + s.a0, off + s.a1 + 1, pos) - off) - 1;
-            return fail(SG_ERR_BAD_BASE, std::string("non-ACGT character in ") + (in_text ? "text" : "query") + " of pair " +
-                                             std::to_string(p) + " at position " + std::to_string(pos - off[p]));
+            return bad_base_error(in_text ? "text" : "query", "pair", off, s.a0, s.a1, (in_text ? h[0] : h[1]) + off[s.a0]);
         }
         uint32_t r0 = w.cand_read[s.a0], r1 = r0;
         for (uint64_t c = s.a0; c < s.a1; c++) { r0 = std::min(r0, w.cand_read[c]); r1 = std::max(r1, w.cand_read[c]); }
-        const uint64_t pos = h[1] + w.roff[r0];
-        const uint64_t r = (uint64_t)(std::upper_bound(w.roff + r0, w.roff + r1 + 2, pos) - w.roff) - 1;
-        return fail(SG_ERR_BAD_BASE, "non-ACGT character in read " + std::to_string(r) + " at position " + std::to_string(pos - w.roff[r]));
+        return bad_base_error("content", "read", w.roff, r0, (uint64_t)r1 + 1, h[1] + w.roff[r0]);
     }
     if (want_cigar) {
         s.total_runs = h[2];
@@ -557,6 +587,14 @@ int sg_ctx_create(sg_ctx **out, const int *device_ids, int n_devices, int W)
         const long mb = std::atol(v);
         if (mb > 0) ctx->batch_bytes = (uint64_t)mb << 20;
     }
+    {
+        // host threads this context may use for packing: SG_HOST_THREADS, else all hardware threads shared by its GPUs
+        int hw = (int)std::thread::hardware_concurrency();
+        if (const char *v = std::getenv("SG_HOST_THREADS")) hw = std::max(1, std::atoi(v));
+        ctx->host_threads = std::max(1, hw / n_devices);
+        ctx->host_pack = ctx->host_threads >= 10;   // ~7-10 GB/s of ASCII per thread against ~47 GB/s of PCIe per GPU
+        if (const char *v = std::getenv("SG_HOST_PACK")) ctx->host_pack = std::atoi(v) != 0;
+    }
     if (const char *v = std::getenv("SG_MAX_BATCH_MB")) {
         const long mb = std::atol(v);
         if (mb > 0) ctx->max_batch_bytes = (uint64_t)mb << 20;
@@ -569,7 +607,8 @@ int sg_ctx_create(sg_ctx **out, const int *device_ids, int n_devices, int W)
         for (Slot &s : d.slots) R(s.create());
         int wps = 0, sms = 0;
         R(sg_dev_align_geometry(W, &wps, nullptr, &sms));
-        ctx->min_batch_units = std::max<uint64_t>(ctx->min_batch_units, 2ull * 32ull * (uint64_t)wps * (uint64_t)sms);
+        // one alignment per resident lane fills the device (75 776 lanes on a B200 at W=64)
+        ctx->min_batch_units = std::max<uint64_t>(ctx->min_batch_units, 32ull * (uint64_t)wps * (uint64_t)sms);
     }
     *out = ctx.release();
     return SG_OK;

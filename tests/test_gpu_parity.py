@@ -237,10 +237,11 @@ def test_multi_gpu_context_matches_single(oracle, sglib):
     assert list(got.edit_distances) == list(want.edit) and got.cigars() == want.cigars
 
 
-@pytest.mark.parametrize("forefront", ["smem", "tmem"])
-def test_both_forefront_variants(forefront):
-    """The kernel has two bit-identical variants (forefront in shared memory or in tensor memory); the default is
-    picked per W, so run the non-default ones too, in a fresh process (the choice is made once per process)."""
+@pytest.mark.parametrize("forefront,host_pack", [("smem", "0"), ("tmem", "1"), ("smem", "1"), ("tmem", "0")])
+def test_kernel_and_ingest_variants(forefront, host_pack):
+    """The kernel has two bit-identical variants (forefront in shared memory or in tensor memory) and the host API two
+    ingest paths (pack on the device or on the host); the defaults depend on W and on the host's core count, so run
+    every combination, each in a fresh process (the choices are made once per process / context)."""
     import subprocess
     import sys
     code = (
@@ -258,10 +259,15 @@ def test_both_forefront_variants(forefront):
         "    want = o.align_pairs(T, Q, W=W, threads=4)\n"
         "    assert list(got.edit_distances) == list(want.edit) and got.cigars() == want.cigars, W\n"
         "    assert list(got.ref_consumed) == list(want.ref_consumed)\n"
+        "try:\n"
+        "    scrooge_b200.Aligner(W=64, n_gpus=1).align_pairs(['ACGT', 'ACGTACGTNACGT'], ['ACG', 'ACGT'])\n"
+        "    raise SystemExit('bad base not detected')\n"
+        "except scrooge_b200.ScroogeError as e:\n"
+        "    assert e.code == 2 and 'pair 1' in str(e) and 'position 8' in str(e), str(e)\n"
         "print('variant ok')\n"
     )
     import os
-    env = dict(os.environ, SG_FOREFRONT=forefront)
+    env = dict(os.environ, SG_FOREFRONT=forefront, SG_HOST_PACK=host_pack)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "variant ok" in r.stdout, r.stderr[-2000:]
