@@ -1,6 +1,6 @@
 # Builds the product library (sm_100a only) in-tree:
 #   scrooge_b200/lib/libscrooge_b200.so   C ABI of include/scrooge_b200.h + C++ drop-in genasm_gpu::align_all
-#   build/library_example, build/sg_tests  (C++ programs mirroring the reference's library_example / tests)
+#   build/library_example, build/sg_tests  (C++ programs mirroring the reference's library_example / tests binaries)
 # The oracle (test infrastructure) is built by oracle/Makefile.
 NVCC ?= /usr/local/cuda/bin/nvcc
 CCBIN ?= /usr/bin/g++
@@ -9,10 +9,10 @@ NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -ccbin $(CCBIN) -Xcompiler -fPIC,-fo
            -Xptxas -v -Iinclude
 SRC := scrooge_b200/csrc
 LIB := scrooge_b200/lib/libscrooge_b200.so
-OBJS := build/sg_device_api.o build/sg_host_api.o build/genasm_gpu.o build/sg_host_pack.o
+OBJS := build/sg_device_api.o build/sg_host_api.o build/genasm_gpu.o build/sg_host_pack.o build/sg_io.o
 HDRS := $(wildcard $(SRC)/*.cuh $(SRC)/*.h include/*.h include/*.hpp)
 
-all: $(LIB) build/library_example
+all: $(LIB) build/library_example build/sg_tests
 
 build/%.o: $(SRC)/%.cu $(HDRS)
 	@mkdir -p build
@@ -22,6 +22,10 @@ build/%.o: $(SRC)/%.cu $(HDRS)
 build/sg_host_pack.o: $(SRC)/sg_host_pack.cpp
 	@mkdir -p build
 	$(CCBIN) -O3 -std=c++17 -fPIC -fopenmp -Wall -c $< -o $@
+
+build/sg_io.o: $(SRC)/sg_io.cpp include/scrooge_io.hpp include/scrooge_types.hpp
+	@mkdir -p build
+	$(CCBIN) -O2 -std=c++17 -fPIC -Wall -c $< -o $@
 
 build/%.o: $(SRC)/%.cpp $(HDRS)
 	@mkdir -p build
@@ -33,6 +37,9 @@ $(LIB): $(OBJS)
 
 build/library_example: examples/library_example.cpp $(LIB) $(HDRS)
 	$(CCBIN) -O2 -std=c++17 -Iinclude -o $@ $< -Lscrooge_b200/lib -lscrooge_b200 -Wl,-rpath,'$$ORIGIN/../scrooge_b200/lib'
+
+build/sg_tests: apps/sg_tests.cpp $(LIB) $(HDRS)
+	$(CCBIN) -O2 -std=c++17 -Wall -Iinclude -o $@ $< -Lscrooge_b200/lib -lscrooge_b200 -Wl,-rpath,'$$ORIGIN/../scrooge_b200/lib'
 
 clean:
 	rm -rf build scrooge_b200/lib
