@@ -109,6 +109,10 @@ int64_t sg_result_render_cigar(const sg_result *r, uint64_t idx, char *buf, uint
 /* Expand alignment idx's runs into CigarEntry_t-shaped entries; returns the number written, -1 if cap is
  * too small. */
 int64_t sg_result_entries(const sg_result *r, uint64_t idx, sg_cigar_entry *out, uint64_t cap);
+/* All CIGAR texts at once, rendered by `threads` host threads (0 = all): alignment a's text is
+ * blob[text_off[a] .. text_off[a+1]) (no terminators); text_off has count+1 entries.  Returns the total text length;
+ * when blob is NULL or blob_cap is too small only text_off is filled (call again with a big enough blob). */
+uint64_t sg_result_render_all(const sg_result *r, char *blob, uint64_t blob_cap, uint64_t *text_off, int threads);
 void sg_result_free(sg_result *r);
 
 /* Page-locked host memory for input blobs: uploads from it run at full PCIe speed and overlap with compute
@@ -183,6 +187,15 @@ int sg_synth_pairs_host(uint64_t seed, uint64_t first_pair, uint64_t n_pairs, ui
 int sg_dev_synth_pairs(uint64_t seed, uint64_t first_pair, uint64_t n_pairs, uint32_t read_len, double err,
                        uint32_t w_sub, uint32_t w_ins, uint32_t w_del, uint32_t slack, char *d_text,
                        uint64_t text_stride, uint64_t *d_text_len, char *d_reads, void *stream);
+
+/* Read-mapping workload (BASELINE.json configs[3]).  sg_synth_genome writes bases [first, first+n) of the i.i.d.
+ * uniform genome `seed` to host memory `out` and/or device memory `d_out` (either may be NULL).  sg_synth_reads draws
+ * read r at a uniform position of `genome` (host or device memory according to on_device, like reads / pos) and
+ * mutates it as sg_synth_pairs does; pos[r] receives the true start. */
+int sg_synth_genome(uint64_t seed, uint64_t first, uint64_t n, char *out, void *d_out, void *stream);
+int sg_synth_reads(uint64_t seed, uint64_t first_read, uint64_t n_reads, uint32_t read_len, double err, uint32_t w_sub,
+                   uint32_t w_ins, uint32_t w_del, const char *genome, uint64_t genome_len, char *reads, uint64_t *pos,
+                   int on_device, void *stream);
 
 #ifdef __cplusplus
 }

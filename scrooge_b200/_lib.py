@@ -45,6 +45,7 @@ SIGNATURES = {
     "sg_result_cigar_len": (u64, [vp, u64]),
     "sg_result_render_cigar": (i64, [vp, u64, vp, u64]),
     "sg_result_entries": (i64, [vp, u64, vp, u64]),
+    "sg_result_render_all": (u64, [vp, vp, u64, vp, i32]),
     "sg_result_free": (None, [vp]),
     "sg_host_alloc": (vp, [u64]),
     "sg_host_free": (None, [vp]),
@@ -61,6 +62,8 @@ SIGNATURES = {
     "sg_synth_text_stride": (u64, [u32, u32]),
     "sg_synth_pairs_host": (i32, [u64, u64, u64, u32, dbl, u32, u32, u32, u32, vp, u64, vp, vp]),
     "sg_dev_synth_pairs": (i32, [u64, u64, u64, u32, dbl, u32, u32, u32, u32, vp, u64, vp, vp, vp]),
+    "sg_synth_genome": (i32, [u64, u64, u64, vp, vp, vp]),
+    "sg_synth_reads": (i32, [u64, u64, u64, u32, dbl, u32, u32, u32, vp, u64, vp, vp, i32, vp]),
 }
 
 _lib = None

@@ -107,25 +107,19 @@ class Result:
             raise ScroogeError(_lib.SG_ERR_BAD_ARG, "render_cigar failed")
         return buf.value.decode()
 
+    def cigar_text(self, threads: int = 0):
+        """All CIGAR texts as one uint8 array + offsets (count+1), rendered by the library's host threads."""
+        off = np.zeros(self.count + 1, dtype=np.uint64)
+        total = int(lib().sg_result_render_all(self._h, None, 0, off.ctypes.data, threads))
+        blob = np.empty(max(total, 1), dtype=np.uint8)
+        lib().sg_result_render_all(self._h, blob.ctypes.data, total, off.ctypes.data, threads)
+        return blob[:total], off
+
     def cigars(self) -> List[str]:
-        """All CIGAR strings, rendered with numpy from the packed runs ("%d%c" per run)."""
-        off = self.run_offsets
-        if len(off) == 0:
-            return [""] * self.count
-        runs = self.runs
-        cnt = (runs & 63).astype(np.int64)
-        op = np.frombuffer(OPS.encode(), dtype=np.uint8)[runs >> 6]
-        width = np.where(cnt >= 10, 3, 2)
-        pos = np.zeros(len(runs) + 1, dtype=np.int64)
-        np.cumsum(width, out=pos[1:])
-        text = np.zeros(int(pos[-1]), dtype=np.uint8)
-        two = cnt >= 10
-        text[pos[:-1][two]] = 48 + cnt[two] // 10
-        text[pos[1:] - 2] = 48 + cnt % 10
-        text[pos[1:] - 1] = op
-        raw = text.tobytes()
-        bounds = pos[off.astype(np.int64)]
-        return [raw[bounds[i]:bounds[i + 1]].decode() for i in range(self.count)]
+        """All CIGAR strings ("%d%c" per run, reference src/genasm_gpu.cu:881-888)."""
+        blob, off = self.cigar_text()
+        raw = blob.tobytes()
+        return [raw[int(off[i]):int(off[i + 1])].decode() for i in range(self.count)]
 
     def alignments(self) -> List[Alignment]:
         ed, rc, cg = self.edit_distances, self.ref_consumed, self.cigars()

@@ -65,14 +65,14 @@ std::vector<Alignment_t> collect(sg_result *res, Extra *extra, long long *core_a
     const int64_t *ed = sg_result_edit_distances(res);
     const uint64_t *rc = sg_result_ref_consumed(res);
     if (extra) extra->ref_consumed.resize(n);
-#pragma omp parallel for schedule(dynamic, 256)
+    // one multi-threaded pass renders every CIGAR text; the strings are then cut out of the blob
+    std::vector<uint64_t> off(n + 1);
+    const uint64_t total = sg_result_render_all(res, nullptr, 0, off.data(), 0);
+    std::string blob(total, '\0');
+    sg_result_render_all(res, &blob[0], total, off.data(), 0);
+#pragma omp parallel for schedule(static)
     for (long long i = 0; i < (long long)n; i++) {
-        const uint64_t len = sg_result_cigar_len(res, (uint64_t)i);
-        out[i].cigar.resize(len);
-        if (len) {
-            // render straight into the string's buffer (cap counts the NUL the string already owns)
-            sg_result_render_cigar(res, (uint64_t)i, &out[i].cigar[0], len + 1);
-        }
+        out[i].cigar.assign(blob, off[i], off[i + 1] - off[i]);
         out[i].edit_distance = ed[i];
         if (extra) extra->ref_consumed[i] = rc[i];
     }

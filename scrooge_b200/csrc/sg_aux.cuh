@@ -186,6 +186,20 @@ __global__ void __launch_bounds__(128) synth_pairs_kernel(SgSynthParams p, uint6
     for (uint64_t x = tl; x < text_stride; x++) t[x] = 'A';  // keep the whole slot packable
 }
 
+__global__ void __launch_bounds__(256) synth_genome_kernel(uint64_t seed, uint64_t first, uint64_t n, char *__restrict__ out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = sg_synth_genome_base(seed, first + i);
+}
+
+__global__ void __launch_bounds__(128) synth_reads_kernel(SgSynthParams p, uint64_t first, uint64_t n, const char *__restrict__ genome,
+                                                           uint64_t genome_len, char *__restrict__ reads, uint64_t *__restrict__ pos)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    pos[k] = sg_synth_read_from_genome(p, first + k, genome, genome_len, reads + k * (uint64_t)p.read_len);
+}
+
 // ---- integer-ALU peak probe -----------------------------------------------------------------------------
 // Independent chains of the DC recurrence's own instructions.  kind 0: LOP3 only; 1: SHF (funnel shift) only;
 // 2: two LOP3 per SHF (the DC mix); 3: LOP3 + IMAD alternating (alu pipe + fma pipe); 4-6: one DC entry

@@ -107,10 +107,16 @@ static int device_info(DeviceInfo **out)
 template <int W, bool TMEM> static int launch_align(const DeviceInfo &di, const AlignParams &P, cudaStream_t st)
 {
     using L = SmemLayout<W, TMEM>;
-    // persistent CTAs: a multiple of the SM count, never more lanes than work
-    uint64_t ctas = (uint64_t)di.sms * (uint64_t)di.ctas_per_sm[W == 64 ? 0 : 1][TMEM ? 1 : 0];
-    const uint64_t needed = (P.n + 32ull * L::WARPS_PER_CTA - 1) / (32ull * L::WARPS_PER_CTA);
-    if (ctas > needed) ctas = needed;
+    // Persistent CTAs, a lane per alignment at a time.  With n alignments and at most `max_lanes` resident lanes every lane
+    // runs k = ceil(n / max_lanes) alignments back to back; launching only ceil(n / k) lanes gives every lane the same
+    // count, so that a batch of few, long alignments (100 kbp reads: 1.3 per resident lane) does not end with most of the
+    // device idle while a third of the lanes run their second alignment.
+    const uint64_t lanes_per_cta = 32ull * L::WARPS_PER_CTA;
+    const uint64_t max_ctas = (uint64_t)di.sms * (uint64_t)di.ctas_per_sm[W == 64 ? 0 : 1][TMEM ? 1 : 0];
+    const uint64_t k = (P.n + max_ctas * lanes_per_cta - 1) / (max_ctas * lanes_per_cta);
+    const uint64_t lanes = (P.n + k - 1) / k;
+    uint64_t ctas = (lanes + lanes_per_cta - 1) / lanes_per_cta;
+    if (k >= 8 || ctas > max_ctas) ctas = max_ctas;  // many alignments per lane: the dynamic queue evens things out
     genasm_align_kernel<W, TMEM><<<(unsigned)ctas, L::WARPS_PER_CTA * 32, L::BYTES_PER_CTA, st>>>(P);
     SG_CUDA(cudaGetLastError());
     return SG_OK;
@@ -327,6 +333,40 @@ int sg_dev_synth_pairs(uint64_t seed, uint64_t first_pair, uint64_t n_pairs, uin
     synth_pairs_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(p, first_pair, n_pairs, d_text, text_stride,
                                                                 d_text_len, d_reads);
     SG_CUDA(cudaGetLastError());
+    return SG_OK;
+}
+
+int sg_synth_genome(uint64_t seed, uint64_t first, uint64_t n, char *out, void *d_out, void *stream)
+{
+    if (out) {
+#pragma omp parallel for schedule(static)
+        for (long long i = 0; i < (long long)n; i++) out[i] = sg_synth_genome_base(seed, first + (uint64_t)i);
+    }
+    if (d_out && n) {
+        DeviceInfo *di;
+        int rc = device_info(&di);
+        if (rc) return rc;
+        synth_genome_kernel<<<di->sms * 8, 256, 0, (cudaStream_t)stream>>>(seed, first, n, (char *)d_out);
+        SG_CUDA(cudaGetLastError());
+    }
+    return SG_OK;
+}
+
+int sg_synth_reads(uint64_t seed, uint64_t first_read, uint64_t n_reads, uint32_t read_len, double err, uint32_t w_sub, uint32_t w_ins,
+                   uint32_t w_del, const char *genome, uint64_t genome_len, char *reads, uint64_t *pos, int on_device, void *stream)
+{
+    if (genome_len <= 2ull * read_len + 64ull) return fail(SG_ERR_BAD_ARG, "genome too short for this read length");
+    if (n_reads == 0) return SG_OK;
+    const SgSynthParams p = make_synth(seed, read_len, err, w_sub, w_ins, w_del, 0);
+    if (on_device) {
+        synth_reads_kernel<<<(unsigned)((n_reads + 127ull) / 128ull), 128, 0, (cudaStream_t)stream>>>(p, first_read, n_reads, genome, genome_len,
+                                                                                                reads, pos);
+        SG_CUDA(cudaGetLastError());
+        return SG_OK;
+    }
+#pragma omp parallel for schedule(static)
+    for (long long k = 0; k < (long long)n_reads; k++)
+        pos[k] = sg_synth_read_from_genome(p, first_read + (uint64_t)k, genome, genome_len, reads + (uint64_t)k * read_len);
     return SG_OK;
 }
 

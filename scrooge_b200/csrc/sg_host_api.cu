@@ -772,6 +772,54 @@ int64_t sg_result_entries(const sg_result *r, uint64_t idx, sg_cigar_entry *out,
     return (int64_t)cnt;
 }
 
+uint64_t sg_result_render_all(const sg_result *r, char *blob, uint64_t blob_cap, uint64_t *text_off, int threads)
+{
+    // "%d%c" per run (reference src/genasm_gpu.cu:881-888), all alignments, all host threads: two passes over the
+    // packed runs (lengths, then characters).  The reference renders one alignment at a time through a stringstream.
+    if (!r || !text_off) return 0;
+    const uint64_t n = r->n;
+    if (threads < 1) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    text_off[0] = 0;
+    if (!r->has_cigar) {
+        for (uint64_t a = 0; a < n; a++) text_off[a + 1] = 0;
+        return 0;
+    }
+    auto parallel = [&](auto &&fn) {
+        const int nt = (int)std::min<uint64_t>((uint64_t)threads, std::max<uint64_t>(1, n / 1024));
+        if (nt <= 1) { fn(0, n); return; }
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) th.emplace_back([&, t]() { fn(n * t / nt, n * (t + 1) / nt); });
+        for (auto &x : th) x.join();
+    };
+    parallel([&](uint64_t a0, uint64_t a1) {
+        for (uint64_t a = a0; a < a1; a++) {
+            uint64_t cnt;
+            const uint8_t *p = runs_of(r, a, &cnt);
+            uint64_t len = 2 * cnt;
+            for (uint64_t k = 0; k < cnt; k++) len += SG_RUN_COUNT(p[k]) >= 10;
+            text_off[a + 1] = len;
+        }
+    });
+    for (uint64_t a = 0; a < n; a++) text_off[a + 1] += text_off[a];
+    const uint64_t total = text_off[n];
+    if (!blob || blob_cap < total) return total;  // sizes only: call again with a big enough blob
+    static const char ops[4] = {'=', 'X', 'I', 'D'};
+    parallel([&](uint64_t a0, uint64_t a1) {
+        for (uint64_t a = a0; a < a1; a++) {
+            uint64_t cnt;
+            const uint8_t *p = runs_of(r, a, &cnt);
+            char *o = blob + text_off[a];
+            for (uint64_t k = 0; k < cnt; k++) {
+                const unsigned c = SG_RUN_COUNT(p[k]);
+                if (c >= 10) *o++ = (char)('0' + c / 10);
+                *o++ = (char)('0' + c % 10);
+                *o++ = ops[SG_RUN_OP(p[k])];
+            }
+        }
+    });
+    return total;
+}
+
 void sg_result_free(sg_result *r) { delete r; }
 
 void *sg_host_alloc(uint64_t bytes)

@@ -75,3 +75,47 @@ SG_HD uint64_t sg_synth_pair(const SgSynthParams &p, uint64_t pair, char *text, 
     }
     return tl;
 }
+
+// i.i.d. uniform genome base number `i` of genome `seed` (stateless, so any thread can produce any stretch)
+SG_HD char sg_synth_genome_base(uint64_t seed, uint64_t i)
+{
+    uint64_t st = seed ^ ((i >> 5) * 0x9FB21C651E98DF25ull);
+    const uint64_t r = sg_splitmix64(st);  // 32 bases per draw
+    const char bases[4] = {'A', 'C', 'G', 'T'};
+    return bases[(r >> (2 * (i & 31))) & 3u];
+}
+
+// Read `idx` of a read-mapping workload (BASELINE.json configs[3]): sampled at a uniform position of the genome and
+// mutated like sg_synth_pair.  Returns the true start position.  genome_len must exceed 2 * read_len + 64.
+SG_HD uint64_t sg_synth_read_from_genome(const SgSynthParams &p, uint64_t idx, const char *genome, uint64_t genome_len, char *read)
+{
+    const char bases[4] = {'A', 'C', 'G', 'T'};
+    uint64_t state = p.seed ^ (idx * 0xD1342543DE82EF95ull + 0x632BE59BD9B4E019ull);
+    sg_splitmix64(state);
+    const uint64_t span = genome_len - 2ull * p.read_len - 64ull;
+    const uint64_t pos = sg_splitmix64(state) % span;
+    const uint32_t wsum = p.w_sub + p.w_ins + p.w_del;
+    uint64_t t = pos;
+    uint32_t rl = 0;
+    while (rl < p.read_len) {
+        const uint64_t r = sg_splitmix64(state);
+        const bool room = t + 1 < pos + 2ull * p.read_len;  // the walk never leaves [pos, pos + 2L)
+        const char g = genome[t];
+        uint32_t tb = g == 'A' ? 0u : (g == 'C' ? 1u : (g == 'G' ? 2u : 3u));
+        bool edit = (uint32_t)(r >> 32) < p.err_threshold && wsum > 0;
+        const uint32_t pick = edit ? (uint32_t)((r >> 8) & 0xFFFFFFu) % wsum : 0u;
+        if (edit && pick >= p.w_sub + p.w_ins && !room) edit = false;
+        if (!edit) {
+            read[rl++] = bases[tb];
+            if (room) t++;
+        } else if (pick < p.w_sub) {
+            read[rl++] = bases[(tb + 1u + (uint32_t)((r >> 4) & 0xFu) % 3u) & 3u];
+            if (room) t++;
+        } else if (pick < p.w_sub + p.w_ins) {
+            read[rl++] = bases[(r >> 2) & 3u];
+        } else {
+            t++;
+        }
+    }
+    return pos;
+}
