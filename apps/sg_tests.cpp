@@ -161,6 +161,42 @@ static int gpu_algorithm_performance_test(const string &reference_file, const st
     return failures ? 1 : 0;
 }
 
+// Synthetic end-to-end run of the drop-in C++ interface (BASELINE.json configs[2] shape): n pairs of 10 kbp reads at 10 %,
+// std::vector<std::string> in, std::vector<Alignment_t> (rendered CIGAR strings) out, every CIGAR validated.
+static int synthetic_performance_test(uint64_t n_pairs, uint32_t read_len)
+{
+    const uint64_t stride = sg_synth_text_stride(read_len, 64);
+    vector<char> text(n_pairs * stride), rd(n_pairs * (uint64_t)read_len);
+    vector<uint64_t> tlen(n_pairs);
+    sg_synth_pairs_host(0x5C2006E + 3, 0, n_pairs, read_len, 0.10, 6, 50, 54, 64, text.data(), stride, tlen.data(), rd.data());
+    vector<string> texts(n_pairs), queries(n_pairs);
+    for (uint64_t p = 0; p < n_pairs; p++) {
+        texts[p].assign(text.data() + p * stride, tlen[p]);
+        queries[p].assign(rd.data() + p * read_len, read_len);
+    }
+    vector<char>().swap(text);
+    vector<char>().swap(rd);
+    vector<Alignment_t> alignments;
+    long long core_ns = 0, best_ns = 0;
+    for (int rep = 0; rep < 3; rep++) {  // the first call also creates the context and sizes its buffers
+        const long long ns = measure_ns([&]() { alignments = genasm_gpu::align_all(texts, queries, &core_ns); });
+        if (rep == 0 || ns < best_ns) best_ns = ns;
+        cout << "align_all() took " << (ns / 1000000) << "ms (data transfers, conversion, gpu kernel and post-processing), GPU kernel "
+             << (core_ns / 1000000) << "ms" << endl;
+    }
+    size_t failures = 0;
+    Genome_t g;
+    for (uint64_t p = 0; p < n_pairs; p += 97) {
+        g.content = texts[p];
+        CandidateLocation_t loc{};
+        Read_t r{"", queries[p], {}};
+        if (!validate_cigar(alignments[p], loc, r, g).empty()) failures++;
+    }
+    cout << "end to end " << (long long)((double)n_pairs * 1e9 / (double)best_ns) << " aligns/second, GPU kernel "
+         << (long long)((double)n_pairs * 1e9 / (double)core_ns) << " aligns/second, " << failures << " failed the sanity check" << endl;
+    return failures ? 1 : 0;
+}
+
 static void dump_inputs(const string &reference_file, const string &reads_file, const string &seeds_file)
 {
     Genome_t genome;
@@ -184,13 +220,16 @@ int main(int argc, char **argv)
     const bool verbose = OPT_EXISTS == get_cmd_option(argc, argv, "--verbose");
     const bool unit_tests = OPT_EXISTS == get_cmd_option(argc, argv, "--unit_tests");
     const bool dump = OPT_EXISTS == get_cmd_option(argc, argv, "--dump_inputs");
+    string synthetic;
+    const int has_synth = get_cmd_option(argc, argv, "--synthetic", synthetic);
     bool help = false;
     help |= OPT_INVALID == get_cmd_option(argc, argv, "--reference", reference_file);
     help |= OPT_INVALID == get_cmd_option(argc, argv, "--reads", reads_file);
     help |= OPT_INVALID == get_cmd_option(argc, argv, "--seeds", seeds_file);
     for (const char *flag : {"--gpu_info_only", "--verbose", "--unit_tests", "--dump_inputs"}) help |= OPT_INVALID == get_cmd_option(argc, argv, flag);
     help |= OPT_MISSING != get_cmd_option(argc, argv, "--help");
-    help |= !check_options(argc, argv, {"--reference", "--reads", "--seeds", "--help", "--gpu_info_only", "--verbose", "--unit_tests", "--dump_inputs"});
+    help |= has_synth == OPT_INVALID;
+    help |= !check_options(argc, argv, {"--reference", "--reads", "--seeds", "--help", "--gpu_info_only", "--verbose", "--unit_tests", "--dump_inputs", "--synthetic"});
     if (help) {
         cout << "sg_tests [options]\n"
                 "Options:\n"
@@ -201,6 +240,7 @@ int main(int argc, char **argv)
                 "--verbose                             -- print progress to stderr\n"
                 "--unit_tests                          -- run unit tests (default: performance test)\n"
                 "--dump_inputs                         -- parse the input files and print them (no GPU needed)\n"
+                "--synthetic=[pairs]                   -- end-to-end run of align_all() on synthetic 10 kbp / 10 % pairs\n"
                 "--help                                -- displays this information\n";
         return 0;
     }
@@ -210,6 +250,7 @@ int main(int argc, char **argv)
     try {
         if (dump) { dump_inputs(reference_file, reads_file, seeds_file); return 0; }
         print_gpu_info();
+        if (has_synth == OPT_EXISTS) return synthetic_performance_test(strtoull(synthetic.c_str(), nullptr, 10), 10000);
         if (unit_tests) {
             ascii_to_two_bit_correctness_test();
             gpu_algorithm_correctness_test();

@@ -79,6 +79,11 @@ int sg_ctx_num_devices(const sg_ctx *ctx);
  * Results come back in input order in *out (release with sg_result_free). */
 int sg_align_pairs(sg_ctx *ctx, const char *text_blob, const uint64_t *text_off, const char *query_blob,
                    const uint64_t *query_off, uint64_t n_pairs, uint32_t flags, sg_result **out);
+/* The same over separate strings (pointer + length per string, e.g. the data() / size() of the std::strings of the
+ * reference's std::vector<std::string> arguments): nothing is flattened, every string is packed in place by the host
+ * threads (or gathered into pinned staging for the device ingest). */
+int sg_align_pairs_v(sg_ctx *ctx, const char *const *texts, const uint64_t *text_len, const char *const *queries,
+                     const uint64_t *query_len, uint64_t n_pairs, uint32_t flags, sg_result **out);
 
 /* Read-mapping interface (reference src/genasm_gpu.cu:890-980).  sg_set_reference packs the genome to
  * 2 bit/base once and replicates it into every GPU's HBM (reference twobit_reference, :692-748).
@@ -89,6 +94,9 @@ int sg_set_reference(sg_ctx *ctx, const char *genome_ascii, uint64_t genome_len)
 int sg_align_candidates(sg_ctx *ctx, const char *read_blob, const uint64_t *read_off, uint64_t n_reads,
                         const uint64_t *cand_start, const uint32_t *cand_read, uint64_t n_cand,
                         uint32_t flags, sg_result **out);
+int sg_align_candidates_v(sg_ctx *ctx, const char *const *reads, const uint64_t *read_len, uint64_t n_reads,
+                          const uint64_t *cand_start, const uint32_t *cand_read, uint64_t n_cand,
+                          uint32_t flags, sg_result **out);
 
 /* Result accessors.  All pointers stay valid until sg_result_free. */
 uint64_t sg_result_count(const sg_result *r);

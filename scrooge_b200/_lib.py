@@ -33,8 +33,10 @@ SIGNATURES = {
     "sg_ctx_destroy": (None, [vp]),
     "sg_ctx_num_devices": (i32, [vp]),
     "sg_align_pairs": (i32, [vp, vp, vp, vp, vp, u64, u32, C.POINTER(vp)]),
+    "sg_align_pairs_v": (i32, [vp, vp, vp, vp, vp, u64, u32, C.POINTER(vp)]),
     "sg_set_reference": (i32, [vp, vp, u64]),
     "sg_align_candidates": (i32, [vp, vp, vp, u64, vp, vp, u64, u32, C.POINTER(vp)]),
+    "sg_align_candidates_v": (i32, [vp, vp, vp, u64, vp, vp, u64, u32, C.POINTER(vp)]),
     "sg_result_count": (u64, [vp]),
     "sg_result_edit_distances": (vp, [vp]),
     "sg_result_ref_consumed": (vp, [vp]),

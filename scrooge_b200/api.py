@@ -170,6 +170,36 @@ class Aligner:
         qblob, qoff = _blob(queries)
         return self.align_pairs_blob(tblob, toff, qblob, qoff, distance_only)
 
+    def align_pairs_v(self, texts: Sequence[Union[str, bytes]], queries: Sequence[Union[str, bytes]],
+                      distance_only: bool = False) -> Result:
+        """Same as align_pairs through the vectored entry point (sg_align_pairs_v): one pointer + length per string,
+        nothing is concatenated -- the form the C++ drop-in uses for std::vector<std::string>."""
+        if len(texts) != len(queries):
+            raise ValueError("texts and queries differ in size")
+        tb = [t.encode() if isinstance(t, str) else bytes(t) for t in texts]
+        qb = [q.encode() if isinstance(q, str) else bytes(q) for q in queries]
+        n = len(tb)
+        tp = (C.c_char_p * max(n, 1))(*tb)
+        qp = (C.c_char_p * max(n, 1))(*qb)
+        tl = np.asarray([len(b) for b in tb], dtype=np.uint64)
+        ql = np.asarray([len(b) for b in qb], dtype=np.uint64)
+        out = C.c_void_p()
+        check(lib().sg_align_pairs_v(self._h, C.cast(tp, C.c_void_p), tl.ctypes.data, C.cast(qp, C.c_void_p), ql.ctypes.data, n,
+                                     SG_FLAG_DISTANCE_ONLY if distance_only else 0, C.byref(out)))
+        return Result(out)
+
+    def align_candidates_v(self, reads: Sequence[Union[str, bytes]], cand_start: Sequence[int], cand_read: Sequence[int],
+                           distance_only: bool = False) -> Result:
+        rb = [r.encode() if isinstance(r, str) else bytes(r) for r in reads]
+        rp = (C.c_char_p * max(len(rb), 1))(*rb)
+        rl = np.asarray([len(b) for b in rb], dtype=np.uint64)
+        cs = np.ascontiguousarray(cand_start, dtype=np.uint64)
+        cr = np.ascontiguousarray(cand_read, dtype=np.uint32)
+        out = C.c_void_p()
+        check(lib().sg_align_candidates_v(self._h, C.cast(rp, C.c_void_p), rl.ctypes.data, len(rb), cs.ctypes.data, cr.ctypes.data,
+                                          len(cs), SG_FLAG_DISTANCE_ONLY if distance_only else 0, C.byref(out)))
+        return Result(out)
+
     def set_reference(self, genome: Union[str, bytes, np.ndarray]) -> None:
         g = genome.encode() if isinstance(genome, str) else genome
         check(lib().sg_set_reference(self._h, _ptr(g), len(g)))

@@ -65,14 +65,12 @@ std::vector<Alignment_t> collect(sg_result *res, Extra *extra, long long *core_a
     const int64_t *ed = sg_result_edit_distances(res);
     const uint64_t *rc = sg_result_ref_consumed(res);
     if (extra) extra->ref_consumed.resize(n);
-    // one multi-threaded pass renders every CIGAR text; the strings are then cut out of the blob
-    std::vector<uint64_t> off(n + 1);
-    const uint64_t total = sg_result_render_all(res, nullptr, 0, off.data(), 0);
-    std::string blob(total, '\0');
-    sg_result_render_all(res, &blob[0], total, off.data(), 0);
-#pragma omp parallel for schedule(static)
+    // every string is sized and rendered in place, all host threads at once
+#pragma omp parallel for schedule(dynamic, 64)
     for (long long i = 0; i < (long long)n; i++) {
-        out[i].cigar.assign(blob, off[i], off[i + 1] - off[i]);
+        const uint64_t len = sg_result_cigar_len(res, (uint64_t)i);
+        out[i].cigar.resize(len);
+        if (len) sg_result_render_cigar(res, (uint64_t)i, &out[i].cigar[0], len + 1);  // the string owns the NUL slot
         out[i].edit_distance = ed[i];
         if (extra) extra->ref_consumed[i] = rc[i];
     }
@@ -85,16 +83,11 @@ std::vector<Alignment_t> collect(sg_result *res, Extra *extra, long long *core_a
     return out;
 }
 
-void flatten(const std::vector<std::string> &v, std::string &blob, std::vector<uint64_t> &off)
+void views(const std::vector<std::string> &v, std::vector<const char *> &ptr, std::vector<uint64_t> &len)
 {
-    off.resize(v.size() + 1);
-    uint64_t total = 0;
-    for (size_t i = 0; i < v.size(); i++) { off[i] = total; total += v[i].size(); }
-    off[v.size()] = total;
-    blob.resize(total);
-#pragma omp parallel for schedule(static)
-    for (long long i = 0; i < (long long)v.size(); i++)
-        if (!v[i].empty()) std::memcpy(&blob[off[i]], v[i].data(), v[i].size());
+    ptr.resize(v.size());
+    len.resize(v.size());
+    for (size_t i = 0; i < v.size(); i++) { ptr[i] = v[i].data(); len[i] = v[i].size(); }
 }
 
 std::vector<Alignment_t> pairs_impl(std::vector<std::string> &texts, std::vector<std::string> &queries, Extra *extra,
@@ -105,12 +98,13 @@ std::vector<Alignment_t> pairs_impl(std::vector<std::string> &texts, std::vector
     std::lock_guard<std::mutex> lock(g_mutex);
     sg_ctx *ctx = context();
     if (enabled_algorithm_log) std::cerr << "Preparing data..." << std::endl;
-    std::string tblob, qblob;
-    std::vector<uint64_t> toff, qoff;
-    flatten(texts, tblob, toff);
-    flatten(queries, qblob, qoff);
+    // the strings are handed over where they lie (pointer + length); nothing is flattened or copied on this side
+    std::vector<const char *> tptr, qptr;
+    std::vector<uint64_t> tlen, qlen;
+    views(texts, tptr, tlen);
+    views(queries, qptr, qlen);
     sg_result *res = nullptr;
-    check(sg_align_pairs(ctx, tblob.data(), toff.data(), qblob.data(), qoff.data(), texts.size(), 0, &res));
+    check(sg_align_pairs_v(ctx, tptr.data(), tlen.data(), qptr.data(), qlen.data(), texts.size(), 0, &res));
     return collect(res, extra, core_algorithm_ns);
 }
 
@@ -120,17 +114,15 @@ std::vector<Alignment_t> mapping_impl(Genome_t &reference, std::vector<Read_t> &
     sg_ctx *ctx = context();
     if (enabled_algorithm_log) std::cerr << "Preparing data..." << std::endl;
     check(sg_set_reference(ctx, reference.content.data(), reference.content.size()));
-    std::vector<uint64_t> roff(reads.size() + 1);
-    uint64_t total = 0, n_cand = 0;
-    for (size_t r = 0; r < reads.size(); r++) { roff[r] = total; total += reads[r].content.size(); n_cand += reads[r].locations.size(); }
-    roff[reads.size()] = total;
-    std::string rblob(total, '\0');
+    std::vector<const char *> rptr(reads.size());
+    std::vector<uint64_t> rlen(reads.size());
+    uint64_t n_cand = 0;
+    for (size_t r = 0; r < reads.size(); r++) { rptr[r] = reads[r].content.data(); rlen[r] = reads[r].content.size(); n_cand += reads[r].locations.size(); }
     std::vector<uint64_t> cstart;
     std::vector<uint32_t> cread;
     cstart.reserve(n_cand);
     cread.reserve(n_cand);
     for (size_t r = 0; r < reads.size(); r++) {
-        if (!reads[r].content.empty()) std::memcpy(&rblob[roff[r]], reads[r].content.data(), reads[r].content.size());
         for (const CandidateLocation_t &loc : reads[r].locations) {  // read-major, then location order (src/genasm_gpu.cu:961-967)
             if (loc.start_in_reference < 0) throw std::runtime_error("scrooge_b200: negative start_in_reference");
             cstart.push_back((uint64_t)loc.start_in_reference);
@@ -138,7 +130,7 @@ std::vector<Alignment_t> mapping_impl(Genome_t &reference, std::vector<Read_t> &
         }
     }
     sg_result *res = nullptr;
-    check(sg_align_candidates(ctx, rblob.data(), roff.data(), reads.size(), cstart.data(), cread.data(), n_cand, 0, &res));
+    check(sg_align_candidates_v(ctx, rptr.data(), rlen.data(), reads.size(), cstart.data(), cread.data(), n_cand, 0, &res));
     return collect(res, extra, core_algorithm_ns);
 }
 

@@ -134,41 +134,7 @@ struct PinnedPool {
 };
 static PinnedPool g_pool;
 
-// descriptors from offset arrays: start[a] = off[a] - off[0], len[a] = off[a+1]-off[a], slab offsets
-__global__ void __launch_bounds__(256) pair_descriptors_kernel(const uint64_t *__restrict__ toff, const uint64_t *__restrict__ qoff,
-                                                                uint64_t n, uint64_t *__restrict__ tstart, uint64_t *__restrict__ tlen,
-                                                                uint64_t *__restrict__ qstart, uint64_t *__restrict__ qlen,
-                                                                uint64_t *__restrict__ slab_off)
-{
-    const uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (a > n) return;
-    const uint64_t q0 = qoff[0];
-    slab_off[a] = 2ull * (qoff[a] - q0) + 8ull * a;
-    if (a == n) return;
-    tstart[a] = toff[a] - toff[0];
-    tlen[a] = toff[a + 1] - toff[a];
-    qstart[a] = qoff[a] - q0;
-    qlen[a] = qoff[a + 1] - qoff[a];
-}
-
-// mapping mode: candidate c -> text = genome suffix at cand_start[c], query = read cand_read[c]
-__global__ void __launch_bounds__(256) cand_descriptors_kernel(const uint64_t *__restrict__ cand_start, const uint32_t *__restrict__ cand_read,
-                                                                const uint64_t *__restrict__ roff, uint32_t read_base, uint64_t genome_len, uint64_t n,
-                                                                uint64_t *__restrict__ tstart, uint64_t *__restrict__ tlen,
-                                                                uint64_t *__restrict__ qstart, uint64_t *__restrict__ qlen,
-                                                                uint32_t *__restrict__ cap32)
-{
-    const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
-    const uint64_t s = cand_start[c];
-    const uint32_t r = cand_read[c] - read_base;
-    tstart[c] = s;
-    tlen[c] = genome_len - s;  // the text runs to the end of the genome (src/genasm_cpu.cpp:512-514)
-    qstart[c] = roff[r] - roff[0];
-    const uint64_t ql = roff[r + 1] - roff[r];
-    qlen[c] = ql;
-    cap32[c] = (uint32_t)(2ull * ql + 8ull);  // slab capacity; scanned into slab offsets
-}
+extern "C" uint64_t sg_host_pack_2bit_st(const char *ascii, uint64_t n_bases, uint32_t *packed);
 
 constexpr int kSlots = 3;
 
@@ -176,9 +142,8 @@ constexpr int kSlots = 3;
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_mid = nullptr, ev_end = nullptr;
-    DevBuf ascii_t, ascii_q, packed_t, packed_q, toff, qoff, tstart, tlen, qstart, qlen, slab_off, slab, counter, edit,
-        refc, nruns, status, run_off, scan_tmp, runs, bad, cstart, cread, cap32;
-    PinBuf h_small, h_edit, h_refc, h_runoff, h_status, h_packed_t, h_packed_q;
+    DevBuf ascii_t, ascii_q, packed_t, packed_q, desc, slab, counter, edit, refc, nruns, status, run_off, scan_tmp, runs, bad;
+    PinBuf h_small, h_edit, h_refc, h_runoff, h_status, h_stage_t, h_stage_q, h_desc;
     PinnedPool::Block piece{nullptr, 0};
     // the batch in flight
     bool busy = false, mid_done = false;
@@ -194,10 +159,10 @@ struct Slot {
     }
     void destroy()
     {
-        for (DevBuf *b : {&ascii_t, &ascii_q, &packed_t, &packed_q, &toff, &qoff, &tstart, &tlen, &qstart, &qlen, &slab_off,
-                          &slab, &counter, &edit, &refc, &nruns, &status, &run_off, &scan_tmp, &runs, &bad, &cstart, &cread, &cap32})
+        for (DevBuf *b : {&ascii_t, &ascii_q, &packed_t, &packed_q, &desc, &slab, &counter, &edit, &refc, &nruns, &status, &run_off,
+                          &scan_tmp, &runs, &bad})
             b->release();
-        for (PinBuf *b : {&h_small, &h_edit, &h_refc, &h_runoff, &h_status, &h_packed_t, &h_packed_q}) b->release();
+        for (PinBuf *b : {&h_small, &h_edit, &h_refc, &h_runoff, &h_status, &h_stage_t, &h_stage_q, &h_desc}) b->release();
         g_pool.release(piece);
         piece = {nullptr, 0};
         if (ev_k0) cudaEventDestroy(ev_k0);
@@ -264,48 +229,93 @@ struct ShardOut {
     ~ShardOut() { for (auto &b : pieces) g_pool.release(b); }
 };
 
-// What differs between the two interfaces: how a sub-batch's inputs get to the device.
+// n strings, given either as one blob + n+1 offsets or as n pointers + n lengths (no flattening needed)
+struct Strings {
+    const char *blob = nullptr; const uint64_t *off = nullptr;
+    const char *const *ptr = nullptr; const uint64_t *len = nullptr;
+    const char *data(uint64_t i) const { return ptr ? ptr[i] : blob + off[i]; }
+    uint64_t size(uint64_t i) const { return ptr ? len[i] : off[i + 1] - off[i]; }
+};
+
+// What differs between the two interfaces: where a sub-batch's texts and queries come from.
 struct Workload {
     bool mapping = false;
-    // pairs
-    const char *tb = nullptr; const uint64_t *toff = nullptr; const char *qb = nullptr; const uint64_t *qoff = nullptr;
-    // mapping
-    const char *rb = nullptr; const uint64_t *roff = nullptr; const uint64_t *cand_start = nullptr; const uint32_t *cand_read = nullptr;
-    const uint64_t *woff = nullptr;  // per-candidate query-length prefix sums
+    Strings text, query;   // pairs: text p / query p.  mapping: `query` holds the reads, the text is the resident genome
+    const uint64_t *cand_start = nullptr; const uint32_t *cand_read = nullptr;
     uint32_t flags = 0;
 };
 
 #define R(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
 
-// One ASCII blob -> packed words on the device, through the device ingest kernel or through the host packer.
-// *bad_pos receives the first offending position when the host packer finds one (the device path reports through
-// d_bad after the fact).
-int upload_packed(sg_ctx *ctx, cudaStream_t st, const char *ascii, uint64_t nbytes, DevBuf &d_ascii, DevBuf &d_packed, PinBuf &h_packed,
-                  uint64_t *d_bad, uint64_t *bad_pos)
+int bad_base_error(const char *what, const char *unit, uint64_t index, uint64_t pos)
 {
-    const uint64_t words = sg_packed_words(nbytes);
-    R(d_packed.reserve(words * 4));
-    if (ctx->host_pack) {
-        R(h_packed.reserve(words * 4));
-        uint32_t *hp = h_packed.as<uint32_t>();
+    // names the offender like the reference's assert would have stopped on it (src/genasm_gpu.cu:636)
+    return fail(SG_ERR_BAD_BASE, std::string("non-ACGT character in ") + what + " of " + unit + " " + std::to_string(index) + " at position " +
+                                     std::to_string(pos));
+}
+
+// Strings [i0, i1) -> packed words on the device; start[k] receives the first base of string i0+k in the packed blob.
+//   host_pack: packed by the host threads straight into pinned staging (a blob as one stream, separate strings each
+//              at a word boundary), a quarter of the bytes cross PCIe;
+//   else:      ASCII crosses PCIe (a blob straight from the caller's memory, separate strings gathered into pinned
+//              staging first) and pack_2bit_kernel packs it; an offending base is then reported through d_bad.
+int upload_strings(sg_ctx *ctx, cudaStream_t st, const Strings &S, uint64_t i0, uint64_t i1, const char *what, const char *unit,
+                   DevBuf &d_ascii, DevBuf &d_packed, PinBuf &h_stage, uint64_t *d_bad, uint64_t *start)
+{
+    const uint64_t n = i1 - i0;
+    const int threads = ctx->host_threads;
+    if (S.blob) {
+        const uint64_t base = S.off[i0], nbytes = S.off[i1] - base;
+        for (uint64_t k = 0; k < n; k++) start[k] = S.off[i0 + k] - base;
+        const uint64_t words = sg_packed_words(nbytes);
+        R(d_packed.reserve(words * 4));
+        if (!ctx->host_pack) {
+            R(d_ascii.reserve(nbytes + 64));
+            SG_CUDA(cudaMemcpyAsync(d_ascii.p, S.blob + base, nbytes, cudaMemcpyHostToDevice, st));
+            return sg_dev_pack_2bit(d_ascii.as<char>(), nbytes, d_packed.as<uint32_t>(), d_bad, st);
+        }
+        R(h_stage.reserve(words * 4));
+        uint32_t *hp = h_stage.as<uint32_t>();
         const uint64_t used = (nbytes + 15) / 16;
-        const uint64_t bad = sg_host_pack_2bit(ascii, nbytes, hp, ctx->host_threads);
+        const uint64_t bad = sg_host_pack_2bit(S.blob + base, nbytes, hp, threads);
+        if (bad != ~0ull) {
+            const uint64_t i = (uint64_t)(std::upper_bound(S.off + i0, S.off + i1 + 1, base + bad) - S.off) - 1;
+            return bad_base_error(what, unit, i, base + bad - S.off[i]);
+        }
         memset(hp + used, 0, (words - used) * 4);  // padding words the aligner may read
-        if (bad != ~0ull) { *bad_pos = bad; return SG_OK; }
         SG_CUDA(cudaMemcpyAsync(d_packed.p, hp, words * 4, cudaMemcpyHostToDevice, st));
         return SG_OK;
     }
-    R(d_ascii.reserve(nbytes + 64));
-    SG_CUDA(cudaMemcpyAsync(d_ascii.p, ascii, nbytes, cudaMemcpyHostToDevice, st));
-    return sg_dev_pack_2bit(d_ascii.as<char>(), nbytes, d_packed.as<uint32_t>(), d_bad, st);
-}
-
-// error text for an offending base at `pos` of a blob whose strings start at off[first..last]
-int bad_base_error(const char *what, const char *unit, const uint64_t *off, uint64_t first, uint64_t last, uint64_t pos)
-{
-    const uint64_t p = (uint64_t)(std::upper_bound(off + first, off + last + 1, pos) - off) - 1;
-    return fail(SG_ERR_BAD_BASE, std::string("non-ACGT character in ") + what + " of " + unit + " " + std::to_string(p) + " at position " +
-                                     std::to_string(pos - off[p]));
+    if (ctx->host_pack) {
+        uint64_t w = 0;
+        for (uint64_t k = 0; k < n; k++) { start[k] = w * 16; w += (S.len[i0 + k] + 15) / 16; }
+        const uint64_t words = w + 8;
+        R(d_packed.reserve(words * 4));
+        R(h_stage.reserve(words * 4));
+        uint32_t *hp = h_stage.as<uint32_t>();
+        uint64_t bad_k = ~0ull;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(threads) reduction(min : bad_k)
+        for (long long k = 0; k < (long long)n; k++)
+            if (sg_host_pack_2bit_st(S.ptr[i0 + k], S.len[i0 + k], hp + start[k] / 16) != ~0ull) bad_k = std::min<uint64_t>(bad_k, (uint64_t)k);
+        if (bad_k != ~0ull) {
+            std::vector<uint32_t> tmp((S.len[i0 + bad_k] + 15) / 16 + 1);
+            return bad_base_error(what, unit, i0 + bad_k, sg_host_pack_2bit_st(S.ptr[i0 + bad_k], S.len[i0 + bad_k], tmp.data()));
+        }
+        memset(hp + w, 0, 8 * 4);
+        SG_CUDA(cudaMemcpyAsync(d_packed.p, hp, words * 4, cudaMemcpyHostToDevice, st));
+        return SG_OK;
+    }
+    uint64_t bytes = 0;
+    for (uint64_t k = 0; k < n; k++) { start[k] = bytes; bytes += S.len[i0 + k]; }
+    R(h_stage.reserve(bytes + 64));
+    R(d_ascii.reserve(bytes + 64));
+    R(d_packed.reserve(sg_packed_words(bytes) * 4));
+    char *ha = h_stage.as<char>();
+#pragma omp parallel for schedule(dynamic, 16) num_threads(threads)
+    for (long long k = 0; k < (long long)n; k++)
+        if (S.len[i0 + k]) memcpy(ha + start[k], S.ptr[i0 + k], S.len[i0 + k]);
+    SG_CUDA(cudaMemcpyAsync(d_ascii.p, ha, bytes, cudaMemcpyHostToDevice, st));
+    return sg_dev_pack_2bit(d_ascii.as<char>(), bytes, d_packed.as<uint32_t>(), d_bad, st);
 }
 
 // stage A: uploads, ingest, descriptors, alignment kernel, run-count scan; ends with ev_mid
@@ -315,59 +325,49 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
     const bool want_cigar = !(w.flags & SG_FLAG_DISTANCE_ONLY);
     cudaStream_t st = s.stream;
     s.a0 = a0; s.a1 = a1; s.busy = true; s.mid_done = false; s.total_runs = 0;
-    R(s.tstart.reserve(n * 8)); R(s.tlen.reserve(n * 8)); R(s.qstart.reserve(n * 8)); R(s.qlen.reserve(n * 8));
-    R(s.slab_off.reserve((n + 1) * 8)); R(s.counter.reserve(8)); R(s.edit.reserve(n * 8)); R(s.refc.reserve(n * 8));
+    R(s.desc.reserve((5 * n + 1) * 8)); R(s.h_desc.reserve((5 * n + 1) * 8));
+    R(s.counter.reserve(8)); R(s.edit.reserve(n * 8)); R(s.refc.reserve(n * 8));
     R(s.nruns.reserve(n * 4)); R(s.status.reserve(n)); R(s.run_off.reserve((n + 1) * 8));
     R(s.scan_tmp.reserve(sg_scan_tmp_bytes(n))); R(s.bad.reserve(16)); R(s.h_small.reserve(64));
     R(s.h_edit.reserve(n * 8)); R(s.h_refc.reserve(n * 8)); R(s.h_runoff.reserve((n + 1) * 8)); R(s.h_status.reserve(n));
     SG_CUDA(cudaMemsetAsync(s.bad.p, 0xFF, 16, st));
-    const uint32_t *d_text, *d_query;
-    uint64_t slab_bytes;
+    // descriptors are built on the host: [tstart | tlen | qstart | qlen | slab_off (n+1)]
+    uint64_t *h_tstart = s.h_desc.as<uint64_t>(), *h_tlen = h_tstart + n, *h_qstart = h_tlen + n, *h_qlen = h_qstart + n, *h_slab = h_qlen + n;
+    uint64_t *d_tstart = s.desc.as<uint64_t>(), *d_tlen = d_tstart + n, *d_qstart = d_tlen + n, *d_qlen = d_qstart + n, *d_slab = d_qlen + n;
+    const uint32_t *d_text;
     if (!w.mapping) {
-        const uint64_t tbytes = w.toff[a1] - w.toff[a0], qbytes = w.qoff[a1] - w.qoff[a0];
-        R(s.toff.reserve((n + 1) * 8)); R(s.qoff.reserve((n + 1) * 8));
-        slab_bytes = 2ull * qbytes + 8ull * n;
-        uint64_t bad_t = ~0ull, bad_q = ~0ull;
-        R(upload_packed(ctx, st, w.tb + w.toff[a0], tbytes, s.ascii_t, s.packed_t, s.h_packed_t, s.bad.as<uint64_t>(), &bad_t));
-        if (bad_t != ~0ull) return bad_base_error("text", "pair", w.toff, a0, a1, bad_t + w.toff[a0]);
-        R(upload_packed(ctx, st, w.qb + w.qoff[a0], qbytes, s.ascii_q, s.packed_q, s.h_packed_q, s.bad.as<uint64_t>() + 1, &bad_q));
-        if (bad_q != ~0ull) return bad_base_error("query", "pair", w.qoff, a0, a1, bad_q + w.qoff[a0]);
-        SG_CUDA(cudaMemcpyAsync(s.toff.p, w.toff + a0, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-        SG_CUDA(cudaMemcpyAsync(s.qoff.p, w.qoff + a0, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-        pair_descriptors_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(
-            s.toff.as<uint64_t>(), s.qoff.as<uint64_t>(), n, s.tstart.as<uint64_t>(), s.tlen.as<uint64_t>(),
-            s.qstart.as<uint64_t>(), s.qlen.as<uint64_t>(), s.slab_off.as<uint64_t>());
-        SG_CUDA(cudaGetLastError());
+        R(upload_strings(ctx, st, w.text, a0, a1, "text", "pair", s.ascii_t, s.packed_t, s.h_stage_t, s.bad.as<uint64_t>(), h_tstart));
+        R(upload_strings(ctx, st, w.query, a0, a1, "query", "pair", s.ascii_q, s.packed_q, s.h_stage_q, s.bad.as<uint64_t>() + 1, h_qstart));
+        for (uint64_t k = 0; k < n; k++) { h_tlen[k] = w.text.size(a0 + k); h_qlen[k] = w.query.size(a0 + k); }
         d_text = s.packed_t.as<uint32_t>();
-        d_query = s.packed_q.as<uint32_t>();
     } else {
-        // reads referenced by this sub-batch: the contiguous index range [r0, r1] (candidates arrive read-major,
-        // so the range is tight; each read is uploaded and packed once and shared by its candidates,
-        // cf. reference twobit_reads, src/genasm_gpu.cu:784-796)
+        // reads referenced by this sub-batch: the contiguous index range [r0, r1] (candidates arrive read-major, so the
+        // range is tight; each read is uploaded and packed once and shared by its candidates, cf. reference
+        // twobit_reads, src/genasm_gpu.cu:784-796)
         uint32_t r0 = w.cand_read[a0], r1 = w.cand_read[a0];
         for (uint64_t c = a0; c < a1; c++) { r0 = std::min(r0, w.cand_read[c]); r1 = std::max(r1, w.cand_read[c]); }
-        const uint64_t nr = (uint64_t)r1 - r0 + 1, rbytes = w.roff[r1 + 1] - w.roff[r0];
-        slab_bytes = 2ull * (w.woff[a1] - w.woff[a0]) + 8ull * n;
-        R(s.qoff.reserve((nr + 1) * 8)); R(s.cstart.reserve(n * 8)); R(s.cread.reserve(n * 4)); R(s.cap32.reserve(n * 4));
-        uint64_t bad_q = ~0ull;
-        R(upload_packed(ctx, st, w.rb + w.roff[r0], rbytes, s.ascii_q, s.packed_q, s.h_packed_q, s.bad.as<uint64_t>() + 1, &bad_q));
-        if (bad_q != ~0ull) return bad_base_error("content", "read", w.roff, r0, (uint64_t)r1 + 1, bad_q + w.roff[r0]);
-        SG_CUDA(cudaMemcpyAsync(s.qoff.p, w.roff + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, st));
-        SG_CUDA(cudaMemcpyAsync(s.cstart.p, w.cand_start + a0, n * 8, cudaMemcpyHostToDevice, st));
-        SG_CUDA(cudaMemcpyAsync(s.cread.p, w.cand_read + a0, n * 4, cudaMemcpyHostToDevice, st));
-        cand_descriptors_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-            s.cstart.as<uint64_t>(), s.cread.as<uint32_t>(), s.qoff.as<uint64_t>(), r0, d.genome_len, n, s.tstart.as<uint64_t>(),
-            s.tlen.as<uint64_t>(), s.qstart.as<uint64_t>(), s.qlen.as<uint64_t>(), s.cap32.as<uint32_t>());
-        SG_CUDA(cudaGetLastError());
-        R(sg_dev_scan_runs(s.cap32.as<uint32_t>(), n, s.slab_off.as<uint64_t>(), s.scan_tmp.p, st));
+        std::vector<uint64_t> rstart((uint64_t)r1 - r0 + 1);
+        R(upload_strings(ctx, st, w.query, r0, (uint64_t)r1 + 1, "content", "read", s.ascii_q, s.packed_q, s.h_stage_q,
+                         s.bad.as<uint64_t>() + 1, rstart.data()));
+        for (uint64_t k = 0; k < n; k++) {
+            const uint64_t cs = w.cand_start[a0 + k];
+            const uint32_t r = w.cand_read[a0 + k];
+            h_tstart[k] = cs;
+            h_tlen[k] = d.genome_len - cs;  // the text runs to the end of the genome (src/genasm_cpu.cpp:512-514)
+            h_qstart[k] = rstart[r - r0];
+            h_qlen[k] = w.query.size(r);
+        }
         d_text = d.genome.as<uint32_t>();
-        d_query = s.packed_q.as<uint32_t>();
     }
+    uint64_t slab_bytes = 0;
+    for (uint64_t k = 0; k < n; k++) { h_slab[k] = slab_bytes; slab_bytes += 2ull * h_qlen[k] + 8ull; }
+    h_slab[n] = slab_bytes;
+    SG_CUDA(cudaMemcpyAsync(s.desc.p, s.h_desc.p, (5 * n + 1) * 8, cudaMemcpyHostToDevice, st));
     if (want_cigar) R(s.slab.reserve(slab_bytes + 16));
     SG_CUDA(cudaEventRecord(s.ev_k0, st));
-    R(sg_dev_align(ctx->W, d_text, s.tstart.as<uint64_t>(), s.tlen.as<uint64_t>(), d_query, s.qstart.as<uint64_t>(),
-                   s.qlen.as<uint64_t>(), n, w.flags, s.slab.as<uint8_t>(), s.slab_off.as<uint64_t>(), s.counter.as<uint64_t>(),
-                   s.edit.as<int64_t>(), s.refc.as<uint64_t>(), s.nruns.as<uint32_t>(), s.status.as<uint8_t>(), nullptr, st));
+    R(sg_dev_align(ctx->W, d_text, d_tstart, d_tlen, s.packed_q.as<uint32_t>(), d_qstart, d_qlen, n, w.flags, s.slab.as<uint8_t>(), d_slab,
+                   s.counter.as<uint64_t>(), s.edit.as<int64_t>(), s.refc.as<uint64_t>(), s.nruns.as<uint32_t>(), s.status.as<uint8_t>(),
+                   nullptr, st));
     SG_CUDA(cudaEventRecord(s.ev_k1, st));
     uint64_t *h = s.h_small.as<uint64_t>();
     SG_CUDA(cudaMemcpyAsync(h, s.bad.p, 16, cudaMemcpyDeviceToHost, st));
@@ -393,15 +393,19 @@ int stage_b(Slot &s, const Workload &w)
     s.mid_done = true;
     const uint64_t *h = s.h_small.as<uint64_t>();
     if (h[0] != ~0ull || h[1] != ~0ull) {
-        // name the offender like the reference's assert would have stopped on it (src/genasm_gpu.cu:636)
+        // device ingest found an offending base at position h[] of the uploaded ASCII: find its string via the starts
+        const bool in_text = h[0] != ~0ull;
+        const uint64_t pos = in_text ? h[0] : h[1];
+        const uint64_t *hd = s.h_desc.as<uint64_t>();
         if (!w.mapping) {
-            const bool in_text = h[0] != ~0ull;
-            const uint64_t *off = in_text ? w.toff : w.qoff;
-            return bad_base_error(in_text ? "text" : "query", "pair", off, s.a0, s.a1, (in_text ? h[0] : h[1]) + off[s.a0]);
+            const uint64_t *start = in_text ? hd : hd + 2 * n;
+            const uint64_t k = (uint64_t)(std::upper_bound(start, start + n, pos) - start) - 1;
+            return bad_base_error(in_text ? "text" : "query", "pair", s.a0 + k, pos - start[k]);
         }
-        uint32_t r0 = w.cand_read[s.a0], r1 = r0;
-        for (uint64_t c = s.a0; c < s.a1; c++) { r0 = std::min(r0, w.cand_read[c]); r1 = std::max(r1, w.cand_read[c]); }
-        return bad_base_error("content", "read", w.roff, r0, (uint64_t)r1 + 1, h[1] + w.roff[r0]);
+        uint64_t best = 0, best_start = 0;  // candidates of one read share a start: pick the read with the largest start <= pos
+        for (uint64_t k = 0; k < n; k++)
+            if (hd[2 * n + k] <= pos && hd[2 * n + k] >= best_start) { best_start = hd[2 * n + k]; best = w.cand_read[s.a0 + k]; }
+        return bad_base_error("content", "read", best, pos - best_start);
     }
     if (want_cigar) {
         s.total_runs = h[2];
@@ -409,7 +413,7 @@ int stage_b(Slot &s, const Workload &w)
         g_pool.release(s.piece);
         s.piece = {nullptr, 0};
         R(g_pool.acquire(s.total_runs + 16, &s.piece));
-        R(sg_dev_gather_runs(s.slab.as<uint8_t>(), s.slab_off.as<uint64_t>(), s.nruns.as<uint32_t>(), s.run_off.as<uint64_t>(), n,
+        R(sg_dev_gather_runs(s.slab.as<uint8_t>(), s.desc.as<uint64_t>() + 4 * n, s.nruns.as<uint32_t>(), s.run_off.as<uint64_t>(), n,
                              s.runs.as<uint8_t>(), st));
         SG_CUDA(cudaMemcpyAsync(s.piece.p, s.runs.p, s.total_runs, cudaMemcpyDeviceToHost, st));
         SG_CUDA(cudaMemcpyAsync(s.h_runoff.p, s.run_off.p, n * 8, cudaMemcpyDeviceToHost, st));
@@ -627,17 +631,40 @@ void sg_ctx_destroy(sg_ctx *ctx)
 
 int sg_ctx_num_devices(const sg_ctx *ctx) { return ctx ? (int)ctx->devs.size() : 0; }
 
+static int align_pairs_common(sg_ctx *ctx, const Strings &text, const Strings &query, uint64_t n_pairs, uint32_t flags, sg_result **out)
+{
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    Workload w;
+    w.text = text; w.query = query; w.flags = flags;
+    // sub-batches are cut by uploaded bytes (text + query), shards by the same weight
+    std::vector<uint64_t> woff(n_pairs + 1);
+    woff[0] = 0;
+    for (uint64_t p = 0; p < n_pairs; p++) woff[p + 1] = woff[p] + text.size(p) + query.size(p);
+    return run_all(ctx, w, woff.data(), 48, n_pairs, out);
+}
+
 int sg_align_pairs(sg_ctx *ctx, const char *text_blob, const uint64_t *text_off, const char *query_blob,
                    const uint64_t *query_off, uint64_t n_pairs, uint32_t flags, sg_result **out)
 {
     if (!ctx || !out || !text_off || !query_off) return fail(SG_ERR_BAD_ARG, "sg_align_pairs: null argument");
-    std::lock_guard<std::mutex> lock(ctx->mu);
-    Workload w;
-    w.tb = text_blob; w.toff = text_off; w.qb = query_blob; w.qoff = query_off; w.flags = flags;
-    // sub-batches are cut by uploaded bytes (text + query), shards by the same weight
-    std::vector<uint64_t> woff(n_pairs + 1);
-    for (uint64_t p = 0; p <= n_pairs; p++) woff[p] = (text_off[p] - text_off[0]) + (query_off[p] - query_off[0]);
-    return run_all(ctx, w, woff.data(), 48, n_pairs, out);
+    Strings t, q;
+    t.blob = text_blob; t.off = text_off;
+    q.blob = query_blob; q.off = query_off;
+    return align_pairs_common(ctx, t, q, n_pairs, flags, out);
+}
+
+int sg_align_pairs_v(sg_ctx *ctx, const char *const *texts, const uint64_t *text_len, const char *const *queries,
+                     const uint64_t *query_len, uint64_t n_pairs, uint32_t flags, sg_result **out)
+{
+    if (!ctx || !out || (n_pairs && (!texts || !text_len || !queries || !query_len)))
+        return fail(SG_ERR_BAD_ARG, "sg_align_pairs_v: null argument");
+    Strings t, q;
+    t.ptr = texts; t.len = text_len;
+    q.ptr = queries; q.len = query_len;
+    static const char *const none[1] = {nullptr};
+    static const uint64_t zero[1] = {0};
+    if (!n_pairs) { t.ptr = q.ptr = none; t.len = q.len = zero; }
+    return align_pairs_common(ctx, t, q, n_pairs, flags, out);
 }
 
 int sg_set_reference(sg_ctx *ctx, const char *genome_ascii, uint64_t genome_len)
@@ -687,12 +714,9 @@ int sg_set_reference(sg_ctx *ctx, const char *genome_ascii, uint64_t genome_len)
     return SG_OK;
 }
 
-int sg_align_candidates(sg_ctx *ctx, const char *read_blob, const uint64_t *read_off, uint64_t n_reads,
-                        const uint64_t *cand_start, const uint32_t *cand_read, uint64_t n_cand, uint32_t flags,
-                        sg_result **out)
+static int align_candidates_common(sg_ctx *ctx, const Strings &reads, uint64_t n_reads, const uint64_t *cand_start, const uint32_t *cand_read,
+                                   uint64_t n_cand, uint32_t flags, sg_result **out)
 {
-    if (!ctx || !out || !read_off || (n_cand && (!cand_start || !cand_read)))
-        return fail(SG_ERR_BAD_ARG, "sg_align_candidates: null argument");
     std::lock_guard<std::mutex> lock(ctx->mu);
     for (Device &d : ctx->devs)
         if (!d.has_genome) return fail(SG_ERR_NO_REFERENCE, "sg_align_candidates: call sg_set_reference first");
@@ -701,12 +725,34 @@ int sg_align_candidates(sg_ctx *ctx, const char *read_blob, const uint64_t *read
     for (uint64_t c = 0; c < n_cand; c++) {
         if (cand_read[c] >= n_reads) return fail(SG_ERR_BAD_ARG, "candidate " + std::to_string(c) + ": read index out of range");
         if (cand_start[c] > genome_len) return fail(SG_ERR_BAD_ARG, "candidate " + std::to_string(c) + ": start beyond the reference");
-        woff[c + 1] = woff[c] + (read_off[cand_read[c] + 1] - read_off[cand_read[c]]);
+        woff[c + 1] = woff[c] + reads.size(cand_read[c]);
     }
     Workload w;
     w.mapping = true;
-    w.rb = read_blob; w.roff = read_off; w.cand_start = cand_start; w.cand_read = cand_read; w.woff = woff.data(); w.flags = flags;
+    w.query = reads; w.cand_start = cand_start; w.cand_read = cand_read; w.flags = flags;
     return run_all(ctx, w, woff.data(), 64, n_cand, out);
+}
+
+int sg_align_candidates(sg_ctx *ctx, const char *read_blob, const uint64_t *read_off, uint64_t n_reads,
+                        const uint64_t *cand_start, const uint32_t *cand_read, uint64_t n_cand, uint32_t flags,
+                        sg_result **out)
+{
+    if (!ctx || !out || !read_off || (n_cand && (!cand_start || !cand_read)))
+        return fail(SG_ERR_BAD_ARG, "sg_align_candidates: null argument");
+    Strings r;
+    r.blob = read_blob; r.off = read_off;
+    return align_candidates_common(ctx, r, n_reads, cand_start, cand_read, n_cand, flags, out);
+}
+
+int sg_align_candidates_v(sg_ctx *ctx, const char *const *reads, const uint64_t *read_len, uint64_t n_reads,
+                          const uint64_t *cand_start, const uint32_t *cand_read, uint64_t n_cand, uint32_t flags,
+                          sg_result **out)
+{
+    if (!ctx || !out || (n_reads && (!reads || !read_len)) || (n_cand && (!cand_start || !cand_read)))
+        return fail(SG_ERR_BAD_ARG, "sg_align_candidates_v: null argument");
+    Strings r;
+    r.ptr = reads; r.len = read_len;
+    return align_candidates_common(ctx, r, n_reads, cand_start, cand_read, n_cand, flags, out);
 }
 
 uint64_t sg_result_count(const sg_result *r) { return r ? r->n : 0; }

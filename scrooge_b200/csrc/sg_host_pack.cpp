@@ -128,6 +128,31 @@ uint64_t sg_host_pack_2bit(const char *ascii, uint64_t n_bases, uint32_t *packed
     return bad;
 }
 
+// Single-threaded variant for callers that parallelise over strings themselves: packs one string into whole words
+// starting at `packed` (bases past n_bases in the last word are zero).
+uint64_t sg_host_pack_2bit_st(const char *ascii, uint64_t n_bases, uint32_t *packed)
+{
+    if (g_isa < 0) sg_host_pack_2bit("", 0, packed, 1);
+    const uint8_t *a = (const uint8_t *)ascii;
+    uint8_t *out = (uint8_t *)packed;
+    const uint64_t whole = n_bases & ~63ull;
+    uint64_t bad = ~0ull;
+    if (whole) {
+        if (g_isa == 2) bad = pack_avx512(a, whole, out);
+        else if (g_isa == 1) bad = pack_avx2(a, whole, out);
+        else bad = pack_scalar(a, whole, out);
+    }
+    if (whole < n_bases) {
+        uint8_t tmp[64];
+        const uint64_t rem = n_bases - whole, padded = (rem + 15) & ~15ull;
+        memset(tmp, 'A', sizeof tmp);
+        memcpy(tmp, a + whole, rem);
+        const uint64_t r = pack_scalar(tmp, padded, out + whole / 4);
+        if (r != ~0ull && r < rem) bad = std::min(bad, whole + r);
+    }
+    return bad;
+}
+
 int sg_host_pack_isa(void)
 {
     if (g_isa < 0) {

@@ -259,6 +259,19 @@ def test_kernel_and_ingest_variants(forefront, host_pack):
         "    want = o.align_pairs(T, Q, W=W, threads=4)\n"
         "    assert list(got.edit_distances) == list(want.edit) and got.cigars() == want.cigars, W\n"
         "    assert list(got.ref_consumed) == list(want.ref_consumed)\n"
+        "    al = scrooge_b200.Aligner(W=W, n_gpus=1)\n"
+        "    gv = al.align_pairs_v(T, Q)\n"
+        "    assert list(gv.edit_distances) == list(want.edit) and gv.cigars() == want.cigars, ('vectored', W)\n"
+        "    m = json.load(open(f'tests/golden/golden_w{W}.json'))['mapping']\n"
+        "    cs = [s for l in m['locations'] for s in l]; cr = [r for r, l in enumerate(m['locations']) for _ in l]\n"
+        "    al.set_reference(m['genome'])\n"
+        "    for res in (al.align_candidates(m['reads'], cs, cr), al.align_candidates_v(m['reads'], cs, cr)):\n"
+        "        assert [int(x) for x in res.edit_distances] == m['edit'] and res.cigars() == m['cigar'], ('mapping', W)\n"
+        "try:\n"
+        "    scrooge_b200.Aligner(W=64, n_gpus=1).align_pairs_v(['ACGT', 'ACGTACGTNACGT'], ['ACG', 'ACGT'])\n"
+        "    raise SystemExit('bad base not detected (vectored)')\n"
+        "except scrooge_b200.ScroogeError as e:\n"
+        "    assert e.code == 2 and 'pair 1' in str(e) and 'position 8' in str(e), str(e)\n"
         "try:\n"
         "    scrooge_b200.Aligner(W=64, n_gpus=1).align_pairs(['ACGT', 'ACGTACGTNACGT'], ['ACG', 'ACGT'])\n"
         "    raise SystemExit('bad base not detected')\n"
