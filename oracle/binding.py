@@ -6,6 +6,8 @@ legs may import this module.  The product package ``scrooge_b200`` never does.
 * ``Oracle``   -- our plain-C restatement (oracle/genasm_oracle.c -> oracle/libsgoracle.so)
 * ``RefCpu``   -- the UNMODIFIED reference genasm_cpu.cpp behind oracle/ref_shim.cpp
                   (oracle/_ref/libscrooge_ref_w{64,32}.so), when it has been built.
+* ``RefGpu``   -- the UNMODIFIED reference genasm_gpu.cu compiled for sm_100a behind oracle/ref_gpu_shim.cpp
+                  (oracle/_ref/libscrooge_refgpu_{default,best}.so): same-box GPU comparison point.
 """
 from __future__ import annotations
 
@@ -32,6 +34,12 @@ def build(force: bool = False) -> None:
     ):
         subprocess.check_call(["make", "-s", "-C", HERE, "all"])
     subprocess.check_call(["make", "-s", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
+    # the reference's own CUDA kernel for sm_100a (same-box comparison point); ~30 s, only when stale or absent
+    src = "/root/reference/src/genasm_gpu.cu"
+    out = os.path.join(REF_DIR, "libscrooge_refgpu_best.so")
+    if os.path.exists(src) and (force or not os.path.exists(out)
+                                or os.path.getmtime(out) < os.path.getmtime(os.path.join(HERE, "ref_gpu_shim.cpp"))):
+        subprocess.check_call(["make", "-s", "-C", HERE, "refgpu"], stdout=subprocess.DEVNULL)
 
 
 def _blob(strings: Sequence[str | bytes]) -> Tuple[bytes, np.ndarray]:
@@ -236,3 +244,42 @@ class RefCpu:
         raw = cig.raw
         cigars = [raw[int(coff[c]):raw.index(b"\0", int(coff[c]))].decode() for c in range(n)]
         return AlignResult(edit, cigars, None, None, int(ns.value))
+
+
+class RefGpu:
+    """The unmodified reference GPU aligner (genasm_gpu::align_all, src/genasm_gpu.cu:982-1065) built for sm_100a.
+    ``build``: "default" = in-file knobs (SENE+DENT, no ET, 20 blocks/SM); "best" = the paper's headline knobs
+    (SENE+DENT+ET, 28 blocks/SM, scripts/plot.py:1277).  It exit()s on CUDA errors, so run it in a subprocess."""
+
+    def __init__(self, build: str = "best"):
+        path = os.path.join(REF_DIR, f"libscrooge_refgpu_{build}.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.build = build
+        self.lib = C.CDLL(path)
+        self.lib.refgpu_align_pairs.restype = C.c_int
+        self.lib.refgpu_config_w.restype = C.c_int
+
+    @staticmethod
+    def available(build: str = "best") -> bool:
+        return os.path.exists(os.path.join(REF_DIR, f"libscrooge_refgpu_{build}.so"))
+
+    def align_pairs_blob(self, tblob: bytes, toff: np.ndarray, qblob: bytes, qoff: np.ndarray,
+                         want_cigars: bool = True) -> AlignResult:
+        n = len(toff) - 1
+        edit = np.zeros(n, dtype=np.int64)
+        cig = C.create_string_buffer(int(4 * int(qoff[-1]) + n + 1))
+        ns, total = C.c_int64(0), C.c_int64(0)
+        rc = self.lib.refgpu_align_pairs(tblob, _u64p(toff), qblob, _u64p(qoff), C.c_uint64(n), _i64p(edit), cig,
+                                         C.byref(ns), C.byref(total))
+        if rc != 0:
+            raise RuntimeError(f"reference genasm_gpu::align_all returned {rc}")
+        cigars = []
+        if want_cigars:
+            raw = cig.raw
+            for p in range(n):
+                s = 4 * int(qoff[p]) + p
+                cigars.append(raw[s:raw.index(b"\0", s)].decode())
+        res = AlignResult(edit, cigars, None, None, int(ns.value))
+        res.total_ns = int(total.value)
+        return res
