@@ -1,0 +1,274 @@
+// sg_align_delta.cuh -- the delta-encoded alignment kernel: same results as genasm_align_kernel (sg_align.cuh), bit
+// for bit, with the window's distance calculation done COLUMN-WISE ON +-1 DELTAS instead of row-wise on K+1 threshold
+// vectors.
+//
+// What the reference computes (src/genasm_cpu.cpp:210-288): R[d][i], d = 0..d_w, i = n..0, with
+//     bit J of R[d][i] == 0   <=>   D(i,J) <= d,
+// where D(i,J) is the window's semi-global edit-distance matrix
+//     D(i,m) = 0,  D(n,J) = m-J,  D(i,J) = min( D(i+1,J+1) + [text[i] != pattern[J]],  D(i,J+1) + 1,  D(i+1,J) + 1 ).
+// Everything the path returns is a function of D alone: the window distance d_w = D(0,0) (:278-283) and the
+// traceback's tests (:321-343), which sg_align.cuh already evaluates on two words per text column,
+//     V_i bit J  <=>  D(i,J+1) = D(i,J) - 1        H_i bit J  <=>  D(i+1,J) = D(i,J) - 1.
+// The row-wise kernel builds V_i/H_i by OR-ing over d_w+1 (in practice 8 or 16) rows of R, 6 instructions per row
+// and column.  But V_i and H_i ARE the vertical / horizontal "+1" delta vectors of D, and adjacent cells of D differ
+// by -1, 0 or +1, so a whole column of D is two bit-vectors (Pv: +1, Mv: -1) that follow from the previous column
+// with one addition and a handful of logic operations (Myers 1999, Hyyro 2001 -- here run from column n down to 0 on
+// left-aligned vectors: pattern position J at bit W-1-J, padding bits below W-m behave as extra rows of zeros):
+//     x   = (((Eq & Pv) + Pv) ^ Pv) | Eq              Eq = ~pm[text[i]]
+//     Ph  = Mv | ~(x | Pv)          Mh = Pv & x       horizontal deltas column i+1 -> i       (H_i = Ph)
+//     Pv' = (Mh << 1) | ~(Eq | Mv | (Ph << 1))        Mv' = (Ph << 1) & (Eq | Mv)             (V_i = Pv')
+// That is 20 instructions per column at W=64 whatever the window distance is -- against 6 x 11.2 computed rows at
+// 10 % error -- with no chunks, no forefront, no early-termination granularity, and d_w = popc(Pv) - popc(Mv) at
+// column 0.  A text that runs out (n < W) needs no special column code either: a column whose character matches
+// nothing (pm = all real bits set) maps the boundary state Pv = ones << (W-m), Mv = 0 onto itself, so lanes with
+// n < W feed that fifth "code" to columns i >= n.
+//
+// The algorithmic work the roofline is quoted on stays the reference's: sum over windows of (d_w+1)(n+1) entries
+// (SURVEY.md section 8d), counted per alignment exactly as before.
+//
+// Per-warp shared memory (W=64): pattern masks 5 x 256 B, traceback columns 32 x 512 B ({V,H,E,-} per lane), staged
+// runs 2 KB = 19.25 KB; every array [column][lane] so that all accesses are conflict free.
+#pragma once
+#include "sg_align.cuh"
+
+namespace sg {
+
+template <int W> struct DeltaLayout {
+    static constexpr int NW = W / 32;
+    static constexpr int TBL = W - WinCfg<W>::O;
+    static constexpr int TBCOLS = TBL + 1;
+    static constexpr int PM_WORDS = 5 * NW * 32;        // [base code 0..3, 4 = "matches nothing"][lane][NW]
+    static constexpr int TB_WORDS = TBCOLS * 4 * 32;    // [column][lane][V,H,E,-]
+    static constexpr int STAGE_WORDS = W * 32 / 4;      // [run][lane] bytes
+    static constexpr int WORDS_PER_WARP = PM_WORDS + TB_WORDS + STAGE_WORDS;
+    static constexpr int BYTES_PER_WARP = WORDS_PER_WARP * 4;
+    static constexpr int WARPS_PER_CTA = 1;
+    static constexpr int BYTES_PER_CTA = BYTES_PER_WARP * WARPS_PER_CTA;
+};
+
+// NW-word addition with carry propagation
+template <int NW> __device__ __forceinline__ void add_vec(const uint32_t (&a)[NW], const uint32_t (&b)[NW], uint32_t (&s)[NW]);
+template <> __device__ __forceinline__ void add_vec<1>(const uint32_t (&a)[1], const uint32_t (&b)[1], uint32_t (&s)[1]) { s[0] = a[0] + b[0]; }
+template <> __device__ __forceinline__ void add_vec<2>(const uint32_t (&a)[2], const uint32_t (&b)[2], uint32_t (&s)[2])
+{
+    const uint64_t r = (((uint64_t)a[1] << 32) | a[0]) + (((uint64_t)b[1] << 32) | b[0]);
+    s[0] = (uint32_t)r;
+    s[1] = (uint32_t)(r >> 32);
+}
+
+// One column: (Pv, Mv) of column i+1 -> column i, Ph = the horizontal +1 deltas between them.
+template <int NW>
+__device__ __forceinline__ void delta_column(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&pm)[NW], uint32_t (&Ph)[NW])
+{
+    uint32_t t[NW], s[NW], x[NW], Mh[NW], Phs[NW], Mhs[NW];
+#pragma unroll
+    for (int k = 0; k < NW; k++) t[k] = ~pm[k] & Pv[k];
+    add_vec<NW>(t, Pv, s);
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        x[k] = (s[k] ^ Pv[k]) | ~pm[k];
+        Ph[k] = Mv[k] | ~(x[k] | Pv[k]);
+        Mh[k] = Pv[k] & x[k];
+    }
+    shl1<NW>(Ph, Phs);   // carry-in 0: D(i,m) = 0 for every column
+    shl1<NW>(Mh, Mhs);
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        const uint32_t xv = ~pm[k] | Mv[k];
+        Pv[k] = Mhs[k] | ~(xv | Phs[k]);
+        Mv[k] = Phs[k] & xv;
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_delta_kernel(const AlignParams P)
+{
+    using L = DeltaLayout<W>;
+    constexpr int NW = L::NW;
+    constexpr int NWIN = 2 * NW;
+    constexpr int TBL = L::TBL;
+    constexpr int TBCOLS = L::TBCOLS;
+    constexpr int TOP = NW - 1;
+    constexpr int PMS = NW * 32;   // words between the masks of consecutive base codes
+    constexpr int TBS = 4 * 32;    // words between traceback columns
+
+    extern __shared__ __align__(16) uint32_t smem_all[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint32_t *smem = smem_all + warp * L::WORDS_PER_WARP;
+    uint32_t *pm_s = smem + lane * NW;
+    uint32_t *tb_s = smem + L::PM_WORDS + lane * 4;
+    uint8_t *stage_s = reinterpret_cast<uint8_t *>(smem + L::PM_WORDS + L::TB_WORDS) + lane;
+
+    const bool want_cigar = !(P.flags & 1u);
+
+    bool have = false, drained = false;
+    uint64_t pair = 0, t_pos = 0, t_begin = 0, t_end = 0, q_pos = 0, q_end = 0;
+    int64_t ed = 0;
+    uint8_t *out = nullptr, *out_end = nullptr;
+    uint32_t nruns = 0;
+    uint64_t entries = 0;
+    bool overflow = false;
+    int n = -1, m = 0;
+    uint32_t tw[NWIN];
+#pragma unroll
+    for (int k = 0; k < NWIN; k++) tw[k] = 0;
+
+    while (true) {
+        // ---- work queue: a lane without an alignment takes the next one ----------------------------
+        if (!have && !drained) {
+            while (true) {
+                uint64_t idx = atomicAdd(P.counter, 1ull);
+                if (idx >= P.n) { drained = true; break; }
+                uint64_t ql = P.query_len[idx];
+                if (ql == 0) {  // zero windows: distance 0, empty CIGAR (src/tests.cu:243,246)
+                    P.edit[idx] = 0;
+                    P.ref_consumed[idx] = 0;
+                    P.nruns[idx] = 0;
+                    P.status[idx] = 0;
+                    if (P.dc_entries) P.dc_entries[idx] = 0;
+                    continue;
+                }
+                pair = idx;
+                t_begin = t_pos = P.text_start[idx];
+                t_end = t_pos + P.text_len[idx];
+                q_pos = P.query_start[idx];
+                q_end = q_pos + ql;
+                ed = 0;
+                nruns = 0;
+                entries = 0;
+                overflow = false;
+                if (want_cigar) {
+                    out = P.slab + P.slab_off[idx];
+                    out_end = P.slab + P.slab_off[idx + 1];
+                }
+                have = true;
+                break;
+            }
+        }
+        if (__all_sync(0xFFFFFFFFu, !have)) break;
+
+        // ---- window setup ------------------------------------------------------------------------------
+        uint32_t Pv[NW], Mv[NW];
+#pragma unroll
+        for (int k = 0; k < NW; k++) { Pv[k] = 0; Mv[k] = 0; }
+        n = -1;
+        if (have) {
+            uint64_t tl = t_end - t_pos, ql = q_end - q_pos;
+            n = tl < (uint64_t)W ? (int)tl : W;
+            m = ql < (uint64_t)W ? (int)ql : W;
+            load_window<NWIN>(P.text, t_pos, tw);
+            uint32_t pw[NWIN];
+            load_window<NWIN>(P.query, q_pos, pw);
+            uint32_t p0[NW], p1[NW], hm[NW];
+            pattern_planes<NW>(pw, p0, p1);
+            ones_shl<NW>(W - m, hm);
+            // pm[c]: zero where pattern[J] == c (src/genasm_cpu.cpp:178-198) and in the W-m padding bits
+            uint32_t m0[NW], m1[NW], m2[NW], m3[NW];
+#pragma unroll
+            for (int k = 0; k < NW; k++) {
+                m0[k] = (p1[k] | p0[k]) & hm[k];
+                m1[k] = (p1[k] | ~p0[k]) & hm[k];
+                m2[k] = (~p1[k] | p0[k]) & hm[k];
+                m3[k] = (~p1[k] | ~p0[k]) & hm[k];
+                Pv[k] = hm[k];   // boundary column D(n,J) = m-J (src/genasm_cpu.cpp:225-231): every vertical delta is +1
+            }
+            sts_vec<NW>(pm_s + 0 * PMS, m0);
+            sts_vec<NW>(pm_s + 1 * PMS, m1);
+            sts_vec<NW>(pm_s + 2 * PMS, m2);
+            sts_vec<NW>(pm_s + 3 * PMS, m3);
+            sts_vec<NW>(pm_s + 4 * PMS, hm);   // a character that matches nothing: columns i >= n
+        }
+        const bool uniform = __all_sync(0xFFFFFFFFu, !have || n == W);
+
+        // ---- DC: columns W-1 .. 0, two delta vectors per lane ----------------------------------------------
+        // lanes without work ride along on whatever their scratch holds; nothing of it is ever read
+        auto columns = [&](auto uni) {
+            constexpr bool UNI = decltype(uni)::value;
+#pragma unroll
+            for (int blk = NWIN - 1; blk >= 0; blk--) {
+                uint32_t cw = tw[blk];
+#pragma unroll
+                for (int ii = 15; ii >= 0; ii--) {
+                    const int i = blk * 16 + ii;
+                    uint32_t code = cw >> 30;
+                    cw <<= 2;
+                    if (!UNI) code = i < n ? code : 4u;
+                    uint32_t pm[NW], Ph[NW];
+                    lds_vec<NW>(pm_s + code * PMS, pm);
+                    delta_column<NW>(Pv, Mv, pm, Ph);
+                    if (i < TBCOLS) {
+                        *reinterpret_cast<uint4 *>(tb_s + i * TBS) = make_uint4(Pv[TOP], Ph[TOP], pm[TOP], 0u);
+                    }
+                }
+            }
+        };
+        if (uniform) columns(std::true_type{});
+        else columns(std::false_type{});
+
+        if (!have) continue;
+
+        {   // window distance d_w = D(0,0) = sum of the vertical deltas of column 0 (src/genasm_cpu.cpp:278-283)
+            int dw = 0;
+#pragma unroll
+            for (int k = 0; k < NW; k++) dw += __popc(Pv[k]) - __popc(Mv[k]);
+            entries += (uint64_t)(dw + 1) * (uint64_t)(n + 1);
+        }
+
+        // ---- TB: walk the V/H/E words from (0,0); priority I > D > X > '=' (src/genasm_cpu.cpp:321-370) ----
+        const int jmax = m < TBL ? m : TBL;
+        const uint32_t mask_end = 0x80000000u >> jmax;   // jmax <= W-O <= 31
+        int tcol = 0;                                    // word offset of column i
+        int stage = 0;                                   // byte offset of the next staged run
+        uint32_t mask = 0x80000000u;
+        uint32_t prev = 0u, cnt = 0u;
+        uint4 c = *reinterpret_cast<const uint4 *>(tb_s);
+        while (mask != mask_end && tcol != TBL * TBS) {
+            const bool is_i = (c.x & mask) != 0;
+            const bool has_d = (c.y & mask) != 0;
+            const bool has_x = (c.z & mask) != 0;
+            uint32_t op = has_x ? 1u : 0u;  // 0 '=', 1 'X', 2 'I', 3 'D'
+            op = has_d ? 3u : op;
+            op = is_i ? 2u : op;
+            const bool brk = op != prev;
+            if (brk && cnt != 0u) {
+                stage_s[stage] = (uint8_t)(prev * 64u + cnt);
+                stage += 32;
+            }
+            cnt = brk ? 1u : cnt + 1u;
+            prev = op;
+            if (!is_i) tcol += TBS;
+            if (is_i || !has_d) mask >>= 1;
+            c = *reinterpret_cast<const uint4 *>(tb_s + tcol);
+        }
+        if (cnt != 0u) {  // runs are flushed at window end, never merged across windows (quirk Q2)
+            stage_s[stage] = (uint8_t)(prev * 64u + cnt);
+            stage += 32;
+        }
+        const int i = tcol / TBS;
+        const int j = __clz(mask);
+        const uint32_t nb = (uint32_t)(stage / 32);
+        uint32_t edits = 0u;
+        const bool fits = !want_cigar || (uint64_t)(out_end - out) >= (uint64_t)nb;
+        for (int k = 0; k < stage; k += 32) {
+            const uint32_t run = stage_s[k];
+            edits += run >= 64u ? (run & 63u) : 0u;   // every op but '=' is an edit
+            if (want_cigar && fits) *out++ = (uint8_t)run;
+        }
+        if (!fits) overflow = true;
+        nruns += nb;
+        ed += edits;
+        t_pos += (uint64_t)i;
+        q_pos += (uint64_t)j;
+        if (q_pos >= q_end) {
+            P.edit[pair] = ed;
+            P.ref_consumed[pair] = t_pos - t_begin;
+            P.nruns[pair] = nruns;
+            P.status[pair] = overflow ? 5 : 0;
+            if (P.dc_entries) P.dc_entries[pair] = entries;
+            have = false;
+        }
+    }
+}
+
+}  // namespace sg

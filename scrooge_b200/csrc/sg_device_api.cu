@@ -11,6 +11,7 @@
 #include "../../include/scrooge_b200.h"
 #include "sg_internal.h"
 #include "sg_align.cuh"
+#include "sg_align_delta.cuh"
 #include "sg_aux.cuh"
 
 namespace sg {
@@ -30,7 +31,8 @@ int cuda_fail(cudaError_t e, const char *what)
 
 struct DeviceInfo {
     int sms = 0;
-    int ctas_per_sm[2][2] = {{0, 0}, {0, 0}};  // [W=64 | W=32][smem forefront | TMEM forefront]
+    int ctas_per_sm[2][2] = {{0, 0}, {0, 0}};  // row-wise kernel: [W=64 | W=32][smem forefront | TMEM forefront]
+    int delta_ctas_per_sm[2] = {0, 0};         // delta kernel: [W=64 | W=32]
     bool ready = false;
 };
 static DeviceInfo g_dev_info[64];
@@ -47,6 +49,34 @@ static bool use_tmem(int W)
         return -1;
     }();
     return forced >= 0 ? forced == 1 : W == 64;
+}
+
+// Which distance-calculation formulation sg_dev_align launches: "delta" (sg_align_delta.cuh, column-wise +-1 deltas,
+// the default) or "rows" (sg_align.cuh, the reference's row-wise threshold vectors in G-row chunks).  Bit-identical.
+static bool use_delta()
+{
+    static const bool v = [] {
+        const char *e = std::getenv("SG_DC");
+        return !(e && std::string(e) == "rows");
+    }();
+    return v;
+}
+
+template <int W> static int setup_delta_kernel(int *ctas_per_sm)
+{
+    using L = DeltaLayout<W>;
+    auto kern = genasm_delta_kernel<W>;
+    SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES_PER_CTA));
+    SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kern, L::WARPS_PER_CTA * 32, L::BYTES_PER_CTA));
+    if (std::getenv("SG_DEBUG")) {
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, kern);
+        fprintf(stderr, "[sg] delta W=%d: occupancy %d CTAs/SM, %d regs, %d dyn smem, %d threads/CTA\n", W, *ctas_per_sm, fa.numRegs,
+                L::BYTES_PER_CTA, L::WARPS_PER_CTA * 32);
+    }
+    if (*ctas_per_sm < 1) return fail(SG_ERR_CUDA, "alignment kernel does not fit on this device");
+    return SG_OK;
 }
 
 template <int W, bool TMEM> static int setup_kernel(int *ctas_per_sm)
@@ -97,10 +127,32 @@ static int device_info(DeviceInfo **out)
         if (!rc) rc = setup_kernel<64, true>(&di.ctas_per_sm[0][1]);
         if (!rc) rc = setup_kernel<32, false>(&di.ctas_per_sm[1][0]);
         if (!rc) rc = setup_kernel<32, true>(&di.ctas_per_sm[1][1]);
+        if (!rc) rc = setup_delta_kernel<64>(&di.delta_ctas_per_sm[0]);
+        if (!rc) rc = setup_delta_kernel<32>(&di.delta_ctas_per_sm[1]);
         if (rc) return rc;
         di.ready = true;
     }
     *out = &di;
+    return SG_OK;
+}
+
+// Persistent lane count shared by both kernels, see launch_align.
+static uint64_t balanced_ctas(uint64_t n, uint64_t max_ctas, uint64_t lanes_per_cta)
+{
+    const uint64_t k = (n + max_ctas * lanes_per_cta - 1) / (max_ctas * lanes_per_cta);
+    const uint64_t lanes = (n + k - 1) / k;
+    uint64_t ctas = (lanes + lanes_per_cta - 1) / lanes_per_cta;
+    if (k >= 8 || ctas > max_ctas) ctas = max_ctas;  // many alignments per lane: the dynamic queue evens things out
+    return ctas;
+}
+
+template <int W> static int launch_delta(const DeviceInfo &di, const AlignParams &P, cudaStream_t st)
+{
+    using L = DeltaLayout<W>;
+    const uint64_t max_ctas = (uint64_t)di.sms * (uint64_t)di.delta_ctas_per_sm[W == 64 ? 0 : 1];
+    const uint64_t ctas = balanced_ctas(P.n, max_ctas, 32ull * L::WARPS_PER_CTA);
+    genasm_delta_kernel<W><<<(unsigned)ctas, L::WARPS_PER_CTA * 32, L::BYTES_PER_CTA, st>>>(P);
+    SG_CUDA(cudaGetLastError());
     return SG_OK;
 }
 
@@ -166,6 +218,12 @@ int sg_dev_align_geometry(int W, int *warps_per_sm, int *smem_per_warp, int *num
     DeviceInfo *di;
     int rc = device_info(&di);
     if (rc) return rc;
+    if (use_delta()) {
+        if (warps_per_sm) *warps_per_sm = di->delta_ctas_per_sm[W == 64 ? 0 : 1] * DeltaLayout<64>::WARPS_PER_CTA;
+        if (smem_per_warp) *smem_per_warp = W == 64 ? DeltaLayout<64>::BYTES_PER_WARP : DeltaLayout<32>::BYTES_PER_WARP;
+        if (num_sms) *num_sms = di->sms;
+        return SG_OK;
+    }
     const bool t = use_tmem(W);
     if (warps_per_sm) *warps_per_sm = di->ctas_per_sm[W == 64 ? 0 : 1][t ? 1 : 0] * (t ? 4 : 1);
     if (smem_per_warp)
@@ -199,6 +257,7 @@ int sg_dev_align(int W, const uint32_t *d_text, const uint64_t *d_text_start, co
     P.n = n; P.flags = flags; P.slab = d_slab; P.slab_off = d_slab_off;
     P.counter = (unsigned long long *)d_counter;
     P.edit = d_edit; P.ref_consumed = d_ref_consumed; P.nruns = d_nruns; P.status = d_status; P.dc_entries = d_dc_entries;
+    if (use_delta()) return W == 64 ? launch_delta<64>(*di, P, st) : launch_delta<32>(*di, P, st);
     if (use_tmem(W)) return W == 64 ? launch_align<64, true>(*di, P, st) : launch_align<32, true>(*di, P, st);
     return W == 64 ? launch_align<64, false>(*di, P, st) : launch_align<32, false>(*di, P, st);
 }

@@ -105,3 +105,83 @@ def align(text: str, read: str, W: int = 64, O: int = 33, G: int = 8) -> Tuple[i
         t_pos += i
         q_pos += j
     return ed, "".join(out), t_pos
+
+
+def align_delta(text: str, read: str, W: int = 64, O: int = 33) -> Tuple[int, str, int, int]:
+    """Model of the delta-encoded DC (sg_align_delta.cuh): the same window matrix D(i,J) -- the one the R rows of
+    src/genasm_cpu.cpp:210-288 encode as D(i,J) = min{d : bit J of R[d][i] is 0} -- computed column by column as
+    vertical/horizontal +-1 deltas (Myers 1999 / Hyyro 2001 bit-vector recurrences run from column n down to 0 on
+    left-aligned vectors), instead of row by row as K+1 threshold vectors.  V_i = vertical +1 deltas of column i,
+    H_i = horizontal +1 deltas between columns i+1 and i: the very words the row-wise kernel ORs together.
+    Returns (edit distance, cigar, consumed reference prefix, sum over windows of (d_w+1)(n+1))."""
+    MASK = (1 << W) - 1
+    TBL = W - O
+    TOP_SHIFT = W - 32
+    t = [CODE[c] for c in text]
+    q = [CODE[c] for c in read]
+    t_pos = q_pos = 0
+    ed = 0
+    entries = 0
+    out: List[str] = []
+    while q_pos < len(q):
+        n = min(W, len(t) - t_pos)
+        m = min(W, len(q) - q_pos)
+        hm = (MASK << (W - m)) & MASK
+        pm = [0, 0, 0, 0]
+        for c in range(4):
+            v = 0
+            for J in range(m):
+                if q[q_pos + J] != c:
+                    v |= 1 << (W - 1 - J)
+            pm[c] = v & hm
+        V = [0] * (TBL + 1)
+        H = [0] * (TBL + 1)
+        E = [0] * (TBL + 1)
+        top = lambda x: (x & MASK) >> TOP_SHIFT
+        Pv, Mv = hm, 0          # boundary column D(n,J) = m-J: every vertical delta is +1
+        if n <= TBL:
+            V[n] = top(Pv)
+        for i in range(n - 1, -1, -1):
+            p = pm[t[t_pos + i]]
+            Eq = ~p & MASK      # padding bits (below W-m) match everything: zero rows stay zero rows
+            D0 = ((((Eq & Pv) + Pv) & MASK) ^ Pv) | Eq | Mv
+            Ph = Mv | (~(D0 | Pv) & MASK)
+            Mh = Pv & D0
+            Phs = (Ph << 1) & MASK   # carry-in 0: D(i,m) = 0 for every i
+            Mhs = (Mh << 1) & MASK
+            Pv = Mhs | (~(D0 | Phs) & MASK)
+            Mv = Phs & D0
+            if i <= TBL:
+                V[i], H[i], E[i] = top(Pv), top(Ph), top(p)
+        d_w = bin(Pv).count("1") - bin(Mv).count("1")   # D(0,0) = sum of the vertical deltas of column 0
+        entries += (d_w + 1) * (n + 1)
+        i = j = 0
+        mask = 1 << 31
+        cur_op, cur_cnt = None, 0
+        while j < m and i < TBL and j < TBL:
+            if V[i] & mask:
+                op = 2
+            elif H[i] & mask:
+                op = 3
+            elif E[i] & mask:
+                op = 1
+            else:
+                op = 0
+            if op != 2:
+                i += 1
+            if op != 3:
+                j += 1
+                mask >>= 1
+            if op != 0:
+                ed += 1
+            if op != cur_op:
+                if cur_cnt:
+                    out.append(f"{cur_cnt}{OPS[cur_op]}")
+                cur_op, cur_cnt = op, 1
+            else:
+                cur_cnt += 1
+        if cur_cnt:
+            out.append(f"{cur_cnt}{OPS[cur_op]}")
+        t_pos += i
+        q_pos += j
+    return ed, "".join(out), t_pos, entries

@@ -19,3 +19,26 @@ def test_model_golden_kats(golden):
     for x in golden[64]["groups"]["kat_tests_cu"] + golden[64]["groups"]["differential_tests_cu"]:
         ed, cg, _ = align(x["text"], x["query"])
         assert ed == x["edit"] and cg == x["cigar"]
+
+
+@pytest.mark.parametrize("W,O", [(64, 33), (32, 17)])
+def test_delta_model_matches_oracle(oracle, W, O):
+    """The delta-encoded (column-wise +-1) DC yields the same distances, CIGARs, consumed prefixes and the same
+    early-termination-minimal entry count as the reference's row-wise threshold vectors."""
+    from kernel_model import align_delta
+    T, Q = random_pairs(23 + W, 300, [0, 1, 2, 15, 16, 17, 31, 32, 33, 63, 64, 65, 100, 200, 500], [0, 0.05, 0.15, 0.4, 0.8])
+    res = oracle.align_pairs(T, Q, W=W)
+    total = 0
+    for k in range(len(T)):
+        ed, cg, rc, ent = align_delta(T[k], Q[k], W, O)
+        total += ent
+        assert (ed, cg, rc) == (int(res.edit[k]), res.cigars[k], int(res.ref_consumed[k])), (T[k], Q[k])
+    assert total == res.stats["dc_entries"]
+
+
+def test_delta_model_golden_kats(golden):
+    from kernel_model import align_delta
+    for W in (64, 32):
+        for x in golden[W]["groups"]["kat_tests_cu"] + golden[W]["groups"]["differential_tests_cu"]:
+            ed, cg, _, _ = align_delta(x["text"], x["query"], W, 33 if W == 64 else 17)
+            assert ed == x["edit"] and cg == x["cigar"]
