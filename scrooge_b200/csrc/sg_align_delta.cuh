@@ -26,8 +26,16 @@
 // The algorithmic work the roofline is quoted on stays the reference's: sum over windows of (d_w+1)(n+1) entries
 // (SURVEY.md section 8d), counted per alignment exactly as before.
 //
-// Per-warp shared memory (W=64): pattern masks 5 x 256 B, traceback columns 32 x 512 B ({V,H,E,-} per lane), staged
-// runs 2 KB = 19.25 KB; every array [column][lane] so that all accesses are conflict free.
+// Traceback.  For every traceback column the DC stores the op the walk would take at each pattern position as two bit
+// planes, A = V | H and B = ~V & (H | E) (E = pm[text[i]]): op = 2A + B = 0 '=', 1 'X', 2 'I', 3 'D', which is the
+// reference's priority I > D > X > '=' (src/genasm_cpu.cpp:346-370).  The walk itself is 16 instructions per step: one
+// LDS.64, two bit tests, and the 2-bit op appended to a register-resident op stream at a position that is the same for
+// every lane of the warp (all lanes are at the same step).  Run-length encoding happens after the walk, on the stream,
+// with bit tricks (run boundaries = non-zero 2-bit fields of S ^ S >> 2), one loop iteration per RUN instead of
+// bookkeeping per step.
+//
+// Per-warp shared memory (W=64): pattern masks 5 x 256 B + traceback columns 32 x 256 B = 9.25 KB (22 warps per SM);
+// every array [column][lane] so that all accesses are conflict free.
 #pragma once
 #include "sg_align.cuh"
 
@@ -38,9 +46,8 @@ template <int W> struct DeltaLayout {
     static constexpr int TBL = W - WinCfg<W>::O;
     static constexpr int TBCOLS = TBL + 1;
     static constexpr int PM_WORDS = 5 * NW * 32;        // [base code 0..3, 4 = "matches nothing"][lane][NW]
-    static constexpr int TB_WORDS = TBCOLS * 4 * 32;    // [column][lane][V,H,E,-]
-    static constexpr int STAGE_WORDS = W * 32 / 4;      // [run][lane] bytes
-    static constexpr int WORDS_PER_WARP = PM_WORDS + TB_WORDS + STAGE_WORDS;
+    static constexpr int TB_WORDS = TBCOLS * 2 * 32;    // [column][lane][A,B]: the traceback's op per pattern position, 2 bit planes
+    static constexpr int WORDS_PER_WARP = PM_WORDS + TB_WORDS;
     static constexpr int BYTES_PER_WARP = WORDS_PER_WARP * 4;
     static constexpr int WARPS_PER_CTA = 1;
     static constexpr int BYTES_PER_CTA = BYTES_PER_WARP * WARPS_PER_CTA;
@@ -90,15 +97,14 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
     constexpr int TBCOLS = L::TBCOLS;
     constexpr int TOP = NW - 1;
     constexpr int PMS = NW * 32;   // words between the masks of consecutive base codes
-    constexpr int TBS = 4 * 32;    // words between traceback columns
+    constexpr int TBS = 2 * 32;    // words between traceback columns
 
     extern __shared__ __align__(16) uint32_t smem_all[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     uint32_t *smem = smem_all + warp * L::WORDS_PER_WARP;
     uint32_t *pm_s = smem + lane * NW;
-    uint32_t *tb_s = smem + L::PM_WORDS + lane * 4;
-    uint8_t *stage_s = reinterpret_cast<uint8_t *>(smem + L::PM_WORDS + L::TB_WORDS) + lane;
+    uint32_t *tb_s = smem + L::PM_WORDS + lane * 2;
 
     const bool want_cigar = !(P.flags & 1u);
 
@@ -198,7 +204,8 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
                     lds_vec<NW>(pm_s + code * PMS, pm);
                     delta_column<NW>(Pv, Mv, pm, Ph);
                     if (i < TBCOLS) {
-                        *reinterpret_cast<uint4 *>(tb_s + i * TBS) = make_uint4(Pv[TOP], Ph[TOP], pm[TOP], 0u);
+                        const uint32_t v = Pv[TOP], hh = Ph[TOP], e = pm[TOP];
+                        *reinterpret_cast<uint2 *>(tb_s + i * TBS) = make_uint2(v | hh, ~v & (hh | e));
                     }
                 }
             }
@@ -215,48 +222,68 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
             entries += (uint64_t)(dw + 1) * (uint64_t)(n + 1);
         }
 
-        // ---- TB: walk the V/H/E words from (0,0); priority I > D > X > '=' (src/genasm_cpu.cpp:321-370) ----
+        // ---- TB: walk the op planes from (0,0), append every op to the op stream ---------------------------
         const int jmax = m < TBL ? m : TBL;
         const uint32_t mask_end = 0x80000000u >> jmax;   // jmax <= W-O <= 31
-        int tcol = 0;                                    // word offset of column i
-        int stage = 0;                                   // byte offset of the next staged run
-        uint32_t mask = 0x80000000u;
-        uint32_t prev = 0u, cnt = 0u;
-        uint4 c = *reinterpret_cast<const uint4 *>(tb_s);
-        while (mask != mask_end && tcol != TBL * TBS) {
-            const bool is_i = (c.x & mask) != 0;
-            const bool has_d = (c.y & mask) != 0;
-            const bool has_x = (c.z & mask) != 0;
-            uint32_t op = has_x ? 1u : 0u;  // 0 '=', 1 'X', 2 'I', 3 'D'
-            op = has_d ? 3u : op;
-            op = is_i ? 2u : op;
-            const bool brk = op != prev;
-            if (brk && cnt != 0u) {
-                stage_s[stage] = (uint8_t)(prev * 64u + cnt);
-                stage += 32;
+        constexpr int TB_END = TBL * TBS * 4;            // byte offset of column TB_LIMIT
+        constexpr int SW = (2 * TBL + 15) / 16;          // stream words: at most 2*TB_LIMIT steps, 16 per word
+        const uint32_t tb_base = (uint32_t)__cvta_generic_to_shared(tb_s);
+        uint32_t tcol = 0;                               // byte offset of column i
+        uint32_t mask = 0x80000000u;                     // pattern position j, one-hot from the top
+        uint32_t acc[SW];
+        int steps = 0;
+        uint32_t op = 0u;
+        uint32_t ca, cb;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ca), "=r"(cb) : "r"(tb_base));
+#pragma unroll
+        for (int w = 0; w < SW; w++) {
+            uint32_t cur = 0u;
+            if (mask != mask_end && tcol != TB_END) {
+                int sh = 0;
+                do {
+                    const bool hi = (ca & mask) != 0u;
+                    const bool lo = (cb & mask) != 0u;
+                    op = (hi ? 2u : 0u) | (lo ? 1u : 0u);
+                    cur |= op << sh;
+                    sh += 2;
+                    if (!(hi && !lo)) tcol += TBS * 4;    // every op but 'I' consumes a text character
+                    if (!(hi && lo)) mask >>= 1;          // every op but 'D' consumes a pattern character
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ca), "=r"(cb) : "r"(tb_base + tcol));
+                } while (sh < 32 && mask != mask_end && tcol != TB_END);
+                steps += sh >> 1;
             }
-            cnt = brk ? 1u : cnt + 1u;
-            prev = op;
-            if (!is_i) tcol += TBS;
-            if (is_i || !has_d) mask >>= 1;
-            c = *reinterpret_cast<const uint4 *>(tb_s + tcol);
+            acc[w] = cur;
         }
-        if (cnt != 0u) {  // runs are flushed at window end, never merged across windows (quirk Q2)
-            stage_s[stage] = (uint8_t)(prev * 64u + cnt);
-            stage += 32;
-        }
-        const int i = tcol / TBS;
+        const int i = (int)(tcol / (TBS * 4));
         const int j = __clz(mask);
-        const uint32_t nb = (uint32_t)(stage / 32);
+
+        // ---- RLE on the op stream: per-window runs, flushed at window end, never merged across windows (quirk Q2) ----
         uint32_t edits = 0u;
-        const bool fits = !want_cigar || (uint64_t)(out_end - out) >= (uint64_t)nb;
-        for (int k = 0; k < stage; k += 32) {
-            const uint32_t run = stage_s[k];
-            edits += run >= 64u ? (run & 63u) : 0u;   // every op but '=' is an edit
-            if (want_cigar && fits) *out++ = (uint8_t)run;
+        auto emit = [&](const uint32_t o, const uint32_t cnt) {
+            edits += o != 0u ? cnt : 0u;   // every op but '=' is an edit
+            nruns++;
+            if (want_cigar) {
+                if (out != out_end) *out++ = (uint8_t)(o * 64u + cnt);
+                else overflow = true;
+            }
+        };
+        int start = 0;
+#pragma unroll
+        for (int w = 0; w < SW; w++) {
+            // a run ends at step k when op k+1 differs; beyond the last step the stream is zero, so a last run of
+            // anything but '=' ends itself and a last run of '=' is emitted below
+            const uint32_t nxt = __funnelshift_r(acc[w], w + 1 < SW ? acc[w + 1] : 0u, 2);
+            const uint32_t t = acc[w] ^ nxt;
+            uint32_t e = (t | (t >> 1)) & 0x55555555u;
+            while (e) {
+                const int p = __ffs((int)e) - 1;
+                const int k = 16 * w + (p >> 1);
+                emit((acc[w] >> p) & 3u, (uint32_t)(k - start + 1));
+                start = k + 1;
+                e &= e - 1u;
+            }
         }
-        if (!fits) overflow = true;
-        nruns += nb;
+        if (start < steps) emit(0u, (uint32_t)(steps - start));
         ed += edits;
         t_pos += (uint64_t)i;
         q_pos += (uint64_t)j;
