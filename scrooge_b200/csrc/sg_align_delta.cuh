@@ -28,11 +28,10 @@
 //
 // Traceback.  For every traceback column the DC stores the op the walk would take at each pattern position as two bit
 // planes, A = V | H and B = ~V & (H | E) (E = pm[text[i]]): op = 2A + B = 0 '=', 1 'X', 2 'I', 3 'D', which is the
-// reference's priority I > D > X > '=' (src/genasm_cpu.cpp:346-370).  The walk itself is 16 instructions per step: one
-// LDS.64, two bit tests, and the 2-bit op appended to a register-resident op stream at a position that is the same for
-// every lane of the warp (all lanes are at the same step).  Run-length encoding happens after the walk, on the stream,
-// with bit tricks (run boundaries = non-zero 2-bit fields of S ^ S >> 2), one loop iteration per RUN instead of
-// bookkeeping per step.
+// reference's priority I > D > X > '=' (src/genasm_cpu.cpp:346-370).  The walk is one LDS.64 and two bit tests per
+// step, and the two op bits of step k go to bit k of two register-resident bit streams.  Run-length encoding, the edit
+// count and the run count happen after the walk, on the streams, with bit tricks (run boundaries = hs ^ hs >> 1 |
+// ls ^ ls >> 1, edits = popc(hs | ls)): one loop iteration per RUN instead of bookkeeping per step.
 //
 // Per-warp shared memory (W=64): pattern masks 5 x 256 B + traceback columns 32 x 256 B = 9.25 KB (22 warps per SM);
 // every array [column][lane] so that all accesses are conflict free.
@@ -222,68 +221,74 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
             entries += (uint64_t)(dw + 1) * (uint64_t)(n + 1);
         }
 
-        // ---- TB: walk the op planes from (0,0), append every op to the op stream ---------------------------
+        // ---- TB: walk the op planes from (0,0); the op of step k goes to bit k of two bit streams (hi, lo) ----
         const int jmax = m < TBL ? m : TBL;
         const uint32_t mask_end = 0x80000000u >> jmax;   // jmax <= W-O <= 31
-        constexpr int TB_END = TBL * TBS * 4;            // byte offset of column TB_LIMIT
-        constexpr int SW = (2 * TBL + 15) / 16;          // stream words: at most 2*TB_LIMIT steps, 16 per word
-        const uint32_t tb_base = (uint32_t)__cvta_generic_to_shared(tb_s);
-        uint32_t tcol = 0;                               // byte offset of column i
+        constexpr int SW = (2 * TBL + 31) / 32;          // stream words: at most 2*TB_LIMIT steps, 32 per word
+        uint32_t tcol = (uint32_t)__cvta_generic_to_shared(tb_s);   // shared-memory address of column i
+        const uint32_t tb_begin = tcol, tb_end = tcol + TBL * TBS * 4;
         uint32_t mask = 0x80000000u;                     // pattern position j, one-hot from the top
-        uint32_t acc[SW];
-        int steps = 0;
-        uint32_t op = 0u;
+        uint32_t hs[SW], ls[SW];
         uint32_t ca, cb;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ca), "=r"(cb) : "r"(tb_base));
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ca), "=r"(cb) : "r"(tcol));
 #pragma unroll
         for (int w = 0; w < SW; w++) {
-            uint32_t cur = 0u;
-            if (mask != mask_end && tcol != TB_END) {
-                int sh = 0;
+            uint32_t h = 0u, l = 0u;
+            if (mask != mask_end && tcol != tb_end) {
+                uint32_t bit = 1u;
                 do {
                     const bool hi = (ca & mask) != 0u;
                     const bool lo = (cb & mask) != 0u;
-                    op = (hi ? 2u : 0u) | (lo ? 1u : 0u);
-                    cur |= op << sh;
-                    sh += 2;
+                    if (hi) h |= bit;
+                    if (lo) l |= bit;
+                    bit <<= 1;
                     if (!(hi && !lo)) tcol += TBS * 4;    // every op but 'I' consumes a text character
                     if (!(hi && lo)) mask >>= 1;          // every op but 'D' consumes a pattern character
-                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ca), "=r"(cb) : "r"(tb_base + tcol));
-                } while (sh < 32 && mask != mask_end && tcol != TB_END);
-                steps += sh >> 1;
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ca), "=r"(cb) : "r"(tcol));
+                } while (bit != 0u && mask != mask_end && tcol != tb_end);
             }
-            acc[w] = cur;
+            hs[w] = h;
+            ls[w] = l;
         }
-        const int i = (int)(tcol / (TBS * 4));
+        const int i = (int)((tcol - tb_begin) / (TBS * 4));
         const int j = __clz(mask);
 
-        // ---- RLE on the op stream: per-window runs, flushed at window end, never merged across windows (quirk Q2) ----
-        uint32_t edits = 0u;
-        auto emit = [&](const uint32_t o, const uint32_t cnt) {
-            edits += o != 0u ? cnt : 0u;   // every op but '=' is an edit
-            nruns++;
-            if (want_cigar) {
-                if (out != out_end) *out++ = (uint8_t)(o * 64u + cnt);
-                else overflow = true;
-            }
-        };
-        int start = 0;
+        // ---- RLE on the streams: per-window runs, flushed at window end, never merged across windows (quirk Q2) ----
+        // a run ends at step k when op k+1 differs (the streams are zero beyond the last step) and at the last step
+        uint32_t e[SW];
+        uint32_t edits = 0u, nb = 0u;
+        int steps = j;                                   // every step but a 'D' consumes a pattern character
 #pragma unroll
         for (int w = 0; w < SW; w++) {
-            // a run ends at step k when op k+1 differs; beyond the last step the stream is zero, so a last run of
-            // anything but '=' ends itself and a last run of '=' is emitted below
-            const uint32_t nxt = __funnelshift_r(acc[w], w + 1 < SW ? acc[w + 1] : 0u, 2);
-            const uint32_t t = acc[w] ^ nxt;
-            uint32_t e = (t | (t >> 1)) & 0x55555555u;
-            while (e) {
-                const int p = __ffs((int)e) - 1;
-                const int k = 16 * w + (p >> 1);
-                emit((acc[w] >> p) & 3u, (uint32_t)(k - start + 1));
-                start = k + 1;
-                e &= e - 1u;
+            steps += __popc(hs[w] & ls[w]);
+            edits += __popc(hs[w] | ls[w]);              // every op but '=' is an edit
+            const uint32_t hn = __funnelshift_r(hs[w], w + 1 < SW ? hs[w + 1] : 0u, 1);
+            const uint32_t ln = __funnelshift_r(ls[w], w + 1 < SW ? ls[w + 1] : 0u, 1);
+            e[w] = (hs[w] ^ hn) | (ls[w] ^ ln);
+        }
+#pragma unroll
+        for (int w = 0; w < SW; w++) {
+            const int last = steps - 1 - 32 * w;         // steps >= 1: a window with m >= 1 takes at least one step
+            if (last >= 0 && last < 32) e[w] |= 1u << last;
+            nb += __popc(e[w]);
+        }
+        const bool fits = !want_cigar || (uint64_t)(out_end - out) >= (uint64_t)nb;
+        if (!fits) overflow = true;
+        if (want_cigar && fits) {
+            int start = -1;                              // step before the current run's first
+#pragma unroll
+            for (int w = 0; w < SW; w++) {
+                uint32_t ew = e[w];
+                while (ew) {
+                    const int p = __ffs((int)ew) - 1;
+                    const uint32_t o = ((hs[w] >> p) & 1u) * 2u + ((ls[w] >> p) & 1u);
+                    *out++ = (uint8_t)(o * 64u + (uint32_t)(32 * w + p - start));
+                    start = 32 * w + p;
+                    ew &= ew - 1u;
+                }
             }
         }
-        if (start < steps) emit(0u, (uint32_t)(steps - start));
+        nruns += nb;
         ed += edits;
         t_pos += (uint64_t)i;
         q_pos += (uint64_t)j;
