@@ -71,7 +71,10 @@ class Result:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib().sg_result_free(self._h)
+            try:
+                lib().sg_result_free(self._h)
+            except Exception:   # interpreter shutdown: the module globals are already gone
+                pass
             self._h = None
 
     def _arr(self, ptr, n, dtype):

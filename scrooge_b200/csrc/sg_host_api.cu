@@ -134,9 +134,19 @@ struct PinnedPool {
 };
 static PinnedPool g_pool;
 
+// SG_DEBUG=1: where the host time of a call goes (printed by run_all)
+struct HostTimes { double pack = 0, wait = 0, desc = 0, copy_out = 0; };
+static HostTimes g_ht;
+static const bool g_debug = std::getenv("SG_DEBUG") != nullptr;
+struct ScopedT {
+    double &acc; std::chrono::steady_clock::time_point t0;
+    explicit ScopedT(double &a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+    ~ScopedT() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 extern "C" uint64_t sg_host_pack_2bit_st(const char *ascii, uint64_t n_bases, uint32_t *packed);
 
-constexpr int kSlots = 3;
+constexpr int kMaxSlots = 8;
 
 // One pipeline stage's worth of buffers: a sub-batch lives in a slot from upload to download.
 struct Slot {
@@ -148,6 +158,7 @@ struct Slot {
     // the batch in flight
     bool busy = false, mid_done = false;
     uint64_t a0 = 0, a1 = 0, total_runs = 0;
+    uint64_t bad_bias[2] = {0, 0};   // hybrid ingest: the device-packed tail of a blob starts at this base
     int create()
     {
         SG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -175,7 +186,8 @@ struct Slot {
 
 struct Device {
     int id = 0;
-    Slot slots[kSlots];
+    Slot slots[kMaxSlots];
+    int n_slots = 3;
     DevBuf genome;  // packed reference, resident across calls
     uint64_t genome_len = 0;
     bool has_genome = false;
@@ -199,6 +211,12 @@ struct sg_ctx {
     // host threads per GPU (measured on the B200 box: 101 GB/s of ASCII on 16 threads vs 47 GB/s over PCIe).
     bool host_pack = false;
     int host_threads = 1;
+    // hybrid ingest (blob inputs with host packing): this fraction of every blob's tail goes over PCIe as ASCII while
+    // the host threads pack the head -- the copy engine and the packer run at the same time, and the device packs its
+    // share in a few hundred microseconds.  Balance: f_ascii = 1 - 1 / (Rpcie / Rhost + 0.75) ~ 0.25 at 47 GB/s of PCIe
+    // and the 79 GB/s the 16 host threads reach while the copy engine reads the same memory (101 GB/s alone).
+    double ascii_frac = 0.25;
+    uint64_t ascii_min_bytes = 8ull << 20;   // blobs smaller than this are not split
     std::mutex mu;  // calls on one context are serialised
 };
 
@@ -260,8 +278,9 @@ int bad_base_error(const char *what, const char *unit, uint64_t index, uint64_t 
 //   else:      ASCII crosses PCIe (a blob straight from the caller's memory, separate strings gathered into pinned
 //              staging first) and pack_2bit_kernel packs it; an offending base is then reported through d_bad.
 int upload_strings(sg_ctx *ctx, cudaStream_t st, const Strings &S, uint64_t i0, uint64_t i1, const char *what, const char *unit,
-                   DevBuf &d_ascii, DevBuf &d_packed, PinBuf &h_stage, uint64_t *d_bad, uint64_t *start)
+                   DevBuf &d_ascii, DevBuf &d_packed, PinBuf &h_stage, uint64_t *d_bad, uint64_t *start, uint64_t *bad_bias)
 {
+    *bad_bias = 0;
     const uint64_t n = i1 - i0;
     const int threads = ctx->host_threads;
     if (S.blob) {
@@ -276,11 +295,25 @@ int upload_strings(sg_ctx *ctx, cudaStream_t st, const Strings &S, uint64_t i0, 
         }
         R(h_stage.reserve(words * 4));
         uint32_t *hp = h_stage.as<uint32_t>();
-        const uint64_t used = (nbytes + 15) / 16;
-        const uint64_t bad = sg_host_pack_2bit(S.blob + base, nbytes, hp, threads);
+        // hybrid: bases [split, nbytes) travel as ASCII (the copy is queued first, so the copy engine works while the
+        // host packs [0, split)) and are packed on the device into the words that follow the host's
+        uint64_t split = nbytes;
+        if (ctx->ascii_frac > 0 && nbytes >= ctx->ascii_min_bytes && nbytes >= 128) split = (uint64_t)((double)nbytes * (1.0 - ctx->ascii_frac)) & ~63ull;
+        if (split < nbytes) {
+            R(d_ascii.reserve(nbytes - split + 64));
+            SG_CUDA(cudaMemcpyAsync(d_ascii.p, S.blob + base + split, nbytes - split, cudaMemcpyHostToDevice, st));
+        }
+        const uint64_t used = (split + 15) / 16;
+        uint64_t bad;
+        { ScopedT t(g_ht.pack); bad = sg_host_pack_2bit(S.blob + base, split, hp, threads); }
         if (bad != ~0ull) {
             const uint64_t i = (uint64_t)(std::upper_bound(S.off + i0, S.off + i1 + 1, base + bad) - S.off) - 1;
             return bad_base_error(what, unit, i, base + bad - S.off[i]);
+        }
+        if (split < nbytes) {
+            SG_CUDA(cudaMemcpyAsync(d_packed.p, hp, used * 4, cudaMemcpyHostToDevice, st));
+            *bad_bias = split;
+            return sg_dev_pack_2bit(d_ascii.as<char>(), nbytes - split, d_packed.as<uint32_t>() + used, d_bad, st);
         }
         memset(hp + used, 0, (words - used) * 4);  // padding words the aligner may read
         SG_CUDA(cudaMemcpyAsync(d_packed.p, hp, words * 4, cudaMemcpyHostToDevice, st));
@@ -336,8 +369,8 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
     uint64_t *d_tstart = s.desc.as<uint64_t>(), *d_tlen = d_tstart + n, *d_qstart = d_tlen + n, *d_qlen = d_qstart + n, *d_slab = d_qlen + n;
     const uint32_t *d_text;
     if (!w.mapping) {
-        R(upload_strings(ctx, st, w.text, a0, a1, "text", "pair", s.ascii_t, s.packed_t, s.h_stage_t, s.bad.as<uint64_t>(), h_tstart));
-        R(upload_strings(ctx, st, w.query, a0, a1, "query", "pair", s.ascii_q, s.packed_q, s.h_stage_q, s.bad.as<uint64_t>() + 1, h_qstart));
+        R(upload_strings(ctx, st, w.text, a0, a1, "text", "pair", s.ascii_t, s.packed_t, s.h_stage_t, s.bad.as<uint64_t>(), h_tstart, &s.bad_bias[0]));
+        R(upload_strings(ctx, st, w.query, a0, a1, "query", "pair", s.ascii_q, s.packed_q, s.h_stage_q, s.bad.as<uint64_t>() + 1, h_qstart, &s.bad_bias[1]));
         for (uint64_t k = 0; k < n; k++) { h_tlen[k] = w.text.size(a0 + k); h_qlen[k] = w.query.size(a0 + k); }
         d_text = s.packed_t.as<uint32_t>();
     } else {
@@ -348,7 +381,7 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
         for (uint64_t c = a0; c < a1; c++) { r0 = std::min(r0, w.cand_read[c]); r1 = std::max(r1, w.cand_read[c]); }
         std::vector<uint64_t> rstart((uint64_t)r1 - r0 + 1);
         R(upload_strings(ctx, st, w.query, r0, (uint64_t)r1 + 1, "content", "read", s.ascii_q, s.packed_q, s.h_stage_q,
-                         s.bad.as<uint64_t>() + 1, rstart.data()));
+                         s.bad.as<uint64_t>() + 1, rstart.data(), &s.bad_bias[1]));
         for (uint64_t k = 0; k < n; k++) {
             const uint64_t cs = w.cand_start[a0 + k];
             const uint32_t r = w.cand_read[a0 + k];
@@ -359,6 +392,7 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
         }
         d_text = d.genome.as<uint32_t>();
     }
+    ScopedT t_desc(g_ht.desc);
     uint64_t slab_bytes = 0;
     for (uint64_t k = 0; k < n; k++) { h_slab[k] = slab_bytes; slab_bytes += 2ull * h_qlen[k] + 8ull; }
     h_slab[n] = slab_bytes;
@@ -389,13 +423,13 @@ int stage_b(Slot &s, const Workload &w)
     const uint64_t n = s.a1 - s.a0;
     const bool want_cigar = !(w.flags & SG_FLAG_DISTANCE_ONLY);
     cudaStream_t st = s.stream;
-    SG_CUDA(cudaEventSynchronize(s.ev_mid));
+    { ScopedT t(g_ht.wait); SG_CUDA(cudaEventSynchronize(s.ev_mid)); }
     s.mid_done = true;
     const uint64_t *h = s.h_small.as<uint64_t>();
     if (h[0] != ~0ull || h[1] != ~0ull) {
         // device ingest found an offending base at position h[] of the uploaded ASCII: find its string via the starts
         const bool in_text = h[0] != ~0ull;
-        const uint64_t pos = in_text ? h[0] : h[1];
+        const uint64_t pos = in_text ? h[0] + s.bad_bias[0] : h[1] + s.bad_bias[1];
         const uint64_t *hd = s.h_desc.as<uint64_t>();
         if (!w.mapping) {
             const uint64_t *start = in_text ? hd : hd + 2 * n;
@@ -429,8 +463,9 @@ int stage_c(Slot &s, const Workload &w, sg_result *res, ShardOut &so)
     const uint64_t n = s.a1 - s.a0;
     const bool want_cigar = !(w.flags & SG_FLAG_DISTANCE_ONLY);
     R(stage_b(s, w));
-    SG_CUDA(cudaEventSynchronize(s.ev_end));
+    { ScopedT t(g_ht.wait); SG_CUDA(cudaEventSynchronize(s.ev_end)); }
     s.busy = false;
+    ScopedT t_out(g_ht.copy_out);
     const uint8_t *status = s.h_status.as<uint8_t>();
     for (uint64_t k = 0; k < n; k++)
         if (status[k]) return fail(SG_ERR_CIGAR_OVERFLOW, "alignment " + std::to_string(s.a0 + k) + " exceeded its run capacity");
@@ -475,6 +510,7 @@ void run_shard(sg_ctx *ctx, Device &d, const Workload &w, const uint64_t *woff, 
         cuts.push_back(b);
     }
     const int nb = (int)cuts.size() - 1;
+    const int kSlots = d.n_slots;
     for (int k = 0; k < nb; k++) {
         Slot &s = d.slots[k % kSlots];
         int rc = stage_c(s, w, res, so);                       // frees the slot used by batch k - kSlots
@@ -568,6 +604,11 @@ int run_all(sg_ctx *ctx, const Workload &w, const uint64_t *woff, uint64_t per_u
     }
     finalize(res.get(), shards);
     res->total_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_begin).count();
+    if (g_debug) {
+        fprintf(stderr, "[sg] call %.1f ms: host pack %.1f, waits %.1f, results out %.1f, descriptors %.1f\n", res->total_ns / 1e6,
+                g_ht.pack * 1e3, g_ht.wait * 1e3, g_ht.copy_out * 1e3, g_ht.desc * 1e3);
+        g_ht = HostTimes();
+    }
     *out = res.release();
     return SG_OK;
 }
@@ -598,6 +639,8 @@ int sg_ctx_create(sg_ctx **out, const int *device_ids, int n_devices, int W)
         ctx->host_threads = std::max(1, hw / n_devices);
         ctx->host_pack = ctx->host_threads >= 10;   // ~7-10 GB/s of ASCII per thread against ~47 GB/s of PCIe per GPU
         if (const char *v = std::getenv("SG_HOST_PACK")) ctx->host_pack = std::atoi(v) != 0;
+        if (const char *v = std::getenv("SG_ASCII_MIN_BYTES")) ctx->ascii_min_bytes = (uint64_t)std::max(0ll, std::atoll(v));
+        if (const char *v = std::getenv("SG_ASCII_PCT")) ctx->ascii_frac = std::min(100, std::max(0, std::atoi(v))) / 100.0;
     }
     if (const char *v = std::getenv("SG_MAX_BATCH_MB")) {
         const long mb = std::atol(v);
@@ -608,12 +651,14 @@ int sg_ctx_create(sg_ctx **out, const int *device_ids, int n_devices, int W)
         d.id = device_ids ? device_ids[k] : k;
         if (d.id < 0 || d.id >= avail) return fail(SG_ERR_BAD_ARG, "device id out of range");
         SG_CUDA(cudaSetDevice(d.id));
-        for (Slot &s : d.slots) R(s.create());
+        if (const char *v = std::getenv("SG_SLOTS")) d.n_slots = std::min(kMaxSlots, std::max(2, std::atoi(v)));
+        for (int q = 0; q < d.n_slots; q++) R(d.slots[q].create());
         int wps = 0, sms = 0;
         R(sg_dev_align_geometry(W, &wps, nullptr, &sms));
-        // one alignment per resident lane fills the device (75 776 lanes on a B200 at W=64)
+        // one alignment per resident lane fills the device (104 192 lanes on a B200 at W=64)
         ctx->min_batch_units = std::max<uint64_t>(ctx->min_batch_units, 32ull * (uint64_t)wps * (uint64_t)sms);
     }
+    if (const char *v = std::getenv("SG_MIN_BATCH_UNITS")) ctx->min_batch_units = (uint64_t)std::max(1ll, std::atoll(v));
     *out = ctx.release();
     return SG_OK;
 }

@@ -237,13 +237,16 @@ def test_multi_gpu_context_matches_single(oracle, sglib):
     assert list(got.edit_distances) == list(want.edit) and got.cigars() == want.cigars
 
 
-@pytest.mark.parametrize("dc,forefront,host_pack", [("delta", "smem", "0"), ("delta", "smem", "1"), ("rows", "smem", "0"),
-                                                    ("rows", "tmem", "1"), ("rows", "smem", "1"), ("rows", "tmem", "0")])
+@pytest.mark.parametrize("dc,forefront,host_pack", [("delta", "smem", "0"), ("delta", "smem", "1"), ("delta", "smem", "hybrid"),
+                                                    ("rows", "smem", "0"), ("rows", "tmem", "1"), ("rows", "smem", "1"),
+                                                    ("rows", "tmem", "0")])
 def test_kernel_and_ingest_variants(dc, forefront, host_pack):
     """The alignment kernel exists in two bit-identical formulations (SG_DC=delta: column-wise +-1 deltas, the default;
     SG_DC=rows: the reference's row-wise threshold vectors, with the forefront in shared memory or in tensor memory) and
     the host API has two ingest paths (pack on the device or on the host); the defaults depend on W and on the host's
-    core count, so run the combinations, each in a fresh process (the choices are made once per process / context)."""
+    core count, so run the combinations, each in a fresh process (the choices are made once per process / context).
+    "hybrid" = host packing with half of every blob's bytes sent as ASCII and packed on the device (the split that large
+    blobs get by default, forced here on the small test inputs)."""
     import subprocess
     import sys
     code = (
@@ -282,7 +285,9 @@ def test_kernel_and_ingest_variants(dc, forefront, host_pack):
         "print('variant ok')\n"
     )
     import os
-    env = dict(os.environ, SG_DC=dc, SG_FOREFRONT=forefront, SG_HOST_PACK=host_pack)
+    env = dict(os.environ, SG_DC=dc, SG_FOREFRONT=forefront, SG_HOST_PACK="1" if host_pack == "hybrid" else host_pack)
+    if host_pack == "hybrid":
+        env.update(SG_ASCII_PCT="50", SG_ASCII_MIN_BYTES="0")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "variant ok" in r.stdout, r.stderr[-2000:]
