@@ -10,7 +10,8 @@ import os
 import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(ROOT, "scrooge_b200", "lib", "libscrooge_b200.so")
+# SG_LIB: another build of the same library (A/B timing of kernel variants by tools/kernel_time.py); never a fallback
+LIB_PATH = os.environ.get("SG_LIB") or os.path.join(ROOT, "scrooge_b200", "lib", "libscrooge_b200.so")
 
 SG_OK = 0
 SG_ERR_CUDA = 1

@@ -40,6 +40,10 @@
 
 namespace sg {
 
+#ifdef SG_STATS
+__device__ unsigned long long g_delta_stats[4];   // warp iterations: uniform DC, generic DC, fast TB, generic TB
+#endif
+
 template <int W> struct DeltaLayout {
     static constexpr int NW = W / 32;
     static constexpr int TBL = W - WinCfg<W>::O;
@@ -185,26 +189,45 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
             sts_vec<NW>(pm_s + 4 * PMS, hm);   // a character that matches nothing: columns i >= n
         }
         const bool uniform = __all_sync(0xFFFFFFFFu, !have || n == W);
+        // the first TB_LIMIT steps of a traceback cannot end it when the window holds at least TB_LIMIT pattern characters
+        // (after k steps i <= k and j <= k): warps whose lanes all have such a window walk them without any end test
+        const bool tb_fast = __all_sync(0xFFFFFFFFu, !have || m >= TBL);
+#ifdef SG_STATS
+        if (lane == 0) {
+            atomicAdd(&g_delta_stats[uniform ? 0 : 1], 1ull);
+            atomicAdd(&g_delta_stats[tb_fast ? 2 : 3], 1ull);
+        }
+#endif
 
         // ---- DC: columns W-1 .. 0, two delta vectors per lane ----------------------------------------------
         // lanes without work ride along on whatever their scratch holds; nothing of it is ever read
+        // Code size matters here: the SM's instruction cache holds 32 KB and 22 warps at different points of the loop
+        // body share it, so the 64 columns are NOT fully unrolled: two loops (columns without / with a traceback
+        // store) of NWIN/2 iterations over one 16-column text word each.
         auto columns = [&](auto uni) {
             constexpr bool UNI = decltype(uni)::value;
+            constexpr int HB = NWIN / 2;   // text words per half
+            static_assert(TBCOLS == HB * 16, "traceback columns = the lower half of the window");
 #pragma unroll
-            for (int blk = NWIN - 1; blk >= 0; blk--) {
-                uint32_t cw = tw[blk];
+            for (int half = 1; half >= 0; half--) {
+#pragma unroll 1
+                for (int b = HB - 1; b >= 0; b--) {
+                    uint32_t cw = tw[half * HB];
+                    if (HB == 2 && b == 1) cw = tw[half * HB + (HB - 1)];
+                    const int nrel = n - (half * HB + b) * 16;          // columns ii < nrel of this word hold text
+                    uint32_t *tbp = tb_s + b * 16 * TBS;
 #pragma unroll
-                for (int ii = 15; ii >= 0; ii--) {
-                    const int i = blk * 16 + ii;
-                    uint32_t code = cw >> 30;
-                    cw <<= 2;
-                    if (!UNI) code = i < n ? code : 4u;
-                    uint32_t pm[NW], Ph[NW];
-                    lds_vec<NW>(pm_s + code * PMS, pm);
-                    delta_column<NW>(Pv, Mv, pm, Ph);
-                    if (i < TBCOLS) {
-                        const uint32_t v = Pv[TOP], hh = Ph[TOP], e = pm[TOP];
-                        *reinterpret_cast<uint2 *>(tb_s + i * TBS) = make_uint2(v | hh, ~v & (hh | e));
+                    for (int ii = 15; ii >= 0; ii--) {
+                        uint32_t code = cw >> 30;
+                        cw <<= 2;
+                        if (!UNI) code = ii < nrel ? code : 4u;
+                        uint32_t pm[NW], Ph[NW];
+                        lds_vec<NW>(pm_s + code * PMS, pm);
+                        delta_column<NW>(Pv, Mv, pm, Ph);
+                        if (half == 0) {
+                            const uint32_t v = Pv[TOP], hh = Ph[TOP], e = pm[TOP];
+                            *reinterpret_cast<uint2 *>(tbp + ii * TBS) = make_uint2(v | hh, ~v & (hh | e));
+                        }
                     }
                 }
             }
@@ -231,19 +254,42 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
         uint32_t hs[SW], ls[SW];
         uint32_t ca, cb;
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ca), "=r"(cb) : "r"(tcol));
+        uint32_t h0 = 0u, l0 = 0u, bit0 = 1u;
+        if (tb_fast) {
+            // software-pipelined: the planes of column i+1 are loaded one step before the walk can reach them, so the
+            // shared-memory latency is off the step's dependence chain (19 of 20 steps move to the next column)
+            uint32_t na, nb;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(na), "=r"(nb) : "r"(tcol), "n"(TBS * 4));
+#pragma unroll
+            for (int k = 0; k < TBL; k++) {
+                const bool hi = (ca & mask) != 0u;
+                const bool lo = (cb & mask) != 0u;
+                if (hi) h0 |= 1u << k;
+                if (lo) l0 |= 1u << k;
+                if (!(hi && !lo)) {                   // every op but 'I' consumes a text character
+                    tcol += TBS * 4;
+                    ca = na;
+                    cb = nb;
+                }
+                if (!(hi && lo)) mask >>= 1;          // every op but 'D' consumes a pattern character
+                if (k + 1 < TBL)                      // (the last prefetch would be column TB_LIMIT+1, which does not exist)
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(na), "=r"(nb) : "r"(tcol), "n"(TBS * 4));
+            }
+            bit0 = TBL < 32 ? 1u << (TBL & 31) : 0u;
+        }
 #pragma unroll
         for (int w = 0; w < SW; w++) {
-            uint32_t h = 0u, l = 0u;
-            if (mask != mask_end && tcol != tb_end) {
-                uint32_t bit = 1u;
+            uint32_t h = w == 0 ? h0 : 0u, l = w == 0 ? l0 : 0u;
+            uint32_t bit = w == 0 ? bit0 : 1u;
+            if (bit != 0u && mask != mask_end && tcol != tb_end) {
                 do {
                     const bool hi = (ca & mask) != 0u;
                     const bool lo = (cb & mask) != 0u;
                     if (hi) h |= bit;
                     if (lo) l |= bit;
                     bit <<= 1;
-                    if (!(hi && !lo)) tcol += TBS * 4;    // every op but 'I' consumes a text character
-                    if (!(hi && lo)) mask >>= 1;          // every op but 'D' consumes a pattern character
+                    if (!(hi && !lo)) tcol += TBS * 4;
+                    if (!(hi && lo)) mask >>= 1;
                     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ca), "=r"(cb) : "r"(tcol));
                 } while (bit != 0u && mask != mask_end && tcol != tb_end);
             }

@@ -262,6 +262,15 @@ int sg_dev_align(int W, const uint32_t *d_text, const uint64_t *d_text_start, co
     return W == 64 ? launch_align<64, false>(*di, P, st) : launch_align<32, false>(*di, P, st);
 }
 
+#ifdef SG_STATS
+int sg_dev_debug_stats(uint64_t *out4, int reset)
+{
+    SG_CUDA(cudaMemcpyFromSymbol(out4, g_delta_stats, 32));
+    if (reset) { uint64_t z[4] = {0, 0, 0, 0}; SG_CUDA(cudaMemcpyToSymbol(g_delta_stats, z, 32)); }
+    return SG_OK;
+}
+#endif
+
 uint64_t sg_scan_tmp_bytes(uint64_t n) { return ((n + kScanTile - 1) / kScanTile + 1) * sizeof(uint64_t); }
 
 int sg_dev_scan_runs(const uint32_t *d_nruns, uint64_t n, uint64_t *d_run_off, void *d_scan_tmp, void *stream)
