@@ -48,11 +48,12 @@ template <int W> struct DeltaLayout {
     static constexpr int NW = W / 32;
     static constexpr int TBL = W - WinCfg<W>::O;
     static constexpr int TBCOLS = TBL + 1;
-    static constexpr int PM_WORDS = 5 * NW * 32;        // [base code 0..3, 4 = "matches nothing"][lane][NW]
+    static constexpr int PMS = 64;                      // words between the masks of consecutive base codes (256 B: see the DC loop)
+    static constexpr int PM_WORDS = 5 * PMS;            // [base code 0..3, 4 = "matches nothing"][lane][NW]
     static constexpr int TB_WORDS = TBCOLS * 2 * 32;    // [column][lane][A,B]: the traceback's op per pattern position, 2 bit planes
     static constexpr int WORDS_PER_WARP = PM_WORDS + TB_WORDS;
     static constexpr int BYTES_PER_WARP = WORDS_PER_WARP * 4;
-    static constexpr int WARPS_PER_CTA = 1;
+    static constexpr int WARPS_PER_CTA = 4;             // 4 x 9.25 KB + 1 KB reserved = 38 KB: 6 CTAs = 24 warps per SM
     static constexpr int BYTES_PER_CTA = BYTES_PER_WARP * WARPS_PER_CTA;
 };
 
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
     constexpr int TBL = L::TBL;
     constexpr int TBCOLS = L::TBCOLS;
     constexpr int TOP = NW - 1;
-    constexpr int PMS = NW * 32;   // words between the masks of consecutive base codes
+    constexpr int PMS = L::PMS;    // words between the masks of consecutive base codes
     constexpr int TBS = 2 * 32;    // words between traceback columns
 
     extern __shared__ __align__(16) uint32_t smem_all[];
@@ -216,13 +217,19 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
                     if (HB == 2 && b == 1) cw = tw[half * HB + (HB - 1)];
                     const int nrel = n - (half * HB + b) * 16;          // columns ii < nrel of this word hold text
                     uint32_t *tbp = tb_s + b * 16 * TBS;
+                    // base codes as shared-memory offsets: four masked copies hold the codes of columns 4q+r in byte q,
+                    // and one byte permute per column moves that byte to bits 15:8 (code * 256 B, the mask table's stride)
+                    uint32_t cq[4];
+                    cq[0] = cw & 0x03030303u;
+                    cq[1] = (cw >> 2) & 0x03030303u;
+                    cq[2] = (cw >> 4) & 0x03030303u;
+                    cq[3] = (cw >> 6) & 0x03030303u;
 #pragma unroll
                     for (int ii = 15; ii >= 0; ii--) {
-                        uint32_t code = cw >> 30;
-                        cw <<= 2;
-                        if (!UNI) code = ii < nrel ? code : 4u;
+                        uint32_t off = __byte_perm(cq[ii & 3], 0u, 0x4404u | ((uint32_t)(ii >> 2) << 4));
+                        if (!UNI) off = ii < nrel ? off : 4u * PMS * 4u;
                         uint32_t pm[NW], Ph[NW];
-                        lds_vec<NW>(pm_s + code * PMS, pm);
+                        lds_vec<NW>(reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(pm_s) + off), pm);
                         delta_column<NW>(Pv, Mv, pm, Ph);
                         if (half == 0) {
                             const uint32_t v = Pv[TOP], hh = Ph[TOP], e = pm[TOP];
@@ -256,24 +263,30 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ca), "=r"(cb) : "r"(tcol));
         uint32_t h0 = 0u, l0 = 0u, bit0 = 1u;
         if (tb_fast) {
-            // software-pipelined: the planes of column i+1 are loaded one step before the walk can reach them, so the
-            // shared-memory latency is off the step's dependence chain (19 of 20 steps move to the next column)
-            uint32_t na, nb;
-            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(na), "=r"(nb) : "r"(tcol), "n"(TBS * 4));
 #pragma unroll
             for (int k = 0; k < TBL; k++) {
-                const bool hi = (ca & mask) != 0u;
-                const bool lo = (cb & mask) != 0u;
-                if (hi) h0 |= 1u << k;
-                if (lo) l0 |= 1u << k;
-                if (!(hi && !lo)) {                   // every op but 'I' consumes a text character
-                    tcol += TBS * 4;
-                    ca = na;
-                    cb = nb;
-                }
-                if (!(hi && lo)) mask >>= 1;          // every op but 'D' consumes a pattern character
-                if (k + 1 < TBL)                      // (the last prefetch would be column TB_LIMIT+1, which does not exist)
-                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(na), "=r"(nb) : "r"(tcol), "n"(TBS * 4));
+                // one step, written out as predicated instructions (the compiler's version spends selects on them):
+                //   hi/lo = the op's two bits; every op but 'I' (hi & !lo) consumes a text character (next column),
+                //   every op but 'D' (hi & lo) consumes a pattern character (mask >>= 1)
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred ph, pl, pi, pd;\n\t"
+                    ".reg .b32 t;\n\t"
+                    "and.b32 t, %2, %4;\n\t"
+                    "setp.ne.u32 ph, t, 0;\n\t"
+                    "and.b32 t, %3, %4;\n\t"
+                    "setp.ne.u32 pl, t, 0;\n\t"
+                    "@ph or.b32 %0, %0, %6;\n\t"
+                    "@pl or.b32 %1, %1, %6;\n\t"
+                    "and.pred pd, ph, pl;\n\t"
+                    "not.pred pi, pl;\n\t"
+                    "and.pred pi, pi, ph;\n\t"
+                    "@!pi add.u32 %5, %5, %7;\n\t"
+                    "@!pd shr.u32 %4, %4, 1;\n\t"
+                    "ld.shared.v2.u32 {%2, %3}, [%5];\n\t"
+                    "}"
+                    : "+r"(h0), "+r"(l0), "+r"(ca), "+r"(cb), "+r"(mask), "+r"(tcol)
+                    : "r"(1u << k), "n"(TBS * 4));
             }
             bit0 = TBL < 32 ? 1u << (TBL & 31) : 0u;
         }
