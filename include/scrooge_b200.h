@@ -156,13 +156,15 @@ int sg_dev_pack_2bit(const char *d_ascii, uint64_t n_bases, uint32_t *d_packed, 
  * outputs per alignment: d_edit (int64), d_ref_consumed (uint64), d_nruns (uint32),
  *   d_status (uint8: SG_OK or SG_ERR_CIGAR_OVERFLOW); optional (may be NULL) d_dc_entries (uint64): the
  *   alignment's algorithmic DC work, sum over its windows of (d_w+1)*(n_w+1) R[d][i] entries -- the
- *   early-termination-minimal count of reference src/genasm_cpu.cpp:214-216,278-283 (roofline numerator)
+ *   early-termination-minimal count of reference src/genasm_cpu.cpp:214-216,278-283 (roofline numerator);
+ *   optional d_windows (uint32): the number of windows the alignment took (iterations of the reference's loop
+ *   src/genasm_cpu.cpp:417-436) -- the unit of the work the delta-encoded kernel actually does
  * Replaces genasm_kernel (reference src/genasm_gpu.cu:583-629).  W is 64 or 32. */
 int sg_dev_align(int W, const uint32_t *d_text, const uint64_t *d_text_start, const uint64_t *d_text_len,
                  const uint32_t *d_query, const uint64_t *d_query_start, const uint64_t *d_query_len,
                  uint64_t n, uint32_t flags, uint8_t *d_slab, const uint64_t *d_slab_off,
                  uint64_t *d_counter, int64_t *d_edit, uint64_t *d_ref_consumed, uint32_t *d_nruns,
-                 uint8_t *d_status, uint64_t *d_dc_entries, void *stream);
+                 uint8_t *d_status, uint64_t *d_dc_entries, uint32_t *d_windows, void *stream);
 
 /* CIGAR compaction: exclusive scan of d_nruns into d_run_off[n+1] (d_scan_tmp: sg_scan_tmp_bytes(n)
  * bytes), then gather every alignment's runs from its slab slot into one dense array.

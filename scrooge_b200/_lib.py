@@ -56,7 +56,7 @@ SIGNATURES = {
     "sg_host_pack_isa": (i32, []),
     "sg_packed_words": (u64, [u64]),
     "sg_dev_pack_2bit": (i32, [vp, u64, vp, vp, vp]),
-    "sg_dev_align": (i32, [i32, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "sg_dev_align": (i32, [i32, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "sg_scan_tmp_bytes": (u64, [u64]),
     "sg_dev_scan_runs": (i32, [vp, u64, vp, vp, vp]),
     "sg_dev_gather_runs": (i32, [vp, vp, vp, vp, u64, vp, vp]),

@@ -97,6 +97,10 @@ template <> __device__ __forceinline__ void tmem_st<2>(uint32_t taddr, const uin
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// The per-lane work counter carries the DC entries in its low 40 bits and the window count above them (one
+// accumulator, no extra register): good for reads up to ~500 Mbp.
+constexpr uint64_t kWindowUnit = 1ull << 40;
+
 struct AlignParams {
     const uint32_t *text;
     const uint64_t *text_start;
@@ -114,6 +118,7 @@ struct AlignParams {
     uint32_t *nruns;
     uint8_t *status;
     uint64_t *dc_entries;  // optional: sum over windows of (d_w+1)*(n+1), the early-termination-minimal DC work
+    uint32_t *windows;     // optional: number of windows of the alignment
 };
 
 // ---- small helpers -------------------------------------------------------------------------------
@@ -332,6 +337,7 @@ __global__ void __launch_bounds__(SmemLayout<W, TMEM>::WARPS_PER_CTA * 32, TMEM 
                     P.nruns[idx] = 0;
                     P.status[idx] = 0;
                     if (P.dc_entries) P.dc_entries[idx] = 0;
+                    if (P.windows) P.windows[idx] = 0;
                     continue;
                 }
                 pair = idx;
@@ -493,7 +499,7 @@ __global__ void __launch_bounds__(SmemLayout<W, TMEM>::WARPS_PER_CTA * 32, TMEM 
             d0 += G;
             continue;
         }
-        entries += (uint64_t)(d0 + above + 1) * (uint64_t)(n + 1);  // d_w = d0 + above
+        entries += (uint64_t)(d0 + above + 1) * (uint64_t)(n + 1) + kWindowUnit;  // d_w = d0 + above
         d0 = 0;
 
         // ---- TB: walk the V/H words and the mismatch bits from (0,0) ----------------------------------
@@ -569,7 +575,8 @@ __global__ void __launch_bounds__(SmemLayout<W, TMEM>::WARPS_PER_CTA * 32, TMEM 
             P.ref_consumed[pair] = t_pos - t_begin;
             P.nruns[pair] = nruns;
             P.status[pair] = overflow ? 5 : 0;
-            if (P.dc_entries) P.dc_entries[pair] = entries;
+            if (P.dc_entries) P.dc_entries[pair] = entries & (kWindowUnit - 1);
+            if (P.windows) P.windows[pair] = (uint32_t)(entries >> 40);
             have = false;
         }
     }

@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
                     P.nruns[idx] = 0;
                     P.status[idx] = 0;
                     if (P.dc_entries) P.dc_entries[idx] = 0;
+                    if (P.windows) P.windows[idx] = 0;
                     continue;
                 }
                 pair = idx;
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
             int dw = 0;
 #pragma unroll
             for (int k = 0; k < NW; k++) dw += __popc(Pv[k]) - __popc(Mv[k]);
-            entries += (uint64_t)(dw + 1) * (uint64_t)(n + 1);
+            entries += (uint64_t)(dw + 1) * (uint64_t)(n + 1) + kWindowUnit;
         }
 
         // ---- TB: walk the op planes from (0,0); the op of step k goes to bit k of two bit streams (hi, lo) ----
@@ -356,7 +357,8 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
             P.ref_consumed[pair] = t_pos - t_begin;
             P.nruns[pair] = nruns;
             P.status[pair] = overflow ? 5 : 0;
-            if (P.dc_entries) P.dc_entries[pair] = entries;
+            if (P.dc_entries) P.dc_entries[pair] = entries & (kWindowUnit - 1);
+            if (P.windows) P.windows[pair] = (uint32_t)(entries >> 40);
             have = false;
         }
     }

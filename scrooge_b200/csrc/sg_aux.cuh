@@ -19,15 +19,12 @@ __device__ __forceinline__ uint32_t pack4(uint32_t w, uint32_t &bad)
 {
     const uint32_t u = w & 0xDFDFDFDFu;                         // fold case
     const uint32_t x = ((u >> 1) ^ (u >> 2)) & 0x03030303u;     // 2-bit code in each byte
-    // every byte of x is 0x0k, so the low 16 bits of x are a PRMT selector (k0, 0, k1, 0): the permute
-    // returns (letter[k0], 'A', letter[k1], 'A'); same for the upper two bytes.  Compare with the input
-    // bytes spread the same way.
+    // every byte of x is 0x0k, so the low 16 bits of x | x >> 12 are the PRMT selector (k0, k2, k1, k3): one permute
+    // returns (letter[k0], letter[k2], letter[k1], letter[k3]); compare with the input bytes in the same order.
     const uint32_t letters = 0x54474341u;  // "ACGT"
-    const uint32_t e_lo = __byte_perm(letters, 0u, x);
-    const uint32_t e_hi = __byte_perm(letters, 0u, x >> 16);
-    const uint32_t u_lo = __byte_perm(u, 0x41414141u, 0x4140u);  // (b0, 'A', b1, 'A')
-    const uint32_t u_hi = __byte_perm(u, 0x41414141u, 0x4342u);  // (b2, 'A', b3, 'A')
-    bad |= (e_lo ^ u_lo) | (e_hi ^ u_hi);
+    const uint32_t e = __byte_perm(letters, 0u, x | (x >> 12));
+    const uint32_t v = __byte_perm(u, 0u, 0x3120u);              // (b0, b2, b1, b3)
+    bad |= e ^ v;
     return (x * 0x01041040u) >> 24;                             // 4 codes -> 8 bits, base k at bits 2k+1:2k
 }
 

@@ -237,7 +237,7 @@ int sg_dev_align(int W, const uint32_t *d_text, const uint64_t *d_text_start, co
                  const uint32_t *d_query, const uint64_t *d_query_start, const uint64_t *d_query_len,
                  uint64_t n, uint32_t flags, uint8_t *d_slab, const uint64_t *d_slab_off,
                  uint64_t *d_counter, int64_t *d_edit, uint64_t *d_ref_consumed, uint32_t *d_nruns,
-                 uint8_t *d_status, uint64_t *d_dc_entries, void *stream)
+                 uint8_t *d_status, uint64_t *d_dc_entries, uint32_t *d_windows, void *stream)
 {
     if (W != 64 && W != 32) return fail(SG_ERR_BAD_ARG, "W must be 64 or 32");
     if (n == 0) return SG_OK;
@@ -256,7 +256,7 @@ int sg_dev_align(int W, const uint32_t *d_text, const uint64_t *d_text_start, co
     P.query = d_query; P.query_start = d_query_start; P.query_len = d_query_len;
     P.n = n; P.flags = flags; P.slab = d_slab; P.slab_off = d_slab_off;
     P.counter = (unsigned long long *)d_counter;
-    P.edit = d_edit; P.ref_consumed = d_ref_consumed; P.nruns = d_nruns; P.status = d_status; P.dc_entries = d_dc_entries;
+    P.edit = d_edit; P.ref_consumed = d_ref_consumed; P.nruns = d_nruns; P.status = d_status; P.dc_entries = d_dc_entries; P.windows = d_windows;
     if (use_delta()) return W == 64 ? launch_delta<64>(*di, P, st) : launch_delta<32>(*di, P, st);
     if (use_tmem(W)) return W == 64 ? launch_align<64, true>(*di, P, st) : launch_align<32, true>(*di, P, st);
     return W == 64 ? launch_align<64, false>(*di, P, st) : launch_align<32, false>(*di, P, st);

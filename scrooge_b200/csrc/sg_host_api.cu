@@ -401,7 +401,7 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
     SG_CUDA(cudaEventRecord(s.ev_k0, st));
     R(sg_dev_align(ctx->W, d_text, d_tstart, d_tlen, s.packed_q.as<uint32_t>(), d_qstart, d_qlen, n, w.flags, s.slab.as<uint8_t>(), d_slab,
                    s.counter.as<uint64_t>(), s.edit.as<int64_t>(), s.refc.as<uint64_t>(), s.nruns.as<uint32_t>(), s.status.as<uint8_t>(),
-                   nullptr, st));
+                   nullptr, nullptr, st));
     SG_CUDA(cudaEventRecord(s.ev_k1, st));
     uint64_t *h = s.h_small.as<uint64_t>();
     SG_CUDA(cudaMemcpyAsync(h, s.bad.p, 16, cudaMemcpyDeviceToHost, st));

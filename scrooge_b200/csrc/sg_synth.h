@@ -32,9 +32,10 @@ SG_HD uint64_t sg_splitmix64(uint64_t &state)
 
 SG_HD uint64_t sg_synth_stride(uint32_t read_len, uint32_t slack)
 {
-    // deletions lengthen the text relative to the read; 2*L + 64 is far above anything the error models
-    // produce and the generator stops deleting when it gets there.
-    return 2ull * read_len + 64ull + slack;
+    // deletions lengthen the text relative to the read; the generator stops deleting once the text is L/8 + 32 bases
+    // ahead of the read (30 sigma above what the PacBio-like model does at 15 % error on 10 kbp), so a text never
+    // exceeds L + L/8 + 32 bases + slack.  Rounded up to a multiple of 16 (whole packed words per row).
+    return ((uint64_t)read_len + read_len / 8u + 32ull + slack + 15ull) & ~15ull;
 }
 
 // Generates pair `pair`; returns the text length.  text must hold sg_synth_stride() bytes, read read_len.
@@ -52,8 +53,8 @@ SG_HD uint64_t sg_synth_pair(const SgSynthParams &p, uint64_t pair, char *text, 
         uint32_t ob = (uint32_t)((r >> 2) & 3u);
         bool edit = (uint32_t)(r >> 32) < p.err_threshold && wsum > 0;
         uint32_t pick = edit ? (uint32_t)((r >> 8) & 0xFFFFFFu) % wsum : 0u;
-        // a deletion is only taken while tl <= rl + L + 32, so tl never exceeds 2L + 32 (+ slack)
-        if (edit && pick >= p.w_sub + p.w_ins && tl >= (uint64_t)rl + p.read_len + 32ull) edit = false;
+        // a deletion is only taken while tl < rl + L/8 + 32, so tl never exceeds L + L/8 + 32 (+ slack)
+        if (edit && pick >= p.w_sub + p.w_ins && tl >= (uint64_t)rl + p.read_len / 8u + 32ull) edit = false;
         if (!edit) {
             text[tl++] = bases[tb];
             read[rl++] = bases[tb];

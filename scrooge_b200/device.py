@@ -44,6 +44,7 @@ class AlignOut:
     nruns: torch.Tensor         # int32 storage of uint32 [n]
     status: torch.Tensor        # uint8 [n]
     dc_entries: torch.Tensor    # int64 storage of uint64 [n]: sum over windows of (d_w+1)*(n_w+1)
+    windows: torch.Tensor       # int32 storage of uint32 [n]: windows per alignment
 
 
 class DeviceAligner:
@@ -58,6 +59,7 @@ class DeviceAligner:
             nruns=torch.empty(n, dtype=torch.int32, device=device),
             status=torch.empty(n, dtype=torch.uint8, device=device),
             dc_entries=torch.empty(n, dtype=torch.int64, device=device),
+            windows=torch.empty(n, dtype=torch.int32, device=device),
         )
         self.slab = torch.empty(max(slab_bytes, 16), dtype=torch.uint8, device=device) if slab_bytes else None
         self.run_off = torch.empty(n + 1, dtype=torch.int64, device=device)
@@ -70,7 +72,7 @@ class DeviceAligner:
         o = self.out
         check(lib().sg_dev_align(self.W, _p(text), _p(text_start), _p(text_len), _p(query), _p(query_start), _p(query_len),
                                  self.n, flags, _p(self.slab), _p(slab_off), _p(self.counter), _p(o.edit),
-                                 _p(o.ref_consumed), _p(o.nruns), _p(o.status), _p(o.dc_entries), _stream()))
+                                 _p(o.ref_consumed), _p(o.nruns), _p(o.status), _p(o.dc_entries), _p(o.windows), _stream()))
         return o
 
     def compact(self, slab_off: torch.Tensor, runs: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:

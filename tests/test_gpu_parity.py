@@ -178,6 +178,7 @@ def test_device_api_resident_inputs(oracle, sglib):
     assert np.array_equal(out.edit.cpu().numpy(), want.edit)
     assert np.array_equal(out.ref_consumed.cpu().numpy().astype(np.uint64), want.ref_consumed)
     assert int(out.dc_entries.sum().item()) == want.stats["dc_entries"]  # the roofline's algorithmic work counter
+    assert int(out.windows.sum().item()) == want.stats["windows"]        # unit of the delta kernel's own work
     ro, rr = run_off.cpu().numpy(), runs.cpu().numpy()
     ops = "=XID"
     for k in (0, 1, 17, n - 1):
