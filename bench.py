@@ -270,13 +270,20 @@ def main():
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         e2e_s = sharding.max_over_ranks(e2e_s)
+        # the end-to-end results must be the device-resident path's results on the same pairs (those are checked against
+        # the CPU reference below): distances and run offsets of every pair
+        if not np.array_equal(np.asarray(res.edit_distances), da.out.edit[:ne].cpu().numpy()) or \
+                not np.array_equal(np.asarray(res.run_offsets, dtype=np.int64), da.run_off[:ne + 1].cpu().numpy()):
+            raise SystemExit("PARITY FAILURE: the end-to-end path and the device-resident path disagree")
         d2h = ne * 16 + (ne + 1) * 8 + int(res.run_offsets[-1]) + ne
         e2e = {"value": world * ne * args.steps / e2e_s, "unit": "alignments/s",
                "h2d_bytes_per_step": int(tb.nbytes + qb.nbytes + 2 * (ne + 1) * 8), "d2h_bytes_per_step": int(d2h),
                "pairs_per_step": ne, "ms_per_step": e2e_s / args.steps * 1e3,
                "host_threads_per_gpu": int(os.environ["SG_HOST_THREADS"]),
-               "api": "sg_align_pairs (C ABI, pinned host ASCII blobs in, distances + packed CIGAR runs out); ingest on the "
-                      "host (AVX-512, 2 bit/base before the upload) when a GPU has >= 10 host threads, else on the device"}
+               "api": "sg_align_pairs (C ABI, pinned host ASCII blobs in, distances + packed CIGAR runs out); adaptive ingest: "
+                      "host threads pack chunks to 2 bit/base (AVX-512) from the front of a blob while the copy engine "
+                      "takes ASCII chunks from its back for the device to pack",
+               "checked": "distances and run offsets equal to the device-resident path on all pairs"}
         del tb_pin, qb_pin
         al.close()
 
@@ -301,6 +308,16 @@ def main():
     # algorithmic HBM bytes of the alignment kernel per launch: packed text+query read once, runs + 28 B results written
     algo_bytes = int(tlen.sum()) / 4 + n * L / 4 + total_runs + n * (8 + 8 + 4 + 1 + 8) + n * 40
     wps, smem_warp, sms = device.align_geometry(W)
+    # DRAM traffic of the kernel from the committed `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum
+    # of one launch), scaled from that launch's pair count to this one's
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        if tr["workload"] == wl.name and delta:
+            traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["pairs_in_launch"] * n
+            traffic_src = tr["source"]
+    except (OSError, KeyError, ValueError):
+        pass
     # `achieved`/`frac`: the INT32 operations of the formulation the kernel RUNS (delta-encoded columns: windows x W
     # columns x 20 INT32 ops) against the measured LOP3/SHF issue peak -- a real fraction of the machine.
     # `reference_formulation`: SURVEY.md section 8(d)'s count (R[d][i] entries x 14 INT32 ops, what the reference's
@@ -310,7 +327,7 @@ def main():
     roofline = {"bound": "int32_alu",
                 "kernel": f"genasm_delta_kernel<{W}>" if delta else f"genasm_align_kernel<{W}>",
                 "achieved": own_gops / 1e3, "peak": peak_gops / 1e3, "unit": "TIOP/s", "frac": own_gops / peak_gops,
-                "traffic": None,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "sg_dev_int32_peak (LOP3+SHF 2:1 probe) measured in this run",
                 "algorithmic_ops_per_launch": own_ops,
                 "algorithmic_unit": (f"window column of the delta recurrence, {DELTA_OPS_PER_COLUMN[W]} INT32 ops; "

@@ -119,6 +119,7 @@ struct AlignParams {
     uint8_t *status;
     uint64_t *dc_entries;  // optional: sum over windows of (d_w+1)*(n+1), the early-termination-minimal DC work
     uint32_t *windows;     // optional: number of windows of the alignment
+    uint32_t k_one, k_two; // the constants 1 and 2, opaque to the compiler (sg_align_delta.cuh: fma-pipe shifts and adds)
 };
 
 // ---- small helpers -------------------------------------------------------------------------------

@@ -38,6 +38,26 @@
 #pragma once
 #include "sg_align.cuh"
 
+// Compile-time switches for A/B builds (tools/build_variants.sh).  All three were measured on a B200 against the plain
+// version (1 M x 10 kbp pairs, alignment kernel alone: 37.0 ms) and all three LOSE, so they are off:
+//   SG_DELTA_PFPM   pattern masks of column i-1 fetched from shared memory while column i is computed (37.8 ms: the
+//                   short-scoreboard stalls the ncu source view shows at the first use of an LDS are already covered
+//                   by the other warps of the scheduler -- the alu pipe is the limit -- and two more registers are live)
+//   SG_DELTA_FMA    the 64-bit addition and the two shifts of a column on the fma pipe (IMAD / IMAD.WIDE.U32 with run-time
+//                   multipliers 1 and 2 that ptxas cannot turn back into alu-pipe shifts: a column drops from 18 to 15
+//                   alu-pipe instructions, yet 39.8 ms: IMAD.WIDE issues too slowly to pay for the three SHF/IADD3 it saves)
+//   SG_DELTA_EARLY  the next window's text and pattern words requested right after the traceback, so that their L2
+//                   latency is covered by the run-length encoding (37.9 ms; 69 registers instead of 62)
+#ifndef SG_DELTA_PFPM
+#define SG_DELTA_PFPM 0
+#endif
+#ifndef SG_DELTA_FMA
+#define SG_DELTA_FMA 0
+#endif
+#ifndef SG_DELTA_EARLY
+#define SG_DELTA_EARLY 0
+#endif
+
 namespace sg {
 
 #ifdef SG_STATS
@@ -91,6 +111,49 @@ __device__ __forceinline__ void delta_column(uint32_t (&Pv)[NW], uint32_t (&Mv)[
     }
 }
 
+// The same column with the addition and the shifts on the fma pipe: the kernel is bound by the alu pipe (LOP3, SHF, IADD3,
+// PRMT: 18 of a column's 23 instructions at W=64) while the fma pipe idles.  one == 1 and two == 2 arrive as kernel
+// parameters so that the multiplications stay IMADs:
+//   t + Pv      = IMAD.WIDE.U32(t.lo, one, Pv) ; hi += t.hi * one          (was IADD3 + IMAD.X)
+//   x << 1      = IMAD.WIDE.U32(x.lo, two, 0)  ; hi = x.hi * two + carry   (was IMAD.IADD + SHF.L.W.HI)
+template <int NW>
+__device__ __forceinline__ void delta_column_fma(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&pm)[NW], uint32_t (&Ph)[NW],
+                                                 const uint32_t one, const uint32_t two)
+{
+    uint32_t t[NW], s[NW], x[NW], Mh[NW], Phs[NW], Mhs[NW];
+#pragma unroll
+    for (int k = 0; k < NW; k++) t[k] = ~pm[k] & Pv[k];
+    if constexpr (NW == 2) {
+        const uint64_t w = (uint64_t)t[0] * one + (((uint64_t)Pv[1] << 32) | Pv[0]);
+        s[0] = (uint32_t)w;
+        s[1] = t[1] * one + (uint32_t)(w >> 32);
+    } else {
+        s[0] = t[0] * one + Pv[0];
+    }
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        x[k] = (s[k] ^ Pv[k]) | ~pm[k];
+        Ph[k] = Mv[k] | ~(x[k] | Pv[k]);
+        Mh[k] = Pv[k] & x[k];
+    }
+    if constexpr (NW == 2) {
+        const uint64_t wp = (uint64_t)Ph[0] * two, wm = (uint64_t)Mh[0] * two;
+        Phs[0] = (uint32_t)wp;
+        Phs[1] = Ph[1] * two + (uint32_t)(wp >> 32);
+        Mhs[0] = (uint32_t)wm;
+        Mhs[1] = Mh[1] * two + (uint32_t)(wm >> 32);
+    } else {
+        Phs[0] = Ph[0] * two;
+        Mhs[0] = Mh[0] * two;
+    }
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        const uint32_t xv = ~pm[k] | Mv[k];
+        Pv[k] = Mhs[k] | ~(xv | Phs[k]);
+        Mv[k] = Phs[k] & xv;
+    }
+}
+
 template <int W>
 __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_delta_kernel(const AlignParams P)
 {
@@ -120,9 +183,9 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
     uint64_t entries = 0;
     bool overflow = false;
     int n = -1, m = 0;
-    uint32_t tw[NWIN];
+    uint32_t tw[NWIN], pw[NWIN];   // the window's text / pattern words
 #pragma unroll
-    for (int k = 0; k < NWIN; k++) tw[k] = 0;
+    for (int k = 0; k < NWIN; k++) { tw[k] = 0; pw[k] = 0; }
 
     while (true) {
         // ---- work queue: a lane without an alignment takes the next one ----------------------------
@@ -153,6 +216,10 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
                     out = P.slab + P.slab_off[idx];
                     out_end = P.slab + P.slab_off[idx + 1];
                 }
+#if SG_DELTA_EARLY
+                load_window<NWIN>(P.text, t_pos, tw);
+                load_window<NWIN>(P.query, q_pos, pw);
+#endif
                 have = true;
                 break;
             }
@@ -168,9 +235,10 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
             uint64_t tl = t_end - t_pos, ql = q_end - q_pos;
             n = tl < (uint64_t)W ? (int)tl : W;
             m = ql < (uint64_t)W ? (int)ql : W;
+#if !SG_DELTA_EARLY
             load_window<NWIN>(P.text, t_pos, tw);
-            uint32_t pw[NWIN];
             load_window<NWIN>(P.query, q_pos, pw);
+#endif
             uint32_t p0[NW], p1[NW], hm[NW];
             pattern_planes<NW>(pw, p0, p1);
             ones_shl<NW>(W - m, hm);
@@ -209,7 +277,19 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
         auto columns = [&](auto uni) {
             constexpr bool UNI = decltype(uni)::value;
             constexpr int HB = NWIN / 2;   // text words per half
+            constexpr uint32_t NONE = 4u * PMS * 4u;   // byte offset of the "matches nothing" masks
             static_assert(TBCOLS == HB * 16, "traceback columns = the lower half of the window");
+            const char *pmb = reinterpret_cast<const char *>(pm_s);
+#if SG_DELTA_PFPM
+            // the masks of a column are requested one column ahead: an LDS issued right before its first use costs a
+            // third of the column's time in short-scoreboard stalls (ncu source view of the previous version)
+            uint32_t pmn[NW];
+            {
+                uint32_t off = (tw[NWIN - 1] >> 22) & 0x300u;   // column 15 of the last word: code * 256 B
+                if (!UNI) off = 15 < n - (NWIN - 1) * 16 ? off : NONE;
+                lds_vec<NW>(reinterpret_cast<const uint32_t *>(pmb + off), pmn);
+            }
+#endif
 #pragma unroll
             for (int half = 1; half >= 0; half--) {
 #pragma unroll 1
@@ -225,13 +305,37 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
                     cq[1] = (cw >> 2) & 0x03030303u;
                     cq[2] = (cw >> 4) & 0x03030303u;
                     cq[3] = (cw >> 6) & 0x03030303u;
+#if SG_DELTA_PFPM
+                    // column 15 of the word that follows (none after the last word: any valid offset will do)
+                    uint32_t nwv = half == 1 ? tw[HB - 1] : 0u;
+                    if (HB == 2 && b == 1) nwv = tw[half * HB];
+                    uint32_t off15 = (nwv >> 22) & 0x300u;
+                    if (!UNI) off15 = nrel >= 0 ? off15 : NONE;      // 15 < nrel + 16
+#endif
 #pragma unroll
                     for (int ii = 15; ii >= 0; ii--) {
-                        uint32_t off = __byte_perm(cq[ii & 3], 0u, 0x4404u | ((uint32_t)(ii >> 2) << 4));
-                        if (!UNI) off = ii < nrel ? off : 4u * PMS * 4u;
                         uint32_t pm[NW], Ph[NW];
-                        lds_vec<NW>(reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(pm_s) + off), pm);
+#if SG_DELTA_PFPM
+#pragma unroll
+                        for (int k = 0; k < NW; k++) pm[k] = pmn[k];
+                        {
+                            uint32_t off = off15;
+                            if (ii > 0) {
+                                off = __byte_perm(cq[(ii - 1) & 3], 0u, 0x4404u | ((uint32_t)((ii - 1) >> 2) << 4));
+                                if (!UNI) off = ii - 1 < nrel ? off : NONE;
+                            }
+                            lds_vec<NW>(reinterpret_cast<const uint32_t *>(pmb + off), pmn);
+                        }
+#else
+                        uint32_t off = __byte_perm(cq[ii & 3], 0u, 0x4404u | ((uint32_t)(ii >> 2) << 4));
+                        if (!UNI) off = ii < nrel ? off : NONE;
+                        lds_vec<NW>(reinterpret_cast<const uint32_t *>(pmb + off), pm);
+#endif
+#if SG_DELTA_FMA
+                        delta_column_fma<NW>(Pv, Mv, pm, Ph, P.k_one, P.k_two);
+#else
                         delta_column<NW>(Pv, Mv, pm, Ph);
+#endif
                         if (half == 0) {
                             const uint32_t v = Pv[TOP], hh = Ph[TOP], e = pm[TOP];
                             *reinterpret_cast<uint2 *>(tbp + ii * TBS) = make_uint2(v | hh, ~v & (hh | e));
@@ -312,6 +416,14 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
         }
         const int i = (int)((tcol - tb_begin) / (TBS * 4));
         const int j = __clz(mask);
+        t_pos += (uint64_t)i;
+        q_pos += (uint64_t)j;
+#if SG_DELTA_EARLY
+        if (q_pos < q_end) {   // the next window's words travel while the runs are encoded and stored
+            load_window<NWIN>(P.text, t_pos, tw);
+            load_window<NWIN>(P.query, q_pos, pw);
+        }
+#endif
 
         // ---- RLE on the streams: per-window runs, flushed at window end, never merged across windows (quirk Q2) ----
         // a run ends at step k when op k+1 differs (the streams are zero beyond the last step) and at the last step
@@ -350,8 +462,6 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
         }
         nruns += nb;
         ed += edits;
-        t_pos += (uint64_t)i;
-        q_pos += (uint64_t)j;
         if (q_pos >= q_end) {
             P.edit[pair] = ed;
             P.ref_consumed[pair] = t_pos - t_begin;

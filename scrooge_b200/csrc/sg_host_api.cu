@@ -21,6 +21,7 @@
 #include <chrono>
 #include <algorithm>
 #include <memory>
+#include <omp.h>
 #include <cuda_runtime.h>
 
 #include "../../include/scrooge_b200.h"
@@ -147,11 +148,13 @@ struct ScopedT {
 extern "C" uint64_t sg_host_pack_2bit_st(const char *ascii, uint64_t n_bases, uint32_t *packed);
 
 constexpr int kMaxSlots = 8;
+constexpr int kMaxDmaDepth = 8;
 
 // One pipeline stage's worth of buffers: a sub-batch lives in a slot from upload to download.
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_mid = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_dma[kMaxDmaDepth] = {};   // adaptive ingest: one per ASCII chunk copy in flight
     DevBuf ascii_t, ascii_q, packed_t, packed_q, desc, slab, counter, edit, refc, nruns, status, run_off, scan_tmp, runs, bad;
     PinBuf h_small, h_edit, h_refc, h_runoff, h_status, h_stage_t, h_stage_q, h_desc;
     PinnedPool::Block piece{nullptr, 0};
@@ -166,6 +169,7 @@ struct Slot {
         SG_CUDA(cudaEventCreate(&ev_k1));
         SG_CUDA(cudaEventCreateWithFlags(&ev_mid, cudaEventDisableTiming));
         SG_CUDA(cudaEventCreateWithFlags(&ev_end, cudaEventDisableTiming));
+        for (cudaEvent_t &e : ev_dma) SG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
         return SG_OK;
     }
     void destroy()
@@ -180,6 +184,7 @@ struct Slot {
         if (ev_k1) cudaEventDestroy(ev_k1);
         if (ev_mid) cudaEventDestroy(ev_mid);
         if (ev_end) cudaEventDestroy(ev_end);
+        for (cudaEvent_t e : ev_dma) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -216,6 +221,13 @@ struct sg_ctx {
     // share in a few hundred microseconds.  Balance: f_ascii = 1 - 1 / (Rpcie / Rhost + 0.75) ~ 0.25 at 47 GB/s of PCIe
     // and the 79 GB/s the 16 host threads reach while the copy engine reads the same memory (101 GB/s alone).
     double ascii_frac = 0.25;
+    // adaptive ingest (the default for blob inputs): the blob is cut into chunks; the host threads pack chunks from the
+    // front (each packed chunk is uploaded as soon as it is done) while a feeder thread keeps `dma_depth` ASCII chunk
+    // copies from the back in flight; the device packs whatever arrived as ASCII.  Whoever is faster takes more: no
+    // tuned fraction, and it degrades gracefully when several ranks share the host's threads.
+    bool adaptive = true;
+    uint64_t chunk_bytes = 8ull << 20;
+    int dma_depth = 4;
     uint64_t ascii_min_bytes = 8ull << 20;   // blobs smaller than this are not split
     std::mutex mu;  // calls on one context are serialised
 };
@@ -272,12 +284,75 @@ int bad_base_error(const char *what, const char *unit, uint64_t index, uint64_t 
                                      std::to_string(pos));
 }
 
+// Adaptive ingest of one blob range (see sg_ctx::adaptive).  All copies go to `st` in issue order.
+int upload_blob_adaptive(sg_ctx *ctx, int dev_id, cudaStream_t st, cudaEvent_t *ev_dma, const char *src, uint64_t nbytes, DevBuf &d_ascii,
+                         DevBuf &d_packed, PinBuf &h_stage, uint64_t *d_bad, uint64_t *bad_pos, uint64_t *split_out)
+{
+    const uint64_t words = sg_packed_words(nbytes);
+    R(d_packed.reserve(words * 4));
+    R(h_stage.reserve(words * 4 + 64));
+    R(d_ascii.reserve(nbytes + 64));
+    uint32_t *hp = h_stage.as<uint32_t>();
+    const uint64_t C = ctx->chunk_bytes;   // a multiple of 256: chunks start on whole packed words and whole output cache lines
+    const long long nch = (long long)((nbytes + C - 1) / C);
+    const int depth = std::min(kMaxDmaDepth, std::max(1, ctx->dma_depth));
+    const int packers = std::max(1, ctx->host_threads);
+    std::mutex mu;
+    long long front = 0, back = nch;   // host threads take chunk `front++`, the feeder chunk `--back`
+    auto take_front = [&]() -> long long { std::lock_guard<std::mutex> g(mu); return front < back ? front++ : -1; };
+    auto take_back = [&]() -> long long { std::lock_guard<std::mutex> g(mu); return back > front ? --back : -1; };
+    uint64_t bad = ~0ull;
+    int cuda_rc = 0;   // shared; only ever set to 1
+    ScopedT t_pack(g_ht.pack);
+#pragma omp parallel num_threads(packers + 1) reduction(min : bad)
+    {
+        // the team may be smaller than asked for: the feeder role exists only when there is a second thread
+        const int tid = omp_get_thread_num(), team = omp_get_num_threads();
+        bool ok = cudaSetDevice(dev_id) == cudaSuccess;
+        if (ok && team > 1 && tid == 0) {
+            int issued = 0;
+            while (true) {
+                if (issued >= depth && cudaEventSynchronize(ev_dma[issued % depth]) != cudaSuccess) { ok = false; break; }
+                const long long c = take_back();
+                if (c < 0) break;
+                const uint64_t off = (uint64_t)c * C, len = std::min(C, nbytes - off);
+                if (cudaMemcpyAsync(d_ascii.as<char>() + off, src + off, len, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+                    cudaEventRecord(ev_dma[issued % depth], st) != cudaSuccess) { ok = false; break; }
+                issued++;
+            }
+        } else if (ok) {
+            while (true) {
+                const long long c = take_front();
+                if (c < 0) break;
+                const uint64_t off = (uint64_t)c * C, len = std::min(C, nbytes - off);
+                const uint64_t r = sg_host_pack_2bit_st(src + off, len, hp + off / 16);
+                if (r != ~0ull) { bad = std::min(bad, off + r); break; }
+                if (cudaMemcpyAsync(d_packed.as<uint32_t>() + off / 16, hp + off / 16, ((len + 15) / 16) * 4, cudaMemcpyHostToDevice, st) !=
+                    cudaSuccess) { ok = false; break; }
+            }
+        }
+        if (!ok) {
+#pragma omp atomic write
+            cuda_rc = 1;
+        }
+    }
+    if (cuda_rc) { cudaGetLastError(); return fail(SG_ERR_CUDA, "adaptive ingest: a CUDA call failed"); }
+    *bad_pos = bad;
+    if (bad != ~0ull) return SG_OK;   // the caller names the offender
+    const uint64_t split = std::min(nbytes, (uint64_t)back * C);   // [0, split) packed by the host, [split, nbytes) arrived as ASCII
+    *split_out = split;
+    if (split < nbytes) return sg_dev_pack_2bit(d_ascii.as<char>() + split, nbytes - split, d_packed.as<uint32_t>() + split / 16, d_bad, st);
+    const uint64_t used = (nbytes + 15) / 16;
+    SG_CUDA(cudaMemsetAsync(d_packed.as<uint32_t>() + used, 0, (words - used) * 4, st));  // padding words the aligner may read
+    return SG_OK;
+}
+
 // Strings [i0, i1) -> packed words on the device; start[k] receives the first base of string i0+k in the packed blob.
 //   host_pack: packed by the host threads straight into pinned staging (a blob as one stream, separate strings each
 //              at a word boundary), a quarter of the bytes cross PCIe;
 //   else:      ASCII crosses PCIe (a blob straight from the caller's memory, separate strings gathered into pinned
 //              staging first) and pack_2bit_kernel packs it; an offending base is then reported through d_bad.
-int upload_strings(sg_ctx *ctx, cudaStream_t st, const Strings &S, uint64_t i0, uint64_t i1, const char *what, const char *unit,
+int upload_strings(sg_ctx *ctx, int dev_id, cudaStream_t st, cudaEvent_t *ev_dma, const Strings &S, uint64_t i0, uint64_t i1, const char *what, const char *unit,
                    DevBuf &d_ascii, DevBuf &d_packed, PinBuf &h_stage, uint64_t *d_bad, uint64_t *start, uint64_t *bad_bias)
 {
     *bad_bias = 0;
@@ -287,6 +362,16 @@ int upload_strings(sg_ctx *ctx, cudaStream_t st, const Strings &S, uint64_t i0, 
         const uint64_t base = S.off[i0], nbytes = S.off[i1] - base;
         for (uint64_t k = 0; k < n; k++) start[k] = S.off[i0 + k] - base;
         const uint64_t words = sg_packed_words(nbytes);
+        if (ctx->adaptive && nbytes >= ctx->ascii_min_bytes && nbytes >= 256) {
+            uint64_t bad = ~0ull, split = nbytes;
+            R(upload_blob_adaptive(ctx, dev_id, st, ev_dma, S.blob + base, nbytes, d_ascii, d_packed, h_stage, d_bad, &bad, &split));
+            if (bad != ~0ull) {
+                const uint64_t i = (uint64_t)(std::upper_bound(S.off + i0, S.off + i1 + 1, base + bad) - S.off) - 1;
+                return bad_base_error(what, unit, i, base + bad - S.off[i]);
+            }
+            *bad_bias = split < nbytes ? split : 0;
+            return SG_OK;
+        }
         R(d_packed.reserve(words * 4));
         if (!ctx->host_pack) {
             R(d_ascii.reserve(nbytes + 64));
@@ -369,8 +454,8 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
     uint64_t *d_tstart = s.desc.as<uint64_t>(), *d_tlen = d_tstart + n, *d_qstart = d_tlen + n, *d_qlen = d_qstart + n, *d_slab = d_qlen + n;
     const uint32_t *d_text;
     if (!w.mapping) {
-        R(upload_strings(ctx, st, w.text, a0, a1, "text", "pair", s.ascii_t, s.packed_t, s.h_stage_t, s.bad.as<uint64_t>(), h_tstart, &s.bad_bias[0]));
-        R(upload_strings(ctx, st, w.query, a0, a1, "query", "pair", s.ascii_q, s.packed_q, s.h_stage_q, s.bad.as<uint64_t>() + 1, h_qstart, &s.bad_bias[1]));
+        R(upload_strings(ctx, d.id, st, s.ev_dma, w.text, a0, a1, "text", "pair", s.ascii_t, s.packed_t, s.h_stage_t, s.bad.as<uint64_t>(), h_tstart, &s.bad_bias[0]));
+        R(upload_strings(ctx, d.id, st, s.ev_dma, w.query, a0, a1, "query", "pair", s.ascii_q, s.packed_q, s.h_stage_q, s.bad.as<uint64_t>() + 1, h_qstart, &s.bad_bias[1]));
         for (uint64_t k = 0; k < n; k++) { h_tlen[k] = w.text.size(a0 + k); h_qlen[k] = w.query.size(a0 + k); }
         d_text = s.packed_t.as<uint32_t>();
     } else {
@@ -380,7 +465,7 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
         uint32_t r0 = w.cand_read[a0], r1 = w.cand_read[a0];
         for (uint64_t c = a0; c < a1; c++) { r0 = std::min(r0, w.cand_read[c]); r1 = std::max(r1, w.cand_read[c]); }
         std::vector<uint64_t> rstart((uint64_t)r1 - r0 + 1);
-        R(upload_strings(ctx, st, w.query, r0, (uint64_t)r1 + 1, "content", "read", s.ascii_q, s.packed_q, s.h_stage_q,
+        R(upload_strings(ctx, d.id, st, s.ev_dma, w.query, r0, (uint64_t)r1 + 1, "content", "read", s.ascii_q, s.packed_q, s.h_stage_q,
                          s.bad.as<uint64_t>() + 1, rstart.data(), &s.bad_bias[1]));
         for (uint64_t k = 0; k < n; k++) {
             const uint64_t cs = w.cand_start[a0 + k];
@@ -641,6 +726,12 @@ int sg_ctx_create(sg_ctx **out, const int *device_ids, int n_devices, int W)
         if (const char *v = std::getenv("SG_HOST_PACK")) ctx->host_pack = std::atoi(v) != 0;
         if (const char *v = std::getenv("SG_ASCII_MIN_BYTES")) ctx->ascii_min_bytes = (uint64_t)std::max(0ll, std::atoll(v));
         if (const char *v = std::getenv("SG_ASCII_PCT")) ctx->ascii_frac = std::min(100, std::max(0, std::atoi(v))) / 100.0;
+        // SG_INGEST=adaptive (default) | fixed: the pre-adaptive policies (host packing with a fixed ASCII share when the
+        // GPU has >= 10 host threads, else ASCII upload + device packing); SG_HOST_PACK / SG_ASCII_PCT imply fixed
+        ctx->adaptive = !std::getenv("SG_HOST_PACK") && !std::getenv("SG_ASCII_PCT");
+        if (const char *v = std::getenv("SG_INGEST")) ctx->adaptive = std::string(v) == "adaptive";
+        if (const char *v = std::getenv("SG_CHUNK_KB")) ctx->chunk_bytes = std::max<uint64_t>(256, ((uint64_t)std::max(1ll, std::atoll(v)) << 10) & ~255ull);
+        if (const char *v = std::getenv("SG_DMA_DEPTH")) ctx->dma_depth = std::min(kMaxDmaDepth, std::max(1, std::atoi(v)));
     }
     if (const char *v = std::getenv("SG_MAX_BATCH_MB")) {
         const long mb = std::atol(v);

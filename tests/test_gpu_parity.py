@@ -239,6 +239,7 @@ def test_multi_gpu_context_matches_single(oracle, sglib):
 
 
 @pytest.mark.parametrize("dc,forefront,host_pack", [("delta", "smem", "0"), ("delta", "smem", "1"), ("delta", "smem", "hybrid"),
+                                                    ("delta", "smem", "adaptive"),
                                                     ("rows", "smem", "0"), ("rows", "tmem", "1"), ("rows", "smem", "1"),
                                                     ("rows", "tmem", "0")])
 def test_kernel_and_ingest_variants(dc, forefront, host_pack):
@@ -246,8 +247,9 @@ def test_kernel_and_ingest_variants(dc, forefront, host_pack):
     SG_DC=rows: the reference's row-wise threshold vectors, with the forefront in shared memory or in tensor memory) and
     the host API has two ingest paths (pack on the device or on the host); the defaults depend on W and on the host's
     core count, so run the combinations, each in a fresh process (the choices are made once per process / context).
-    "hybrid" = host packing with half of every blob's bytes sent as ASCII and packed on the device (the split that large
-    blobs get by default, forced here on the small test inputs)."""
+    "hybrid" = host packing with half of every blob's bytes sent as ASCII and packed on the device; "adaptive" = host
+    threads and the copy engine share a blob chunk by chunk (the default for large blobs; forced here on the small test
+    inputs with 1 KB chunks)."""
     import subprocess
     import sys
     code = (
@@ -283,10 +285,22 @@ def test_kernel_and_ingest_variants(dc, forefront, host_pack):
         "    raise SystemExit('bad base not detected')\n"
         "except scrooge_b200.ScroogeError as e:\n"
         "    assert e.code == 2 and 'pair 1' in str(e) and 'position 8' in str(e), str(e)\n"
+        "for T, Q, where in ((['ACGT' * 200, 'ACGT' * 100 + 'N' + 'ACGT' * 100], ['ACGT', 'ACGT'], ('pair 1', 'position 400')),\n"
+        "                    (['ACGN' + 'ACGT' * 400, 'ACGT' * 200], ['ACGT', 'ACGT'], ('pair 0', 'position 3')),\n"
+        "                    (['ACGT' * 300, 'ACGT' * 300], ['ACGT' * 200, 'ACGT' * 100 + 'acgtn' + 'ACGT' * 100], ('pair 1', 'position 404'))):\n"
+        "    try:\n"
+        "        scrooge_b200.Aligner(W=64, n_gpus=1).align_pairs(T, Q)\n"
+        "        raise SystemExit('bad base not detected (long strings)')\n"
+        "    except scrooge_b200.ScroogeError as e:\n"
+        "        assert e.code == 2 and all(x in str(e) for x in where), str(e)\n"
         "print('variant ok')\n"
     )
     import os
-    env = dict(os.environ, SG_DC=dc, SG_FOREFRONT=forefront, SG_HOST_PACK="1" if host_pack == "hybrid" else host_pack)
+    env = dict(os.environ, SG_DC=dc, SG_FOREFRONT=forefront)
+    if host_pack == "adaptive":   # the default for large blobs, forced here on the small test inputs with 1 KB chunks
+        env.update(SG_INGEST="adaptive", SG_ASCII_MIN_BYTES="0", SG_CHUNK_KB="1")
+    else:
+        env.update(SG_HOST_PACK="1" if host_pack == "hybrid" else host_pack)
     if host_pack == "hybrid":
         env.update(SG_ASCII_PCT="50", SG_ASCII_MIN_BYTES="0")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

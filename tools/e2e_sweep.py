@@ -19,11 +19,9 @@ tb, toff, qb, qoff = synth.pairs_as_blobs(text, tlen, reads)
 del text
 tb_pin = torch.from_numpy(tb).pin_memory()
 qb_pin = torch.from_numpy(qb).pin_memory()
-SETTINGS = [dict(), dict(SG_ASCII_PCT="0"), dict(SG_ASCII_PCT="30"),
-            dict(SG_MIN_BATCH_UNITS="16384", SG_SLOTS="4"), dict(SG_MIN_BATCH_UNITS="16384", SG_SLOTS="6"),
-            dict(SG_MIN_BATCH_UNITS="32768", SG_SLOTS="4"), dict(SG_MIN_BATCH_UNITS="32768", SG_SLOTS="6", SG_ASCII_PCT="30"),
-            dict(SG_MIN_BATCH_UNITS="8192", SG_SLOTS="8"), dict(SG_MIN_BATCH_UNITS="16384", SG_SLOTS="8", SG_ASCII_PCT="25"),
-            dict(SG_HOST_PACK="0", SG_MIN_BATCH_UNITS="16384", SG_SLOTS="6")]
+SETTINGS = [dict(), dict(SG_INGEST="fixed"), dict(SG_CHUNK_KB="2048"), dict(SG_CHUNK_KB="32768"), dict(SG_DMA_DEPTH="2"),
+            dict(SG_DMA_DEPTH="8"), dict(SG_CHUNK_KB="4096", SG_DMA_DEPTH="8"), dict(SG_SLOTS="4"),
+            dict(SG_HOST_THREADS="15"), dict(SG_HOST_THREADS="8"), dict(SG_HOST_THREADS="2"), dict(SG_HOST_PACK="0")]
 KEYS = sorted({k for s in SETTINGS for k in s})
 for st in SETTINGS:
     for k in KEYS:
