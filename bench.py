@@ -247,11 +247,18 @@ def main():
     windows = int(da.out.windows.sum())      # windows of this rank's batch: the delta kernel runs W columns for each
     total_runs = int(da.run_off[-1])
     mean_ed = float(da.out.edit.double().mean())
+    # every alignment of the timed batch: run counts in range and consistent with query length, consumed reference prefix
+    # and edit distance (the sequence-independent validateCigarString properties, src/tests.cu:106-169)
+    n_inconsistent = device.check_runs(runs, da.run_off, qlen, da.out, W)
+    if n_inconsistent:
+        raise SystemExit(f"PARITY FAILURE: {n_inconsistent} alignments of the timed batch have inconsistent CIGAR runs")
 
     # ---- end to end through the host C ABI (host buffers, copies inside the timed region) ----------
     e2e = None
     if not args.no_e2e:
-        ne = min(args.e2e_pairs, n)
+        # the ranks of a box share one host (its cores and its DRAM bandwidth bound this path), so the end-to-end batch
+        # per GPU shrinks with the GPU count -- but never below one alignment per resident lane
+        ne = min(max(args.e2e_pairs // world, 131_072), n)
         h_text, h_tlen, h_reads = synth.pairs_host(wl, first_pair, ne)
         tb, toff, qb, qoff = synth.pairs_as_blobs(h_text, h_tlen, h_reads)
         del h_text
@@ -360,7 +367,10 @@ def main():
             if s is not None and s != ref.cigars[k]:
                 ok = False
                 break
-        parity = {"pairs": ns, "cigars_compared": (ns + 15) // 16, "bit_exact": ok, "against": cpu["kind"]}
+        parity = {"pairs": ns, "cigars_compared": (ns + 15) // 16, "bit_exact": ok, "against": cpu["kind"],
+                  "full_batch_properties": {"alignments": n, "inconsistent": n_inconsistent,
+                                            "checked": "run counts in [1, W-O]; sum(=XI) == |query|; sum(=XD) == consumed "
+                                                       "reference prefix; sum(XID) == edit distance"}}
         if not ok:
             raise SystemExit("PARITY FAILURE against the CPU reference on the benchmark sample")
 

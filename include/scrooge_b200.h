@@ -174,6 +174,14 @@ int sg_dev_scan_runs(const uint32_t *d_nruns, uint64_t n, uint64_t *d_run_off, v
 int sg_dev_gather_runs(const uint8_t *d_slab, const uint64_t *d_slab_off, const uint32_t *d_nruns,
                        const uint64_t *d_run_off, uint64_t n, uint8_t *d_runs, void *stream);
 
+/* Measurement / test helper: consistency of a batch's compacted runs with its other results, for EVERY alignment --
+ * the sequence-independent properties of the reference's validateCigarString (src/tests.cu:106-169): every run count
+ * in [1, max_count] (W-O: 31 at W=64, 15 at W=32), counts of =,X,I sum to d_query_len, of =,X,D to d_ref_consumed, of
+ * X,I,D to d_edit.  *d_n_bad (device uint64, caller-initialised) is incremented once per offending alignment. */
+int sg_dev_check_runs(const uint8_t *d_runs, const uint64_t *d_run_off, uint64_t n, const uint64_t *d_query_len,
+                      const int64_t *d_edit, const uint64_t *d_ref_consumed, uint32_t max_count, uint64_t *d_n_bad,
+                      void *stream);
+
 /* Launch geometry of sg_dev_align on the current device: persistent warps per SM and shared memory per
  * warp (for reports). */
 int sg_dev_align_geometry(int W, int *warps_per_sm, int *smem_per_warp, int *num_sms);

@@ -63,6 +63,7 @@ SIGNATURES = {
     "sg_dev_align_geometry": (i32, [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
     "sg_dev_int32_peak": (i32, [i32, dbl, C.POINTER(dbl)]),
     "sg_synth_text_stride": (u64, [u32, u32]),
+    "sg_dev_check_runs": (i32, [vp, vp, u64, vp, vp, vp, u32, vp, vp]),
     "sg_synth_pairs_host": (i32, [u64, u64, u64, u32, dbl, u32, u32, u32, u32, vp, u64, vp, vp]),
     "sg_dev_synth_pairs": (i32, [u64, u64, u64, u32, dbl, u32, u32, u32, u32, vp, u64, vp, vp, vp]),
     "sg_synth_genome": (i32, [u64, u64, u64, vp, vp, vp]),

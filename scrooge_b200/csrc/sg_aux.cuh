@@ -28,38 +28,55 @@ __device__ __forceinline__ uint32_t pack4(uint32_t w, uint32_t &bad)
     return (x * 0x01041040u) >> 24;                             // 4 codes -> 8 bits, base k at bits 2k+1:2k
 }
 
+__device__ __forceinline__ void pack_word_slow(const char *__restrict__ ascii, uint64_t n_bases, uint64_t base, uint32_t &out, uint32_t &bad)
+{
+    out = 0;   // tail (or padding) word: byte by byte, missing bases are zero
+    for (int k = 0; k < 16; k++) {
+        if (base + k < n_bases) {
+            uint32_t b1 = 0;
+            uint32_t code = pack4((uint32_t)(uint8_t)ascii[base + k] | 0x41414100u, b1);
+            bad |= b1 ? 1u : 0u;
+            out |= (code & 3u) << (2 * k);
+        }
+    }
+}
+
+__device__ __forceinline__ void pack_report_bad(const char *__restrict__ ascii, uint64_t n_bases, uint64_t base, unsigned long long *bad_pos)
+{
+    for (int k = 0; k < 16 && base + k < n_bases; k++) {   // rare: find the first offending base of this word
+        const uint32_t c = (uint32_t)(uint8_t)ascii[base + k] & 0xDFu;
+        if (c != 'A' && c != 'C' && c != 'G' && c != 'T') {
+            atomicMin(bad_pos, (unsigned long long)(base + k));
+            break;
+        }
+    }
+}
+
+// Two words per thread and iteration, `stride` words apart (both 16-byte loads are in flight before either is used:
+// 32 bytes per thread outstanding is what it takes to cover the HBM latency at this occupancy).
 __global__ void __launch_bounds__(256) pack_2bit_kernel(const char *__restrict__ ascii, uint64_t n_bases,
                                                          uint32_t *__restrict__ packed, uint64_t n_words,
                                                          unsigned long long *__restrict__ bad_pos)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < n_words; wi += stride) {
-        const uint64_t base = wi * 16ull;
-        uint32_t bad = 0, out;
-        if (base + 16ull <= n_bases) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(ascii + base));
-            out = pack4(v.x, bad) | (pack4(v.y, bad) << 8) | (pack4(v.z, bad) << 16) | (pack4(v.w, bad) << 24);
-        } else {  // tail (or padding) word: byte by byte, missing bases are zero
-            out = 0;
-            for (int k = 0; k < 16; k++) {
-                if (base + k < n_bases) {
-                    uint32_t b1 = 0;
-                    uint32_t code = pack4((uint32_t)(uint8_t)ascii[base + k] | 0x41414100u, b1);
-                    bad |= b1 ? 1u : 0u;
-                    out |= (code & 3u) << (2 * k);
-                }
-            }
+    for (uint64_t w0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w0 < n_words; w0 += 2 * stride) {
+        const uint64_t w1 = w0 + stride;
+        const uint64_t b0 = w0 * 16ull, b1 = w1 * 16ull;
+        const bool full0 = b0 + 16ull <= n_bases, full1 = w1 < n_words && b1 + 16ull <= n_bases;
+        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = make_uint4(0, 0, 0, 0);
+        if (full0) v0 = __ldg(reinterpret_cast<const uint4 *>(ascii + b0));
+        if (full1) v1 = __ldg(reinterpret_cast<const uint4 *>(ascii + b1));
+        uint32_t bad0 = 0, bad1 = 0, out0, out1 = 0;
+        if (full0) out0 = pack4(v0.x, bad0) | (pack4(v0.y, bad0) << 8) | (pack4(v0.z, bad0) << 16) | (pack4(v0.w, bad0) << 24);
+        else pack_word_slow(ascii, n_bases, b0, out0, bad0);
+        packed[w0] = out0;
+        if (w1 < n_words) {
+            if (full1) out1 = pack4(v1.x, bad1) | (pack4(v1.y, bad1) << 8) | (pack4(v1.z, bad1) << 16) | (pack4(v1.w, bad1) << 24);
+            else pack_word_slow(ascii, n_bases, b1, out1, bad1);
+            packed[w1] = out1;
         }
-        packed[wi] = out;
-        if (bad) {  // rare: find the first offending base of this word
-            for (int k = 0; k < 16 && base + k < n_bases; k++) {
-                const uint32_t c = (uint32_t)(uint8_t)ascii[base + k] & 0xDFu;
-                if (c != 'A' && c != 'C' && c != 'G' && c != 'T') {
-                    atomicMin(bad_pos, (unsigned long long)(base + k));
-                    break;
-                }
-            }
-        }
+        if (bad0) pack_report_bad(ascii, n_bases, b0, bad_pos);
+        if (bad1) pack_report_bad(ascii, n_bases, b1, bad_pos);
     }
 }
 
@@ -153,7 +170,9 @@ __global__ void __launch_bounds__(kScanBlock) scan_finish_kernel(const uint32_t 
     }
 }
 
-// gather: GROUP lanes per alignment copy its runs from the slab slot to the dense array
+// gather: GROUP lanes per alignment copy its runs from the slab slot to the dense array.  Source and destination have
+// unrelated byte alignments, so the body is copied as 32-bit words aligned to the DESTINATION, each assembled from the
+// two aligned source words it straddles (one funnel shift); at most 3 head and 3 tail bytes go byte by byte.
 template <int GROUP>
 __global__ void __launch_bounds__(256) gather_runs_kernel(const uint8_t *__restrict__ slab, const uint64_t *__restrict__ slab_off,
                                                            const uint32_t *__restrict__ nruns, const uint64_t *__restrict__ run_off,
@@ -166,7 +185,53 @@ __global__ void __launch_bounds__(256) gather_runs_kernel(const uint8_t *__restr
         const uint8_t *src = slab + slab_off[a];
         uint8_t *dst = runs + run_off[a];
         const uint32_t cnt = nruns[a];
-        for (uint32_t k = sub; k < cnt; k += GROUP) dst[k] = src[k];
+        const uint32_t head = min(cnt, (uint32_t)((4u - ((uint32_t)(uintptr_t)dst & 3u)) & 3u));
+        if (sub < head) dst[sub] = src[sub];
+        const uint32_t body = (cnt - head) >> 2;                       // whole destination words
+        const uint8_t *s = src + head;
+        const uint32_t m = (uint32_t)(uintptr_t)s & 3u;
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(s - m);
+        uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
+        const uint32_t src_words = (m + 4u * body + 3u) >> 2;          // aligned source words that hold the body
+        for (uint32_t w = sub; w < body; w += GROUP) {
+            const uint32_t lo = sw[w];
+            const uint32_t hi = (m != 0u && w + 1u < src_words) ? sw[w + 1u] : 0u;
+            dw[w] = __funnelshift_r(lo, hi, 8u * m);
+        }
+        const uint32_t done = head + 4u * body;
+        if (sub < cnt - done) dst[done + sub] = src[done + sub];
+    }
+}
+
+// ---- full-batch consistency check of the compacted runs (measurement / test helper) -----------------------
+// The size-independent properties of reference validateCigarString (src/tests.cu:106-169) that need no sequence data,
+// for EVERY alignment of a batch: every run has a count in [1, max_count]; the counts of =,X,I sum to the query
+// length, those of =,X,D to the consumed reference prefix, those of X,I,D to the edit distance.  One warp per alignment.
+__global__ void __launch_bounds__(256) check_runs_kernel(const uint8_t *__restrict__ runs, const uint64_t *__restrict__ run_off,
+                                                         uint64_t n, const uint64_t *__restrict__ query_len,
+                                                         const int64_t *__restrict__ edit, const uint64_t *__restrict__ ref_consumed,
+                                                         uint32_t max_count, unsigned long long *__restrict__ n_bad)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x / 32);
+    for (uint64_t a = (uint64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); a < n; a += warps) {
+        const uint64_t r0 = run_off[a], r1 = run_off[a + 1];
+        uint32_t q = 0, t = 0, e = 0, bad = 0;
+        for (uint64_t k = r0 + lane; k < r1; k += 32) {
+            const uint32_t b = runs[k], op = b >> 6, c = b & 63u;
+            bad |= (c == 0u || c > max_count) ? 1u : 0u;
+            q += op != 3u ? c : 0u;   // '=', 'X', 'I' consume the query
+            t += op != 2u ? c : 0u;   // '=', 'X', 'D' consume the text
+            e += op != 0u ? c : 0u;   // 'X', 'I', 'D' are edits
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            q += __shfl_xor_sync(0xFFFFFFFFu, q, o);
+            t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
+            e += __shfl_xor_sync(0xFFFFFFFFu, e, o);
+            bad |= __shfl_xor_sync(0xFFFFFFFFu, bad, o);
+        }
+        if (lane == 0 && (bad || q != query_len[a] || t != ref_consumed[a] || (int64_t)e != edit[a])) atomicAdd(n_bad, 1ull);
     }
 }
 

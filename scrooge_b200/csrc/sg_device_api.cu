@@ -263,6 +263,21 @@ int sg_dev_align(int W, const uint32_t *d_text, const uint64_t *d_text_start, co
     return W == 64 ? launch_align<64, false>(*di, P, st) : launch_align<32, false>(*di, P, st);
 }
 
+int sg_dev_check_runs(const uint8_t *d_runs, const uint64_t *d_run_off, uint64_t n, const uint64_t *d_query_len,
+                      const int64_t *d_edit, const uint64_t *d_ref_consumed, uint32_t max_count, uint64_t *d_n_bad, void *stream)
+{
+    if (n == 0) return SG_OK;
+    if (!d_runs || !d_run_off || !d_query_len || !d_edit || !d_ref_consumed || !d_n_bad)
+        return fail(SG_ERR_BAD_ARG, "sg_dev_check_runs: null pointer");
+    DeviceInfo *di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    check_runs_kernel<<<di->sms * 8, 256, 0, (cudaStream_t)stream>>>(d_runs, d_run_off, n, d_query_len, d_edit, d_ref_consumed, max_count,
+                                                                      (unsigned long long *)d_n_bad);
+    SG_CUDA(cudaGetLastError());
+    return SG_OK;
+}
+
 #ifdef SG_STATS
 int sg_dev_debug_stats(uint64_t *out4, int reset)
 {

@@ -86,6 +86,16 @@ class DeviceAligner:
         return self.run_off, runs
 
 
+def check_runs(runs: torch.Tensor, run_off: torch.Tensor, query_len: torch.Tensor, out: "AlignOut", W: int) -> int:
+    """Number of alignments whose compacted runs contradict their query length, consumed reference prefix or edit
+    distance (sg_dev_check_runs: the sequence-independent validateCigarString properties on the whole batch)."""
+    n = query_len.numel()
+    bad = torch.zeros(1, dtype=torch.int64, device=runs.device)
+    check(lib().sg_dev_check_runs(_p(runs), _p(run_off), n, _p(query_len), _p(out.edit), _p(out.ref_consumed),
+                                  31 if W == 64 else 15, _p(bad), _stream()))
+    return int(bad.item())
+
+
 def align_geometry(W: int) -> Tuple[int, int, int]:
     a, b, c = C.c_int(), C.c_int(), C.c_int()
     check(lib().sg_dev_align_geometry(W, C.byref(a), C.byref(b), C.byref(c)))

@@ -179,6 +179,13 @@ def test_device_api_resident_inputs(oracle, sglib):
     assert np.array_equal(out.ref_consumed.cpu().numpy().astype(np.uint64), want.ref_consumed)
     assert int(out.dc_entries.sum().item()) == want.stats["dc_entries"]  # the roofline's algorithmic work counter
     assert int(out.windows.sum().item()) == want.stats["windows"]        # unit of the delta kernel's own work
+    # the whole-batch consistency checker bench.py uses: clean on these results, and it does notice a corrupted run
+    qlen = torch.full((n,), L, dtype=torch.int64, device=dev)
+    assert device.check_runs(runs, run_off, qlen, out, 64) == 0
+    broken = runs.clone()
+    broken[int(run_off[5].item())] ^= 0x01   # one count off by one in alignment 5
+    broken[int(run_off[9].item())] = 0       # a zero-length run in alignment 9
+    assert device.check_runs(broken, run_off, qlen, out, 64) == 2
     ro, rr = run_off.cpu().numpy(), runs.cpu().numpy()
     ops = "=XID"
     for k in (0, 1, 17, n - 1):
