@@ -149,7 +149,10 @@ class Aligner:
             self._h = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:   # interpreter shutdown: the module globals lib() needs may already be gone
+            pass
 
     @property
     def num_devices(self) -> int:

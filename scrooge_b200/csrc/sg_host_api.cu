@@ -145,6 +145,18 @@ struct ScopedT {
     ~ScopedT() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
 };
 
+// Per-alignment host loops (descriptor arithmetic): serial up to a million alignments -- a sub-batch of long reads --
+// and split over plain threads above that (batches of millions of short reads).  Deliberately not OpenMP: an OpenMP
+// team that fits the cores spin-waits after its region and delays the CUDA calls that follow.
+template <class F> void parallel_for(uint64_t n, int threads, F &&fn)
+{
+    const int nt = (int)std::min<uint64_t>((uint64_t)std::max(1, threads), n >> 20);
+    if (nt <= 1) { fn((uint64_t)0, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back([&fn, n, t, nt]() { fn(n * (uint64_t)t / nt, n * (uint64_t)(t + 1) / nt); });
+    for (auto &x : th) x.join();
+}
+
 extern "C" uint64_t sg_host_pack_2bit_st(const char *ascii, uint64_t n_bases, uint32_t *packed);
 
 constexpr int kMaxSlots = 8;
@@ -156,7 +168,7 @@ struct Slot {
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_mid = nullptr, ev_end = nullptr;
     cudaEvent_t ev_dma[kMaxDmaDepth] = {};   // adaptive ingest: one per ASCII chunk copy in flight
     DevBuf ascii_t, ascii_q, packed_t, packed_q, desc, slab, counter, edit, refc, nruns, status, run_off, scan_tmp, runs, bad;
-    PinBuf h_small, h_edit, h_refc, h_runoff, h_status, h_stage_t, h_stage_q, h_desc;
+    PinBuf h_small, h_status, h_stage_t, h_stage_q, h_desc;
     PinnedPool::Block piece{nullptr, 0};
     // the batch in flight
     bool busy = false, mid_done = false;
@@ -177,7 +189,7 @@ struct Slot {
         for (DevBuf *b : {&ascii_t, &ascii_q, &packed_t, &packed_q, &desc, &slab, &counter, &edit, &refc, &nruns, &status, &run_off,
                           &scan_tmp, &runs, &bad})
             b->release();
-        for (PinBuf *b : {&h_small, &h_edit, &h_refc, &h_runoff, &h_status, &h_stage_t, &h_stage_q, &h_desc}) b->release();
+        for (PinBuf *b : {&h_small, &h_status, &h_stage_t, &h_stage_q, &h_desc}) b->release();
         g_pool.release(piece);
         piece = {nullptr, 0};
         if (ev_k0) cudaEventDestroy(ev_k0);
@@ -235,9 +247,12 @@ struct sg_ctx {
 struct sg_result {
     uint64_t n = 0;
     bool has_cigar = false;
-    std::vector<int64_t> edit;
-    std::vector<uint64_t> refc;
-    std::vector<uint64_t> run_off;  // n+1
+    // distances, consumed prefixes and run offsets (n+1) live in ONE pinned block from the pool: the device-to-host
+    // copies of every sub-batch land at their final place, nothing is copied or zero-filled on the host
+    PinnedPool::Block store{nullptr, 0};
+    int64_t *edit = nullptr;
+    uint64_t *refc = nullptr;
+    uint64_t *run_off = nullptr;  // n+1
     // packed runs, one pinned piece per processed sub-batch, in alignment order
     std::vector<PinnedPool::Block> pieces;
     std::vector<uint64_t> piece_first;   // first alignment of each piece
@@ -245,7 +260,7 @@ struct sg_result {
     std::vector<uint64_t> piece_runs;    // runs in each piece
     std::vector<uint8_t> flat;           // lazily flattened view for sg_result_runs
     int64_t kernel_ns = 0, total_ns = 0;
-    ~sg_result() { for (auto &b : pieces) g_pool.release(b); }
+    ~sg_result() { for (auto &b : pieces) g_pool.release(b); g_pool.release(store); }
 };
 
 namespace {
@@ -360,7 +375,7 @@ int upload_strings(sg_ctx *ctx, int dev_id, cudaStream_t st, cudaEvent_t *ev_dma
     const int threads = ctx->host_threads;
     if (S.blob) {
         const uint64_t base = S.off[i0], nbytes = S.off[i1] - base;
-        for (uint64_t k = 0; k < n; k++) start[k] = S.off[i0 + k] - base;
+        parallel_for(n, threads, [&](uint64_t k0, uint64_t k1) { for (uint64_t k = k0; k < k1; k++) start[k] = S.off[i0 + k] - base; });
         const uint64_t words = sg_packed_words(nbytes);
         if (ctx->adaptive && nbytes >= ctx->ascii_min_bytes && nbytes >= 256) {
             uint64_t bad = ~0ull, split = nbytes;
@@ -437,7 +452,7 @@ int upload_strings(sg_ctx *ctx, int dev_id, cudaStream_t st, cudaEvent_t *ev_dma
 }
 
 // stage A: uploads, ingest, descriptors, alignment kernel, run-count scan; ends with ev_mid
-int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uint64_t a1)
+int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uint64_t a1, sg_result *res)
 {
     const uint64_t n = a1 - a0;
     const bool want_cigar = !(w.flags & SG_FLAG_DISTANCE_ONLY);
@@ -447,7 +462,7 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
     R(s.counter.reserve(8)); R(s.edit.reserve(n * 8)); R(s.refc.reserve(n * 8));
     R(s.nruns.reserve(n * 4)); R(s.status.reserve(n)); R(s.run_off.reserve((n + 1) * 8));
     R(s.scan_tmp.reserve(sg_scan_tmp_bytes(n))); R(s.bad.reserve(16)); R(s.h_small.reserve(64));
-    R(s.h_edit.reserve(n * 8)); R(s.h_refc.reserve(n * 8)); R(s.h_runoff.reserve((n + 1) * 8)); R(s.h_status.reserve(n));
+    R(s.h_status.reserve(n));
     SG_CUDA(cudaMemsetAsync(s.bad.p, 0xFF, 16, st));
     // descriptors are built on the host: [tstart | tlen | qstart | qlen | slab_off (n+1)]
     uint64_t *h_tstart = s.h_desc.as<uint64_t>(), *h_tlen = h_tstart + n, *h_qstart = h_tlen + n, *h_qlen = h_qstart + n, *h_slab = h_qlen + n;
@@ -456,7 +471,9 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
     if (!w.mapping) {
         R(upload_strings(ctx, d.id, st, s.ev_dma, w.text, a0, a1, "text", "pair", s.ascii_t, s.packed_t, s.h_stage_t, s.bad.as<uint64_t>(), h_tstart, &s.bad_bias[0]));
         R(upload_strings(ctx, d.id, st, s.ev_dma, w.query, a0, a1, "query", "pair", s.ascii_q, s.packed_q, s.h_stage_q, s.bad.as<uint64_t>() + 1, h_qstart, &s.bad_bias[1]));
-        for (uint64_t k = 0; k < n; k++) { h_tlen[k] = w.text.size(a0 + k); h_qlen[k] = w.query.size(a0 + k); }
+        parallel_for(n, ctx->host_threads, [&](uint64_t k0, uint64_t k1) {
+            for (uint64_t k = k0; k < k1; k++) { h_tlen[k] = w.text.size(a0 + k); h_qlen[k] = w.query.size(a0 + k); }
+        });
         d_text = s.packed_t.as<uint32_t>();
     } else {
         // reads referenced by this sub-batch: the contiguous index range [r0, r1] (candidates arrive read-major, so the
@@ -479,8 +496,14 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
     }
     ScopedT t_desc(g_ht.desc);
     uint64_t slab_bytes = 0;
-    for (uint64_t k = 0; k < n; k++) { h_slab[k] = slab_bytes; slab_bytes += 2ull * h_qlen[k] + 8ull; }
-    h_slab[n] = slab_bytes;
+    if (!w.mapping && w.query.blob) {   // capacity 2*|query|+8 per alignment: the prefix sum is a difference of offsets
+        const uint64_t *qo = w.query.off + a0;
+        parallel_for(n + 1, ctx->host_threads, [&](uint64_t k0, uint64_t k1) { for (uint64_t k = k0; k < k1; k++) h_slab[k] = 2ull * (qo[k] - qo[0]) + 8ull * k; });
+        slab_bytes = h_slab[n];
+    } else {
+        for (uint64_t k = 0; k < n; k++) { h_slab[k] = slab_bytes; slab_bytes += 2ull * h_qlen[k] + 8ull; }
+        h_slab[n] = slab_bytes;
+    }
     SG_CUDA(cudaMemcpyAsync(s.desc.p, s.h_desc.p, (5 * n + 1) * 8, cudaMemcpyHostToDevice, st));
     if (want_cigar) R(s.slab.reserve(slab_bytes + 16));
     SG_CUDA(cudaEventRecord(s.ev_k0, st));
@@ -494,15 +517,15 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
         R(sg_dev_scan_runs(s.nruns.as<uint32_t>(), n, s.run_off.as<uint64_t>(), s.scan_tmp.p, st));
         SG_CUDA(cudaMemcpyAsync(h + 2, s.run_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
     }
-    SG_CUDA(cudaMemcpyAsync(s.h_edit.p, s.edit.p, n * 8, cudaMemcpyDeviceToHost, st));
-    SG_CUDA(cudaMemcpyAsync(s.h_refc.p, s.refc.p, n * 8, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(res->edit + a0, s.edit.p, n * 8, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(res->refc + a0, s.refc.p, n * 8, cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaMemcpyAsync(s.h_status.p, s.status.p, n, cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaEventRecord(s.ev_mid, st));
     return SG_OK;
 }
 
 // stage B: once the run total is known, gather the runs and send everything home; ends with ev_end
-int stage_b(Slot &s, const Workload &w)
+int stage_b(Slot &s, const Workload &w, sg_result *res)
 {
     if (!s.busy || s.mid_done) return SG_OK;
     const uint64_t n = s.a1 - s.a0;
@@ -535,7 +558,7 @@ int stage_b(Slot &s, const Workload &w)
         R(sg_dev_gather_runs(s.slab.as<uint8_t>(), s.desc.as<uint64_t>() + 4 * n, s.nruns.as<uint32_t>(), s.run_off.as<uint64_t>(), n,
                              s.runs.as<uint8_t>(), st));
         SG_CUDA(cudaMemcpyAsync(s.piece.p, s.runs.p, s.total_runs, cudaMemcpyDeviceToHost, st));
-        SG_CUDA(cudaMemcpyAsync(s.h_runoff.p, s.run_off.p, n * 8, cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaMemcpyAsync(res->run_off + s.a0, s.run_off.p, n * 8, cudaMemcpyDeviceToHost, st));  // sub-batch-local, rebased in finalize()
     }
     SG_CUDA(cudaEventRecord(s.ev_end, st));
     return SG_OK;
@@ -547,20 +570,17 @@ int stage_c(Slot &s, const Workload &w, sg_result *res, ShardOut &so)
     if (!s.busy) return SG_OK;
     const uint64_t n = s.a1 - s.a0;
     const bool want_cigar = !(w.flags & SG_FLAG_DISTANCE_ONLY);
-    R(stage_b(s, w));
+    R(stage_b(s, w, res));
     { ScopedT t(g_ht.wait); SG_CUDA(cudaEventSynchronize(s.ev_end)); }
     s.busy = false;
     ScopedT t_out(g_ht.copy_out);
     const uint8_t *status = s.h_status.as<uint8_t>();
-    for (uint64_t k = 0; k < n; k++)
-        if (status[k]) return fail(SG_ERR_CIGAR_OVERFLOW, "alignment " + std::to_string(s.a0 + k) + " exceeded its run capacity");
-    memcpy(res->edit.data() + s.a0, s.h_edit.p, n * 8);
-    memcpy(res->refc.data() + s.a0, s.h_refc.p, n * 8);
+    if (const void *hit = n ? memchr(status, SG_ERR_CIGAR_OVERFLOW, n) : nullptr)
+        return fail(SG_ERR_CIGAR_OVERFLOW, "alignment " + std::to_string(s.a0 + (uint64_t)((const uint8_t *)hit - status)) + " exceeded its run capacity");
     float ms = 0;
     SG_CUDA(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
     so.kernel_ms += ms;
     if (want_cigar) {
-        memcpy(res->run_off.data() + s.a0, s.h_runoff.p, n * 8);  // sub-batch-local offsets, rebased in finalize()
         so.pieces.push_back(s.piece);
         so.piece_first.push_back(s.a0);
         so.piece_runs.push_back(s.total_runs);
@@ -585,22 +605,28 @@ void run_shard(sg_ctx *ctx, Device &d, const Workload &w, const uint64_t *woff, 
     if (cudaSetDevice(d.id) != cudaSuccess) { cudaGetLastError(); fail(SG_ERR_CUDA, "cudaSetDevice failed"); bail(SG_ERR_CUDA); return; }
     std::vector<uint64_t> cuts{c0};
     while (cuts.back() < c1) {
-        uint64_t a = cuts.back(), b = a + 1;
-        while (b < c1) {
+        // the sub-batch [a, b): b grows while the batch stays under max_batch_bytes and is either still small in bytes or
+        // still short of min_batch_units alignments.  Both stop conditions are monotone in b: binary search for the
+        // first b in (a, c1) that stops (a batch always takes at least one alignment).
+        const uint64_t a = cuts.back();
+        auto stops = [&](uint64_t b) {
             const uint64_t bytes = (woff[b + 1] - woff[a]) + per_unit_extra * (b + 1 - a);
-            if (bytes > ctx->max_batch_bytes) break;
-            if (bytes > ctx->batch_bytes && b - a >= ctx->min_batch_units) break;
-            b++;
+            return bytes > ctx->max_batch_bytes || (bytes > ctx->batch_bytes && b - a >= ctx->min_batch_units);
+        };
+        uint64_t lo = a + 1, hi = c1;
+        while (lo < hi) {
+            const uint64_t mid = lo + (hi - lo) / 2;
+            if (stops(mid)) hi = mid; else lo = mid + 1;
         }
-        cuts.push_back(b);
+        cuts.push_back(lo);
     }
     const int nb = (int)cuts.size() - 1;
     const int kSlots = d.n_slots;
     for (int k = 0; k < nb; k++) {
         Slot &s = d.slots[k % kSlots];
         int rc = stage_c(s, w, res, so);                       // frees the slot used by batch k - kSlots
-        if (!rc) rc = stage_a(ctx, d, s, w, cuts[k], cuts[k + 1]);
-        if (!rc && k >= 1) rc = stage_b(d.slots[(k - 1) % kSlots], w);
+        if (!rc) rc = stage_a(ctx, d, s, w, cuts[k], cuts[k + 1], res);
+        if (!rc && k >= 1) rc = stage_b(d.slots[(k - 1) % kSlots], w, res);
         if (rc) { bail(rc); return; }
     }
     for (int k = std::max(0, nb - kSlots); k < nb; k++) {
@@ -649,8 +675,10 @@ void finalize(sg_result *res, std::vector<ShardOut> &shards)
         const uint64_t a0 = res->piece_first[k];
         const uint64_t a1 = k + 1 < res->pieces.size() ? res->piece_first[k + 1] : res->n;
         const uint64_t base = res->piece_run0[k];
-        if (base)
-            for (uint64_t a = a0; a < a1; a++) res->run_off[a] += base;
+        if (base) {
+            uint64_t *ro = res->run_off + a0;
+            parallel_for(a1 - a0, (int)std::thread::hardware_concurrency(), [&](uint64_t k0, uint64_t k1) { for (uint64_t k = k0; k < k1; k++) ro[k] += base; });
+        }
     }
     res->run_off[res->n] = run0;
 }
@@ -669,9 +697,12 @@ int run_all(sg_ctx *ctx, const Workload &w, const uint64_t *woff, uint64_t per_u
     std::unique_ptr<sg_result> res(new sg_result);
     res->n = n;
     res->has_cigar = !(w.flags & SG_FLAG_DISTANCE_ONLY);
-    res->edit.resize(n);
-    res->refc.resize(n);
-    res->run_off.assign(res->has_cigar ? n + 1 : 1, 0);
+    if (int rc = g_pool.acquire((3 * n + 2) * 8, &res->store)) return rc;
+    res->edit = reinterpret_cast<int64_t *>(res->store.p);
+    res->refc = reinterpret_cast<uint64_t *>(res->store.p) + n;
+    res->run_off = reinterpret_cast<uint64_t *>(res->store.p) + 2 * n;
+    res->run_off[0] = 0;
+    res->run_off[n] = 0;
     const int nd = (int)ctx->devs.size();
     std::vector<ShardOut> shards(nd);
     if (n) {
@@ -773,10 +804,17 @@ static int align_pairs_common(sg_ctx *ctx, const Strings &text, const Strings &q
     Workload w;
     w.text = text; w.query = query; w.flags = flags;
     // sub-batches are cut by uploaded bytes (text + query), shards by the same weight
-    std::vector<uint64_t> woff(n_pairs + 1);
-    woff[0] = 0;
-    for (uint64_t p = 0; p < n_pairs; p++) woff[p + 1] = woff[p] + text.size(p) + query.size(p);
-    return run_all(ctx, w, woff.data(), 48, n_pairs, out);
+    std::unique_ptr<uint64_t[]> woff(new uint64_t[n_pairs + 1]);
+    if (text.blob && query.blob) {   // a prefix sum of sizes is a difference of offsets: no serial pass over the pairs
+        const uint64_t t0 = text.off[0], q0 = query.off[0];
+        parallel_for(n_pairs + 1, ctx->host_threads, [&](uint64_t p0, uint64_t p1) {
+            for (uint64_t p = p0; p < p1; p++) woff[p] = (text.off[p] - t0) + (query.off[p] - q0);
+        });
+    } else {
+        woff[0] = 0;
+        for (uint64_t p = 0; p < n_pairs; p++) woff[p + 1] = woff[p] + text.size(p) + query.size(p);
+    }
+    return run_all(ctx, w, woff.get(), 48, n_pairs, out);
 }
 
 int sg_align_pairs(sg_ctx *ctx, const char *text_blob, const uint64_t *text_off, const char *query_blob,
@@ -892,9 +930,9 @@ int sg_align_candidates_v(sg_ctx *ctx, const char *const *reads, const uint64_t 
 }
 
 uint64_t sg_result_count(const sg_result *r) { return r ? r->n : 0; }
-const int64_t *sg_result_edit_distances(const sg_result *r) { return r ? r->edit.data() : nullptr; }
-const uint64_t *sg_result_ref_consumed(const sg_result *r) { return r ? r->refc.data() : nullptr; }
-const uint64_t *sg_result_run_offsets(const sg_result *r) { return r && r->has_cigar ? r->run_off.data() : nullptr; }
+const int64_t *sg_result_edit_distances(const sg_result *r) { return r ? r->edit : nullptr; }
+const uint64_t *sg_result_ref_consumed(const sg_result *r) { return r ? r->refc : nullptr; }
+const uint64_t *sg_result_run_offsets(const sg_result *r) { return r && r->has_cigar ? r->run_off : nullptr; }
 
 const uint8_t *sg_result_runs(const sg_result *r)
 {

@@ -1,0 +1,7 @@
+#!/bin/bash
+TAG=${1:-s}
+mkdir -p gpurun_out
+SG_DEBUG=1 timeout 600 python tools/e2e_workloads.py long_10kbp 524288 2>&1 | grep "call\|aligns" | tail -3
+SG_DEBUG=1 timeout 600 python tools/e2e_workloads.py short_150bp 10000000 2>&1 | grep "call\|aligns" | tail -3
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${TAG}_pytest.log
+tail -3 gpurun_out/${TAG}_pytest.log
