@@ -13,19 +13,26 @@ namespace sg {
 // one 16-byte load, SWAR conversion of 4 bases per 32-bit register, one 4-byte store; a warp reads 512
 // contiguous bytes and writes 128.  HBM-bound: 1 B read + 0.25 B written per base.
 //
-// code = ((c >> 1) ^ (c >> 2)) & 3 maps A,C,G,T (either case) to 0,1,2,3 (src/genasm_cpu.cpp:87-90);
-// validity is checked by mapping the code back to its letter with a byte permute and comparing.
+// Bits 2:1 of a letter (either case) are A 0, C 1, T 2, G 3 -- the code with G and T swapped.  pack4 works on these raw
+// codes (4 bases of a register -> 8 bits, base k at bits 2k+1:2k, in the TOP byte of the result); the swap is undone
+// once per packed word: code = raw ^ (raw >> 1 & 0x55555555) (src/genasm_cpu.cpp:87-90: A0 C1 G2 T3).
+// Validity: every byte of v is 0x0k, so the low 16 bits of v | v >> 12 are the PRMT selector (k0, k2, k1, k3): one permute
+// of "ACTG" reproduces the letters the codes stand for, one permute brings the (case-folded) input into the same order.
 __device__ __forceinline__ uint32_t pack4(uint32_t w, uint32_t &bad)
 {
-    const uint32_t u = w & 0xDFDFDFDFu;                         // fold case
-    const uint32_t x = ((u >> 1) ^ (u >> 2)) & 0x03030303u;     // 2-bit code in each byte
-    // every byte of x is 0x0k, so the low 16 bits of x | x >> 12 are the PRMT selector (k0, k2, k1, k3): one permute
-    // returns (letter[k0], letter[k2], letter[k1], letter[k3]); compare with the input bytes in the same order.
-    const uint32_t letters = 0x54474341u;  // "ACGT"
-    const uint32_t e = __byte_perm(letters, 0u, x | (x >> 12));
-    const uint32_t v = __byte_perm(u, 0u, 0x3120u);              // (b0, b2, b1, b3)
-    bad |= e ^ v;
-    return (x * 0x01041040u) >> 24;                             // 4 codes -> 8 bits, base k at bits 2k+1:2k
+    const uint32_t v = (w >> 1) & 0x03030303u;                  // raw 2-bit code in each byte
+    const uint32_t e = __byte_perm(0x47544341u /* "ACTG" */, 0u, v | (v >> 12));
+    const uint32_t u = __byte_perm(w & 0xDFDFDFDFu, 0u, 0x3120u);  // folded case, bytes (b0, b2, b1, b3)
+    bad |= e ^ u;
+    return v * 0x01041040u;                                     // 4 codes -> bits 31:24
+}
+
+// the four top bytes of a..d as one word (a's in the lowest byte), G/T swap undone
+__device__ __forceinline__ uint32_t pack16(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    const uint32_t lo = __byte_perm(a, b, 0x0073u), hi = __byte_perm(c, d, 0x0073u);   // (a.b3, b.b3, 0.., ..)
+    const uint32_t raw = __byte_perm(lo, hi, 0x5410u);
+    return raw ^ ((raw >> 1) & 0x55555555u);
 }
 
 __device__ __forceinline__ void pack_word_slow(const char *__restrict__ ascii, uint64_t n_bases, uint64_t base, uint32_t &out, uint32_t &bad)
@@ -34,9 +41,10 @@ __device__ __forceinline__ void pack_word_slow(const char *__restrict__ ascii, u
     for (int k = 0; k < 16; k++) {
         if (base + k < n_bases) {
             uint32_t b1 = 0;
-            uint32_t code = pack4((uint32_t)(uint8_t)ascii[base + k] | 0x41414100u, b1);
+            uint32_t raw = pack4((uint32_t)(uint8_t)ascii[base + k] | 0x41414100u, b1) >> 24;
             bad |= b1 ? 1u : 0u;
-            out |= (code & 3u) << (2 * k);
+            raw &= 3u;
+            out |= (raw ^ (raw >> 1)) << (2 * k);
         }
     }
 }
@@ -67,11 +75,11 @@ __global__ void __launch_bounds__(256) pack_2bit_kernel(const char *__restrict__
         if (full0) v0 = __ldg(reinterpret_cast<const uint4 *>(ascii + b0));
         if (full1) v1 = __ldg(reinterpret_cast<const uint4 *>(ascii + b1));
         uint32_t bad0 = 0, bad1 = 0, out0, out1 = 0;
-        if (full0) out0 = pack4(v0.x, bad0) | (pack4(v0.y, bad0) << 8) | (pack4(v0.z, bad0) << 16) | (pack4(v0.w, bad0) << 24);
+        if (full0) out0 = pack16(pack4(v0.x, bad0), pack4(v0.y, bad0), pack4(v0.z, bad0), pack4(v0.w, bad0));
         else pack_word_slow(ascii, n_bases, b0, out0, bad0);
         packed[w0] = out0;
         if (w1 < n_words) {
-            if (full1) out1 = pack4(v1.x, bad1) | (pack4(v1.y, bad1) << 8) | (pack4(v1.z, bad1) << 16) | (pack4(v1.w, bad1) << 24);
+            if (full1) out1 = pack16(pack4(v1.x, bad1), pack4(v1.y, bad1), pack4(v1.z, bad1), pack4(v1.w, bad1));
             else pack_word_slow(ascii, n_bases, b1, out1, bad1);
             packed[w1] = out1;
         }

@@ -145,12 +145,12 @@ struct ScopedT {
     ~ScopedT() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
 };
 
-// Per-alignment host loops (descriptor arithmetic): serial up to a million alignments -- a sub-batch of long reads --
-// and split over plain threads above that (batches of millions of short reads).  Deliberately not OpenMP: an OpenMP
+// Per-alignment host loops (descriptor arithmetic): serial up to a quarter of a million alignments -- a sub-batch of long reads --
+// and split over plain threads (131 072 alignments each) above that (batches of short reads).  Deliberately not OpenMP: an OpenMP
 // team that fits the cores spin-waits after its region and delays the CUDA calls that follow.
 template <class F> void parallel_for(uint64_t n, int threads, F &&fn)
 {
-    const int nt = (int)std::min<uint64_t>((uint64_t)std::max(1, threads), n >> 20);
+    const int nt = (int)std::min<uint64_t>((uint64_t)std::max(1, threads), n >> 17);
     if (nt <= 1) { fn((uint64_t)0, n); return; }
     std::vector<std::thread> th;
     for (int t = 0; t < nt; t++) th.emplace_back([&fn, n, t, nt]() { fn(n * (uint64_t)t / nt, n * (uint64_t)(t + 1) / nt); });
