@@ -4,6 +4,8 @@
 // sg_set_reference + sg_align_candidates, renders the packed runs to CIGAR text with all host threads
 // (the reference renders serially through a stringstream per alignment, src/genasm_gpu.cu:881-888,
 // 1049-1053 -- 20x its kernel time in its own README transcript, README.md:103-108).
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
@@ -60,6 +62,7 @@ void check(int rc)
 
 std::vector<Alignment_t> collect(sg_result *res, Extra *extra, long long *core_algorithm_ns)
 {
+    const auto t_begin = std::chrono::steady_clock::now();
     const uint64_t n = sg_result_count(res);
     std::vector<Alignment_t> out(n);
     const int64_t *ed = sg_result_edit_distances(res);
@@ -79,6 +82,9 @@ std::vector<Alignment_t> collect(sg_result *res, Extra *extra, long long *core_a
     if (extra) extra->total_ns = sg_result_total_ns(res);
     if (enabled_algorithm_log && ns > 0)  // same line the reference prints (src/genasm_gpu.cu:950-951)
         std::cerr << "core algorithm ran at " << (long long)((double)n * 1e9 / (double)ns) << " aligns/second" << std::endl;
+    if (std::getenv("SG_DEBUG"))
+        fprintf(stderr, "[sg] align_all: C ABI call %.1f ms, rendering %llu CIGAR strings %.1f ms\n", sg_result_total_ns(res) / 1e6,
+                (unsigned long long)n, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count() * 1e3);
     sg_result_free(res);
     return out;
 }

@@ -949,33 +949,67 @@ const uint8_t *sg_result_runs(const sg_result *r)
 int64_t sg_result_kernel_ns(const sg_result *r) { return r ? r->kernel_ns : 0; }
 int64_t sg_result_total_ns(const sg_result *r) { return r ? r->total_ns : 0; }
 
+// "%d%c" of one packed run (reference src/genasm_gpu.cu:881-888) from a 256-entry table: the text of run byte b padded
+// to 4 characters, and its length (2 or 3; count 0 never occurs).  A run is rendered with one 4-byte store.
+struct RunText {
+    uint32_t text[256];
+    uint8_t len[256];
+    RunText()
+    {
+        static const char ops[4] = {'=', 'X', 'I', 'D'};
+        for (unsigned b = 0; b < 256; b++) {
+            const unsigned c = SG_RUN_COUNT(b);
+            char t[4] = {0, 0, 0, 0};
+            unsigned l = 0;
+            if (c >= 10) t[l++] = (char)('0' + c / 10);
+            t[l++] = (char)('0' + c % 10);
+            t[l++] = ops[SG_RUN_OP(b)];
+            memcpy(&text[b], t, 4);
+            len[b] = (uint8_t)l;
+        }
+    }
+};
+static const RunText g_run_text;
+
+static inline uint64_t runs_text_len(const uint8_t *p, uint64_t cnt)
+{
+    uint64_t len = 0;
+    for (uint64_t k = 0; k < cnt; k++) len += g_run_text.len[p[k]];
+    return len;
+}
+
+// renders cnt runs at o; the caller guarantees room for the text (+ nothing else): the last run is written byte by byte
+static inline char *runs_render(const uint8_t *p, uint64_t cnt, char *o)
+{
+    if (!cnt) return o;
+    for (uint64_t k = 0; k + 1 < cnt; k++) {   // a 4-byte store may spill 1-2 bytes into the next run's place: fine
+        memcpy(o, &g_run_text.text[p[k]], 4);
+        o += g_run_text.len[p[k]];
+    }
+    const uint8_t b = p[cnt - 1];
+    memcpy(o, &g_run_text.text[b], g_run_text.len[b]);
+    return o + g_run_text.len[b];
+}
+
 uint64_t sg_result_cigar_len(const sg_result *r, uint64_t idx)
 {
     if (!r || !r->has_cigar || idx >= r->n) return 0;
     uint64_t cnt;
     const uint8_t *p = runs_of(r, idx, &cnt);
-    uint64_t len = 0;
-    for (uint64_t k = 0; k < cnt; k++) len += SG_RUN_COUNT(p[k]) >= 10 ? 3 : 2;
-    return len;
+    return runs_text_len(p, cnt);
 }
 
 int64_t sg_result_render_cigar(const sg_result *r, uint64_t idx, char *buf, uint64_t cap)
 {
     if (!r || !r->has_cigar || idx >= r->n || !buf) return -1;
-    static const char ops[4] = {'=', 'X', 'I', 'D'};
     uint64_t cnt;
     const uint8_t *p = runs_of(r, idx, &cnt);
-    uint64_t len = 0;
-    for (uint64_t k = 0; k < cnt; k++) {
-        const unsigned c = SG_RUN_COUNT(p[k]);
-        if (len + (c >= 10 ? 3u : 2u) + 1u > cap) return -1;
-        if (c >= 10) buf[len++] = (char)('0' + c / 10);
-        buf[len++] = (char)('0' + c % 10);
-        buf[len++] = ops[SG_RUN_OP(p[k])];
-    }
+    // 3 characters per run at most: when the buffer is that large no length pass is needed
+    const uint64_t len = 3 * cnt + 1 <= cap ? 0 : runs_text_len(p, cnt);
     if (len + 1 > cap) return -1;
-    buf[len] = '\0';
-    return (int64_t)len;
+    char *end = runs_render(p, cnt, buf);
+    *end = '\0';
+    return (int64_t)(end - buf);
 }
 
 int64_t sg_result_entries(const sg_result *r, uint64_t idx, sg_cigar_entry *out, uint64_t cap)
@@ -1015,26 +1049,17 @@ uint64_t sg_result_render_all(const sg_result *r, char *blob, uint64_t blob_cap,
         for (uint64_t a = a0; a < a1; a++) {
             uint64_t cnt;
             const uint8_t *p = runs_of(r, a, &cnt);
-            uint64_t len = 2 * cnt;
-            for (uint64_t k = 0; k < cnt; k++) len += SG_RUN_COUNT(p[k]) >= 10;
-            text_off[a + 1] = len;
+            text_off[a + 1] = runs_text_len(p, cnt);
         }
     });
     for (uint64_t a = 0; a < n; a++) text_off[a + 1] += text_off[a];
     const uint64_t total = text_off[n];
     if (!blob || blob_cap < total) return total;  // sizes only: call again with a big enough blob
-    static const char ops[4] = {'=', 'X', 'I', 'D'};
     parallel([&](uint64_t a0, uint64_t a1) {
         for (uint64_t a = a0; a < a1; a++) {
             uint64_t cnt;
             const uint8_t *p = runs_of(r, a, &cnt);
-            char *o = blob + text_off[a];
-            for (uint64_t k = 0; k < cnt; k++) {
-                const unsigned c = SG_RUN_COUNT(p[k]);
-                if (c >= 10) *o++ = (char)('0' + c / 10);
-                *o++ = (char)('0' + c % 10);
-                *o++ = ops[SG_RUN_OP(p[k])];
-            }
+            runs_render(p, cnt, blob + text_off[a]);
         }
     });
     return total;
