@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <memory>
 #include <omp.h>
+#include <unistd.h>
 #include <cuda_runtime.h>
 
 #include "../../include/scrooge_b200.h"
@@ -85,7 +86,14 @@ struct PinnedPool {
     std::mutex mu;
     std::vector<Block> free_blocks;
     size_t cached = 0;
-    static constexpr size_t kMaxCached = 16ull << 30;
+    // how much pinned memory the pool keeps for reuse: a quarter of the machine's RAM, at most 64 GB (a read-mapping
+    // call over 8 M candidates returns 19 GB of runs; re-pinning that much costs seconds), SG_PINNED_CACHE_GB overrides
+    const size_t kMaxCached = [] {
+        if (const char *v = std::getenv("SG_PINNED_CACHE_GB")) return (size_t)std::max(0ll, std::atoll(v)) << 30;
+        const long pages = sysconf(_SC_PHYS_PAGES), psz = sysconf(_SC_PAGE_SIZE);
+        const size_t ram = pages > 0 && psz > 0 ? (size_t)pages * (size_t)psz : (size_t)64 << 30;
+        return std::min<size_t>(ram / 4, (size_t)64 << 30);
+    }();
 
     int acquire(size_t bytes, Block *out)
     {
