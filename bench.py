@@ -257,8 +257,8 @@ def main():
     e2e = None
     if not args.no_e2e:
         # the ranks of a box share one host (its cores and its DRAM bandwidth bound this path), so the end-to-end batch
-        # per GPU shrinks with the GPU count -- but never below one alignment per resident lane
-        ne = min(max(args.e2e_pairs // world, 131_072), n)
+        # per GPU shrinks with the GPU count -- but never below two sub-batches (the pipeline needs something to overlap)
+        ne = min(max(args.e2e_pairs // world, 262_144), n)
         h_text, h_tlen, h_reads = synth.pairs_host(wl, first_pair, ne)
         tb, toff, qb, qoff = synth.pairs_as_blobs(h_text, h_tlen, h_reads)
         del h_text
