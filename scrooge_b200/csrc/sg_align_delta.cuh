@@ -38,16 +38,22 @@
 #pragma once
 #include "sg_align.cuh"
 
-// Compile-time switches for A/B builds (tools/build_variants.sh).  All three were measured on a B200 against the plain
-// version (1 M x 10 kbp pairs, alignment kernel alone: 37.0 ms) and all three LOSE, so they are off:
-//   SG_DELTA_PFPM   pattern masks of column i-1 fetched from shared memory while column i is computed (37.8 ms: the
+// Compile-time switches for A/B builds (tools/build_variants.sh).  Measured on a B200 against the plain version
+// (1 M x 10 kbp pairs, alignment kernel alone, +-0.01 ms run to run); only RLE2 pays and is on:
+//   SG_DELTA_PFPM   pattern masks of column i-1 fetched from shared memory while column i is computed: 37.0 -> 37.8 ms (the
 //                   short-scoreboard stalls the ncu source view shows at the first use of an LDS are already covered
-//                   by the other warps of the scheduler -- the alu pipe is the limit -- and two more registers are live)
-//   SG_DELTA_FMA    the 64-bit addition and the two shifts of a column on the fma pipe (IMAD / IMAD.WIDE.U32 with run-time
-//                   multipliers 1 and 2 that ptxas cannot turn back into alu-pipe shifts: a column drops from 18 to 15
-//                   alu-pipe instructions, yet 39.8 ms: IMAD.WIDE issues too slowly to pay for the three SHF/IADD3 it saves)
+//                   by the other warps of the scheduler, and two more registers are live)
+//   SG_DELTA_FMA    the 64-bit addition and/or the two shifts of a column on the fma pipe (IMAD / IMAD.WIDE.U32 with
+//                   run-time multipliers 1 and 2 that ptxas cannot turn back into alu-pipe instructions; a column drops
+//                   from 18 to 15 alu-pipe instructions).  1 = both: 39.8 ms; 2 = addition only: 36.6 -> 39.8 ms;
+//                   3 = shifts only: 36.6 -> 38.0 ms.  IMAD.WIDE costs about 6 issue cycles more than the IADD3 it replaces.
 //   SG_DELTA_EARLY  the next window's text and pattern words requested right after the traceback, so that their L2
-//                   latency is covered by the run-length encoding (37.9 ms; 69 registers instead of 62)
+//                   latency is covered by the run-length encoding: 37.0 -> 37.9 ms (69 registers instead of 62)
+//   SG_DELTA_TBFMA  fast traceback steps accumulate their stream bits (and, with 1, the column address) with predicated
+//                   IMADs instead of the VIADDs the compiler emits: 89 fewer alu-pipe... in fact no change at all
+//                   (36.59 vs 36.59 ms): VIADD does not compete with LOP3/SHF for the alu pipe, and the traceback is not
+//                   what the alu pipe waits for.
+//   SG_DELTA_RLE2   leaner run-emission loop (op bits rotated into place, one output pointer): 36.90 -> 36.59 ms.  ON.
 #ifndef SG_DELTA_PFPM
 #define SG_DELTA_PFPM 0
 #endif
@@ -56,6 +62,12 @@
 #endif
 #ifndef SG_DELTA_EARLY
 #define SG_DELTA_EARLY 0
+#endif
+#ifndef SG_DELTA_TBFMA
+#define SG_DELTA_TBFMA 0
+#endif
+#ifndef SG_DELTA_RLE2
+#define SG_DELTA_RLE2 1
 #endif
 
 namespace sg {
@@ -124,9 +136,13 @@ __device__ __forceinline__ void delta_column_fma(uint32_t (&Pv)[NW], uint32_t (&
 #pragma unroll
     for (int k = 0; k < NW; k++) t[k] = ~pm[k] & Pv[k];
     if constexpr (NW == 2) {
-        const uint64_t w = (uint64_t)t[0] * one + (((uint64_t)Pv[1] << 32) | Pv[0]);
-        s[0] = (uint32_t)w;
-        s[1] = t[1] * one + (uint32_t)(w >> 32);
+        if (SG_DELTA_FMA != 3) {
+            const uint64_t w = (uint64_t)t[0] * one + (((uint64_t)Pv[1] << 32) | Pv[0]);
+            s[0] = (uint32_t)w;
+            s[1] = t[1] * one + (uint32_t)(w >> 32);
+        } else {
+            add_vec<NW>(t, Pv, s);
+        }
     } else {
         s[0] = t[0] * one + Pv[0];
     }
@@ -137,11 +153,16 @@ __device__ __forceinline__ void delta_column_fma(uint32_t (&Pv)[NW], uint32_t (&
         Mh[k] = Pv[k] & x[k];
     }
     if constexpr (NW == 2) {
-        const uint64_t wp = (uint64_t)Ph[0] * two, wm = (uint64_t)Mh[0] * two;
-        Phs[0] = (uint32_t)wp;
-        Phs[1] = Ph[1] * two + (uint32_t)(wp >> 32);
-        Mhs[0] = (uint32_t)wm;
-        Mhs[1] = Mh[1] * two + (uint32_t)(wm >> 32);
+        if (SG_DELTA_FMA != 2) {
+            const uint64_t wp = (uint64_t)Ph[0] * two, wm = (uint64_t)Mh[0] * two;
+            Phs[0] = (uint32_t)wp;
+            Phs[1] = Ph[1] * two + (uint32_t)(wp >> 32);
+            Mhs[0] = (uint32_t)wm;
+            Mhs[1] = Mh[1] * two + (uint32_t)(wm >> 32);
+        } else {
+            shl1<NW>(Ph, Phs);
+            shl1<NW>(Mh, Mhs);
+        }
     } else {
         Phs[0] = Ph[0] * two;
         Mhs[0] = Mh[0] * two;
@@ -373,6 +394,33 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
                 // one step, written out as predicated instructions (the compiler's version spends selects on them):
                 //   hi/lo = the op's two bits; every op but 'I' (hi & !lo) consumes a text character (next column),
                 //   every op but 'D' (hi & lo) consumes a pattern character (mask >>= 1)
+#if SG_DELTA_TBFMA
+                // the same step with the three accumulations (two stream bits, the column address) as predicated IMADs
+                // on the idle fma pipe: x += k_one * constant, k_one == 1 being a kernel parameter ptxas cannot fold
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred ph, pl, pi, pd;\n\t"
+                    ".reg .b32 t;\n\t"
+                    "and.b32 t, %2, %4;\n\t"
+                    "setp.ne.u32 ph, t, 0;\n\t"
+                    "and.b32 t, %3, %4;\n\t"
+                    "setp.ne.u32 pl, t, 0;\n\t"
+                    "@ph mad.lo.u32 %0, %8, %6, %0;\n\t"
+                    "@pl mad.lo.u32 %1, %8, %6, %1;\n\t"
+                    "and.pred pd, ph, pl;\n\t"
+                    "not.pred pi, pl;\n\t"
+                    "and.pred pi, pi, ph;\n\t"
+#if SG_DELTA_TBFMA == 2
+                    "@!pi add.u32 %5, %5, %7;\n\t"                 // the address stays on the alu pipe: it is on the load's critical path
+#else
+                    "@!pi mad.lo.u32 %5, %8, %7, %5;\n\t"
+#endif
+                    "@!pd shr.u32 %4, %4, 1;\n\t"
+                    "ld.shared.v2.u32 {%2, %3}, [%5];\n\t"
+                    "}"
+                    : "+r"(h0), "+r"(l0), "+r"(ca), "+r"(cb), "+r"(mask), "+r"(tcol)
+                    : "r"(1u << k), "n"(TBS * 4), "r"(P.k_one));
+#else
                 asm volatile(
                     "{\n\t"
                     ".reg .pred ph, pl, pi, pd;\n\t"
@@ -392,6 +440,7 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
                     "}"
                     : "+r"(h0), "+r"(l0), "+r"(ca), "+r"(cb), "+r"(mask), "+r"(tcol)
                     : "r"(1u << k), "n"(TBS * 4));
+#endif
             }
             bit0 = TBL < 32 ? 1u << (TBL & 31) : 0u;
         }
@@ -447,6 +496,27 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
         const bool fits = !want_cigar || (uint64_t)(out_end - out) >= (uint64_t)nb;
         if (!fits) overflow = true;
         if (want_cigar && fits) {
+#if SG_DELTA_RLE2
+            // one byte per run, (op << 6) | length.  The op bits of step p are brought to bits 7 and 6 by one rotation each
+            // (the streams are pre-rotated by 7 and 6 per word), merged by one LOP3 and joined with the length by another.
+            uint8_t *o = out;
+            out += nb;                                   // the run count is known: the loop carries one pointer only
+            int st = -1;                                 // step before the current run's first, relative to word w
+#pragma unroll
+            for (int w = 0; w < SW; w++) {
+                uint32_t ew = e[w];
+                const uint32_t h7 = __funnelshift_l(hs[w], hs[w], 7), l6 = __funnelshift_l(ls[w], ls[w], 6);
+                while (ew) {
+                    const int p = __ffs((int)ew) - 1;
+                    const uint32_t rh = __funnelshift_r(h7, h7, p), rl = __funnelshift_r(l6, l6, p);
+                    const uint32_t t = (rh & 0x80u) | (rl & ~0x80u);
+                    *o++ = (uint8_t)((t & 0xC0u) | (uint32_t)(p - st));
+                    st = p;
+                    ew &= ew - 1u;
+                }
+                st -= 32;
+            }
+#else
             int start = -1;                              // step before the current run's first
 #pragma unroll
             for (int w = 0; w < SW; w++) {
@@ -459,6 +529,7 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
                     ew &= ew - 1u;
                 }
             }
+#endif
         }
         nruns += nb;
         ed += edits;

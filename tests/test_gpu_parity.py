@@ -88,6 +88,33 @@ def test_short_reads_config2_shape(oracle, aligners):
     check_against_oracle(oracle, aligners[32], T, Q, 32)
 
 
+def test_many_short_pairs_host_paths(oracle, aligners):
+    """800 000 x 150 bp pairs in one call (two sub-batches): large enough that the host side splits its per-alignment
+    descriptor loops over threads, cuts sub-batches by binary search and lets the results of both sub-batches land in
+    the one pinned result block.  Checked against the oracle on a sample spread over the whole call, and on EVERY pair
+    through the sequence-independent CIGAR properties (numpy)."""
+    from scrooge_b200 import synth
+    wl = synth.WORKLOADS["short_150bp"]
+    n = 800_000
+    text, tlen, reads = synth.pairs_host(wl, 0, n)
+    tb, toff, qb, qoff = synth.pairs_as_blobs(text, tlen, reads)
+    got = aligners[64].align_pairs_blob(tb, toff, qb, qoff)
+    ed, rc, ro, runs = got.edit_distances, got.ref_consumed, got.run_offsets.astype(np.int64), got.runs
+    assert len(ed) == n and int(ro[-1]) == len(runs)
+    cnt, op = (runs & 63).astype(np.int64), runs >> 6
+    assert cnt.min() >= 1 and cnt.max() <= 31
+    csum = lambda sel: np.concatenate(([0], np.cumsum(np.where(sel, cnt, 0))))
+    for sel, want in ((op != 3, np.full(n, 150)), (op != 2, rc.astype(np.int64)), (op != 0, ed)):
+        c = csum(sel)
+        assert np.array_equal(c[ro[1:]] - c[ro[:-1]], want)
+    idx = list(range(0, n, 997)) + [n - 1]
+    T, Q = synth.pairs_as_strings(text[idx], tlen[idx], reads[idx])
+    want = oracle.align_pairs(T, Q, threads=4)
+    assert [int(ed[i]) for i in idx] == list(want.edit)
+    assert [got.cigar(i) for i in idx] == list(want.cigars)
+    assert [int(rc[i]) for i in idx] == [int(x) for x in want.ref_consumed]
+
+
 def test_very_long_and_unrelated(oracle, aligners):
     rng = __import__("random").Random(9)
     t = rand_seq(rng, 120000)
