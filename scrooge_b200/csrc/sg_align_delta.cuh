@@ -50,9 +50,9 @@
 //   SG_DELTA_EARLY  the next window's text and pattern words requested right after the traceback, so that their L2
 //                   latency is covered by the run-length encoding: 37.0 -> 37.9 ms (69 registers instead of 62)
 //   SG_DELTA_TBFMA  fast traceback steps accumulate their stream bits (and, with 1, the column address) with predicated
-//                   IMADs instead of the VIADDs the compiler emits: 89 fewer alu-pipe... in fact no change at all
-//                   (36.59 vs 36.59 ms): VIADD does not compete with LOP3/SHF for the alu pipe, and the traceback is not
-//                   what the alu pipe waits for.
+//                   IMADs instead of the 89 VIADDs per window the compiler emits: no change at all (36.59 vs 36.59 ms) --
+//                   VIADD does not compete with LOP3/SHF for the alu pipe, and the traceback is not what that pipe
+//                   waits for.
 //   SG_DELTA_RLE2   leaner run-emission loop (op bits rotated into place, one output pointer): 36.90 -> 36.59 ms.  ON.
 #ifndef SG_DELTA_PFPM
 #define SG_DELTA_PFPM 0
