@@ -7,8 +7,9 @@
 //     src/genasm_gpu.cu:67) -- alignments are independent, results are identical for any GPU count;
 //   * errors throw std::runtime_error instead of exit()/assert() (src/cuda_util.hpp:3-10,
 //     src/genasm_gpu.cu:636,984);
-//   * the window configuration is a run-time choice: SG_WINDOW=32 selects W=32/O=17, default W=64/O=33
-//     (the reference needs a recompile with -DCLI_W..., src/genasm_gpu.cu:1-63);
+//   * the window configuration is a run-time choice: SG_WINDOW=<W> and SG_OVERLAP=<O> (default W=64, O=min(W/2+1, W-1):
+//     64/33 and 32/17 as the reference ships them; any 2 <= W <= 128, 0 <= O < W with W-O <= 63 is accepted) where
+//     the reference needs a recompile with -DCLI_W/-DCLI_K/-DCLI_O (src/genasm_gpu.cu:1-63);
 //   * align_all_ex additionally returns the consumed reference prefix of every alignment.
 // The reference also exports a __global__ ascii_to_twobit_strings used only by its own unit test
 // (src/genasm_gpu.hpp:9, src/tests.cu:626); the equivalent here is sg_dev_pack_2bit in scrooge_b200.h.

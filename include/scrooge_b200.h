@@ -22,9 +22,13 @@
  * SG_ERR_CUDA (and a message in sg_last_error) when there is none.
  *
  * Semantics (bit-exact with reference src/genasm_cpu.cpp): semi-global edit distance of the whole query
- * against a prefix of the text, computed over a chain of W x W windows with overlap O (W=64,O=33 or
- * W=32,O=17; K=W); traceback priority I > D > X > '='; CIGAR runs are run-length encoded within a window
- * and never merged across windows.
+ * against a prefix of the text, computed over a chain of W x W windows with overlap O (K=W); traceback
+ * priority I > D > X > '='; CIGAR runs are run-length encoded within a window and never merged across windows.
+ * The window configuration is a run-time choice where the reference needs a rebuild (-DCLI_W/-DCLI_O,
+ * src/genasm_cpu.cpp:22-35): W=64/O=33 (in-file default, src/genasm_cpu.cpp:7-9) and W=32/O=17 (README.md:208)
+ * run on kernels tuned for them, any other 2 <= W <= 128, 0 <= O < W with W-O <= 63 (the axes of
+ * scripts/profile.py:66-100,595-640) on a general kernel; results are bit-exact with the reference built at
+ * the same (W, O).
  */
 #ifndef SCROOGE_B200_H
 #define SCROOGE_B200_H
@@ -71,6 +75,14 @@ int sg_device_count(void);
 /* Create a context over n_devices GPUs (device_ids == NULL: devices 0..n_devices-1; n_devices == 0: all).
  * W is 64 (O=33) or 32 (O=17).  Replaces the reference's hard-wired GPU_ID 0 (src/genasm_gpu.cu:67). */
 int sg_ctx_create(sg_ctx **out, const int *device_ids, int n_devices, int W);
+/* The same with an explicit window configuration: 2 <= W <= 128, 0 <= O < W, W-O <= 63 (a run is one byte,
+ * see SG_RUN_COUNT).  Replaces a rebuild of the reference with -DCLI_W=<W> -DCLI_K=<W> -DCLI_O=<O>
+ * (src/genasm_cpu.cpp:22-35, scripts/profile.py:29,132). */
+int sg_ctx_create_wo(sg_ctx **out, const int *device_ids, int n_devices, int W, int O);
+/* O = min(W/2+1, W-1): the overlap the reference pairs with a window size (scripts/profile.py:78,619). */
+int sg_default_overlap(int W);
+int sg_ctx_window(const sg_ctx *ctx);
+int sg_ctx_overlap(const sg_ctx *ctx);
 void sg_ctx_destroy(sg_ctx *ctx);
 int sg_ctx_num_devices(const sg_ctx *ctx);
 
@@ -165,6 +177,13 @@ int sg_dev_align(int W, const uint32_t *d_text, const uint64_t *d_text_start, co
                  uint64_t n, uint32_t flags, uint8_t *d_slab, const uint64_t *d_slab_off,
                  uint64_t *d_counter, int64_t *d_edit, uint64_t *d_ref_consumed, uint32_t *d_nruns,
                  uint8_t *d_status, uint64_t *d_dc_entries, uint32_t *d_windows, void *stream);
+/* The same for any window configuration (limits as sg_ctx_create_wo); sg_dev_align(W, ...) is
+ * sg_dev_align_wo(W, sg_default_overlap(W), ...). */
+int sg_dev_align_wo(int W, int O, const uint32_t *d_text, const uint64_t *d_text_start, const uint64_t *d_text_len,
+                    const uint32_t *d_query, const uint64_t *d_query_start, const uint64_t *d_query_len,
+                    uint64_t n, uint32_t flags, uint8_t *d_slab, const uint64_t *d_slab_off,
+                    uint64_t *d_counter, int64_t *d_edit, uint64_t *d_ref_consumed, uint32_t *d_nruns,
+                    uint8_t *d_status, uint64_t *d_dc_entries, uint32_t *d_windows, void *stream);
 
 /* CIGAR compaction: exclusive scan of d_nruns into d_run_off[n+1] (d_scan_tmp: sg_scan_tmp_bytes(n)
  * bytes), then gather every alignment's runs from its slab slot into one dense array.
@@ -176,7 +195,7 @@ int sg_dev_gather_runs(const uint8_t *d_slab, const uint64_t *d_slab_off, const 
 
 /* Measurement / test helper: consistency of a batch's compacted runs with its other results, for EVERY alignment --
  * the sequence-independent properties of the reference's validateCigarString (src/tests.cu:106-169): every run count
- * in [1, max_count] (W-O: 31 at W=64, 15 at W=32), counts of =,X,I sum to d_query_len, of =,X,D to d_ref_consumed, of
+ * in [1, max_count] (W-O: 31 at W=64/O=33, 15 at W=32/O=17), counts of =,X,I sum to d_query_len, of =,X,D to d_ref_consumed, of
  * X,I,D to d_edit.  *d_n_bad (device uint64, caller-initialised) is incremented once per offending alignment. */
 int sg_dev_check_runs(const uint8_t *d_runs, const uint64_t *d_run_off, uint64_t n, const uint64_t *d_query_len,
                       const int64_t *d_edit, const uint64_t *d_ref_consumed, uint32_t max_count, uint64_t *d_n_bad,
@@ -185,6 +204,7 @@ int sg_dev_check_runs(const uint8_t *d_runs, const uint64_t *d_run_off, uint64_t
 /* Launch geometry of sg_dev_align on the current device: persistent warps per SM and shared memory per
  * warp (for reports). */
 int sg_dev_align_geometry(int W, int *warps_per_sm, int *smem_per_warp, int *num_sms);
+int sg_dev_align_geometry_wo(int W, int O, int *warps_per_sm, int *smem_per_warp, int *num_sms);
 
 /* Sustained 32-bit integer ALU throughput probe (LOP3 + SHF mix, the instruction mix of the DC
  * recurrence): runs for roughly `ms` milliseconds and returns giga-ops/s through *gops.  kind: 0 LOP3 only,

@@ -25,6 +25,16 @@ REF_DIR = os.path.join(HERE, "_ref")
 # (W, O) pairs the reference is used with: in-file default (src/genasm_cpu.cpp:7-9) and the
 # short-read setting (README.md:208, scripts/profile.py:78: O = min(W//2+1, W-1)).
 CONFIGS = {64: 33, 32: 17}
+# Further (W, O) builds of the unmodified reference (oracle/Makefile EXTRA_WO): the axes of the reference's window sweep
+# (scripts/profile.py:66-100 cpu_sweep_wo / cpu_sweep_o, :595-640 accuracy sweeps with W in 32, 64, 96, 128 and
+# O = min(W//2+1, W-1) or free), restricted to what the run format holds (W <= 128, W - O <= 63).
+EXTRA_CONFIGS = [(64, 20), (64, 48), (64, 1), (48, 25), (32, 8), (16, 9), (96, 49), (128, 65), (128, 100)]
+
+
+def ref_lib_path(W: int, O: Optional[int] = None) -> str:
+    if O is None or CONFIGS.get(W) == O:
+        return os.path.join(REF_DIR, f"libscrooge_ref_w{W}.so")
+    return os.path.join(REF_DIR, f"libscrooge_ref_w{W}_o{O}.so")
 
 
 def build(force: bool = False) -> None:
@@ -180,19 +190,20 @@ class Oracle:
 class RefCpu:
     """The unmodified reference CPU aligner (genasm_cpu::align_all) for one (W, O) build."""
 
-    def __init__(self, W: int = 64):
-        path = os.path.join(REF_DIR, f"libscrooge_ref_w{W}.so")
+    def __init__(self, W: int = 64, O: Optional[int] = None):
+        path = ref_lib_path(W, O)
         if not os.path.exists(path):
             raise FileNotFoundError(path)
         self.W = W
+        self.O = CONFIGS[W] if O is None else O
         self.lib = C.CDLL(path)
         for f in ("ref_align_pairs", "ref_align_mapping", "ref_config_w", "ref_config_o", "ref_max_threads"):
             getattr(self.lib, f).restype = C.c_int
-        assert self.lib.ref_config_w() == W and self.lib.ref_config_o() == CONFIGS[W]
+        assert self.lib.ref_config_w() == W and self.lib.ref_config_o() == self.O
 
     @staticmethod
-    def available(W: int = 64) -> bool:
-        return os.path.exists(os.path.join(REF_DIR, f"libscrooge_ref_w{W}.so"))
+    def available(W: int = 64, O: Optional[int] = None) -> bool:
+        return os.path.exists(ref_lib_path(W, O))
 
     def max_threads(self) -> int:
         return int(self.lib.ref_max_threads())

@@ -30,7 +30,12 @@
 #include <omp.h>
 #endif
 
-#define SGO_MAX_W 64
+#define SGO_MAX_W 128
+
+/* one W-bit vector, W <= 128 (the reference switches to arrays of 32-bit words above 64 bits,
+ * src/bitvector.hpp:42-47; the arithmetic is the same) */
+typedef unsigned __int128 vec_t;
+#define VEC_ONES (~(vec_t)0)
 
 typedef struct {
     int W;        /* window size in characters; K == W (src/genasm_cpu.cpp:7-8, scripts/profile.py:29) */
@@ -41,7 +46,7 @@ typedef struct {
 /* scratch for one worker thread: R[d][i] for d in [0,W], i in [0,W]
  * (src/genasm_cpu.cpp:71-78, SENE indexing COLUMNS*d + i) */
 typedef struct {
-    uint64_t R[(SGO_MAX_W + 1) * (SGO_MAX_W + 1)];
+    vec_t R[(SGO_MAX_W + 1) * (SGO_MAX_W + 1)];
 } sgo_scratch;
 
 typedef struct {
@@ -51,7 +56,7 @@ typedef struct {
     uint64_t tb_steps;   /* number of traceback steps */
 } sgo_stats;
 
-static inline uint64_t low_mask(int bits) { return bits >= 64 ? ~0ull : ((1ull << bits) - 1ull); }
+static inline vec_t low_mask(int bits) { return bits >= 128 ? VEC_ONES : ((((vec_t)1) << bits) - 1); }
 
 /* ASCII -> base codes A0 C1 G2 T3, case-insensitive (src/genasm_cpu.cpp:462-493).
  * Returns -1 and the offending position through *bad_pos instead of assert(false). */
@@ -88,50 +93,52 @@ int sgo_ascii_to_twobit_ref_layout(const char *ascii, size_t len, uint8_t *out)
 
 /* Pattern bitmasks (src/genasm_cpu.cpp:178-198): bit b of masks[c] is 0 iff pattern[m-1-b] == c,
  * every other bit (including b >= m) is 1. */
-static void pattern_masks(int m, const uint8_t *pattern, uint64_t masks[4])
+static void pattern_masks(int m, const uint8_t *pattern, vec_t masks[4])
 {
-    masks[0] = masks[1] = masks[2] = masks[3] = ~0ull;
+    masks[0] = masks[1] = masks[2] = masks[3] = VEC_ONES;
     for (int b = 0; b < m; b++) {
-        masks[pattern[m - 1 - b]] &= ~(1ull << b);
+        masks[pattern[m - 1 - b]] &= ~(((vec_t)1) << b);
     }
 }
 
 /* Distance calculation for one window (src/genasm_cpu.cpp:210-288), SENE + early termination.
- * Vectors are W-bit; they are held in uint64_t and truncated to W bits after every shift so that
- * W = 32 behaves like the reference's 32-bit element type (src/bitvector.hpp:32-49,115-140).
+ * Vectors are W-bit; they are held in a 128-bit integer and truncated to W bits after every shift so
+ * that W = 32 behaves like the reference's 32-bit element type (src/bitvector.hpp:32-49,115-140); bits
+ * at and above m are never examined and shifts only move bits upwards, so the truncation is neutral
+ * for every other W as well.
  * Returns d_w, the smallest d for which bit m-1 of R[d][0] is zero. */
 static int window_dc(const sgo_cfg *cfg, int n, const uint8_t *text, int m, const uint8_t *pattern,
-                     uint64_t *R)
+                     vec_t *R)
 {
     const int W = cfg->W;
     const int cols = W + 1;
-    const uint64_t wmask = low_mask(W);
-    uint64_t pm[4];
+    const vec_t wmask = low_mask(W);
+    vec_t pm[4];
     pattern_masks(m, pattern, pm);
 
     for (int d = 0; d <= W; d++) {
         for (int i = n; i >= 0; i--) {
-            uint64_t center;
+            vec_t center;
             if (i == n) {
                 /* boundary column: all ones shifted left by d (src/genasm_cpu.cpp:225-231,239-245) */
-                center = d >= 64 ? 0ull : ((~0ull << d) & wmask);
+                center = d >= 128 ? (vec_t)0 : ((VEC_ONES << d) & wmask);
             } else {
                 /* note: text[i] is only touched for i < n (quirk Q6) */
-                uint64_t right = R[cols * d + (i + 1)];
-                uint64_t mat = ((right << 1) | pm[text[i]]) & wmask;
+                vec_t right = R[cols * d + (i + 1)];
+                vec_t mat = ((right << 1) | pm[text[i]]) & wmask;
                 if (d == 0) {
                     center = mat; /* src/genasm_cpu.cpp:232-238 */
                 } else {
-                    uint64_t top = R[cols * (d - 1) + i];
-                    uint64_t topright = R[cols * (d - 1) + (i + 1)];
-                    uint64_t sub = (topright << 1) & wmask;
-                    uint64_t ins = (top << 1) & wmask;
-                    uint64_t del = topright;
+                    vec_t top = R[cols * (d - 1) + i];
+                    vec_t topright = R[cols * (d - 1) + (i + 1)];
+                    vec_t sub = (topright << 1) & wmask;
+                    vec_t ins = (top << 1) & wmask;
+                    vec_t del = topright;
                     center = mat & sub & ins & del; /* src/genasm_cpu.cpp:246-252 */
                 }
             }
             R[cols * d + i] = center;
-            if (i == 0 && ((center >> (m - 1)) & 1ull) == 0) {
+            if (i == 0 && ((center >> (m - 1)) & 1) == 0) {
                 return d; /* early termination, src/genasm_cpu.cpp:278-283 */
             }
         }
@@ -142,7 +149,8 @@ static int window_dc(const sgo_cfg *cfg, int n, const uint8_t *text, int m, cons
 static char *emit_run(char *out, int count, char type)
 {
     /* the reference prints "%d%c" per run (src/genasm_cpu.cpp:389,401) */
-    if (count >= 10) *out++ = (char)('0' + count / 10);
+    if (count >= 100) *out++ = (char)('0' + count / 100);
+    if (count >= 10) *out++ = (char)('0' + (count / 10) % 10);
     *out++ = (char)('0' + count % 10);
     *out++ = type;
     return out;
@@ -150,7 +158,7 @@ static char *emit_run(char *out, int count, char type)
 
 /* Traceback of one window (src/genasm_cpu.cpp:290-409), SENE bit tests, priority I > D > X > '='.
  * Runs are encoded per window and flushed at window end (quirk Q2). */
-static int window_tb(const sgo_cfg *cfg, int n, int m, const uint64_t *R, int d_w,
+static int window_tb(const sgo_cfg *cfg, int n, int m, const vec_t *R, int d_w,
                      int *text_consumed, int *pattern_consumed, char **cigar, uint64_t *steps)
 {
     const int cols = cfg->W + 1;
@@ -167,9 +175,9 @@ static int window_tb(const sgo_cfg *cfg, int n, int m, const uint64_t *R, int d_
         int can_ins, can_del, can_sub;
         if (j < m - 1) {
             /* bit index of pattern position J is m-1-J (src/genasm_cpu.cpp:59,321-323) */
-            can_ins = !d_limit && !((R[cols * (d - 1) + i] >> (m - 1 - (j + 1))) & 1ull);
-            can_del = !d_limit && !i_limit && !((R[cols * (d - 1) + (i + 1)] >> (m - 1 - j)) & 1ull);
-            can_sub = !d_limit && !i_limit && !((R[cols * (d - 1) + (i + 1)] >> (m - 1 - (j + 1))) & 1ull);
+            can_ins = !d_limit && !((R[cols * (d - 1) + i] >> (m - 1 - (j + 1))) & 1);
+            can_del = !d_limit && !i_limit && !((R[cols * (d - 1) + (i + 1)] >> (m - 1 - j)) & 1);
+            can_sub = !d_limit && !i_limit && !((R[cols * (d - 1) + (i + 1)] >> (m - 1 - (j + 1))) & 1);
         } else {
             can_ins = !d_limit; /* src/genasm_cpu.cpp:336-343 */
             can_del = 0;

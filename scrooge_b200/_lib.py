@@ -31,6 +31,10 @@ SIGNATURES = {
     "sg_version": (i32, []),
     "sg_device_count": (i32, []),
     "sg_ctx_create": (i32, [C.POINTER(vp), C.POINTER(i32), i32, i32]),
+    "sg_ctx_create_wo": (i32, [C.POINTER(vp), C.POINTER(i32), i32, i32, i32]),
+    "sg_default_overlap": (i32, [i32]),
+    "sg_ctx_window": (i32, [vp]),
+    "sg_ctx_overlap": (i32, [vp]),
     "sg_ctx_destroy": (None, [vp]),
     "sg_ctx_num_devices": (i32, [vp]),
     "sg_align_pairs": (i32, [vp, vp, vp, vp, vp, u64, u32, C.POINTER(vp)]),
@@ -57,6 +61,8 @@ SIGNATURES = {
     "sg_packed_words": (u64, [u64]),
     "sg_dev_pack_2bit": (i32, [vp, u64, vp, vp, vp]),
     "sg_dev_align": (i32, [i32, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "sg_dev_align_wo": (i32, [i32, i32, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "sg_dev_align_geometry_wo": (i32, [i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
     "sg_scan_tmp_bytes": (u64, [u64]),
     "sg_dev_scan_runs": (i32, [vp, u64, vp, vp, vp]),
     "sg_dev_gather_runs": (i32, [vp, vp, vp, vp, u64, vp, vp]),

@@ -130,17 +130,22 @@ class Result:
 
 
 class Aligner:
-    """sg_ctx wrapper.  W=64 -> O=33 (reference default), W=32 -> O=17 (reference short-read setting)."""
+    """sg_ctx wrapper.  W=64 -> O=33 (reference default), W=32 -> O=17 (reference short-read setting); any other
+    window configuration the reference can be rebuilt with (-DCLI_W/-DCLI_O, src/genasm_cpu.cpp:22-35) within
+    2 <= W <= 128, 0 <= O < W, W-O <= 63 by passing O (default O = min(W//2+1, W-1), scripts/profile.py:78)."""
 
-    def __init__(self, W: int = 64, n_gpus: int = 0, device_ids: Optional[Sequence[int]] = None):
+    def __init__(self, W: int = 64, n_gpus: int = 0, device_ids: Optional[Sequence[int]] = None, O: Optional[int] = None):
         h = C.c_void_p()
+        if O is None:
+            O = min(W // 2 + 1, W - 1)
         if device_ids is not None:
             ids = (C.c_int * len(device_ids))(*device_ids)
-            check(lib().sg_ctx_create(C.byref(h), ids, len(device_ids), W))
+            check(lib().sg_ctx_create_wo(C.byref(h), ids, len(device_ids), W, O))
         else:
-            check(lib().sg_ctx_create(C.byref(h), None, n_gpus, W))
+            check(lib().sg_ctx_create_wo(C.byref(h), None, n_gpus, W, O))
         self._h = h
         self.W = W
+        self.O = O
         self._genome_keepalive = None
 
     def close(self):
@@ -234,20 +239,21 @@ def _ptr(buf) -> int:
 _default: dict = {}
 
 
-def _aligner(W: int) -> Aligner:
-    if W not in _default:
-        _default[W] = Aligner(W=W)
-    return _default[W]
+def _aligner(W: int, O: Optional[int] = None) -> Aligner:
+    key = (W, min(W // 2 + 1, W - 1) if O is None else O)
+    if key not in _default:
+        _default[key] = Aligner(W=W, O=key[1])
+    return _default[key]
 
 
-def align_all(a, b, W: int = 64) -> List[Alignment]:
+def align_all(a, b, W: int = 64, O: Optional[int] = None) -> List[Alignment]:
     """The reference's two overloads in one function.
 
     ``align_all(texts, queries)``   -- unstructured interface (src/genasm_gpu.hpp:8): lists of strings.
     ``align_all(reference, reads)`` -- read-mapping interface (src/genasm_gpu.hpp:7): a ``Genome`` and a list of
     ``Read``; one result per (read, location), read-major.
     """
-    al = _aligner(W)
+    al = _aligner(W, O)
     if isinstance(a, Genome):
         reads: Sequence[Read] = b
         al.set_reference(a.content)

@@ -25,7 +25,7 @@ namespace {
 
 struct Holder {
     sg_ctx *ctx = nullptr;
-    int W = 0, n_gpus = 0;
+    int W = 0, O = 0, n_gpus = 0;
     ~Holder() { if (ctx) sg_ctx_destroy(ctx); }
 };
 
@@ -41,15 +41,17 @@ int env_int(const char *name, int dflt)
 sg_ctx *context()
 {
     const int W = env_int("SG_WINDOW", 64);
+    const int O = env_int("SG_OVERLAP", sg_default_overlap(W));
     const int n = env_int("SG_NUM_GPUS", 0);
-    if (g_holder.ctx && (g_holder.W != W || g_holder.n_gpus != n)) {
+    if (g_holder.ctx && (g_holder.W != W || g_holder.O != O || g_holder.n_gpus != n)) {
         sg_ctx_destroy(g_holder.ctx);
         g_holder.ctx = nullptr;
     }
     if (!g_holder.ctx) {
-        if (sg_ctx_create(&g_holder.ctx, nullptr, n, W) != SG_OK)
+        if (sg_ctx_create_wo(&g_holder.ctx, nullptr, n, W, O) != SG_OK)
             throw std::runtime_error(std::string("scrooge_b200: ") + sg_last_error());
         g_holder.W = W;
+        g_holder.O = O;
         g_holder.n_gpus = n;
     }
     return g_holder.ctx;

@@ -12,6 +12,7 @@
 #include "sg_internal.h"
 #include "sg_align.cuh"
 #include "sg_align_delta.cuh"
+#include "sg_align_generic.cuh"
 #include "sg_aux.cuh"
 
 namespace sg {
@@ -137,6 +138,72 @@ static int device_info(DeviceInfo **out)
 }
 
 // Persistent lane count shared by both kernels, see launch_align.
+static uint64_t balanced_ctas(uint64_t n, uint64_t max_ctas, uint64_t lanes_per_cta);
+
+// The window configurations genasm_delta_kernel / genasm_align_kernel are built for (src/genasm_cpu.cpp:7-9, README.md:208);
+// every other (W, O) runs on genasm_generic_kernel, and so do these two with SG_GENERIC=1 (A/B and parity tests).
+static bool tuned_config(int W, int O)
+{
+    static const bool force_generic = [] {
+        const char *e = std::getenv("SG_GENERIC");
+        return e && *e && std::string(e) != "0";
+    }();
+    return !force_generic && ((W == 64 && O == 33) || (W == 32 && O == 17));
+}
+
+static int check_window(int W, int O)
+{
+    if (W < 2 || W > 128 || O < 0 || O >= W || W - O > 63)
+        return fail(SG_ERR_BAD_ARG, "window configuration out of range: need 2 <= W <= 128, 0 <= O < W, W - O <= 63");
+    return SG_OK;
+}
+
+template <int NW> static int generic_occupancy(int smem_bytes, int *ctas_per_sm)
+{
+    auto kern = genasm_generic_kernel<NW>;
+    SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kern, 32, smem_bytes));
+    if (std::getenv("SG_DEBUG")) {
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, kern);
+        fprintf(stderr, "[sg] generic NW=%d: occupancy %d CTAs/SM, %d regs, %d dyn smem\n", NW, *ctas_per_sm, fa.numRegs, smem_bytes);
+    }
+    if (*ctas_per_sm < 1) return fail(SG_ERR_CUDA, "generic alignment kernel does not fit on this device");
+    return SG_OK;
+}
+
+static int generic_geometry(const DeviceInfo &di, int W, int O, int *ctas_per_sm, int *smem_bytes)
+{
+    (void)di;
+    const int NW = (W + 31) / 32;
+    *smem_bytes = generic_smem_words(NW, W, W - O) * 4;
+    switch (NW) {
+        case 1: return generic_occupancy<1>(*smem_bytes, ctas_per_sm);
+        case 2: return generic_occupancy<2>(*smem_bytes, ctas_per_sm);
+        case 3: return generic_occupancy<3>(*smem_bytes, ctas_per_sm);
+        default: return generic_occupancy<4>(*smem_bytes, ctas_per_sm);
+    }
+}
+
+static int launch_generic(const DeviceInfo &di, const AlignParams &P, int W, int O, cudaStream_t st)
+{
+    int per_sm = 0, smem = 0;
+    int rc = generic_geometry(di, W, O, &per_sm, &smem);
+    if (rc) return rc;
+    GenericGeom G;
+    G.W = W; G.TBL = W - O; G.NWT = (G.TBL + 31) / 32;
+    const unsigned ctas = (unsigned)balanced_ctas(P.n, (uint64_t)di.sms * (uint64_t)per_sm, 32ull);
+    switch ((W + 31) / 32) {
+        case 1: genasm_generic_kernel<1><<<ctas, 32, smem, st>>>(P, G); break;
+        case 2: genasm_generic_kernel<2><<<ctas, 32, smem, st>>>(P, G); break;
+        case 3: genasm_generic_kernel<3><<<ctas, 32, smem, st>>>(P, G); break;
+        default: genasm_generic_kernel<4><<<ctas, 32, smem, st>>>(P, G); break;
+    }
+    SG_CUDA(cudaGetLastError());
+    return SG_OK;
+}
+
+// Persistent lane count shared by both kernels, see launch_align.
 static uint64_t balanced_ctas(uint64_t n, uint64_t max_ctas, uint64_t lanes_per_cta)
 {
     const uint64_t k = (n + max_ctas * lanes_per_cta - 1) / (max_ctas * lanes_per_cta);
@@ -212,12 +279,30 @@ int sg_dev_pack_2bit(const char *d_ascii, uint64_t n_bases, uint32_t *d_packed, 
     return SG_OK;
 }
 
+int sg_default_overlap(int W) { return W / 2 + 1 < W - 1 ? W / 2 + 1 : W - 1; }
+
 int sg_dev_align_geometry(int W, int *warps_per_sm, int *smem_per_warp, int *num_sms)
 {
     if (W != 64 && W != 32) return fail(SG_ERR_BAD_ARG, "W must be 64 or 32");
-    DeviceInfo *di;
-    int rc = device_info(&di);
+    return sg_dev_align_geometry_wo(W, sg_default_overlap(W), warps_per_sm, smem_per_warp, num_sms);
+}
+
+int sg_dev_align_geometry_wo(int W, int O, int *warps_per_sm, int *smem_per_warp, int *num_sms)
+{
+    int rc = check_window(W, O);
     if (rc) return rc;
+    DeviceInfo *di;
+    rc = device_info(&di);
+    if (rc) return rc;
+    if (!tuned_config(W, O)) {
+        int per_sm = 0, smem = 0;
+        rc = generic_geometry(*di, W, O, &per_sm, &smem);
+        if (rc) return rc;
+        if (warps_per_sm) *warps_per_sm = per_sm;
+        if (smem_per_warp) *smem_per_warp = smem;
+        if (num_sms) *num_sms = di->sms;
+        return SG_OK;
+    }
     if (use_delta()) {
         if (warps_per_sm) *warps_per_sm = di->delta_ctas_per_sm[W == 64 ? 0 : 1] * DeltaLayout<64>::WARPS_PER_CTA;
         if (smem_per_warp) *smem_per_warp = W == 64 ? DeltaLayout<64>::BYTES_PER_WARP : DeltaLayout<32>::BYTES_PER_WARP;
@@ -240,6 +325,20 @@ int sg_dev_align(int W, const uint32_t *d_text, const uint64_t *d_text_start, co
                  uint8_t *d_status, uint64_t *d_dc_entries, uint32_t *d_windows, void *stream)
 {
     if (W != 64 && W != 32) return fail(SG_ERR_BAD_ARG, "W must be 64 or 32");
+    return sg_dev_align_wo(W, sg_default_overlap(W), d_text, d_text_start, d_text_len, d_query, d_query_start, d_query_len, n, flags,
+                           d_slab, d_slab_off, d_counter, d_edit, d_ref_consumed, d_nruns, d_status, d_dc_entries, d_windows, stream);
+}
+
+int sg_dev_align_wo(int W, int O, const uint32_t *d_text, const uint64_t *d_text_start, const uint64_t *d_text_len,
+                    const uint32_t *d_query, const uint64_t *d_query_start, const uint64_t *d_query_len,
+                    uint64_t n, uint32_t flags, uint8_t *d_slab, const uint64_t *d_slab_off,
+                    uint64_t *d_counter, int64_t *d_edit, uint64_t *d_ref_consumed, uint32_t *d_nruns,
+                    uint8_t *d_status, uint64_t *d_dc_entries, uint32_t *d_windows, void *stream)
+{
+    {
+        const int wrc = check_window(W, O);
+        if (wrc) return wrc;
+    }
     if (n == 0) return SG_OK;
     if (!d_text || !d_text_start || !d_text_len || !d_query || !d_query_start || !d_query_len || !d_counter ||
         !d_edit || !d_ref_consumed || !d_nruns || !d_status)
@@ -258,6 +357,7 @@ int sg_dev_align(int W, const uint32_t *d_text, const uint64_t *d_text_start, co
     P.counter = (unsigned long long *)d_counter;
     P.edit = d_edit; P.ref_consumed = d_ref_consumed; P.nruns = d_nruns; P.status = d_status; P.dc_entries = d_dc_entries; P.windows = d_windows;
     P.k_one = 1u; P.k_two = 2u;
+    if (!tuned_config(W, O)) return launch_generic(*di, P, W, O, st);
     if (use_delta()) return W == 64 ? launch_delta<64>(*di, P, st) : launch_delta<32>(*di, P, st);
     if (use_tmem(W)) return W == 64 ? launch_align<64, true>(*di, P, st) : launch_align<32, true>(*di, P, st);
     return W == 64 ? launch_align<64, false>(*di, P, st) : launch_align<32, false>(*di, P, st);

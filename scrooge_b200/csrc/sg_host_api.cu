@@ -224,6 +224,7 @@ using namespace sg;
 
 struct sg_ctx {
     int W = 64;
+    int O = 33;
     std::vector<Device> devs;
     // sub-batch rule: at least batch_bytes of ASCII AND at least min_batch_units alignments (one alignment
     // occupies one lane for its whole life -- 11 ms for a 10 kbp read with every lane busy -- so a launch needs an
@@ -515,7 +516,7 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
     SG_CUDA(cudaMemcpyAsync(s.desc.p, s.h_desc.p, (5 * n + 1) * 8, cudaMemcpyHostToDevice, st));
     if (want_cigar) R(s.slab.reserve(slab_bytes + 16));
     SG_CUDA(cudaEventRecord(s.ev_k0, st));
-    R(sg_dev_align(ctx->W, d_text, d_tstart, d_tlen, s.packed_q.as<uint32_t>(), d_qstart, d_qlen, n, w.flags, s.slab.as<uint8_t>(), d_slab,
+    R(sg_dev_align_wo(ctx->W, ctx->O, d_text, d_tstart, d_tlen, s.packed_q.as<uint32_t>(), d_qstart, d_qlen, n, w.flags, s.slab.as<uint8_t>(), d_slab,
                    s.counter.as<uint64_t>(), s.edit.as<int64_t>(), s.refc.as<uint64_t>(), s.nruns.as<uint32_t>(), s.status.as<uint8_t>(),
                    nullptr, nullptr, st));
     SG_CUDA(cudaEventRecord(s.ev_k1, st));
@@ -743,13 +744,24 @@ extern "C" {
 
 int sg_ctx_create(sg_ctx **out, const int *device_ids, int n_devices, int W)
 {
+    if (W != 64 && W != 32) return fail(SG_ERR_BAD_ARG, "W must be 64 (O=33) or 32 (O=17); sg_ctx_create_wo takes any window");
+    return sg_ctx_create_wo(out, device_ids, n_devices, W, sg_default_overlap(W));
+}
+
+int sg_ctx_window(const sg_ctx *ctx) { return ctx ? ctx->W : 0; }
+int sg_ctx_overlap(const sg_ctx *ctx) { return ctx ? ctx->O : 0; }
+
+int sg_ctx_create_wo(sg_ctx **out, const int *device_ids, int n_devices, int W, int O)
+{
     if (!out) return fail(SG_ERR_BAD_ARG, "sg_ctx_create: null out");
-    if (W != 64 && W != 32) return fail(SG_ERR_BAD_ARG, "W must be 64 (O=33) or 32 (O=17)");
+    if (W < 2 || W > 128 || O < 0 || O >= W || W - O > 63)
+        return fail(SG_ERR_BAD_ARG, "window configuration out of range: need 2 <= W <= 128, 0 <= O < W, W - O <= 63");
     const int avail = sg_device_count();
     if (avail == 0) return fail(SG_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
     if (n_devices <= 0) n_devices = avail;
     std::unique_ptr<sg_ctx, void (*)(sg_ctx *)> ctx(new sg_ctx, sg_ctx_destroy);
     ctx->W = W;
+    ctx->O = O;
     ctx->devs.resize(n_devices);
     ctx->min_batch_units = 0;
     if (const char *v = std::getenv("SG_BATCH_MB")) {  // tuning knobs for experiments
@@ -784,7 +796,7 @@ int sg_ctx_create(sg_ctx **out, const int *device_ids, int n_devices, int W)
         if (const char *v = std::getenv("SG_SLOTS")) d.n_slots = std::min(kMaxSlots, std::max(2, std::atoi(v)));
         for (int q = 0; q < d.n_slots; q++) R(d.slots[q].create());
         int wps = 0, sms = 0;
-        R(sg_dev_align_geometry(W, &wps, nullptr, &sms));
+        R(sg_dev_align_geometry_wo(W, O, &wps, nullptr, &sms));
         // one alignment per resident lane fills the device (104 192 lanes on a B200 at W=64)
         ctx->min_batch_units = std::max<uint64_t>(ctx->min_batch_units, 32ull * (uint64_t)wps * (uint64_t)sms);
     }

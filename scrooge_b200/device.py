@@ -50,8 +50,9 @@ class AlignOut:
 class DeviceAligner:
     """Preallocated outputs + one sg_dev_align launch per call (inputs resident in HBM)."""
 
-    def __init__(self, W: int, n: int, device: torch.device, slab_bytes: int = 0):
+    def __init__(self, W: int, n: int, device: torch.device, slab_bytes: int = 0, O: Optional[int] = None):
         self.W, self.n, self.device = W, n, device
+        self.O = min(W // 2 + 1, W - 1) if O is None else O
         self.counter = torch.zeros(1, dtype=torch.int64, device=device)
         self.out = AlignOut(
             edit=torch.empty(n, dtype=torch.int64, device=device),
@@ -70,9 +71,9 @@ class DeviceAligner:
               distance_only: bool = False) -> AlignOut:
         flags = SG_FLAG_DISTANCE_ONLY if distance_only else 0
         o = self.out
-        check(lib().sg_dev_align(self.W, _p(text), _p(text_start), _p(text_len), _p(query), _p(query_start), _p(query_len),
-                                 self.n, flags, _p(self.slab), _p(slab_off), _p(self.counter), _p(o.edit),
-                                 _p(o.ref_consumed), _p(o.nruns), _p(o.status), _p(o.dc_entries), _p(o.windows), _stream()))
+        check(lib().sg_dev_align_wo(self.W, self.O, _p(text), _p(text_start), _p(text_len), _p(query), _p(query_start), _p(query_len),
+                                    self.n, flags, _p(self.slab), _p(slab_off), _p(self.counter), _p(o.edit),
+                                    _p(o.ref_consumed), _p(o.nruns), _p(o.status), _p(o.dc_entries), _p(o.windows), _stream()))
         return o
 
     def compact(self, slab_off: torch.Tensor, runs: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -86,19 +87,20 @@ class DeviceAligner:
         return self.run_off, runs
 
 
-def check_runs(runs: torch.Tensor, run_off: torch.Tensor, query_len: torch.Tensor, out: "AlignOut", W: int) -> int:
+def check_runs(runs: torch.Tensor, run_off: torch.Tensor, query_len: torch.Tensor, out: "AlignOut", W: int,
+               O: Optional[int] = None) -> int:
     """Number of alignments whose compacted runs contradict their query length, consumed reference prefix or edit
     distance (sg_dev_check_runs: the sequence-independent validateCigarString properties on the whole batch)."""
     n = query_len.numel()
     bad = torch.zeros(1, dtype=torch.int64, device=runs.device)
     check(lib().sg_dev_check_runs(_p(runs), _p(run_off), n, _p(query_len), _p(out.edit), _p(out.ref_consumed),
-                                  31 if W == 64 else 15, _p(bad), _stream()))
+                                  W - (min(W // 2 + 1, W - 1) if O is None else O), _p(bad), _stream()))
     return int(bad.item())
 
 
-def align_geometry(W: int) -> Tuple[int, int, int]:
+def align_geometry(W: int, O: Optional[int] = None) -> Tuple[int, int, int]:
     a, b, c = C.c_int(), C.c_int(), C.c_int()
-    check(lib().sg_dev_align_geometry(W, C.byref(a), C.byref(b), C.byref(c)))
+    check(lib().sg_dev_align_geometry_wo(W, min(W // 2 + 1, W - 1) if O is None else O, C.byref(a), C.byref(b), C.byref(c)))
     return a.value, b.value, c.value  # warps per SM, smem bytes per warp, SMs
 
 

@@ -2,7 +2,7 @@
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List, Tuple
+from typing import List, Optional, Tuple
 
 import numpy as np
 
@@ -23,6 +23,11 @@ class Workload:
     W: int
     seed: int
     slack: int = 64
+    O: Optional[int] = None   # window overlap; None = min(W//2+1, W-1) (reference scripts/profile.py:78)
+
+    @property
+    def overlap(self) -> int:
+        return min(self.W // 2 + 1, self.W - 1) if self.O is None else self.O
 
 
 WORKLOADS = {

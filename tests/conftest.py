@@ -31,6 +31,18 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_wo():
+    """Golden vectors of the extra window configurations, keyed by (W, O) (oracle/binding.py:EXTRA_CONFIGS)."""
+    from oracle.binding import EXTRA_CONFIGS
+    out = {}
+    for W, O in EXTRA_CONFIGS:
+        with open(os.path.join(ROOT, "tests", "golden", f"golden_w{W}_o{O}.json")) as f:
+            out[(W, O)] = json.load(f)
+        assert out[(W, O)]["W"] == W and out[(W, O)]["O"] == O
+    return out
+
+
+@pytest.fixture(scope="session")
 def sglib():
     import scrooge_b200
     if not os.path.exists(scrooge_b200._lib.LIB_PATH):

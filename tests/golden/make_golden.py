@@ -14,7 +14,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-from oracle.binding import RefCpu  # noqa: E402
+from oracle.binding import CONFIGS, EXTRA_CONFIGS, RefCpu  # noqa: E402
 
 KAT_REF = "AAAACCCCGGGGTTTT"
 KAT_READS = [
@@ -77,10 +77,12 @@ def edge_cases(rng):
 
 
 def main():
-    for W in (64, 32):
-        ref = RefCpu(W)
-        rng = random.Random(1000 + W)
-        out = {"W": W, "O": {64: 33, 32: 17}[W], "generator": "tests/golden/make_golden.py", "groups": {}}
+    # the two configurations the reference ships, then the extra window configurations (smaller sets)
+    for W, O in list(CONFIGS.items()) + list(EXTRA_CONFIGS):
+        extra = CONFIGS.get(W) != O
+        ref = RefCpu(W, O)
+        rng = random.Random(1000 + W if not extra else 5000 + 131 * W + O)
+        out = {"W": W, "O": O, "generator": "tests/golden/make_golden.py", "groups": {}}
 
         def run(name, pairs):
             res = ref.align_pairs([p[0] for p in pairs], [p[1] for p in pairs])
@@ -93,13 +95,13 @@ def main():
         run("library_example", [("ACGTACGT", "ACGTACG")])
         run("edge", edge_cases(rng))
         rnd = []
-        for _ in range(120):
+        for _ in range(30 if extra else 120):
             L = rng.choice([20, 50, 100, 150, 250, 400, 1000])
             e = rng.choice([0.0, 0.02, 0.05, 0.1, 0.15, 0.3])
             t = rand_seq(rng, L + L // 3 + 64)
             rnd.append((t, mutate(rng, t, L, e)))
         run("random", rnd)
-        if W == 64:
+        if W == 64 and not extra:
             assert [g["edit"] for g in out["groups"]["kat_tests_cu"]] == KAT_DISTANCES
         # mapping interface: one genome, reads with several candidate starts (unaligned mod 4, genome end)
         genome = rand_seq(rng, 5000)
@@ -114,7 +116,7 @@ def main():
         res = ref.align_mapping(genome, reads, locs)
         out["mapping"] = {"genome": genome, "reads": reads, "locations": locs,
                           "edit": [int(x) for x in res.edit], "cigar": res.cigars}
-        with open(os.path.join(HERE, f"golden_w{W}.json"), "w") as f:
+        with open(os.path.join(HERE, f"golden_w{W}_o{O}.json" if extra else f"golden_w{W}.json"), "w") as f:
             json.dump(out, f, indent=0)
         print("wrote", f.name, sum(len(v) for v in out["groups"].values()), "pairs +", len(res.cigars), "candidates")
 

@@ -185,3 +185,74 @@ def align_delta(text: str, read: str, W: int = 64, O: int = 33) -> Tuple[int, st
         t_pos += i
         q_pos += j
     return ed, "".join(out), t_pos, entries
+
+
+def align_delta_generic(text: str, read: str, W: int, O: int) -> Tuple[int, str, int, int]:
+    """Model of the run-time (W, O) kernel (sg_align_generic.cuh): the delta recurrence of align_delta on vectors of
+    WP = 32 * ceil(W / 32) bits (pattern position J at bit WP-1-J, so a window narrower than the vector is just a window
+    with more padding rows), always W columns per window with the "matches nothing" mask standing in for the columns
+    i >= n, the op planes A = V | H, B = ~V & (H | E) kept at full width for the W-O+1 traceback columns, and run-length
+    encoding during the walk.  Returns (edit distance, cigar, consumed reference prefix, sum of (d_w+1)(n+1))."""
+    NW = (W + 31) // 32
+    WP = 32 * NW
+    MASK = (1 << WP) - 1
+    TBL = W - O
+    t = [CODE[c] for c in text]
+    q = [CODE[c] for c in read]
+    t_pos = q_pos = 0
+    ed = 0
+    entries = 0
+    out: List[str] = []
+    while q_pos < len(q):
+        n = min(W, len(t) - t_pos)
+        m = min(W, len(q) - q_pos)
+        hm = (MASK << (WP - m)) & MASK
+        pm = [0, 0, 0, 0, hm]           # pm[4]: a character that matches nothing
+        for c in range(4):
+            v = 0
+            for J in range(m):
+                if q[q_pos + J] != c:
+                    v |= 1 << (WP - 1 - J)
+            pm[c] = v & hm
+        A = [0] * (TBL + 1)
+        B = [0] * (TBL + 1)
+        Pv, Mv = hm, 0
+        for i in range(W - 1, -1, -1):
+            p = pm[t[t_pos + i]] if i < n else pm[4]
+            Eq = ~p & MASK
+            x = ((((Eq & Pv) + Pv) & MASK) ^ Pv) | Eq
+            Ph = Mv | (~(x | Pv) & MASK)
+            Mh = Pv & x
+            Phs = (Ph << 1) & MASK
+            Mhs = (Mh << 1) & MASK
+            xv = Eq | Mv
+            Pv = Mhs | (~(xv | Phs) & MASK)
+            Mv = Phs & xv
+            if i <= TBL:
+                A[i] = Pv | Ph
+                B[i] = ~Pv & (Ph | p) & MASK
+        d_w = bin(Pv).count("1") - bin(Mv).count("1")
+        entries += (d_w + 1) * (n + 1)
+        i = j = 0
+        jmax = min(m, TBL)
+        cur_op, cur_cnt = None, 0
+        while j < jmax and i < TBL:
+            bit = 1 << (WP - 1 - j)
+            op = (2 if A[i] & bit else 0) + (1 if B[i] & bit else 0)
+            if op != 2:
+                i += 1
+            if op != 3:
+                j += 1
+            if op != 0:
+                ed += 1
+            if op != cur_op:
+                if cur_cnt:
+                    out.append(f"{cur_cnt}{OPS[cur_op]}")
+                cur_op, cur_cnt = op, 1
+            else:
+                cur_cnt += 1
+        if cur_cnt:
+            out.append(f"{cur_cnt}{OPS[cur_op]}")
+        t_pos += i
+        q_pos += j
+    return ed, "".join(out), t_pos, entries

@@ -73,3 +73,14 @@ def test_synth_error_rate(sglib, oracle):
     assert 0.07 < rate < 0.12  # observed distance is a little under e*L (adjacent edits cancel)
     tb, toff, qb, qoff = synth.pairs_as_blobs(text, tlen, reads)
     assert bytes(tb[int(toff[3]):int(toff[4])]).decode() == T[3] and bytes(qb[int(qoff[3]):int(qoff[4])]).decode() == Q[3]
+
+
+def test_window_configuration_arguments(sglib):
+    """sg_default_overlap follows scripts/profile.py:78 (O = min(W//2+1, W-1)); out-of-range windows are argument errors
+    before any device is touched."""
+    assert [sglib.sg_default_overlap(W) for W in (64, 32, 96, 128, 2, 3)] == [33, 17, 49, 65, 1, 2]
+    h = C.c_void_p()
+    for W, O in ((129, 65), (64, 64), (64, 0), (128, 64), (1, 0), (64, -1)):
+        assert sglib.sg_ctx_create_wo(C.byref(h), None, 1, W, O) == 3, (W, O)
+        assert b"window configuration" in sglib.sg_last_error()
+    assert sglib.sg_ctx_create(C.byref(h), None, 1, 48) == 3

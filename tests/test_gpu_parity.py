@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from conftest import mutate, rand_seq, random_pairs
-from oracle.binding import cigar_ref_consumed
+from oracle.binding import CONFIGS, EXTRA_CONFIGS, RefCpu, cigar_ref_consumed
 
 pytestmark = pytest.mark.gpu
 
@@ -16,8 +16,8 @@ def aligners(sglib):
     return {64: scrooge_b200.Aligner(W=64, n_gpus=1), 32: scrooge_b200.Aligner(W=32, n_gpus=1)}
 
 
-def check_against_oracle(oracle, aligner, T, Q, W):
-    want = oracle.align_pairs(T, Q, W=W, threads=4)
+def check_against_oracle(oracle, aligner, T, Q, W, O=None):
+    want = oracle.align_pairs(T, Q, W=W, O=O, threads=4)
     got = aligner.align_pairs(T, Q)
     ed, rc, cg = got.edit_distances, got.ref_consumed, got.cigars()
     assert got.count == len(T)
@@ -340,3 +340,72 @@ def test_kernel_and_ingest_variants(dc, forefront, host_pack):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "variant ok" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("W,O", EXTRA_CONFIGS)
+def test_window_configurations(oracle, golden_wo, W, O):
+    """Any window configuration at run time (genasm_generic_kernel, sg_ctx_create_wo) where the reference needs a rebuild
+    with -DCLI_W/-DCLI_K/-DCLI_O: goldens made by the unmodified reference at that (W, O), both interfaces, then the
+    oracle on a mixed bag (empty / 1-base / W+-1 lengths, exhausted texts, unrelated pairs), distance-only mode, and --
+    when it travelled to this box -- the unmodified reference itself on the same inputs."""
+    import scrooge_b200
+    al = scrooge_b200.Aligner(W=W, O=O, n_gpus=1)
+    gw = golden_wo[(W, O)]
+    for name, g in gw["groups"].items():
+        got = al.align_pairs([x["text"] for x in g], [x["query"] for x in g])
+        ed, cg = got.edit_distances, got.cigars()
+        for k, x in enumerate(g):
+            assert int(ed[k]) == x["edit"] and cg[k] == x["cigar"], (name, k)
+    m = gw["mapping"]
+    cs = [s for l in m["locations"] for s in l]
+    cr = [r for r, l in enumerate(m["locations"]) for _ in l]
+    al.set_reference(m["genome"])
+    got = al.align_candidates(m["reads"], cs, cr)
+    assert [int(x) for x in got.edit_distances] == m["edit"] and got.cigars() == m["cigar"]
+    T, Q = random_pairs(300 + 131 * W + O, 2500, [0, 1, 2, 3, 15, 16, 17, W - 1, W, W + 1, 2 * W + 1, 150, 400, 1000, 3000],
+                        [0.0, 0.02, 0.05, 0.1, 0.15, 0.3, 0.6])
+    got = check_against_oracle(oracle, al, T, Q, W, O)
+    d = al.align_pairs(T, Q, distance_only=True)
+    assert list(d.edit_distances) == list(got.edit_distances) and list(d.ref_consumed) == list(got.ref_consumed)
+    if RefCpu.available(W, O):
+        ref = RefCpu(W, O).align_pairs(T[:800], Q[:800], threads=4)
+        assert list(ref.edit) == [int(x) for x in got.edit_distances[:800]] and ref.cigars == got.cigars()[:800]
+
+
+def test_generic_kernel_equals_tuned_kernels():
+    """SG_GENERIC=1 sends 64/33 and 32/17 through genasm_generic_kernel as well: same bytes out as the tuned kernels (and
+    as the oracle), incl. 10 kbp pairs of the benchmark generator and the DC-entry / window counters."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, '.'); sys.path.insert(0, 'tests')\n"
+        "import numpy as np, scrooge_b200\n"
+        "from scrooge_b200 import synth\n"
+        "from oracle.binding import Oracle\n"
+        "from conftest import random_pairs\n"
+        "o = Oracle()\n"
+        "for W in (64, 32):\n"
+        "    T, Q = random_pairs(900 + W, 3000, [0, 1, 31, 32, 33, 63, 64, 65, 150, 400, 2000], [0, 0.05, 0.1, 0.3, 0.6])\n"
+        "    if W == 64:\n"
+        "        text, tlen, reads = synth.pairs_host(synth.WORKLOADS['long_10kbp'], 0, 64)\n"
+        "        T2, Q2 = synth.pairs_as_strings(text, tlen, reads)\n"
+        "        T += T2; Q += Q2\n"
+        "    got = scrooge_b200.Aligner(W=W, n_gpus=1).align_pairs(T, Q)\n"
+        "    want = o.align_pairs(T, Q, W=W, threads=4)\n"
+        "    assert list(got.edit_distances) == list(want.edit) and got.cigars() == want.cigars, W\n"
+        "    assert list(got.ref_consumed) == list(want.ref_consumed)\n"
+        "print('generic ok')\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, SG_GENERIC="1"), capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "generic ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_window_limits_are_errors(sglib):
+    import scrooge_b200
+    for W, O in ((129, 65), (64, 64), (64, 0), (128, 64), (1, 0), (64, -1)):
+        with pytest.raises(scrooge_b200.ScroogeError) as e:
+            scrooge_b200.Aligner(W=W, O=O, n_gpus=1)
+        assert e.value.code == 3

@@ -42,3 +42,23 @@ def test_delta_model_golden_kats(golden):
         for x in golden[W]["groups"]["kat_tests_cu"] + golden[W]["groups"]["differential_tests_cu"]:
             ed, cg, _, _ = align_delta(x["text"], x["query"], W, 33 if W == 64 else 17)
             assert ed == x["edit"] and cg == x["cigar"]
+
+
+def _generic_configs():
+    from oracle.binding import CONFIGS, EXTRA_CONFIGS
+    return list(CONFIGS.items()) + list(EXTRA_CONFIGS)
+
+
+@pytest.mark.parametrize("W,O", _generic_configs())
+def test_generic_delta_model_matches_oracle(oracle, W, O):
+    """The run-time (W, O) kernel's formulation -- vectors padded to a multiple of 32 bits, W columns per window whatever
+    n is, full-width op planes, any traceback limit -- against the oracle on every window configuration."""
+    from kernel_model import align_delta_generic
+    T, Q = random_pairs(41 + 7 * W + O, 120, [0, 1, 2, W // 2, W - 1, W, W + 1, 2 * W + 1, 100, 300], [0, 0.05, 0.15, 0.4, 0.8])
+    res = oracle.align_pairs(T, Q, W=W, O=O)
+    total = 0
+    for k in range(len(T)):
+        ed, cg, rc, ent = align_delta_generic(T[k], Q[k], W, O)
+        total += ent
+        assert (ed, cg, rc) == (int(res.edit[k]), res.cigars[k], int(res.ref_consumed[k])), (W, O, T[k], Q[k])
+    assert total == res.stats["dc_entries"]

@@ -3,7 +3,7 @@ vectors made from the unmodified reference, and -- when oracle/_ref is present -
 import pytest
 
 from conftest import random_pairs
-from oracle.binding import RefCpu, cigar_ref_consumed
+from oracle.binding import EXTRA_CONFIGS, RefCpu, cigar_ref_consumed
 
 KAT_REF = "AAAACCCCGGGGTTTT"
 KAT_DIST = [8, 0, 3, 8, 12, 6, 8, 0, 48]  # reference src/tests.cu:246
@@ -56,6 +56,44 @@ def test_live_reference(oracle, W):
     b = ref.align_pairs(T, Q, threads=2)
     assert list(a.edit) == list(b.edit)
     assert a.cigars == b.cigars
+
+
+@pytest.mark.parametrize("W,O", EXTRA_CONFIGS)
+def test_golden_window_configurations(oracle, golden_wo, W, O):
+    """The window sweep's configurations (scripts/profile.py:66-100,595-640): goldens from the unmodified reference built
+    with -DCLI_W=<W> -DCLI_K=<W> -DCLI_O=<O>, W up to 128 (multi-word vectors, src/bitvector.hpp:45-47)."""
+    gw = golden_wo[(W, O)]
+    for name, g in gw["groups"].items():
+        res = oracle.align_pairs([x["text"] for x in g], [x["query"] for x in g], W=W, O=O)
+        for k, x in enumerate(g):
+            assert int(res.edit[k]) == x["edit"], (name, k)
+            assert res.cigars[k] == x["cigar"], (name, k)
+            assert int(res.ref_consumed[k]) == cigar_ref_consumed(x["cigar"])
+            assert oracle.validate_cigar(res.cigars[k], x["text"], x["query"], x["edit"]) == 0
+    m = gw["mapping"]
+    cs = [s for l in m["locations"] for s in l]
+    cr = [r for r, l in enumerate(m["locations"]) for _ in l]
+    res = oracle.align_candidates(m["genome"], m["reads"], cs, cr, W=W, O=O)
+    assert [int(x) for x in res.edit] == m["edit"] and res.cigars == m["cigar"]
+
+
+@pytest.mark.parametrize("W,O", EXTRA_CONFIGS)
+def test_live_reference_window_configurations(oracle, W, O):
+    if not RefCpu.available(W, O):
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    ref = RefCpu(W, O)
+    T, Q = random_pairs(177 + 131 * W + O, 500, [0, 1, 3, W - 1, W, W + 1, 2 * W + 3, 150, 700], [0, 0.03, 0.1, 0.2, 0.5])
+    a = oracle.align_pairs(T, Q, W=W, O=O, threads=2)
+    b = ref.align_pairs(T, Q, threads=2)
+    assert list(a.edit) == list(b.edit)
+    assert a.cigars == b.cigars
+
+
+def test_window_limits(oracle):
+    with pytest.raises(ValueError):
+        oracle.align_pairs(["ACGT"], ["ACG"], W=129, O=65)
+    with pytest.raises(ValueError):
+        oracle.align_pairs(["ACGT"], ["ACG"], W=64, O=64)
 
 
 def test_threads_do_not_change_results(oracle):

@@ -5,6 +5,8 @@ bench.py).  Every point is checked against the oracle on a sample of its own inp
     python tools/bench_configs.py sweep    [--bases 1e10]   configs[4]: L x error x {distance-only, full CIGAR}
     python tools/bench_configs.py mapping  [--genome 3e9]   configs[3]: reads x 8 candidate locations on a replicated genome
     python tools/bench_configs.py short                     configs[1]: 10M x 150 bp pairs, W=64/O=33 and W=32/O=17
+    python tools/bench_configs.py windows  [--pairs 200000] the reference's window sweep (scripts/profile.py:66-100: W with
+                                                            O = min(W//2+1, W-1), and O at W=64) on 10 kbp / 10 % pairs
 
 One JSON object per line on stdout.
 """
@@ -24,8 +26,17 @@ import scrooge_b200  # noqa: E402
 from oracle.binding import Oracle  # noqa: E402  (checker only: never timed)
 from scrooge_b200 import device, synth  # noqa: E402
 
-OPS = {64: 14, 32: 7}          # reference formulation: INT32 ops per R[d][i] entry
-COL_OPS = {64: 20, 32: 10}     # delta kernel: INT32 ops per window column (see bench.py)
+class _PerWord(dict):
+    def __init__(self, per_word):
+        super().__init__()
+        self.per_word = per_word
+
+    def __missing__(self, W):
+        return self.per_word * ((W + 31) // 32)
+
+
+OPS = _PerWord(7)          # reference formulation: INT32 ops per R[d][i] entry: 7 per 32-bit word
+COL_OPS = _PerWord(10)     # delta kernel: INT32 ops per window column (see bench.py): 10 per 32-bit word
 lib = scrooge_b200.lib()
 dev = torch.device("cuda:0")
 p = lambda t: int(t.data_ptr())
@@ -47,7 +58,7 @@ def time_steps(fn, steps=3, warmup=1):
 
 def pairs_point(wl, n, distance_only, peak_gops, check=256):
     """n pairs of workload wl, inputs resident in HBM; kernel-only and ingest+align+compaction timings."""
-    L, W = wl.read_len, wl.W
+    L, W, O = wl.read_len, wl.W, wl.overlap
     text, tlen, reads = device.synth_pairs_device(wl.seed, 0, n, L, wl.err, wl.ratio, wl.slack, dev)
     stride = text.shape[1]
     idx = torch.arange(n, dtype=torch.int64, device=dev)
@@ -55,7 +66,7 @@ def pairs_point(wl, n, distance_only, peak_gops, check=256):
     qlen = torch.full((n,), L, dtype=torch.int64, device=dev)
     cap = 2 * L + 8
     slab_off = None if distance_only else torch.arange(n + 1, dtype=torch.int64, device=dev) * cap
-    da = device.DeviceAligner(W, n, dev, slab_bytes=0 if distance_only else n * cap)
+    da = device.DeviceAligner(W, n, dev, slab_bytes=0 if distance_only else n * cap, O=O)
     ptext, bad_t = device.pack_2bit(text.view(-1))
     pquery, bad_q = device.pack_2bit(reads.view(-1))
 
@@ -83,7 +94,7 @@ def pairs_point(wl, n, distance_only, peak_gops, check=256):
     k = min(check, n)
     h_text, h_tlen, h_reads = synth.pairs_host(wl, 0, k)
     T, Q = synth.pairs_as_strings(h_text, h_tlen, h_reads)
-    want = Oracle().align_pairs(T, Q, W=W, threads=8)
+    want = Oracle().align_pairs(T, Q, W=W, O=O, threads=8)
     ok = bool(np.array_equal(da.out.edit[:k].cpu().numpy(), want.edit)) and \
         bool(np.array_equal(da.out.ref_consumed[:k].cpu().numpy().astype(np.uint64), want.ref_consumed))
     if not distance_only:
@@ -94,7 +105,7 @@ def pairs_point(wl, n, distance_only, peak_gops, check=256):
             ok = ok and s == want.cigars[a]
     gops = windows * W * COL_OPS[W] / (ms_kernel / 1e3) / 1e9
     ref_gops = entries * OPS[W] / (ms_kernel / 1e3) / 1e9
-    out = {"workload": wl.name, "read_len": L, "error_rate": wl.err, "W": W, "pairs": n, "mode": "distance_only" if distance_only else "full_cigar",
+    out = {"workload": wl.name, "read_len": L, "error_rate": wl.err, "W": W, "O": O, "pairs": n, "mode": "distance_only" if distance_only else "full_cigar",
            "alignments_per_s_kernel": n / (ms_kernel / 1e3), "alignments_per_s_step": n / (ms_step / 1e3), "kernel_ms": ms_kernel,
            "step_ms": ms_step, "gcups_kernel": n / (ms_kernel / 1e3) * L * L / 1e9, "dc_entries_per_alignment": entries / n,
            "windows_per_alignment": windows / n, "int32_frac": gops / peak_gops, "reference_formulation_ratio": ref_gops / peak_gops,
@@ -112,6 +123,19 @@ def cmd_sweep(args, peak):
             for dist in (True, False):
                 wl = synth.Workload(f"sweep_{L}bp_{int(e * 100)}pct", L, e, synth.PACBIO, 64, synth.BASE_SEED + 5)
                 print(json.dumps(pairs_point(wl, n, dist, peak, check=max(8, min(256, 2_000_000 // L)))), flush=True)
+
+
+def cmd_windows(args, peak):
+    """The axes of the reference's window sweep (scripts/profile.py:66-100 cpu_sweep_wo / cpu_sweep_o; :595-640): W with the
+    overlap the reference pairs with it, and the overlap at W = 64.  64/33 and 32/17 run on the tuned kernels, everything
+    else on genasm_generic_kernel (64/33 also once on the generic kernel when SG_GENERIC=1 is set by the caller)."""
+    n = args.pairs
+    points = [(16, 9), (32, 17), (48, 25), (64, 33), (96, 49), (128, 65)] + [(64, O) for O in (1, 8, 16, 24, 40, 48, 56, 63)]
+    for W, O in points:
+        wl = synth.Workload(f"long_10kbp_w{W}_o{O}", 10000, 0.10, synth.PACBIO, W, synth.BASE_SEED + 3, O=O)
+        print(json.dumps(pairs_point(wl, n, False, peak, check=64)), flush=True)
+    wl = synth.Workload("short_150bp_w48_o25", 150, 0.05, synth.ILLUMINA, 48, synth.BASE_SEED + 2, O=25)
+    print(json.dumps(pairs_point(wl, 2_000_000, False, peak, check=2048)), flush=True)
 
 
 def cmd_short(args, peak):
@@ -210,7 +234,8 @@ def cmd_mapping(args, peak):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["sweep", "mapping", "short"])
+    ap.add_argument("what", choices=["sweep", "mapping", "short", "windows"])
+    ap.add_argument("--pairs", type=int, default=200_000)
     ap.add_argument("--bases", type=float, default=1e10)
     ap.add_argument("--genome", type=float, default=3e9)
     ap.add_argument("--reads", type=int, default=1_000_000)
@@ -219,7 +244,7 @@ def main():
     args = ap.parse_args()
     torch.cuda.set_device(0)
     peak = device.int32_peak(2, 60.0)
-    {"sweep": cmd_sweep, "mapping": cmd_mapping, "short": cmd_short}[args.what](args, peak)
+    {"sweep": cmd_sweep, "mapping": cmd_mapping, "short": cmd_short, "windows": cmd_windows}[args.what](args, peak)
 
 
 if __name__ == "__main__":
