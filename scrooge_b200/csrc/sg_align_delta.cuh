@@ -39,7 +39,7 @@
 #include "sg_align.cuh"
 
 // Compile-time switches for A/B builds (tools/build_variants.sh).  Measured on a B200 against the plain version
-// (1 M x 10 kbp pairs, alignment kernel alone, +-0.01 ms run to run); only RLE2 pays and is on:
+// (1 M x 10 kbp pairs, alignment kernel alone, +-0.01 ms run to run); only RLE2 and GATHER=2 pay and are on:
 //   SG_DELTA_PFPM   pattern masks of column i-1 fetched from shared memory while column i is computed: 37.0 -> 37.8 ms (the
 //                   short-scoreboard stalls the ncu source view shows at the first use of an LDS are already covered
 //                   by the other warps of the scheduler, and two more registers are live)
@@ -54,6 +54,23 @@
 //                   VIADD does not compete with LOP3/SHF for the alu pipe, and the traceback is not what that pipe
 //                   waits for.
 //   SG_DELTA_RLE2   leaner run-emission loop (op bits rotated into place, one output pointer): 36.90 -> 36.59 ms.  ON.
+//   SG_DELTA_GATHER the pattern bit planes of the window setup gathered by four bit-select LOP3 per plane and 16-base word, with
+//                   the shifted copies made on the fma pipe (multiplications by 2, 4, 16, 256 that arrive as kernel
+//                   parameters) and the halves joined by one PRMT: 36 alu-pipe + 36 fma-pipe instructions per window
+//                   instead of ~80 alu-pipe ones (the compiler's compress_even is LEA.HI + LOP3 per stage): 36.58 -> 36.84 ms.
+//                   2 = the same gathers with plain shifts (IMAD.SHL, the fma pipe's shift form) and one hand-placed
+//                   LOP3 per bit select: 36.64 -> 36.48 ms.  ON.
+//   SG_DELTA_OFFMUL the base code of a column brought to bits 31:30 by an IMAD (k_sel[column]) and to the mask table's
+//                   stride by one SHF + one IMAD, instead of four masked copies per text word + one PRMT per column
+//                   (16 instead of 23 alu-pipe instructions per 16 columns, 32 more IMADs, 72 registers): 36.58 -> 37.62 ms;
+//                   both together 37.51 ms.  Like SG_DELTA_FMA: a real multiplication is not a free ride on the fma pipe
+//                   (both pipes issue once per two cycles per scheduler; what is traded is issue slots, not pipe time).
+#ifndef SG_DELTA_GATHER
+#define SG_DELTA_GATHER 2
+#endif
+#ifndef SG_DELTA_OFFMUL
+#define SG_DELTA_OFFMUL 0
+#endif
 #ifndef SG_DELTA_PFPM
 #define SG_DELTA_PFPM 0
 #endif
@@ -97,6 +114,57 @@ template <> __device__ __forceinline__ void add_vec<2>(const uint32_t (&a)[2], c
     const uint64_t r = (((uint64_t)a[1] << 32) | a[0]) + (((uint64_t)b[1] << 32) | b[0]);
     s[0] = (uint32_t)r;
     s[1] = (uint32_t)(r >> 32);
+}
+
+// Odd bits of x (bit 2k+1, k = 0..15) gathered into bits 16+k of the result; its low half is garbage.  x1 = x << 1.
+// Each stage keeps the upper of two neighbouring groups where it is and takes the lower one from a shifted copy -- a
+// bit select, so the garbage never carries into the payload -- and the shifted copies are IMADs (k4, k16, k256 are the
+// opaque constants 4, 16, 256): 4 alu-pipe + 3 fma-pipe instructions.
+__device__ __forceinline__ uint32_t bit_select(uint32_t a, uint32_t b, uint32_t m)   // (a & m) | (b & ~m) as ONE LOP3
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
+    return d;
+}
+__device__ __forceinline__ uint32_t gather_odd_hi(uint32_t x, uint32_t x1, uint32_t k4, uint32_t k16, uint32_t k256)
+{
+#if SG_DELTA_GATHER == 2
+    // plain shifts (the compiler makes them IMAD.SHL, the shift form of the fma pipe) and hand-placed LOP3s (left to
+    // itself it splits every select into two LOP3 with simplified masks)
+    uint32_t y = bit_select(x, x1, 0x88888888u);
+    y = bit_select(y, y << 2, 0xC0C0C0C0u);
+    y = bit_select(y, y << 4, 0xF000F000u);
+    y = bit_select(y, y << 8, 0xFF000000u);
+    return y;
+#else
+    uint32_t y = (x & 0x88888888u) | (x1 & 0x77777777u);      // pairs at bits 3:2 of every nibble
+    y = (y & 0xC0C0C0C0u) | ((y * k4) & 0x3F3F3F3Fu);         // four bits at 7:4 of every byte
+    y = (y & 0xF000F000u) | ((y * k16) & 0x0FFF0FFFu);        // eight at 15:8 of every half
+    y = (y & 0xFF000000u) | ((y * k256) & 0x00FFFFFFu);       // sixteen at 31:16
+    return y;
+#endif
+}
+
+// pattern_planes (sg_align.cuh) with gather_odd_hi: plane 1 = the odd bits of the 2-bit codes, plane 0 = the odd bits of
+// the word shifted left by one
+template <int NW>
+__device__ __forceinline__ void pattern_planes_fma(const uint32_t (&pw)[2 * NW], uint32_t (&p0)[NW], uint32_t (&p1)[NW],
+                                                   const uint32_t k2, const uint32_t k4, const uint32_t k16, const uint32_t k256)
+{
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        const uint32_t a = pw[2 * k], b = pw[2 * k + 1];
+#if SG_DELTA_GATHER == 2
+        const uint32_t a1 = a << 1, b1 = b << 1, a2 = a << 2, b2 = b << 2;
+#else
+        const uint32_t a1 = a * k2, b1 = b * k2, a2 = a * k4, b2 = b * k4;
+#endif
+        const uint32_t ha = gather_odd_hi(a, a1, k4, k16, k256), hb = gather_odd_hi(b, b1, k4, k16, k256);
+        const uint32_t la = gather_odd_hi(a1, a2, k4, k16, k256), lb = gather_odd_hi(b1, b2, k4, k16, k256);
+        // pattern positions 32k..32k+31 go to word NW-1-k, bit-reversed
+        p0[NW - 1 - k] = __brev(__byte_perm(la, lb, 0x7632));
+        p1[NW - 1 - k] = __brev(__byte_perm(ha, hb, 0x7632));
+    }
 }
 
 // One column: (Pv, Mv) of column i+1 -> column i, Ph = the horizontal +1 deltas between them.
@@ -261,7 +329,11 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
             load_window<NWIN>(P.query, q_pos, pw);
 #endif
             uint32_t p0[NW], p1[NW], hm[NW];
+#if SG_DELTA_GATHER
+            pattern_planes_fma<NW>(pw, p0, p1, P.k_two, P.k_4, P.k_16, P.k_256);
+#else
             pattern_planes<NW>(pw, p0, p1);
+#endif
             ones_shl<NW>(W - m, hm);
             // pm[c]: zero where pattern[J] == c (src/genasm_cpu.cpp:178-198) and in the W-m padding bits
             uint32_t m0[NW], m1[NW], m2[NW], m3[NW];
@@ -321,11 +393,13 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
                     uint32_t *tbp = tb_s + b * 16 * TBS;
                     // base codes as shared-memory offsets: four masked copies hold the codes of columns 4q+r in byte q,
                     // and one byte permute per column moves that byte to bits 15:8 (code * 256 B, the mask table's stride)
+#if !SG_DELTA_OFFMUL || SG_DELTA_PFPM
                     uint32_t cq[4];
                     cq[0] = cw & 0x03030303u;
                     cq[1] = (cw >> 2) & 0x03030303u;
                     cq[2] = (cw >> 4) & 0x03030303u;
                     cq[3] = (cw >> 6) & 0x03030303u;
+#endif
 #if SG_DELTA_PFPM
                     // column 15 of the word that follows (none after the last word: any valid offset will do)
                     uint32_t nwv = half == 1 ? tw[HB - 1] : 0u;
@@ -347,6 +421,11 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
                             }
                             lds_vec<NW>(reinterpret_cast<const uint32_t *>(pmb + off), pmn);
                         }
+#elif SG_DELTA_OFFMUL
+                        // code -> bits 31:30 (IMAD, the lower codes fall off the top), -> bits 1:0 (SHF), x 256 B (IMAD)
+                        uint32_t off = (ii == 15 ? cw : cw * P.k_sel[ii]) >> 30;
+                        if (!UNI) off = ii < nrel ? off : 4u;
+                        lds_vec<NW>(reinterpret_cast<const uint32_t *>(pmb + off * P.k_256), pm);
 #else
                         uint32_t off = __byte_perm(cq[ii & 3], 0u, 0x4404u | ((uint32_t)(ii >> 2) << 4));
                         if (!UNI) off = ii < nrel ? off : NONE;
