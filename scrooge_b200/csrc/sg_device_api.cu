@@ -76,6 +76,7 @@ template <int W> static int setup_delta_kernel(int *ctas_per_sm)
         fprintf(stderr, "[sg] delta W=%d: occupancy %d CTAs/SM, %d regs, %d dyn smem, %d threads/CTA\n", W, *ctas_per_sm, fa.numRegs,
                 L::BYTES_PER_CTA, L::WARPS_PER_CTA * 32);
     }
+    if (const char *e = std::getenv("SG_DELTA_CTAS")) *ctas_per_sm = std::min(*ctas_per_sm, std::max(1, atoi(e)));  // experiment knob
     if (*ctas_per_sm < 1) return fail(SG_ERR_CUDA, "alignment kernel does not fit on this device");
     return SG_OK;
 }
