@@ -12,8 +12,8 @@
 //   * W columns per window whatever n is (the "matches nothing" mask stands in for the columns i >= n), one column =
 //     delta_column<NW> as in the tuned kernel;
 //   * the op planes A = V | H, B = ~V & (H | E) of the W-O+1 traceback columns kept for the top ceil((W-O)/32) words;
-//   * the traceback as a plain per-lane loop with the run-length encoding done during the walk (the tuned kernel's
-//     register-resident op streams assume at most 64 steps).
+//   * the traceback as a per-lane loop over up to 2 (W-O) <= 126 steps into four-word register streams, run-length encoded
+//     after the walk as in the tuned kernel.
 //
 // Limits: 2 <= W <= 128, 0 <= O < W, W - O <= 63 (a run is one byte, (op << 6) | count, and a run can be W - O long).
 // Same one-lane-per-alignment mapping, work queue and outputs as the tuned kernel; one warp per CTA, shared memory sized
@@ -179,24 +179,33 @@ __global__ void __launch_bounds__(32) genasm_generic_kernel(const AlignParams P,
         __syncwarp();
 
         // ---- DC: columns W-1 .. 0 (src/genasm_cpu.cpp:210-288 as +-1 deltas, see sg_align_delta.cuh) ----
-        for (int i = W - 1; i >= 0; i--) {
-            const uint32_t cw = tw_s[(i >> 4) * 32];
-            uint32_t code = (cw >> ((i & 15) * 2)) & 3u;
-            if (i >= n) code = 4u;
-            uint32_t pm[NW], Ph[NW];
+        // one 16-base text word at a time, the code of the current column kept in the word's top two bits
+        for (int wi = (W - 1) >> 4; wi >= 0; wi--) {
+            uint32_t cw = tw_s[wi * 32];
+            const int top = W - 1 - 16 * wi < 15 ? W - 1 - 16 * wi : 15;
+            cw <<= (15 - top) * 2;
+            uint32_t *tbp = tb_s + ((16 * wi + top) * NWT * 2) * 32;   // planes of column 16 wi + top
+            for (int ii = top; ii >= 0; ii--) {
+                const int i = 16 * wi + ii;
+                uint32_t code = cw >> 30;
+                cw <<= 2;
+                if (i >= n) code = 4u;
+                uint32_t pm[NW], Ph[NW];
+                const uint32_t *pmc = pm_s + code * (NW * 32);
 #pragma unroll
-            for (int k = 0; k < NW; k++) pm[k] = pm_s[(code * NW + k) * 32];
-            delta_column_any<NW>(Pv, Mv, pm, Ph);
-            if (i <= TBL) {
+                for (int k = 0; k < NW; k++) pm[k] = pmc[k * 32];
+                delta_column_any<NW>(Pv, Mv, pm, Ph);
+                if (i <= TBL) {
 #pragma unroll
-                for (int kk = 0; kk < NW; kk++) {
-                    if (kk < NWT) {
-                        const int k = NW - 1 - kk;
-                        uint32_t *p = tb_s + ((i * NWT + kk) * 2) * 32;
-                        p[0] = Pv[k] | Ph[k];
-                        p[32] = ~Pv[k] & (Ph[k] | pm[k]);
+                    for (int kk = 0; kk < NW; kk++) {
+                        if (kk < NWT) {
+                            const int k = NW - 1 - kk;
+                            tbp[kk * 64] = Pv[k] | Ph[k];
+                            tbp[kk * 64 + 32] = ~Pv[k] & (Ph[k] | pm[k]);
+                        }
                     }
                 }
+                tbp -= NWT * 64;
             }
         }
         __syncwarp();
@@ -209,33 +218,86 @@ __global__ void __launch_bounds__(32) genasm_generic_kernel(const AlignParams P,
             entries += (uint64_t)(dw + 1) * (uint64_t)(n + 1) + kWindowUnit;
         }
 
-        // ---- TB + RLE (src/genasm_cpu.cpp:290-409): op = 2A + B = 0 '=', 1 'X', 2 'I', 3 'D' ----
+        // ---- TB (src/genasm_cpu.cpp:290-409): op = 2A + B = 0 '=', 1 'X', 2 'I', 3 'D'; the two bits of step k go to bit k of
+        // two register-resident streams (at most 2 (W-O) <= 126 steps), as in genasm_delta_kernel's generic walk ----
+        constexpr int SW = 4;
         const int jmax = m < TBL ? m : TBL;
         int i = 0, j = 0;
-        uint32_t cur_op = 4u, cur_cnt = 0u, edits = 0u;
-        auto flush = [&]() {
-            nruns++;
-            if (want_cigar) {
-                if (out < out_end) *out++ = (uint8_t)((cur_op << 6) | cur_cnt);
-                else overflow = true;
-            }
-        };
-        while (j < jmax && i < TBL) {
-            const uint32_t *p = tb_s + ((i * NWT + (j >> 5)) * 2) * 32;
-            const uint32_t bit = 0x80000000u >> (j & 31);
-            const uint32_t op = ((p[0] & bit) ? 2u : 0u) | ((p[32] & bit) ? 1u : 0u);
-            if (op != 2u) i++;
-            if (op != 3u) j++;
-            if (op != 0u) edits++;
-            if (op != cur_op) {
-                if (cur_cnt) flush();
-                cur_op = op;
-                cur_cnt = 1u;
-            } else {
-                cur_cnt++;
+        uint32_t hs[SW], ls[SW];
+        {
+            const uint32_t col_bytes = (uint32_t)NWT * 256u;   // planes of one column
+            uint32_t addr = (uint32_t)__cvta_generic_to_shared(tb_s);   // column i, word j >> 5
+            uint32_t mask = 0x80000000u;                       // pattern position j & 31, one-hot from the top
+            uint32_t ca, cb;
+            asm volatile("ld.shared.u32 %0, [%2]; ld.shared.u32 %1, [%2+128];" : "=r"(ca), "=r"(cb) : "r"(addr));
+            bool more = true;                                  // jmax >= 1 and TBL >= 1
+#pragma unroll
+            for (int w = 0; w < SW; w++) {
+                uint32_t h = 0u, l = 0u, bit = 1u;
+                if (more) {
+                    do {
+                        const bool hi = (ca & mask) != 0u;
+                        const bool lo = (cb & mask) != 0u;
+                        if (hi) h |= bit;
+                        if (lo) l |= bit;
+                        bit <<= 1;
+                        if (!(hi && !lo)) { i++; addr += col_bytes; }          // every op but 'I' consumes a text character
+                        if (!(hi && lo)) {                                     // every op but 'D' consumes a pattern character
+                            j++;
+                            mask = __funnelshift_r(mask, mask, 1);
+                            if (mask == 0x80000000u) addr += 256u;             // next plane word of the column
+                        }
+                        more = j < jmax && i < TBL;
+                        if (more) asm volatile("ld.shared.u32 %0, [%2]; ld.shared.u32 %1, [%2+128];" : "=r"(ca), "=r"(cb) : "r"(addr));
+                    } while (bit != 0u && more);
+                }
+                hs[w] = h;
+                ls[w] = l;
             }
         }
-        if (cur_cnt) flush();   // runs end with their window (quirk Q2)
+
+        // ---- RLE on the streams: per-window runs, flushed at window end, never merged across windows (quirk Q2); the
+        // procedure of genasm_delta_kernel for SW stream words ----
+        uint32_t e[SW];
+        uint32_t edits = 0u, nb = 0u;
+        int steps = j;                                   // every step but a 'D' consumes a pattern character
+#pragma unroll
+        for (int w = 0; w < SW; w++) {
+            steps += __popc(hs[w] & ls[w]);
+            edits += __popc(hs[w] | ls[w]);              // every op but '=' is an edit
+            const uint32_t hn = __funnelshift_r(hs[w], w + 1 < SW ? hs[w + 1] : 0u, 1);
+            const uint32_t ln = __funnelshift_r(ls[w], w + 1 < SW ? ls[w + 1] : 0u, 1);
+            e[w] = (hs[w] ^ hn) | (ls[w] ^ ln);
+        }
+#pragma unroll
+        for (int w = 0; w < SW; w++) {
+            const int last = steps - 1 - 32 * w;         // steps >= 1: a window with m >= 1 takes at least one step
+            if (last >= 0 && last < 32) e[w] |= 1u << last;
+            if (last < 31) e[w] &= last < 0 ? 0u : (2u << last) - 1u;   // nothing beyond the last step
+            nb += __popc(e[w]);
+        }
+        const bool fits = !want_cigar || (uint64_t)(out_end - out) >= (uint64_t)nb;
+        if (!fits) overflow = true;
+        if (want_cigar && fits) {
+            uint8_t *o = out;
+            out += nb;
+            int st = -1;                                 // step before the current run's first, relative to word w
+#pragma unroll
+            for (int w = 0; w < SW; w++) {
+                uint32_t ew = e[w];
+                const uint32_t h7 = __funnelshift_l(hs[w], hs[w], 7), l6 = __funnelshift_l(ls[w], ls[w], 6);
+                while (ew) {
+                    const int p = __ffs((int)ew) - 1;
+                    const uint32_t rh = __funnelshift_r(h7, h7, p), rl = __funnelshift_r(l6, l6, p);
+                    const uint32_t t = (rh & 0x80u) | (rl & ~0x80u);
+                    *o++ = (uint8_t)((t & 0xC0u) | (uint32_t)(p - st));
+                    st = p;
+                    ew &= ew - 1u;
+                }
+                st -= 32;
+            }
+        }
+        nruns += nb;
         t_pos += (uint64_t)i;
         q_pos += (uint64_t)j;
         ed += edits;

@@ -235,24 +235,57 @@ def align_delta_generic(text: str, read: str, W: int, O: int) -> Tuple[int, str,
         entries += (d_w + 1) * (n + 1)
         i = j = 0
         jmax = min(m, TBL)
-        cur_op, cur_cnt = None, 0
+        # the walk writes the two bits of step k to bit k of two streams of four 32-bit words (at most 2 TBL <= 126 steps)
+        hs, ls, k = [0, 0, 0, 0], [0, 0, 0, 0], 0
         while j < jmax and i < TBL:
             bit = 1 << (WP - 1 - j)
-            op = (2 if A[i] & bit else 0) + (1 if B[i] & bit else 0)
-            if op != 2:
+            hi, lo = bool(A[i] & bit), bool(B[i] & bit)
+            if hi:
+                hs[k >> 5] |= 1 << (k & 31)
+            if lo:
+                ls[k >> 5] |= 1 << (k & 31)
+            k += 1
+            if not (hi and not lo):
                 i += 1
-            if op != 3:
+            if not (hi and lo):
                 j += 1
-            if op != 0:
-                ed += 1
-            if op != cur_op:
-                if cur_cnt:
-                    out.append(f"{cur_cnt}{OPS[cur_op]}")
-                cur_op, cur_cnt = op, 1
-            else:
-                cur_cnt += 1
-        if cur_cnt:
-            out.append(f"{cur_cnt}{OPS[cur_op]}")
+        runs, edits = rle_streams(hs, ls, j)
+        assert sum(c for c, _ in runs) == k
+        ed += edits
+        out.extend(f"{c}{OPS[o]}" for c, o in runs)
         t_pos += i
         q_pos += j
     return ed, "".join(out), t_pos, entries
+
+
+def rle_streams(hs: List[int], ls: List[int], j: int):
+    """The kernels' run-length encoding on the op streams, word by word with their bit tricks: run boundaries
+    hs ^ hs >> 1 | ls ^ ls >> 1 (the streams are zero beyond the last step), the last step forced, steps = j + #D,
+    edits = popc(hs | ls); one (count, op) per set boundary bit, the op read at the boundary's position."""
+    SW = len(hs)
+    M32 = 0xFFFFFFFF
+    steps = j + sum(bin(h & l).count("1") for h, l in zip(hs, ls))
+    edits = sum(bin(h | l).count("1") for h, l in zip(hs, ls))
+    e = []
+    for w in range(SW):
+        hn = ((hs[w] >> 1) | ((hs[w + 1] if w + 1 < SW else 0) << 31)) & M32
+        ln = ((ls[w] >> 1) | ((ls[w + 1] if w + 1 < SW else 0) << 31)) & M32
+        e.append((hs[w] ^ hn) | (ls[w] ^ ln))
+    for w in range(SW):
+        last = steps - 1 - 32 * w
+        if 0 <= last < 32:
+            e[w] |= 1 << last
+        if last < 31:
+            e[w] &= 0 if last < 0 else (2 << last) - 1
+    runs = []
+    st = -1
+    for w in range(SW):
+        ew = e[w]
+        while ew:
+            p = (ew & -ew).bit_length() - 1
+            op = ((hs[w] >> p) & 1) * 2 + ((ls[w] >> p) & 1)
+            runs.append((p - st, op))
+            st = p
+            ew &= ew - 1
+        st -= 32
+    return runs, edits
