@@ -223,13 +223,20 @@ int main(int argc, char **argv)
     string synthetic;
     const int has_synth = get_cmd_option(argc, argv, "--synthetic", synthetic);
     bool help = false;
+    // the window configuration is a run-time choice here (the reference needs a rebuild with -DCLI_W/-DCLI_K/-DCLI_O,
+    // src/genasm_gpu.cu:1-63): --window / --overlap set what the drop-in reads from SG_WINDOW / SG_OVERLAP
+    string window, overlap;
+    const int has_w = get_cmd_option(argc, argv, "--window", window), has_o = get_cmd_option(argc, argv, "--overlap", overlap);
+    help |= has_w == OPT_INVALID || has_o == OPT_INVALID;
+    if (has_w == OPT_EXISTS) setenv("SG_WINDOW", window.c_str(), 1);
+    if (has_o == OPT_EXISTS) setenv("SG_OVERLAP", overlap.c_str(), 1);
     help |= OPT_INVALID == get_cmd_option(argc, argv, "--reference", reference_file);
     help |= OPT_INVALID == get_cmd_option(argc, argv, "--reads", reads_file);
     help |= OPT_INVALID == get_cmd_option(argc, argv, "--seeds", seeds_file);
     for (const char *flag : {"--gpu_info_only", "--verbose", "--unit_tests", "--dump_inputs"}) help |= OPT_INVALID == get_cmd_option(argc, argv, flag);
     help |= OPT_MISSING != get_cmd_option(argc, argv, "--help");
     help |= has_synth == OPT_INVALID;
-    help |= !check_options(argc, argv, {"--reference", "--reads", "--seeds", "--help", "--gpu_info_only", "--verbose", "--unit_tests", "--dump_inputs", "--synthetic"});
+    help |= !check_options(argc, argv, {"--reference", "--reads", "--seeds", "--help", "--gpu_info_only", "--verbose", "--unit_tests", "--dump_inputs", "--synthetic", "--window", "--overlap"});
     if (help) {
         cout << "sg_tests [options]\n"
                 "Options:\n"
@@ -241,6 +248,7 @@ int main(int argc, char **argv)
                 "--unit_tests                          -- run unit tests (default: performance test)\n"
                 "--dump_inputs                         -- parse the input files and print them (no GPU needed)\n"
                 "--synthetic=[pairs]                   -- end-to-end run of align_all() on synthetic 10 kbp / 10 % pairs\n"
+                "--window=[W] --overlap=[O]            -- window configuration (default 64 / min(W/2+1, W-1); W <= 128, W-O <= 63)\n"
                 "--help                                -- displays this information\n";
         return 0;
     }
