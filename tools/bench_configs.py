@@ -161,7 +161,14 @@ def cmd_mapping(args, peak):
     gcpu = torch.Generator(device="cpu").manual_seed(7)
     jitter = torch.randint(-16, 17, (n_reads, ncand), generator=gcpu, dtype=torch.int64)
     jitter[:, 0] = 0
-    cstart = (pos[:, None] + jitter.to(dev)).clamp_(min=0).reshape(-1).contiguous()
+    cstart2d = (pos[:, None] + jitter.to(dev)).clamp_(min=0)
+    if args.stress:
+        # SURVEY 8d's stress variant: candidate 0 = the true start, 1..7 = uniform random loci (unrelated text: window
+        # distances around 32, four times the work of a true candidate in the reference's formulation)
+        rnd = torch.randint(0, G - 3 * L, (n_reads, ncand), generator=gcpu, dtype=torch.int64).to(dev)
+        rnd[:, 0] = cstart2d[:, 0]
+        cstart2d = rnd
+    cstart = cstart2d.reshape(-1).contiguous()
     cread = torch.arange(n_reads, dtype=torch.int64, device=dev).repeat_interleave(ncand)
     n = n_reads * ncand
     tlen = (G - cstart).contiguous()
@@ -171,7 +178,7 @@ def cmd_mapping(args, peak):
     sub = min(n, args.sub_batch)   # alignments per launch: bounds the run slab (20 KB capacity per 10 kbp alignment)
     slab_off = torch.arange(sub + 1, dtype=torch.int64, device=dev) * cap
     da = device.DeviceAligner(W, sub, dev, slab_bytes=sub * cap)
-    runs = torch.empty(sub * 3000, dtype=torch.uint8, device=dev)
+    runs = torch.empty(sub * (12000 if args.stress else 3000), dtype=torch.uint8, device=dev)
     kev = []
     keep = {}
 
@@ -214,21 +221,27 @@ def cmd_mapping(args, peak):
     lo, hi = int(hs.min()), int(hs.max()) + 3 * L
     # the oracle's text is the genome suffix; alignments only ever touch the first ~L*1.3 bases, so a suffix cut
     # 3L after the last candidate gives identical results
-    gwin = genome[lo:min(G, hi)].cpu().numpy().tobytes().decode()
     hreads = [bytes(r).decode() for r in reads[:k_reads].cpu().numpy()]
-    want = Oracle().align_candidates(gwin, hreads, [int(x) - lo for x in hs], [c // ncand for c in range(k_reads * ncand)], threads=8)
+    if args.stress:   # the candidates are spread over the genome: one 3L-base text per candidate, same cut argument
+        texts = [genome[int(x):min(G, int(x) + 3 * L)].cpu().numpy().tobytes().decode() for x in hs]
+        want = Oracle().align_pairs(texts, [hreads[c // ncand] for c in range(k_reads * ncand)], W=W, threads=8)
+        assert int(want.ref_consumed.max()) < 3 * L - W
+    else:
+        gwin = genome[lo:min(G, hi)].cpu().numpy().tobytes().decode()
+        want = Oracle().align_candidates(gwin, hreads, [int(x) - lo for x in hs], [c // ncand for c in range(k_reads * ncand)], threads=8)
     ok = bool(np.array_equal(keep["edit"][: k_reads * ncand], want.edit)) and bool(np.array_equal(keep["refc"][: k_reads * ncand], want.ref_consumed))
     for a in range(k_reads * ncand):
         s = "".join(f"{int(b) & 63}{'=XID'[int(b) >> 6]}" for b in keep["runs"][keep["ro"][a]:keep["ro"][a + 1]])
         ok = ok and s == want.cigars[a]
     entries_per = keep["entries"] / sub
-    print(json.dumps({"workload": "mapping_10kbp_8cand", "genome_bases": G, "reads": n_reads, "candidates_per_read": ncand, "alignments": n,
+    print(json.dumps({"workload": "mapping_10kbp_1true_7random" if args.stress else "mapping_10kbp_8cand", "genome_bases": G, "reads": n_reads, "candidates_per_read": ncand, "alignments": n,
                       "read_len": L, "error_rate": 0.10, "W": W, "sub_batch": sub, "alignments_per_s_kernel": n / (ms_kernel / 1e3),
                       "alignments_per_s_step": n / (ms_step / 1e3), "kernel_ms": ms_kernel, "step_ms": ms_step,
                       "gcups_kernel": n / (ms_kernel / 1e3) * L * L / 1e9, "dc_entries_per_alignment": entries_per,
                       "int32_frac": keep["windows"] / sub * n * W * COL_OPS[W] / (ms_kernel / 1e3) / 1e9 / peak,
                       "reference_formulation_ratio": entries_per * n * OPS[W] / (ms_kernel / 1e3) / 1e9 / peak, "packed_genome_mb": pgenome.numel() * 4 / 1e6,
-                      "generate_and_pack_s": gen_s, "true_start_mean_edit": float(np.mean(keep["edit"][0::ncand])),
+                      "generate_and_pack_s": gen_s, "windows_per_alignment": keep["windows"] / sub,
+                      "mean_edit_distance_first_2048": float(np.mean(keep["edit"])), "true_start_mean_edit": float(np.mean(keep["edit"][0::ncand])),
                       "parity": {"checked": k_reads * ncand, "bit_exact": ok}}), flush=True)
 
 
@@ -241,6 +254,7 @@ def main():
     ap.add_argument("--reads", type=int, default=1_000_000)
     ap.add_argument("--sub-batch", type=int, default=1_000_000)
     ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--stress", action="store_true", help="mapping: 1 true + 7 uniform-random candidate loci per read")
     args = ap.parse_args()
     torch.cuda.set_device(0)
     peak = device.int32_peak(2, 60.0)
