@@ -29,15 +29,20 @@ struct GenericGeom {
     int W;      // window size in characters (columns per window)
     int TBL;    // W - O: traceback limit (src/genasm_cpu.cpp:50)
     int NWT;    // plane words kept per traceback column: pattern positions 0..TBL-1
+    uint32_t *planes;   // GP kernels: per-CTA plane scratch in global memory, generic_plane_words() words each
 };
 
-__host__ __device__ inline int generic_smem_words(int NW, int W, int TBL)
+// op planes of one warp: [column][word][plane][lane]
+__host__ __device__ inline int generic_plane_words(int TBL) { return (TBL + 1) * ((TBL + 31) / 32) * 2 * 32; }
+
+// shared memory of one warp: pattern masks and the window's text codes, plus the op planes unless they live in global
+// memory (GP: a window configuration with W - O > 32 needs 20-32 KB of planes per warp, which would leave 6-9 warps per
+// SM; in global memory the planes of all resident warps fit in the L2 cache and occupancy is bounded by registers)
+__host__ __device__ inline int generic_smem_words(int NW, int W, int TBL, bool global_planes)
 {
-    const int NWT = (TBL + 31) / 32;
     const int pm = 5 * NW * 32;                 // [base code 0..3, 4 = "matches nothing"][word][lane]
     const int tw = ((W + 15) / 16) * 32;        // [text word][lane]: the window's 2-bit codes
-    const int tb = (TBL + 1) * NWT * 2 * 32;    // [column][word][plane][lane]
-    return pm + tw + tb;
+    return pm + tw + (global_planes ? 0 : generic_plane_words(TBL));
 }
 
 // NW-word addition with carry propagation for any NW
@@ -92,7 +97,7 @@ __device__ __forceinline__ void load_bases(const uint32_t *__restrict__ blob, ui
     for (int k = 0; k < NOUT; k++) out[k] = __funnelshift_r(w[k], w[k + 1], sh);
 }
 
-template <int NW>
+template <int NW, bool GP>
 __global__ void __launch_bounds__(32) genasm_generic_kernel(const AlignParams P, const GenericGeom G)
 {
     constexpr int NTW = 2 * NW;                 // text / pattern words of a full-width window (16 bases each)
@@ -101,7 +106,8 @@ __global__ void __launch_bounds__(32) genasm_generic_kernel(const AlignParams P,
     const int W = G.W, TBL = G.TBL, NWT = G.NWT;
     uint32_t *pm_s = smem_all + lane;                                   // + (code * NW + k) * 32
     uint32_t *tw_s = smem_all + 5 * NW * 32 + lane;                     // + word * 32
-    uint32_t *tb_s = smem_all + 5 * NW * 32 + ((W + 15) / 16) * 32 + lane;  // + ((column * NWT + kk) * 2 + plane) * 32
+    // + ((column * NWT + kk) * 2 + plane) * 32
+    uint32_t *tb_s = (GP ? G.planes + (size_t)blockIdx.x * (size_t)generic_plane_words(TBL) : smem_all + 5 * NW * 32 + ((W + 15) / 16) * 32) + lane;
 
     const bool want_cigar = !(P.flags & 1u);
 
@@ -225,11 +231,10 @@ __global__ void __launch_bounds__(32) genasm_generic_kernel(const AlignParams P,
         int i = 0, j = 0;
         uint32_t hs[SW], ls[SW];
         {
-            const uint32_t col_bytes = (uint32_t)NWT * 256u;   // planes of one column
-            uint32_t addr = (uint32_t)__cvta_generic_to_shared(tb_s);   // column i, word j >> 5
+            const uint32_t col_words = (uint32_t)NWT * 64u;    // planes of one column
+            const uint32_t *addr = tb_s;                       // column i, word j >> 5
             uint32_t mask = 0x80000000u;                       // pattern position j & 31, one-hot from the top
-            uint32_t ca, cb;
-            asm volatile("ld.shared.u32 %0, [%2]; ld.shared.u32 %1, [%2+128];" : "=r"(ca), "=r"(cb) : "r"(addr));
+            uint32_t ca = addr[0], cb = addr[32];
             bool more = true;                                  // jmax >= 1 and TBL >= 1
 #pragma unroll
             for (int w = 0; w < SW; w++) {
@@ -241,14 +246,14 @@ __global__ void __launch_bounds__(32) genasm_generic_kernel(const AlignParams P,
                         if (hi) h |= bit;
                         if (lo) l |= bit;
                         bit <<= 1;
-                        if (!(hi && !lo)) { i++; addr += col_bytes; }          // every op but 'I' consumes a text character
+                        if (!(hi && !lo)) { i++; addr += col_words; }          // every op but 'I' consumes a text character
                         if (!(hi && lo)) {                                     // every op but 'D' consumes a pattern character
                             j++;
                             mask = __funnelshift_r(mask, mask, 1);
-                            if (mask == 0x80000000u) addr += 256u;             // next plane word of the column
+                            if (mask == 0x80000000u) addr += 64;               // next plane word of the column
                         }
                         more = j < jmax && i < TBL;
-                        if (more) asm volatile("ld.shared.u32 %0, [%2]; ld.shared.u32 %1, [%2+128];" : "=r"(ca), "=r"(cb) : "r"(addr));
+                        if (more) { ca = addr[0]; cb = addr[32]; }
                     } while (bit != 0u && more);
                 }
                 hs[w] = h;

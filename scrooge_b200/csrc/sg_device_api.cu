@@ -159,15 +159,34 @@ static int check_window(int W, int O)
     return SG_OK;
 }
 
-template <int NW> static int generic_occupancy(int smem_bytes, int *ctas_per_sm)
+// Where the general kernel keeps its op planes: shared memory, or a per-CTA scratch in global memory that stays in the L2
+// cache (SG_GENERIC_PLANES=smem|global forces one).  Measured on 1 M x 10 kbp pairs (profiles/r01_window_sweep.md): global
+// planes pay when the window is wide and the walk short relative to it -- 128/65 (32 KB of planes per warp, 6 warps per SM in
+// shared memory): 8.2 -> 10.1 M alignments/s -- and cost when the traceback dominates (W = 64 with O <= 24, up to 126 dependent
+// plane reads per window: 13-16 -> 11-12 M/s; 96/49: 11.2 -> 10.8), so only four-word windows with more than 24 KB of planes
+// use them.
+static bool generic_global_planes(int W, int O)
 {
-    auto kern = genasm_generic_kernel<NW>;
+    static const int forced = [] {
+        const char *e = std::getenv("SG_GENERIC_PLANES");
+        if (e && std::string(e) == "smem") return 0;
+        if (e && std::string(e) == "global") return 1;
+        return -1;
+    }();
+    if (forced >= 0) return forced == 1;
+    return (W + 31) / 32 >= 4 && generic_plane_words(W - O) * 4 > 24 * 1024;
+}
+
+template <int NW, bool GP> static int generic_occupancy(int smem_bytes, int *ctas_per_sm)
+{
+    auto kern = genasm_generic_kernel<NW, GP>;
     SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kern, 32, smem_bytes));
     if (std::getenv("SG_DEBUG")) {
         cudaFuncAttributes fa;
         cudaFuncGetAttributes(&fa, kern);
-        fprintf(stderr, "[sg] generic NW=%d: occupancy %d CTAs/SM, %d regs, %d dyn smem\n", NW, *ctas_per_sm, fa.numRegs, smem_bytes);
+        fprintf(stderr, "[sg] generic NW=%d planes=%s: occupancy %d CTAs/SM, %d regs, %d dyn smem\n", NW, GP ? "global" : "smem", *ctas_per_sm,
+                fa.numRegs, smem_bytes);
     }
     if (*ctas_per_sm < 1) return fail(SG_ERR_CUDA, "generic alignment kernel does not fit on this device");
     return SG_OK;
@@ -175,15 +194,24 @@ template <int NW> static int generic_occupancy(int smem_bytes, int *ctas_per_sm)
 
 static int generic_geometry(const DeviceInfo &di, int W, int O, int *ctas_per_sm, int *smem_bytes)
 {
-    (void)di;
     const int NW = (W + 31) / 32;
-    *smem_bytes = generic_smem_words(NW, W, W - O) * 4;
+    const bool gp = generic_global_planes(W, O);
+    *smem_bytes = generic_smem_words(NW, W, W - O, gp) * 4;
+    int rc;
     switch (NW) {
-        case 1: return generic_occupancy<1>(*smem_bytes, ctas_per_sm);
-        case 2: return generic_occupancy<2>(*smem_bytes, ctas_per_sm);
-        case 3: return generic_occupancy<3>(*smem_bytes, ctas_per_sm);
-        default: return generic_occupancy<4>(*smem_bytes, ctas_per_sm);
+        case 1: rc = gp ? generic_occupancy<1, true>(*smem_bytes, ctas_per_sm) : generic_occupancy<1, false>(*smem_bytes, ctas_per_sm); break;
+        case 2: rc = gp ? generic_occupancy<2, true>(*smem_bytes, ctas_per_sm) : generic_occupancy<2, false>(*smem_bytes, ctas_per_sm); break;
+        case 3: rc = gp ? generic_occupancy<3, true>(*smem_bytes, ctas_per_sm) : generic_occupancy<3, false>(*smem_bytes, ctas_per_sm); break;
+        default: rc = gp ? generic_occupancy<4, true>(*smem_bytes, ctas_per_sm) : generic_occupancy<4, false>(*smem_bytes, ctas_per_sm); break;
     }
+    if (rc) return rc;
+    if (gp) {
+        // the planes of all resident warps should stay in the L2 cache (126 MB): at most 96 MB of them, at least 8 warps per SM
+        const long long per_warp = (long long)generic_plane_words(W - O) * 4;
+        const long long fit = (96ll << 20) / (per_warp * (long long)di.sms);
+        *ctas_per_sm = (int)std::min<long long>(*ctas_per_sm, std::max<long long>(8, fit));
+    }
+    return SG_OK;
 }
 
 static int launch_generic(const DeviceInfo &di, const AlignParams &P, int W, int O, cudaStream_t st)
@@ -191,16 +219,24 @@ static int launch_generic(const DeviceInfo &di, const AlignParams &P, int W, int
     int per_sm = 0, smem = 0;
     int rc = generic_geometry(di, W, O, &per_sm, &smem);
     if (rc) return rc;
+    const bool gp = generic_global_planes(W, O);
     GenericGeom G;
-    G.W = W; G.TBL = W - O; G.NWT = (G.TBL + 31) / 32;
+    G.W = W; G.TBL = W - O; G.NWT = (G.TBL + 31) / 32; G.planes = nullptr;
     const unsigned ctas = (unsigned)balanced_ctas(P.n, (uint64_t)di.sms * (uint64_t)per_sm, 32ull);
-    switch ((W + 31) / 32) {
-        case 1: genasm_generic_kernel<1><<<ctas, 32, smem, st>>>(P, G); break;
-        case 2: genasm_generic_kernel<2><<<ctas, 32, smem, st>>>(P, G); break;
-        case 3: genasm_generic_kernel<3><<<ctas, 32, smem, st>>>(P, G); break;
-        default: genasm_generic_kernel<4><<<ctas, 32, smem, st>>>(P, G); break;
+    if (gp) {   // stream-ordered scratch: launches on different streams of one device never share it
+        void *scratch = nullptr;
+        SG_CUDA(cudaMallocAsync(&scratch, (size_t)ctas * (size_t)generic_plane_words(G.TBL) * 4, st));
+        G.planes = (uint32_t *)scratch;
     }
-    SG_CUDA(cudaGetLastError());
+    switch ((W + 31) / 32) {
+        case 1: if (gp) genasm_generic_kernel<1, true><<<ctas, 32, smem, st>>>(P, G); else genasm_generic_kernel<1, false><<<ctas, 32, smem, st>>>(P, G); break;
+        case 2: if (gp) genasm_generic_kernel<2, true><<<ctas, 32, smem, st>>>(P, G); else genasm_generic_kernel<2, false><<<ctas, 32, smem, st>>>(P, G); break;
+        case 3: if (gp) genasm_generic_kernel<3, true><<<ctas, 32, smem, st>>>(P, G); else genasm_generic_kernel<3, false><<<ctas, 32, smem, st>>>(P, G); break;
+        default: if (gp) genasm_generic_kernel<4, true><<<ctas, 32, smem, st>>>(P, G); else genasm_generic_kernel<4, false><<<ctas, 32, smem, st>>>(P, G); break;
+    }
+    const cudaError_t le = cudaGetLastError();
+    if (gp) cudaFreeAsync(G.planes, st);
+    if (le != cudaSuccess) return cuda_fail(le, "genasm_generic_kernel launch");
     return SG_OK;
 }
 

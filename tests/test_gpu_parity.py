@@ -409,3 +409,35 @@ def test_window_limits_are_errors(sglib):
         with pytest.raises(scrooge_b200.ScroogeError) as e:
             scrooge_b200.Aligner(W=W, O=O, n_gpus=1)
         assert e.value.code == 3
+
+
+@pytest.mark.parametrize("planes", ["global", "smem"])
+def test_generic_kernel_plane_placement(planes):
+    """The general kernel's op planes forced into global memory (default only for four-word windows) and into shared
+    memory, for every extra window configuration: goldens of the unmodified reference + random pairs against the oracle."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import json, sys; sys.path.insert(0, '.'); sys.path.insert(0, 'tests')\n"
+        "import scrooge_b200\n"
+        "from oracle.binding import Oracle, EXTRA_CONFIGS\n"
+        "from conftest import random_pairs\n"
+        "o = Oracle()\n"
+        "for W, O in EXTRA_CONFIGS:\n"
+        "    g = json.load(open(f'tests/golden/golden_w{W}_o{O}.json'))['groups']\n"
+        "    T = [x['text'] for v in g.values() for x in v]; Q = [x['query'] for v in g.values() for x in v]\n"
+        "    want = [x['cigar'] for v in g.values() for x in v]\n"
+        "    T2, Q2 = random_pairs(17 + W + O, 1500, [0, 1, W - 1, W, W + 1, 150, 400, 2000], [0, 0.05, 0.1, 0.3, 0.6])\n"
+        "    al = scrooge_b200.Aligner(W=W, O=O, n_gpus=1)\n"
+        "    got = al.align_pairs(T + T2, Q + Q2)\n"
+        "    ref = o.align_pairs(T2, Q2, W=W, O=O, threads=4)\n"
+        "    cg = got.cigars()\n"
+        "    assert cg[:len(want)] == want and cg[len(want):] == ref.cigars, (W, O)\n"
+        "    assert list(got.edit_distances[len(want):]) == list(ref.edit) and list(got.ref_consumed[len(want):]) == list(ref.ref_consumed)\n"
+        "print('planes ok')\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, SG_GENERIC_PLANES=planes), capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "planes ok" in r.stdout, r.stderr[-2000:]
