@@ -441,3 +441,19 @@ def test_generic_kernel_plane_placement(planes):
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, SG_GENERIC_PLANES=planes), capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0 and "planes ok" in r.stdout, r.stderr[-2000:]
+
+
+ODD_WINDOWS = [(2, 1), (3, 1), (5, 0), (33, 2), (63, 0), (65, 3), (100, 40), (127, 64)]
+
+
+@pytest.mark.parametrize("W,O", ODD_WINDOWS)
+def test_odd_window_configurations(oracle, W, O):
+    """Window sizes that are not a multiple of 32 (or tiny), overlaps at both ends of the range: against the oracle, which
+    agrees with the unmodified reference rebuilt at each of these (W, O) (checked in the build container; these builds are
+    not shipped) and with the kernel model (tests/test_kernel_model.py::test_odd_windows_model)."""
+    import scrooge_b200
+    al = scrooge_b200.Aligner(W=W, O=O, n_gpus=1)
+    T, Q = random_pairs(700 + 131 * W + O, 1200, [0, 1, 2, 3, W - 1, W, W + 1, 2 * W + 1, 150, 400], [0.0, 0.05, 0.1, 0.3, 0.6])
+    got = check_against_oracle(oracle, al, T, Q, W, O)
+    d = al.align_pairs(T, Q, distance_only=True)
+    assert list(d.edit_distances) == list(got.edit_distances)

@@ -62,3 +62,14 @@ def test_generic_delta_model_matches_oracle(oracle, W, O):
         total += ent
         assert (ed, cg, rc) == (int(res.edit[k]), res.cigars[k], int(res.ref_consumed[k])), (W, O, T[k], Q[k])
     assert total == res.stats["dc_entries"]
+
+
+@pytest.mark.parametrize("W,O", [(2, 1), (3, 1), (5, 0), (33, 2), (63, 0), (65, 3), (100, 40), (127, 64)])
+def test_odd_windows_model(oracle, W, O):
+    """Tiny windows and window sizes that are not a multiple of 32: the general kernel's formulation against the oracle."""
+    from kernel_model import align_delta_generic
+    T, Q = random_pairs(51 + 7 * W + O, 60, [0, 1, 2, W - 1, W, W + 1, 2 * W + 1, 150], [0, 0.1, 0.4])
+    res = oracle.align_pairs(T, Q, W=W, O=O)
+    for k in range(len(T)):
+        ed, cg, rc, _ = align_delta_generic(T[k], Q[k], W, O)
+        assert (ed, cg, rc) == (int(res.edit[k]), res.cigars[k], int(res.ref_consumed[k])), (W, O, T[k], Q[k])
