@@ -15,7 +15,8 @@
 //   * the traceback as a per-lane loop over up to 2 (W-O) <= 126 steps into four-word register streams, run-length encoded
 //     after the walk as in the tuned kernel.
 //
-// Limits: 2 <= W <= 128, 0 <= O < W, W - O <= 63 (a run is one byte, (op << 6) | count, and a run can be W - O long).
+// Limits: 2 <= W <= 128, 0 <= O < W.  A run is one byte, (op << 6) | count, and a run can be W - O long: with W - O > 63 (the
+// WIDE instantiations: eight-word op streams) a longer run is split into bytes with count 0, each meaning "63 more".
 // Same one-lane-per-alignment mapping, work queue and outputs as the tuned kernel; one warp per CTA, shared memory sized
 // at launch.  Checked bit-exact against the unmodified reference built at nine further window
 // configurations (tests/test_gpu_parity.py::test_window_configurations, goldens in tests/golden/golden_w*_o*.json) and
@@ -97,7 +98,7 @@ __device__ __forceinline__ void load_bases(const uint32_t *__restrict__ blob, ui
     for (int k = 0; k < NOUT; k++) out[k] = __funnelshift_r(w[k], w[k + 1], sh);
 }
 
-template <int NW, bool GP>
+template <int NW, bool GP, bool WIDE>
 __global__ void __launch_bounds__(32) genasm_generic_kernel(const AlignParams P, const GenericGeom G)
 {
     constexpr int NTW = 2 * NW;                 // text / pattern words of a full-width window (16 bases each)
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(32) genasm_generic_kernel(const AlignParams P,
 
         // ---- TB (src/genasm_cpu.cpp:290-409): op = 2A + B = 0 '=', 1 'X', 2 'I', 3 'D'; the two bits of step k go to bit k of
         // two register-resident streams (at most 2 (W-O) <= 126 steps), as in genasm_delta_kernel's generic walk ----
-        constexpr int SW = 4;
+        constexpr int SW = WIDE ? 8 : 4;                  // WIDE: W - O up to 127, at most 254 steps per window
         const int jmax = m < TBL ? m : TBL;
         int i = 0, j = 0;
         uint32_t hs[SW], ls[SW];
@@ -281,12 +282,12 @@ __global__ void __launch_bounds__(32) genasm_generic_kernel(const AlignParams P,
             if (last < 31) e[w] &= last < 0 ? 0u : (2u << last) - 1u;   // nothing beyond the last step
             nb += __popc(e[w]);
         }
-        const bool fits = !want_cigar || (uint64_t)(out_end - out) >= (uint64_t)nb;
-        if (!fits) overflow = true;
-        if (want_cigar && fits) {
+        if constexpr (WIDE) {
+            // a run can be up to 127 long and the run byte holds 6 bits: a run of c > 63 is written as (c - 1) / 63 bytes
+            // with count 0 ("63 more of this op follow", SG_RUN_COUNT) and one byte with the rest; nruns counts bytes
             uint8_t *o = out;
-            out += nb;
-            int st = -1;                                 // step before the current run's first, relative to word w
+            nb = 0u;
+            int st = -1;
 #pragma unroll
             for (int w = 0; w < SW; w++) {
                 uint32_t ew = e[w];
@@ -294,12 +295,45 @@ __global__ void __launch_bounds__(32) genasm_generic_kernel(const AlignParams P,
                 while (ew) {
                     const int p = __ffs((int)ew) - 1;
                     const uint32_t rh = __funnelshift_r(h7, h7, p), rl = __funnelshift_r(l6, l6, p);
-                    const uint32_t t = (rh & 0x80u) | (rl & ~0x80u);
-                    *o++ = (uint8_t)((t & 0xC0u) | (uint32_t)(p - st));
+                    const uint32_t opb = ((rh & 0x80u) | (rl & ~0x80u)) & 0xC0u;
+                    uint32_t c = (uint32_t)(p - st);
+                    while (true) {
+                        const uint32_t piece = c > 63u ? 0u : c;
+                        if (want_cigar) {
+                            if (o < out_end) *o++ = (uint8_t)(opb | piece);
+                            else overflow = true;
+                        }
+                        nb++;
+                        if (c <= 63u) break;
+                        c -= 63u;
+                    }
                     st = p;
                     ew &= ew - 1u;
                 }
                 st -= 32;
+            }
+            out = o;
+        } else {
+            const bool fits = !want_cigar || (uint64_t)(out_end - out) >= (uint64_t)nb;
+            if (!fits) overflow = true;
+            if (want_cigar && fits) {
+                uint8_t *o = out;
+                out += nb;
+                int st = -1;                                 // step before the current run's first, relative to word w
+#pragma unroll
+                for (int w = 0; w < SW; w++) {
+                    uint32_t ew = e[w];
+                    const uint32_t h7 = __funnelshift_l(hs[w], hs[w], 7), l6 = __funnelshift_l(ls[w], ls[w], 6);
+                    while (ew) {
+                        const int p = __ffs((int)ew) - 1;
+                        const uint32_t rh = __funnelshift_r(h7, h7, p), rl = __funnelshift_r(l6, l6, p);
+                        const uint32_t t = (rh & 0x80u) | (rl & ~0x80u);
+                        *o++ = (uint8_t)((t & 0xC0u) | (uint32_t)(p - st));
+                        st = p;
+                        ew &= ew - 1u;
+                    }
+                    st -= 32;
+                }
             }
         }
         nruns += nb;

@@ -226,8 +226,10 @@ __global__ void __launch_bounds__(256) check_runs_kernel(const uint8_t *__restri
         const uint64_t r0 = run_off[a], r1 = run_off[a + 1];
         uint32_t q = 0, t = 0, e = 0, bad = 0;
         for (uint64_t k = r0 + lane; k < r1; k += 32) {
-            const uint32_t b = runs[k], op = b >> 6, c = b & 63u;
-            bad |= (c == 0u || c > max_count) ? 1u : 0u;
+            const uint32_t b = runs[k], op = b >> 6;
+            uint32_t c = b & 63u;
+            bad |= ((c == 0u && max_count <= 63u) || c > max_count) ? 1u : 0u;
+            if (c == 0u) c = 63u;     // W - O > 63: a byte with count 0 stands for 63 more of its op (SG_RUN_COUNT)
             q += op != 3u ? c : 0u;   // '=', 'X', 'I' consume the query
             t += op != 2u ? c : 0u;   // '=', 'X', 'D' consume the text
             e += op != 0u ? c : 0u;   // 'X', 'I', 'D' are edits

@@ -154,8 +154,8 @@ static bool tuned_config(int W, int O)
 
 static int check_window(int W, int O)
 {
-    if (W < 2 || W > 128 || O < 0 || O >= W || W - O > 63)
-        return fail(SG_ERR_BAD_ARG, "window configuration out of range: need 2 <= W <= 128, 0 <= O < W, W - O <= 63");
+    if (W < 2 || W > 128 || O < 0 || O >= W)
+        return fail(SG_ERR_BAD_ARG, "window configuration out of range: need 2 <= W <= 128, 0 <= O < W");
     return SG_OK;
 }
 
@@ -164,7 +164,7 @@ static int check_window(int W, int O)
 // planes pay when the window is wide and the walk short relative to it -- 128/65 (32 KB of planes per warp, 6 warps per SM in
 // shared memory): 8.2 -> 10.1 M alignments/s -- and cost when the traceback dominates (W = 64 with O <= 24, up to 126 dependent
 // plane reads per window: 13-16 -> 11-12 M/s; 96/49: 11.2 -> 10.8), so only four-word windows with more than 24 KB of planes
-// use them.
+// use them -- and every configuration whose planes exceed 40 KB per warp (W - O > 63: up to 128 KB).
 static bool generic_global_planes(int W, int O)
 {
     static const int forced = [] {
@@ -174,18 +174,25 @@ static bool generic_global_planes(int W, int O)
         return -1;
     }();
     if (forced >= 0) return forced == 1;
-    return (W + 31) / 32 >= 4 && generic_plane_words(W - O) * 4 > 24 * 1024;
+    const int plane_bytes = generic_plane_words(W - O) * 4;
+    return plane_bytes > 40 * 1024 || ((W + 31) / 32 >= 4 && plane_bytes > 24 * 1024);   // > 40 KB: 5 warps per SM or fewer
 }
 
-template <int NW, bool GP> static int generic_occupancy(int smem_bytes, int *ctas_per_sm)
+template <int NW, bool GP, bool WIDE> static int generic_occupancy(int smem_bytes, int *ctas_per_sm)
 {
-    auto kern = genasm_generic_kernel<NW, GP>;
+    auto kern = genasm_generic_kernel<NW, GP, WIDE>;
+    if (smem_bytes > 48 * 1024) {   // beyond the default limit: opt in (at most cudaDevAttrMaxSharedMemoryPerBlockOptin)
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(SG_ERR_CUDA, "generic alignment kernel: " + std::to_string(smem_bytes) + " bytes of shared memory per warp do not fit on this device");
+        }
+    }
     SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kern, 32, smem_bytes));
     if (std::getenv("SG_DEBUG")) {
         cudaFuncAttributes fa;
         cudaFuncGetAttributes(&fa, kern);
-        fprintf(stderr, "[sg] generic NW=%d planes=%s: occupancy %d CTAs/SM, %d regs, %d dyn smem\n", NW, GP ? "global" : "smem", *ctas_per_sm,
+        fprintf(stderr, "[sg] generic NW=%d planes=%s wide=%d: occupancy %d CTAs/SM, %d regs, %d dyn smem\n", NW, GP ? "global" : "smem", (int)WIDE, *ctas_per_sm,
                 fa.numRegs, smem_bytes);
     }
     if (*ctas_per_sm < 1) return fail(SG_ERR_CUDA, "generic alignment kernel does not fit on this device");
@@ -197,13 +204,17 @@ static int generic_geometry(const DeviceInfo &di, int W, int O, int *ctas_per_sm
     const int NW = (W + 31) / 32;
     const bool gp = generic_global_planes(W, O);
     *smem_bytes = generic_smem_words(NW, W, W - O, gp) * 4;
+    const bool wide = W - O > 63;
     int rc;
+#define SG_GEN_OCC(N) (gp ? (wide ? generic_occupancy<N, true, true>(*smem_bytes, ctas_per_sm) : generic_occupancy<N, true, false>(*smem_bytes, ctas_per_sm)) \
+                          : (wide ? generic_occupancy<N, false, true>(*smem_bytes, ctas_per_sm) : generic_occupancy<N, false, false>(*smem_bytes, ctas_per_sm)))
     switch (NW) {
-        case 1: rc = gp ? generic_occupancy<1, true>(*smem_bytes, ctas_per_sm) : generic_occupancy<1, false>(*smem_bytes, ctas_per_sm); break;
-        case 2: rc = gp ? generic_occupancy<2, true>(*smem_bytes, ctas_per_sm) : generic_occupancy<2, false>(*smem_bytes, ctas_per_sm); break;
-        case 3: rc = gp ? generic_occupancy<3, true>(*smem_bytes, ctas_per_sm) : generic_occupancy<3, false>(*smem_bytes, ctas_per_sm); break;
-        default: rc = gp ? generic_occupancy<4, true>(*smem_bytes, ctas_per_sm) : generic_occupancy<4, false>(*smem_bytes, ctas_per_sm); break;
+        case 1: rc = SG_GEN_OCC(1); break;
+        case 2: rc = SG_GEN_OCC(2); break;
+        case 3: rc = SG_GEN_OCC(3); break;
+        default: rc = SG_GEN_OCC(4); break;
     }
+#undef SG_GEN_OCC
     if (rc) return rc;
     if (gp) {
         // the planes of all resident warps should stay in the L2 cache (126 MB): at most 96 MB of them, at least 8 warps per SM
@@ -228,12 +239,19 @@ static int launch_generic(const DeviceInfo &di, const AlignParams &P, int W, int
         SG_CUDA(cudaMallocAsync(&scratch, (size_t)ctas * (size_t)generic_plane_words(G.TBL) * 4, st));
         G.planes = (uint32_t *)scratch;
     }
+    const bool wide = G.TBL > 63;
+#define SG_GEN_LAUNCH(N)                                                                                   \
+    do {                                                                                                   \
+        if (gp) { if (wide) genasm_generic_kernel<N, true, true><<<ctas, 32, smem, st>>>(P, G); else genasm_generic_kernel<N, true, false><<<ctas, 32, smem, st>>>(P, G); } \
+        else { if (wide) genasm_generic_kernel<N, false, true><<<ctas, 32, smem, st>>>(P, G); else genasm_generic_kernel<N, false, false><<<ctas, 32, smem, st>>>(P, G); } \
+    } while (0)
     switch ((W + 31) / 32) {
-        case 1: if (gp) genasm_generic_kernel<1, true><<<ctas, 32, smem, st>>>(P, G); else genasm_generic_kernel<1, false><<<ctas, 32, smem, st>>>(P, G); break;
-        case 2: if (gp) genasm_generic_kernel<2, true><<<ctas, 32, smem, st>>>(P, G); else genasm_generic_kernel<2, false><<<ctas, 32, smem, st>>>(P, G); break;
-        case 3: if (gp) genasm_generic_kernel<3, true><<<ctas, 32, smem, st>>>(P, G); else genasm_generic_kernel<3, false><<<ctas, 32, smem, st>>>(P, G); break;
-        default: if (gp) genasm_generic_kernel<4, true><<<ctas, 32, smem, st>>>(P, G); else genasm_generic_kernel<4, false><<<ctas, 32, smem, st>>>(P, G); break;
+        case 1: SG_GEN_LAUNCH(1); break;
+        case 2: SG_GEN_LAUNCH(2); break;
+        case 3: SG_GEN_LAUNCH(3); break;
+        default: SG_GEN_LAUNCH(4); break;
     }
+#undef SG_GEN_LAUNCH
     const cudaError_t le = cudaGetLastError();
     if (gp) cudaFreeAsync(G.planes, st);
     if (le != cudaSuccess) return cuda_fail(le, "genasm_generic_kernel launch");

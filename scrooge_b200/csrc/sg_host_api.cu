@@ -256,6 +256,7 @@ struct sg_ctx {
 struct sg_result {
     uint64_t n = 0;
     bool has_cigar = false;
+    bool wide_runs = false;   // W - O > 63: run bytes with count 0 continue into the next byte (SG_RUN_COUNT)
     // distances, consumed prefixes and run offsets (n+1) live in ONE pinned block from the pool: the device-to-host
     // copies of every sub-batch land at their final place, nothing is copied or zero-filled on the host
     PinnedPool::Block store{nullptr, 0};
@@ -706,6 +707,7 @@ int run_all(sg_ctx *ctx, const Workload &w, const uint64_t *woff, uint64_t per_u
     std::unique_ptr<sg_result> res(new sg_result);
     res->n = n;
     res->has_cigar = !(w.flags & SG_FLAG_DISTANCE_ONLY);
+    res->wide_runs = ctx->W - ctx->O > 63;
     if (int rc = g_pool.acquire((3 * n + 2) * 8, &res->store)) return rc;
     res->edit = reinterpret_cast<int64_t *>(res->store.p);
     res->refc = reinterpret_cast<uint64_t *>(res->store.p) + n;
@@ -754,8 +756,8 @@ int sg_ctx_overlap(const sg_ctx *ctx) { return ctx ? ctx->O : 0; }
 int sg_ctx_create_wo(sg_ctx **out, const int *device_ids, int n_devices, int W, int O)
 {
     if (!out) return fail(SG_ERR_BAD_ARG, "sg_ctx_create: null out");
-    if (W < 2 || W > 128 || O < 0 || O >= W || W - O > 63)
-        return fail(SG_ERR_BAD_ARG, "window configuration out of range: need 2 <= W <= 128, 0 <= O < W, W - O <= 63");
+    if (W < 2 || W > 128 || O < 0 || O >= W)
+        return fail(SG_ERR_BAD_ARG, "window configuration out of range: need 2 <= W <= 128, 0 <= O < W");
     const int avail = sg_device_count();
     if (avail == 0) return fail(SG_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
     if (n_devices <= 0) n_devices = avail;
@@ -1011,12 +1013,46 @@ static inline char *runs_render(const uint8_t *p, uint64_t cnt, char *o)
     return o + g_run_text.len[b];
 }
 
+// Window configurations with W - O > 63: a run longer than 63 arrives as bytes with count 0 ("63 more of this op") followed
+// by the byte with the rest.  fn(count, op) is called once per run, the pieces summed.
+extern "C++" {
+template <class F> static inline void for_each_wide_run(const uint8_t *p, uint64_t cnt, F &&fn)
+{
+    unsigned carry = 0;
+    for (uint64_t k = 0; k < cnt; k++) {
+        const unsigned c = SG_RUN_COUNT(p[k]);
+        if (c == 0) { carry += 63; continue; }
+        fn(carry + c, SG_RUN_OP(p[k]));
+        carry = 0;
+    }
+}
+
+static inline uint64_t wide_text_len(const uint8_t *p, uint64_t cnt)
+{
+    uint64_t len = 0;
+    for_each_wide_run(p, cnt, [&](unsigned c, unsigned) { len += c >= 100 ? 4 : (c >= 10 ? 3 : 2); });
+    return len;
+}
+
+static inline char *wide_render(const uint8_t *p, uint64_t cnt, char *o)
+{
+    static const char ops[4] = {'=', 'X', 'I', 'D'};
+    for_each_wide_run(p, cnt, [&](unsigned c, unsigned op) {
+        if (c >= 100) *o++ = (char)('0' + c / 100);
+        if (c >= 10) *o++ = (char)('0' + (c / 10) % 10);
+        *o++ = (char)('0' + c % 10);
+        *o++ = ops[op];
+    });
+    return o;
+}
+}  // extern "C++"
+
 uint64_t sg_result_cigar_len(const sg_result *r, uint64_t idx)
 {
     if (!r || !r->has_cigar || idx >= r->n) return 0;
     uint64_t cnt;
     const uint8_t *p = runs_of(r, idx, &cnt);
-    return runs_text_len(p, cnt);
+    return r->wide_runs ? wide_text_len(p, cnt) : runs_text_len(p, cnt);
 }
 
 int64_t sg_result_render_cigar(const sg_result *r, uint64_t idx, char *buf, uint64_t cap)
@@ -1025,9 +1061,10 @@ int64_t sg_result_render_cigar(const sg_result *r, uint64_t idx, char *buf, uint
     uint64_t cnt;
     const uint8_t *p = runs_of(r, idx, &cnt);
     // 3 characters per run at most: when the buffer is that large no length pass is needed
-    const uint64_t len = 3 * cnt + 1 <= cap ? 0 : runs_text_len(p, cnt);
+    // (a run of several bytes renders to at most 4 characters: the bound holds for them too)
+    const uint64_t len = 3 * cnt + 1 <= cap ? 0 : (r->wide_runs ? wide_text_len(p, cnt) : runs_text_len(p, cnt));
     if (len + 1 > cap) return -1;
-    char *end = runs_render(p, cnt, buf);
+    char *end = r->wide_runs ? wide_render(p, cnt, buf) : runs_render(p, cnt, buf);
     *end = '\0';
     return (int64_t)(end - buf);
 }
@@ -1039,6 +1076,11 @@ int64_t sg_result_entries(const sg_result *r, uint64_t idx, sg_cigar_entry *out,
     uint64_t cnt;
     const uint8_t *p = runs_of(r, idx, &cnt);
     if (cnt > cap) return -1;
+    if (r->wide_runs) {   // runs of up to 127 still fit the reference's uint8 count (src/util.hpp:43-46)
+        uint64_t m = 0;
+        for_each_wide_run(p, cnt, [&](unsigned c, unsigned op) { out[m].edit_count = (uint8_t)c; out[m].edit_type = ops[op]; m++; });
+        return (int64_t)m;
+    }
     for (uint64_t k = 0; k < cnt; k++) {
         out[k].edit_count = (uint8_t)SG_RUN_COUNT(p[k]);
         out[k].edit_type = ops[SG_RUN_OP(p[k])];
@@ -1069,7 +1111,7 @@ uint64_t sg_result_render_all(const sg_result *r, char *blob, uint64_t blob_cap,
         for (uint64_t a = a0; a < a1; a++) {
             uint64_t cnt;
             const uint8_t *p = runs_of(r, a, &cnt);
-            text_off[a + 1] = runs_text_len(p, cnt);
+            text_off[a + 1] = r->wide_runs ? wide_text_len(p, cnt) : runs_text_len(p, cnt);
         }
     });
     for (uint64_t a = 0; a < n; a++) text_off[a + 1] += text_off[a];
@@ -1079,7 +1121,8 @@ uint64_t sg_result_render_all(const sg_result *r, char *blob, uint64_t blob_cap,
         for (uint64_t a = a0; a < a1; a++) {
             uint64_t cnt;
             const uint8_t *p = runs_of(r, a, &cnt);
-            runs_render(p, cnt, blob + text_off[a]);
+            if (r->wide_runs) wide_render(p, cnt, blob + text_off[a]);
+            else runs_render(p, cnt, blob + text_off[a]);
         }
     });
     return total;

@@ -235,8 +235,10 @@ def align_delta_generic(text: str, read: str, W: int, O: int) -> Tuple[int, str,
         entries += (d_w + 1) * (n + 1)
         i = j = 0
         jmax = min(m, TBL)
-        # the walk writes the two bits of step k to bit k of two streams of four 32-bit words (at most 2 TBL <= 126 steps)
-        hs, ls, k = [0, 0, 0, 0], [0, 0, 0, 0], 0
+        # the walk writes the two bits of step k to bit k of two streams of four 32-bit words (at most 2 TBL <= 126 steps),
+        # eight words when W - O > 63 (at most 254 steps)
+        SW = 8 if TBL > 63 else 4
+        hs, ls, k = [0] * SW, [0] * SW, 0
         while j < jmax and i < TBL:
             bit = 1 << (WP - 1 - j)
             hi, lo = bool(A[i] & bit), bool(B[i] & bit)

@@ -405,7 +405,7 @@ def test_generic_kernel_equals_tuned_kernels():
 
 def test_window_limits_are_errors(sglib):
     import scrooge_b200
-    for W, O in ((129, 65), (64, 64), (64, 0), (128, 64), (1, 0), (64, -1)):
+    for W, O in ((129, 65), (64, 64), (256, 129), (1, 0), (64, -1)):
         with pytest.raises(scrooge_b200.ScroogeError) as e:
             scrooge_b200.Aligner(W=W, O=O, n_gpus=1)
         assert e.value.code == 3
@@ -443,7 +443,8 @@ def test_generic_kernel_plane_placement(planes):
     assert r.returncode == 0 and "planes ok" in r.stdout, r.stderr[-2000:]
 
 
-ODD_WINDOWS = [(2, 1), (3, 1), (5, 0), (33, 2), (63, 0), (65, 3), (100, 40), (127, 64)]
+ODD_WINDOWS = [(2, 1), (3, 1), (5, 0), (33, 2), (63, 0), (65, 3), (100, 40), (127, 64),
+               (96, 16), (127, 3), (100, 0), (128, 64)]   # the last four: W - O > 63, runs longer than one run byte holds
 
 
 @pytest.mark.parametrize("W,O", ODD_WINDOWS)
@@ -457,3 +458,45 @@ def test_odd_window_configurations(oracle, W, O):
     got = check_against_oracle(oracle, al, T, Q, W, O)
     d = al.align_pairs(T, Q, distance_only=True)
     assert list(d.edit_distances) == list(got.edit_distances)
+
+
+def test_device_api_wide_runs(oracle, sglib):
+    """W - O > 63 on the device layer: runs longer than 63 arrive as bytes with count 0 ("63 more") + the rest; the
+    whole-batch checker accepts them, and joined they give the oracle's CIGAR (low error: many long '=' runs)."""
+    import torch
+    from scrooge_b200 import device, synth
+    W, O = 128, 1
+    wl = synth.Workload("t", 1000, 0.02, synth.PACBIO, W, 777, O=O)
+    n = 2048
+    dev = torch.device("cuda:0")
+    text, tlen, reads = device.synth_pairs_device(wl.seed, 0, n, wl.read_len, wl.err, wl.ratio, wl.slack, dev)
+    h_text, h_tlen, h_reads = synth.pairs_host(wl, 0, n)
+    stride, L = text.shape[1], wl.read_len
+    ptext, _ = device.pack_2bit(text.view(-1))
+    pquery, _ = device.pack_2bit(reads.view(-1))
+    idx = torch.arange(n, dtype=torch.int64, device=dev)
+    cap = 2 * L + 8
+    slab_off = torch.arange(n + 1, dtype=torch.int64, device=dev) * cap
+    qlen = torch.full((n,), L, dtype=torch.int64, device=dev)
+    da = device.DeviceAligner(W, n, dev, slab_bytes=n * cap, O=O)
+    out = da.align(ptext, idx * stride, tlen, pquery, idx * L, qlen, slab_off)
+    run_off, runs = da.compact(slab_off)
+    torch.cuda.synchronize()
+    assert int(out.status.max().item()) == 0
+    T, Q = synth.pairs_as_strings(h_text, h_tlen, h_reads)
+    want = oracle.align_pairs(T, Q, W=W, O=O, threads=4)
+    assert np.array_equal(out.edit.cpu().numpy(), want.edit)
+    assert np.array_equal(out.ref_consumed.cpu().numpy().astype(np.uint64), want.ref_consumed)
+    assert device.check_runs(runs, run_off, qlen, out, W, O) == 0
+    ro, rr = run_off.cpu().numpy(), runs.cpu().numpy()
+    assert int((rr[: ro[-1]] & 63 == 0).sum()) > 0, "the workload was meant to produce runs longer than 63"
+    for k in range(0, n, 97):
+        s, carry = [], 0
+        for b in rr[ro[k]:ro[k + 1]]:
+            c = int(b) & 63
+            if c == 0:
+                carry += 63
+                continue
+            s.append(f"{carry + c}{'=XID'[int(b) >> 6]}")
+            carry = 0
+        assert "".join(s) == want.cigars[k], k

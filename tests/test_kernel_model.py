@@ -64,7 +64,8 @@ def test_generic_delta_model_matches_oracle(oracle, W, O):
     assert total == res.stats["dc_entries"]
 
 
-@pytest.mark.parametrize("W,O", [(2, 1), (3, 1), (5, 0), (33, 2), (63, 0), (65, 3), (100, 40), (127, 64)])
+@pytest.mark.parametrize("W,O", [(2, 1), (3, 1), (5, 0), (33, 2), (63, 0), (65, 3), (100, 40), (127, 64), (96, 16), (127, 3),
+                                 (100, 0), (128, 64)])
 def test_odd_windows_model(oracle, W, O):
     """Tiny windows and window sizes that are not a multiple of 32: the general kernel's formulation against the oracle."""
     from kernel_model import align_delta_generic
