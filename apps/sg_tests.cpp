@@ -248,7 +248,7 @@ int main(int argc, char **argv)
                 "--unit_tests                          -- run unit tests (default: performance test)\n"
                 "--dump_inputs                         -- parse the input files and print them (no GPU needed)\n"
                 "--synthetic=[pairs]                   -- end-to-end run of align_all() on synthetic 10 kbp / 10 % pairs\n"
-                "--window=[W] --overlap=[O]            -- window configuration (default 64 / min(W/2+1, W-1); W <= 128)\n"
+                "--window=[W] --overlap=[O]            -- window configuration (default 64 / min(W/2+1, W-1); W <= 256, W-O <= 128)\n"
                 "--help                                -- displays this information\n";
         return 0;
     }

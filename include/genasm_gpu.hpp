@@ -8,7 +8,7 @@
 //   * errors throw std::runtime_error instead of exit()/assert() (src/cuda_util.hpp:3-10,
 //     src/genasm_gpu.cu:636,984);
 //   * the window configuration is a run-time choice: SG_WINDOW=<W> and SG_OVERLAP=<O> (default W=64, O=min(W/2+1, W-1):
-//     64/33 and 32/17 as the reference ships them; any 2 <= W <= 128, 0 <= O < W is accepted) where
+//     64/33 and 32/17 as the reference ships them; any 2 <= W <= 256, 0 <= O < W, W-O <= 128 is accepted) where
 //     the reference needs a recompile with -DCLI_W/-DCLI_K/-DCLI_O (src/genasm_gpu.cu:1-63);
 //   * align_all_ex additionally returns the consumed reference prefix of every alignment.
 // The reference also exports a __global__ ascii_to_twobit_strings used only by its own unit test

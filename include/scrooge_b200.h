@@ -26,7 +26,7 @@
  * priority I > D > X > '='; CIGAR runs are run-length encoded within a window and never merged across windows.
  * The window configuration is a run-time choice where the reference needs a rebuild (-DCLI_W/-DCLI_O,
  * src/genasm_cpu.cpp:22-35): W=64/O=33 (in-file default, src/genasm_cpu.cpp:7-9) and W=32/O=17 (README.md:208)
- * run on kernels tuned for them, any other 2 <= W <= 128, 0 <= O < W (the axes of
+ * run on kernels tuned for them, any other 2 <= W <= 256, 0 <= O < W, W-O <= 128 (the axes of
  * scripts/profile.py:66-100,595-640) on a general kernel; results are bit-exact with the reference built at
  * the same (W, O).
  */
@@ -77,7 +77,7 @@ int sg_device_count(void);
 /* Create a context over n_devices GPUs (device_ids == NULL: devices 0..n_devices-1; n_devices == 0: all).
  * W is 64 (O=33) or 32 (O=17).  Replaces the reference's hard-wired GPU_ID 0 (src/genasm_gpu.cu:67). */
 int sg_ctx_create(sg_ctx **out, const int *device_ids, int n_devices, int W);
-/* The same with an explicit window configuration: 2 <= W <= 128, 0 <= O < W.  Replaces a rebuild of the reference with -DCLI_W=<W> -DCLI_K=<W> -DCLI_O=<O>
+/* The same with an explicit window configuration: 2 <= W <= 256, 0 <= O < W, W-O <= 128.  Replaces a rebuild of the reference with -DCLI_W=<W> -DCLI_K=<W> -DCLI_O=<O>
  * (src/genasm_cpu.cpp:22-35, scripts/profile.py:29,132). */
 int sg_ctx_create_wo(sg_ctx **out, const int *device_ids, int n_devices, int W, int O);
 /* O = min(W/2+1, W-1): the overlap the reference pairs with a window size (scripts/profile.py:78,619). */

@@ -27,8 +27,8 @@ REF_DIR = os.path.join(HERE, "_ref")
 CONFIGS = {64: 33, 32: 17}
 # Further (W, O) builds of the unmodified reference (oracle/Makefile EXTRA_WO): the axes of the reference's window sweep
 # (scripts/profile.py:66-100 cpu_sweep_wo / cpu_sweep_o, :595-640 accuracy sweeps with W in 32, 64, 96, 128 and
-# O = min(W//2+1, W-1) or free), up to W = 128; the last two have W - O > 63 (runs longer than a run byte's 6-bit count).
-EXTRA_CONFIGS = [(64, 20), (64, 48), (64, 1), (48, 25), (32, 8), (16, 9), (96, 49), (128, 65), (128, 100), (128, 1), (64, 0)]
+# O = min(W//2+1, W-1) or free), up to W = 256; from (128, 1) on W - O > 63 (runs longer than a run byte's 6-bit count).
+EXTRA_CONFIGS = [(64, 20), (64, 48), (64, 1), (48, 25), (32, 8), (16, 9), (96, 49), (128, 65), (128, 100), (128, 1), (64, 0), (256, 129), (160, 81)]
 
 
 def ref_lib_path(W: int, O: Optional[int] = None) -> str:

@@ -30,12 +30,34 @@
 #include <omp.h>
 #endif
 
-#define SGO_MAX_W 128
+#define SGO_MAX_W 256
+#define SGO_WORDS (SGO_MAX_W / 64)
 
-/* one W-bit vector, W <= 128 (the reference switches to arrays of 32-bit words above 64 bits,
- * src/bitvector.hpp:42-47; the arithmetic is the same) */
-typedef unsigned __int128 vec_t;
-#define VEC_ONES (~(vec_t)0)
+/* one W-bit vector, W <= 256, as 64-bit words, least significant first; only the first ceil(W/64) words are
+ * touched (the reference switches to arrays of 32-bit words above 64 bits, src/bitvector.hpp:42-47; the
+ * arithmetic is the same) */
+typedef struct { uint64_t w[SGO_WORDS]; } vec_t;
+
+static inline vec_t v_fill(int nw, uint64_t x) { vec_t r; for (int k = 0; k < SGO_WORDS; k++) r.w[k] = k < nw ? x : 0; return r; }
+static inline vec_t v_and(int nw, vec_t a, vec_t b) { for (int k = 0; k < nw; k++) a.w[k] &= b.w[k]; return a; }
+static inline vec_t v_or(int nw, vec_t a, vec_t b) { for (int k = 0; k < nw; k++) a.w[k] |= b.w[k]; return a; }
+static inline vec_t v_shl1(int nw, vec_t a)   /* towards higher bit indices, zero fill (src/bitvector.hpp:115-140) */
+{
+    for (int k = nw - 1; k > 0; k--) a.w[k] = (a.w[k] << 1) | (a.w[k - 1] >> 63);
+    a.w[0] <<= 1;
+    return a;
+}
+static inline int v_bit(vec_t a, int b) { return (int)((a.w[b >> 6] >> (b & 63)) & 1ull); }
+/* the `bits` lowest bits set */
+static inline vec_t v_low_mask(int nw, int bits)
+{
+    vec_t r = v_fill(nw, 0);
+    for (int k = 0; k < nw; k++) {
+        int t = bits - 64 * k;
+        r.w[k] = t >= 64 ? ~0ull : (t <= 0 ? 0ull : ((1ull << t) - 1ull));
+    }
+    return r;
+}
 
 typedef struct {
     int W;        /* window size in characters; K == W (src/genasm_cpu.cpp:7-8, scripts/profile.py:29) */
@@ -56,7 +78,6 @@ typedef struct {
     uint64_t tb_steps;   /* number of traceback steps */
 } sgo_stats;
 
-static inline vec_t low_mask(int bits) { return bits >= 128 ? VEC_ONES : ((((vec_t)1) << bits) - 1); }
 
 /* ASCII -> base codes A0 C1 G2 T3, case-insensitive (src/genasm_cpu.cpp:462-493).
  * Returns -1 and the offending position through *bad_pos instead of assert(false). */
@@ -93,16 +114,16 @@ int sgo_ascii_to_twobit_ref_layout(const char *ascii, size_t len, uint8_t *out)
 
 /* Pattern bitmasks (src/genasm_cpu.cpp:178-198): bit b of masks[c] is 0 iff pattern[m-1-b] == c,
  * every other bit (including b >= m) is 1. */
-static void pattern_masks(int m, const uint8_t *pattern, vec_t masks[4])
+static void pattern_masks(int nw, int m, const uint8_t *pattern, vec_t masks[4])
 {
-    masks[0] = masks[1] = masks[2] = masks[3] = VEC_ONES;
+    masks[0] = masks[1] = masks[2] = masks[3] = v_fill(nw, ~0ull);
     for (int b = 0; b < m; b++) {
-        masks[pattern[m - 1 - b]] &= ~(((vec_t)1) << b);
+        masks[pattern[m - 1 - b]].w[b >> 6] &= ~(1ull << (b & 63));
     }
 }
 
 /* Distance calculation for one window (src/genasm_cpu.cpp:210-288), SENE + early termination.
- * Vectors are W-bit; they are held in a 128-bit integer and truncated to W bits after every shift so
+ * Vectors are W-bit; they are held in ceil(W/64) 64-bit words and truncated to W bits after every shift so
  * that W = 32 behaves like the reference's 32-bit element type (src/bitvector.hpp:32-49,115-140); bits
  * at and above m are never examined and shifts only move bits upwards, so the truncation is neutral
  * for every other W as well.
@@ -112,33 +133,36 @@ static int window_dc(const sgo_cfg *cfg, int n, const uint8_t *text, int m, cons
 {
     const int W = cfg->W;
     const int cols = W + 1;
-    const vec_t wmask = low_mask(W);
+    const int nw = (W + 63) / 64;
+    const vec_t wmask = v_low_mask(nw, W);
     vec_t pm[4];
-    pattern_masks(m, pattern, pm);
+    pattern_masks(nw, m, pattern, pm);
 
     for (int d = 0; d <= W; d++) {
         for (int i = n; i >= 0; i--) {
             vec_t center;
             if (i == n) {
                 /* boundary column: all ones shifted left by d (src/genasm_cpu.cpp:225-231,239-245) */
-                center = d >= 128 ? (vec_t)0 : ((VEC_ONES << d) & wmask);
+                vec_t low = v_low_mask(nw, d);
+                center = wmask;
+                for (int k = 0; k < nw; k++) center.w[k] &= ~low.w[k];
             } else {
                 /* note: text[i] is only touched for i < n (quirk Q6) */
                 vec_t right = R[cols * d + (i + 1)];
-                vec_t mat = ((right << 1) | pm[text[i]]) & wmask;
+                vec_t mat = v_and(nw, v_or(nw, v_shl1(nw, right), pm[text[i]]), wmask);
                 if (d == 0) {
                     center = mat; /* src/genasm_cpu.cpp:232-238 */
                 } else {
                     vec_t top = R[cols * (d - 1) + i];
                     vec_t topright = R[cols * (d - 1) + (i + 1)];
-                    vec_t sub = (topright << 1) & wmask;
-                    vec_t ins = (top << 1) & wmask;
+                    vec_t sub = v_and(nw, v_shl1(nw, topright), wmask);
+                    vec_t ins = v_and(nw, v_shl1(nw, top), wmask);
                     vec_t del = topright;
-                    center = mat & sub & ins & del; /* src/genasm_cpu.cpp:246-252 */
+                    center = v_and(nw, v_and(nw, mat, sub), v_and(nw, ins, del)); /* src/genasm_cpu.cpp:246-252 */
                 }
             }
             R[cols * d + i] = center;
-            if (i == 0 && ((center >> (m - 1)) & 1) == 0) {
+            if (i == 0 && v_bit(center, m - 1) == 0) {
                 return d; /* early termination, src/genasm_cpu.cpp:278-283 */
             }
         }
@@ -175,9 +199,9 @@ static int window_tb(const sgo_cfg *cfg, int n, int m, const vec_t *R, int d_w,
         int can_ins, can_del, can_sub;
         if (j < m - 1) {
             /* bit index of pattern position J is m-1-J (src/genasm_cpu.cpp:59,321-323) */
-            can_ins = !d_limit && !((R[cols * (d - 1) + i] >> (m - 1 - (j + 1))) & 1);
-            can_del = !d_limit && !i_limit && !((R[cols * (d - 1) + (i + 1)] >> (m - 1 - j)) & 1);
-            can_sub = !d_limit && !i_limit && !((R[cols * (d - 1) + (i + 1)] >> (m - 1 - (j + 1))) & 1);
+            can_ins = !d_limit && !v_bit(R[cols * (d - 1) + i], m - 1 - (j + 1));
+            can_del = !d_limit && !i_limit && !v_bit(R[cols * (d - 1) + (i + 1)], m - 1 - j);
+            can_sub = !d_limit && !i_limit && !v_bit(R[cols * (d - 1) + (i + 1)], m - 1 - (j + 1));
         } else {
             can_ins = !d_limit; /* src/genasm_cpu.cpp:336-343 */
             can_del = 0;

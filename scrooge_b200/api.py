@@ -132,7 +132,7 @@ class Result:
 class Aligner:
     """sg_ctx wrapper.  W=64 -> O=33 (reference default), W=32 -> O=17 (reference short-read setting); any other
     window configuration the reference can be rebuilt with (-DCLI_W/-DCLI_O, src/genasm_cpu.cpp:22-35) within
-    2 <= W <= 128, 0 <= O < W by passing O (default O = min(W//2+1, W-1), scripts/profile.py:78)."""
+    2 <= W <= 256, 0 <= O < W, W-O <= 128 by passing O (default O = min(W//2+1, W-1), scripts/profile.py:78)."""
 
     def __init__(self, W: int = 64, n_gpus: int = 0, device_ids: Optional[Sequence[int]] = None, O: Optional[int] = None):
         h = C.c_void_p()

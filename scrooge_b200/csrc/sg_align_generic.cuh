@@ -6,7 +6,7 @@
 // configurations the reference ships -- 64/33 and 32/17 -- with everything unrolled around W - O = 31 or 15 traceback
 // steps in one 32-bit word.  This kernel runs the same algorithm with W, O as kernel parameters:
 //
-//   * vectors of NW = ceil(W / 32) words (template parameter, 1..4), pattern position J at bit 32*NW-1-J: a window narrower
+//   * vectors of NW = ceil(W / 32) words (template parameter, 1..8), pattern position J at bit 32*NW-1-J: a window narrower
 //     than the vector is a window with more padding rows, which the recurrence already handles (the last window of every
 //     read has m < W);
 //   * W columns per window whatever n is (the "matches nothing" mask stands in for the columns i >= n), one column =
@@ -15,7 +15,7 @@
 //   * the traceback as a per-lane loop over up to 2 (W-O) <= 126 steps into four-word register streams, run-length encoded
 //     after the walk as in the tuned kernel.
 //
-// Limits: 2 <= W <= 128, 0 <= O < W.  A run is one byte, (op << 6) | count, and a run can be W - O long: with W - O > 63 (the
+// Limits: 2 <= W <= 256, 0 <= O < W, W - O <= 128.  A run is one byte, (op << 6) | count, and a run can be W - O long: with W - O > 63 (the
 // WIDE instantiations: eight-word op streams) a longer run is split into bytes with count 0, each meaning "63 more".
 // Same one-lane-per-alignment mapping, work queue and outputs as the tuned kernel; one warp per CTA, shared memory sized
 // at launch.  Checked bit-exact against the unmodified reference built at nine further window
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(32) genasm_generic_kernel(const AlignParams P,
 
         // ---- TB (src/genasm_cpu.cpp:290-409): op = 2A + B = 0 '=', 1 'X', 2 'I', 3 'D'; the two bits of step k go to bit k of
         // two register-resident streams (at most 2 (W-O) <= 126 steps), as in genasm_delta_kernel's generic walk ----
-        constexpr int SW = WIDE ? 8 : 4;                  // WIDE: W - O up to 127, at most 254 steps per window
+        constexpr int SW = WIDE ? 8 : 4;                  // WIDE: W - O up to 128, at most 256 steps per window
         const int jmax = m < TBL ? m : TBL;
         int i = 0, j = 0;
         uint32_t hs[SW], ls[SW];

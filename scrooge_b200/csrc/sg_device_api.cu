@@ -154,8 +154,8 @@ static bool tuned_config(int W, int O)
 
 static int check_window(int W, int O)
 {
-    if (W < 2 || W > 128 || O < 0 || O >= W)
-        return fail(SG_ERR_BAD_ARG, "window configuration out of range: need 2 <= W <= 128, 0 <= O < W");
+    if (W < 2 || W > 256 || O < 0 || O >= W || W - O > 128)
+        return fail(SG_ERR_BAD_ARG, "window configuration out of range: need 2 <= W <= 256, 0 <= O < W, W - O <= 128");
     return SG_OK;
 }
 
@@ -212,7 +212,11 @@ static int generic_geometry(const DeviceInfo &di, int W, int O, int *ctas_per_sm
         case 1: rc = SG_GEN_OCC(1); break;
         case 2: rc = SG_GEN_OCC(2); break;
         case 3: rc = SG_GEN_OCC(3); break;
-        default: rc = SG_GEN_OCC(4); break;
+        case 4: rc = SG_GEN_OCC(4); break;
+        case 5: rc = SG_GEN_OCC(5); break;
+        case 6: rc = SG_GEN_OCC(6); break;
+        case 7: rc = SG_GEN_OCC(7); break;
+        default: rc = SG_GEN_OCC(8); break;
     }
 #undef SG_GEN_OCC
     if (rc) return rc;
@@ -249,7 +253,11 @@ static int launch_generic(const DeviceInfo &di, const AlignParams &P, int W, int
         case 1: SG_GEN_LAUNCH(1); break;
         case 2: SG_GEN_LAUNCH(2); break;
         case 3: SG_GEN_LAUNCH(3); break;
-        default: SG_GEN_LAUNCH(4); break;
+        case 4: SG_GEN_LAUNCH(4); break;
+        case 5: SG_GEN_LAUNCH(5); break;
+        case 6: SG_GEN_LAUNCH(6); break;
+        case 7: SG_GEN_LAUNCH(7); break;
+        default: SG_GEN_LAUNCH(8); break;
     }
 #undef SG_GEN_LAUNCH
     const cudaError_t le = cudaGetLastError();

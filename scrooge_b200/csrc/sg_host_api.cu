@@ -756,8 +756,8 @@ int sg_ctx_overlap(const sg_ctx *ctx) { return ctx ? ctx->O : 0; }
 int sg_ctx_create_wo(sg_ctx **out, const int *device_ids, int n_devices, int W, int O)
 {
     if (!out) return fail(SG_ERR_BAD_ARG, "sg_ctx_create: null out");
-    if (W < 2 || W > 128 || O < 0 || O >= W)
-        return fail(SG_ERR_BAD_ARG, "window configuration out of range: need 2 <= W <= 128, 0 <= O < W");
+    if (W < 2 || W > 256 || O < 0 || O >= W || W - O > 128)
+        return fail(SG_ERR_BAD_ARG, "window configuration out of range: need 2 <= W <= 256, 0 <= O < W, W - O <= 128");
     const int avail = sg_device_count();
     if (avail == 0) return fail(SG_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
     if (n_devices <= 0) n_devices = avail;

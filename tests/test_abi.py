@@ -80,7 +80,7 @@ def test_window_configuration_arguments(sglib):
     before any device is touched."""
     assert [sglib.sg_default_overlap(W) for W in (64, 32, 96, 128, 2, 3)] == [33, 17, 49, 65, 1, 2]
     h = C.c_void_p()
-    for W, O in ((129, 65), (64, 64), (256, 129), (1, 0), (64, -1)):
+    for W, O in ((257, 129), (64, 64), (256, 127), (1, 0), (64, -1)):
         assert sglib.sg_ctx_create_wo(C.byref(h), None, 1, W, O) == 3, (W, O)
         assert b"window configuration" in sglib.sg_last_error()
     assert sglib.sg_ctx_create(C.byref(h), None, 1, 48) == 3

@@ -405,7 +405,7 @@ def test_generic_kernel_equals_tuned_kernels():
 
 def test_window_limits_are_errors(sglib):
     import scrooge_b200
-    for W, O in ((129, 65), (64, 64), (256, 129), (1, 0), (64, -1)):
+    for W, O in ((257, 129), (64, 64), (256, 127), (1, 0), (64, -1)):
         with pytest.raises(scrooge_b200.ScroogeError) as e:
             scrooge_b200.Aligner(W=W, O=O, n_gpus=1)
         assert e.value.code == 3
@@ -444,7 +444,8 @@ def test_generic_kernel_plane_placement(planes):
 
 
 ODD_WINDOWS = [(2, 1), (3, 1), (5, 0), (33, 2), (63, 0), (65, 3), (100, 40), (127, 64),
-               (96, 16), (127, 3), (100, 0), (128, 64)]   # the last four: W - O > 63, runs longer than one run byte holds
+               (96, 16), (127, 3), (100, 0), (128, 64),   # W - O > 63: runs longer than one run byte holds
+               (128, 0), (192, 97), (255, 127), (200, 72), (256, 250)]   # up to the widest window and the longest walk
 
 
 @pytest.mark.parametrize("W,O", ODD_WINDOWS)

@@ -65,7 +65,7 @@ def test_generic_delta_model_matches_oracle(oracle, W, O):
 
 
 @pytest.mark.parametrize("W,O", [(2, 1), (3, 1), (5, 0), (33, 2), (63, 0), (65, 3), (100, 40), (127, 64), (96, 16), (127, 3),
-                                 (100, 0), (128, 64)])
+                                 (100, 0), (128, 64), (128, 0), (192, 97), (255, 127), (200, 72), (256, 250)])
 def test_odd_windows_model(oracle, W, O):
     """Tiny windows and window sizes that are not a multiple of 32: the general kernel's formulation against the oracle."""
     from kernel_model import align_delta_generic

@@ -91,7 +91,7 @@ def test_live_reference_window_configurations(oracle, W, O):
 
 def test_window_limits(oracle):
     with pytest.raises(ValueError):
-        oracle.align_pairs(["ACGT"], ["ACG"], W=129, O=65)
+        oracle.align_pairs(["ACGT"], ["ACG"], W=257, O=129)
     with pytest.raises(ValueError):
         oracle.align_pairs(["ACGT"], ["ACG"], W=64, O=64)
 
