@@ -43,6 +43,19 @@ p = lambda t: int(t.data_ptr())
 stream = lambda: int(torch.cuda.current_stream().cuda_stream)
 
 
+def runs_to_cigar(seg):
+    """packed run bytes -> CIGAR text; a byte with count 0 stands for 63 more of the same op (W - O > 63, SG_RUN_COUNT)"""
+    out, carry = [], 0
+    for b in seg:
+        c = int(b) & 63
+        if c == 0:
+            carry += 63
+            continue
+        out.append(f"{carry + c}{'=XID'[int(b) >> 6]}")
+        carry = 0
+    return "".join(out)
+
+
 def time_steps(fn, steps=3, warmup=1):
     for _ in range(warmup):
         fn()
@@ -101,8 +114,7 @@ def pairs_point(wl, n, distance_only, peak_gops, check=256):
         ro = da.run_off[: k + 1].cpu().numpy()
         rr = runs[: int(ro[-1])].cpu().numpy()
         for a in range(0, k, 8):
-            s = "".join(f"{int(b) & 63}{'=XID'[int(b) >> 6]}" for b in rr[ro[a]:ro[a + 1]])
-            ok = ok and s == want.cigars[a]
+            ok = ok and runs_to_cigar(rr[ro[a]:ro[a + 1]]) == want.cigars[a]
     gops = windows * W * COL_OPS[W] / (ms_kernel / 1e3) / 1e9
     ref_gops = entries * OPS[W] / (ms_kernel / 1e3) / 1e9
     out = {"workload": wl.name, "read_len": L, "error_rate": wl.err, "W": W, "O": O, "pairs": n, "mode": "distance_only" if distance_only else "full_cigar",
@@ -130,12 +142,16 @@ def cmd_windows(args, peak):
     overlap the reference pairs with it, and the overlap at W = 64.  64/33 and 32/17 run on the tuned kernels, everything
     else on genasm_generic_kernel (64/33 also once on the generic kernel when SG_GENERIC=1 is set by the caller)."""
     n = args.pairs
-    points = [(16, 9), (32, 17), (48, 25), (64, 33), (96, 49), (128, 65)] + [(64, O) for O in (1, 8, 16, 24, 40, 48, 56, 63)]
+    points = [(16, 9), (32, 17), (48, 25), (64, 33), (96, 49), (128, 65), (160, 81), (192, 97), (224, 113), (256, 129)] + \
+             [(64, O) for O in (0, 1, 8, 16, 24, 40, 48, 56, 63)]
+    if args.only:
+        points = [tuple(int(x) for x in p.split('/')) for p in args.only.split(',')]
     for W, O in points:
         wl = synth.Workload(f"long_10kbp_w{W}_o{O}", 10000, 0.10, synth.PACBIO, W, synth.BASE_SEED + 3, O=O)
         print(json.dumps(pairs_point(wl, n, False, peak, check=64)), flush=True)
-    wl = synth.Workload("short_150bp_w48_o25", 150, 0.05, synth.ILLUMINA, 48, synth.BASE_SEED + 2, O=25)
-    print(json.dumps(pairs_point(wl, 2_000_000, False, peak, check=2048)), flush=True)
+    if not args.only:
+        wl = synth.Workload("short_150bp_w48_o25", 150, 0.05, synth.ILLUMINA, 48, synth.BASE_SEED + 2, O=25)
+        print(json.dumps(pairs_point(wl, 2_000_000, False, peak, check=2048)), flush=True)
 
 
 def cmd_short(args, peak):
@@ -249,6 +265,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("what", choices=["sweep", "mapping", "short", "windows"])
     ap.add_argument("--pairs", type=int, default=200_000)
+    ap.add_argument("--only", default="", help="windows: comma-separated W/O points instead of the default list")
     ap.add_argument("--bases", type=float, default=1e10)
     ap.add_argument("--genome", type=float, default=3e9)
     ap.add_argument("--reads", type=int, default=1_000_000)
