@@ -68,8 +68,8 @@ def main():
     ap.add_argument("--len", type=int, default=2000)
     ap.add_argument("--err", default="0.10,0.15")
     args = ap.parse_args()
-    points = [(W, min(W // 2 + 1, W - 1)) for W in (16, 32, 48, 64, 96, 128)] + [(64, O) for O in (1, 8, 16, 24, 40, 48, 56, 63)] + \
-             [(32, O) for O in (0, 8, 24)] + [(128, O) for O in (80, 100, 120)]
+    points = [(W, min(W // 2 + 1, W - 1)) for W in (16, 32, 48, 64, 96, 128, 192, 256)] + [(64, O) for O in (1, 8, 16, 24, 40, 48, 56, 63)] + \
+             [(64, 0)] + [(32, O) for O in (0, 8, 24)] + [(128, O) for O in (1, 32, 80, 100, 120)]
     for err in (float(x) for x in args.err.split(",")):
         wl = synth.Workload(f"accuracy_{args.len}bp_{int(err * 100)}pct", args.len, err, synth.PACBIO, 64, synth.BASE_SEED + 6)
         text, tlen, reads = synth.pairs_host(wl, 0, args.pairs)
