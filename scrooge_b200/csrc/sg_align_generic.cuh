@@ -46,17 +46,77 @@ __host__ __device__ inline int generic_smem_words(int NW, int W, int TBL, bool g
     return pm + tw + (global_planes ? 0 : generic_plane_words(TBL));
 }
 
-// NW-word addition with carry propagation for any NW
+// NW-word addition with carry propagation for any NW: one add.cc / addc.cc chain (a single asm statement, so that nothing
+// can come between the carry-setting and the carry-using instructions)
+template <int NW> struct AddChain;
+template <> struct AddChain<1> {
+    static __device__ __forceinline__ void run(const uint32_t (&a)[1], const uint32_t (&b)[1], uint32_t (&s)[1])
+    {
+        asm("add.u32 %0, %1, %2;"
+            : "=r"(s[0])
+            : "r"(a[0]), "r"(b[0]));
+    }
+};
+template <> struct AddChain<2> {
+    static __device__ __forceinline__ void run(const uint32_t (&a)[2], const uint32_t (&b)[2], uint32_t (&s)[2])
+    {
+        asm("add.cc.u32 %0, %2, %4; addc.u32 %1, %3, %5;"
+            : "=r"(s[0]), "=r"(s[1])
+            : "r"(a[0]), "r"(a[1]), "r"(b[0]), "r"(b[1]));
+    }
+};
+template <> struct AddChain<3> {
+    static __device__ __forceinline__ void run(const uint32_t (&a)[3], const uint32_t (&b)[3], uint32_t (&s)[3])
+    {
+        asm("add.cc.u32 %0, %3, %6; addc.cc.u32 %1, %4, %7; addc.u32 %2, %5, %8;"
+            : "=r"(s[0]), "=r"(s[1]), "=r"(s[2])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(b[0]), "r"(b[1]), "r"(b[2]));
+    }
+};
+template <> struct AddChain<4> {
+    static __device__ __forceinline__ void run(const uint32_t (&a)[4], const uint32_t (&b)[4], uint32_t (&s)[4])
+    {
+        asm("add.cc.u32 %0, %4, %8; addc.cc.u32 %1, %5, %9; addc.cc.u32 %2, %6, %10; addc.u32 %3, %7, %11;"
+            : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]));
+    }
+};
+template <> struct AddChain<5> {
+    static __device__ __forceinline__ void run(const uint32_t (&a)[5], const uint32_t (&b)[5], uint32_t (&s)[5])
+    {
+        asm("add.cc.u32 %0, %5, %10; addc.cc.u32 %1, %6, %11; addc.cc.u32 %2, %7, %12; addc.cc.u32 %3, %8, %13; addc.u32 %4, %9, %14;"
+            : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]));
+    }
+};
+template <> struct AddChain<6> {
+    static __device__ __forceinline__ void run(const uint32_t (&a)[6], const uint32_t (&b)[6], uint32_t (&s)[6])
+    {
+        asm("add.cc.u32 %0, %6, %12; addc.cc.u32 %1, %7, %13; addc.cc.u32 %2, %8, %14; addc.cc.u32 %3, %9, %15; addc.cc.u32 %4, %10, %16; addc.u32 %5, %11, %17;"
+            : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]));
+    }
+};
+template <> struct AddChain<7> {
+    static __device__ __forceinline__ void run(const uint32_t (&a)[7], const uint32_t (&b)[7], uint32_t (&s)[7])
+    {
+        asm("add.cc.u32 %0, %7, %14; addc.cc.u32 %1, %8, %15; addc.cc.u32 %2, %9, %16; addc.cc.u32 %3, %10, %17; addc.cc.u32 %4, %11, %18; addc.cc.u32 %5, %12, %19; addc.u32 %6, %13, %20;"
+            : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]));
+    }
+};
+template <> struct AddChain<8> {
+    static __device__ __forceinline__ void run(const uint32_t (&a)[8], const uint32_t (&b)[8], uint32_t (&s)[8])
+    {
+        asm("add.cc.u32 %0, %8, %16; addc.cc.u32 %1, %9, %17; addc.cc.u32 %2, %10, %18; addc.cc.u32 %3, %11, %19; addc.cc.u32 %4, %12, %20; addc.cc.u32 %5, %13, %21; addc.cc.u32 %6, %14, %22; addc.u32 %7, %15, %23;"
+            : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    }
+};
 template <int NW>
 __device__ __forceinline__ void add_vec_any(const uint32_t (&a)[NW], const uint32_t (&b)[NW], uint32_t (&s)[NW])
 {
-    uint32_t c = 0u;
-#pragma unroll
-    for (int k = 0; k < NW; k++) {
-        const uint64_t r = (uint64_t)a[k] + (uint64_t)b[k] + (uint64_t)c;
-        s[k] = (uint32_t)r;
-        c = (uint32_t)(r >> 32);
-    }
+    AddChain<NW>::run(a, b, s);
 }
 
 // delta_column (sg_align_delta.cuh) for any NW
@@ -192,6 +252,7 @@ __global__ void __launch_bounds__(32) genasm_generic_kernel(const AlignParams P,
             const int top = W - 1 - 16 * wi < 15 ? W - 1 - 16 * wi : 15;
             cw <<= (15 - top) * 2;
             uint32_t *tbp = tb_s + ((16 * wi + top) * NWT * 2) * 32;   // planes of column 16 wi + top
+#pragma unroll 4
             for (int ii = top; ii >= 0; ii--) {
                 const int i = 16 * wi + ii;
                 uint32_t code = cw >> 30;
