@@ -54,6 +54,7 @@
 //                   VIADD does not compete with LOP3/SHF for the alu pipe, and the traceback is not what that pipe
 //                   waits for.
 //   SG_DELTA_RLE2   leaner run-emission loop (op bits rotated into place, one output pointer): 36.90 -> 36.59 ms.  ON.
+//                   2 = the same loop handling two runs per iteration: 36.46 -> 37.52 ms.
 //   SG_DELTA_GATHER the pattern bit planes of the window setup gathered by four bit-select LOP3 per plane and 16-base word, with
 //                   the shifted copies made on the fma pipe (multiplications by 2, 4, 16, 256 that arrive as kernel
 //                   parameters) and the halves joined by one PRMT: 36 alu-pipe + 36 fma-pipe instructions per window
@@ -585,6 +586,29 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
             for (int w = 0; w < SW; w++) {
                 uint32_t ew = e[w];
                 const uint32_t h7 = __funnelshift_l(hs[w], hs[w], 7), l6 = __funnelshift_l(ls[w], ls[w], 6);
+#if SG_DELTA_RLE2 == 2
+                // two runs per iteration: half the loop overhead, and the two extractions overlap
+                while (ew) {
+                    const uint32_t ew2 = ew & (ew - 1u);
+                    const int p = __ffs((int)ew) - 1;
+                    const uint32_t rh = __funnelshift_r(h7, h7, p), rl = __funnelshift_r(l6, l6, p);
+                    const uint32_t t = (rh & 0x80u) | (rl & ~0x80u);
+                    o[0] = (uint8_t)((t & 0xC0u) | (uint32_t)(p - st));
+                    if (ew2) {
+                        const int p2 = __ffs((int)ew2) - 1;
+                        const uint32_t rh2 = __funnelshift_r(h7, h7, p2), rl2 = __funnelshift_r(l6, l6, p2);
+                        const uint32_t t2 = (rh2 & 0x80u) | (rl2 & ~0x80u);
+                        o[1] = (uint8_t)((t2 & 0xC0u) | (uint32_t)(p2 - p));
+                        o += 2;
+                        st = p2;
+                        ew = ew2 & (ew2 - 1u);
+                    } else {
+                        o += 1;
+                        st = p;
+                        ew = 0u;
+                    }
+                }
+#else
                 while (ew) {
                     const int p = __ffs((int)ew) - 1;
                     const uint32_t rh = __funnelshift_r(h7, h7, p), rl = __funnelshift_r(l6, l6, p);
@@ -593,6 +617,7 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
                     st = p;
                     ew &= ew - 1u;
                 }
+#endif
                 st -= 32;
             }
 #else
