@@ -239,6 +239,18 @@ static int launch_generic(const DeviceInfo &di, const AlignParams &P, int W, int
     G.W = W; G.TBL = W - O; G.NWT = (G.TBL + 31) / 32; G.planes = nullptr;
     const unsigned ctas = (unsigned)balanced_ctas(P.n, (uint64_t)di.sms * (uint64_t)per_sm, 32ull);
     if (gp) {   // stream-ordered scratch: launches on different streams of one device never share it
+        static bool pool_kept[64] = {};
+        int dev = 0;
+        SG_CUDA(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 64 && !pool_kept[dev]) {
+            // keep freed scratch in the device's pool across synchronisations (the default threshold of 0 hands it back to
+            // the driver at every sync, and each launch would pay a real allocation)
+            cudaMemPool_t pool;
+            unsigned long long keep = ~0ull;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            cudaGetLastError();
+            pool_kept[dev] = true;
+        }
         void *scratch = nullptr;
         SG_CUDA(cudaMallocAsync(&scratch, (size_t)ctas * (size_t)generic_plane_words(G.TBL) * 4, st));
         G.planes = (uint32_t *)scratch;
