@@ -18,7 +18,7 @@
 // Limits: 2 <= W <= 256, 0 <= O < W, W - O <= 128.  A run is one byte, (op << 6) | count, and a run can be W - O long: with W - O > 63 (the
 // WIDE instantiations: eight-word op streams) a longer run is split into bytes with count 0, each meaning "63 more".
 // Same one-lane-per-alignment mapping, work queue and outputs as the tuned kernel; one warp per CTA, shared memory sized
-// at launch.  Checked bit-exact against the unmodified reference built at nine further window
+// at launch.  Checked bit-exact against the unmodified reference built at thirteen further window
 // configurations (tests/test_gpu_parity.py::test_window_configurations, goldens in tests/golden/golden_w*_o*.json) and
 // against the tuned kernels at 64/33 and 32/17 (::test_generic_kernel_equals_tuned_kernels).
 #pragma once
