@@ -501,3 +501,19 @@ def test_device_api_wide_runs(oracle, sglib):
             s.append(f"{carry + c}{'=XID'[int(b) >> 6]}")
             carry = 0
         assert "".join(s) == want.cigars[k], k
+
+
+def test_random_window_configurations(oracle):
+    """Twenty random (W, O) from the whole supported range with mixed random pairs each (tools/fuzz_windows.py is the long
+    version: 380 configurations x 600-1000 pairs ran clean, profiles/r01_fuzz_windows.txt)."""
+    import random
+    import scrooge_b200
+    rng = random.Random(31337)
+    for _ in range(20):
+        W = rng.choice([rng.randint(2, 256), rng.choice([31, 32, 33, 63, 64, 65, 95, 96, 97, 127, 128, 129, 255, 256])])
+        O = rng.randint(max(0, W - 128), W - 1)
+        T, Q = random_pairs(rng.randrange(1 << 30), 300, [0, 1, 2, 3, W - 1, W, W + 1, 2 * W + 1, 3 * W, 150, 400, 1500],
+                            [0.0, 0.02, 0.05, 0.1, 0.15, 0.3, 0.6])
+        al = scrooge_b200.Aligner(W=W, O=O, n_gpus=1)
+        check_against_oracle(oracle, al, T, Q, W, O)
+        al.close()
