@@ -134,3 +134,15 @@ def test_performance_test_on_files(sglib, dataset, seeds, ref):
     assert "0 failed the sanity check" in r.stdout and "GPU kernel ran at" in r.stdout and "FAILED" not in r.stdout
     n = sum(1 for x in dataset["seeds"] if x["strand"] == "+" and (ref == "ref.fasta" or x["chrom"] == "chrA"))
     assert f"{n} alignments," in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("window,overlap", [(128, 65), (48, 25), (64, 0), (256, 129)])
+def test_performance_test_on_files_other_windows(sglib, dataset, window, overlap):
+    """The reference's file-based workflow at other window configurations (a rebuild there, --window/--overlap here): every
+    CIGAR the C++ drop-in returns passes the validateCigarString port."""
+    d = dataset["dir"]
+    r = subprocess.run([SG_TESTS, f"--reference={d / 'ref.fasta'}", f"--reads={d / 'reads.fastq'}", f"--seeds={d / 'seeds.paf'}",
+                        f"--window={window}", f"--overlap={overlap}"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 failed the sanity check" in r.stdout and "FAILED" not in r.stdout
