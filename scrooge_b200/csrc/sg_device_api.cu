@@ -346,10 +346,32 @@ int sg_dev_pack_2bit(const char *d_ascii, uint64_t n_bases, uint32_t *d_packed, 
     int rc = device_info(&di);
     if (rc) return rc;
     const uint64_t n_words = sg_packed_words(n_bases);  // includes zeroed padding words the aligner may read
-    const uint64_t want = (n_words + 255ull) / 256ull;
+    // the whole 16 KB tiles of the blob through the bulk-copy-staged kernel, the tail through the plain one (SG_PACK=plain:
+    // everything through the plain one)
+    static const bool bulk = [] { const char *e = std::getenv("SG_PACK"); return !(e && std::string(e) == "plain"); }();
+    uint64_t done_bases = 0;
+    if (bulk && n_bases >= (uint64_t)kPackTile) {
+        static bool attr_set[64] = {};
+        int dev = 0;
+        SG_CUDA(cudaGetDevice(&dev));
+        const int smem = kPackTile * kPackStages;
+        if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+            SG_CUDA(cudaFuncSetAttribute(pack_2bit_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_set[dev] = true;
+        }
+        const uint64_t n_tiles = n_bases / (uint64_t)kPackTile;
+        const int per_sm = std::max(1, (227 * 1024) / (smem + 1024));
+        const int blocks = (int)std::min<uint64_t>(n_tiles, (uint64_t)di->sms * (uint64_t)per_sm);
+        pack_2bit_bulk_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(d_ascii, n_tiles, d_packed, (unsigned long long *)d_bad_pos);
+        SG_CUDA(cudaGetLastError());
+        done_bases = n_tiles * (uint64_t)kPackTile;
+    }
+    const uint64_t rest_words = n_words - done_bases / 16ull;
+    const uint64_t want = (rest_words + 255ull) / 256ull;
     const int blocks = (int)std::min<uint64_t>(want, (uint64_t)di->sms * 16ull);
-    pack_2bit_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_ascii, n_bases, d_packed, n_words,
-                                                              (unsigned long long *)d_bad_pos);
+    if (rest_words)
+        pack_2bit_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_ascii, n_bases, d_packed, n_words, (unsigned long long *)d_bad_pos,
+                                                                  done_bases / 16ull);
     SG_CUDA(cudaGetLastError());
     return SG_OK;
 }
