@@ -193,6 +193,12 @@ uint64_t sg_scan_tmp_bytes(uint64_t n);
 int sg_dev_scan_runs(const uint32_t *d_nruns, uint64_t n, uint64_t *d_run_off, void *d_scan_tmp, void *stream);
 int sg_dev_gather_runs(const uint8_t *d_slab, const uint64_t *d_slab_off, const uint32_t *d_nruns,
                        const uint64_t *d_run_off, uint64_t n, uint8_t *d_runs, void *stream);
+/* The same with what the caller knows about the batch: runs_per_alignment_hint = an upper estimate of the runs of a typical
+ * alignment (e.g. its slab capacity; 0 = unknown).  Batches of short alignments (hint <= 1024) are gathered by four lanes
+ * per alignment instead of a warp. */
+int sg_dev_gather_runs_sized(const uint8_t *d_slab, const uint64_t *d_slab_off, const uint32_t *d_nruns,
+                             const uint64_t *d_run_off, uint64_t n, uint8_t *d_runs, uint64_t runs_per_alignment_hint,
+                             void *stream);
 
 /* Measurement / test helper: consistency of a batch's compacted runs with its other results, for EVERY alignment --
  * the sequence-independent properties of the reference's validateCigarString (src/tests.cu:106-169): every run count

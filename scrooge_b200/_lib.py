@@ -66,6 +66,7 @@ SIGNATURES = {
     "sg_scan_tmp_bytes": (u64, [u64]),
     "sg_dev_scan_runs": (i32, [vp, u64, vp, vp, vp]),
     "sg_dev_gather_runs": (i32, [vp, vp, vp, vp, u64, vp, vp]),
+    "sg_dev_gather_runs_sized": (i32, [vp, vp, vp, vp, u64, vp, u64, vp]),
     "sg_dev_align_geometry": (i32, [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
     "sg_dev_int32_peak": (i32, [i32, dbl, C.POINTER(dbl)]),
     "sg_synth_text_stride": (u64, [u32, u32]),

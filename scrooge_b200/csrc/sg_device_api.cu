@@ -508,6 +508,12 @@ int sg_dev_scan_runs(const uint32_t *d_nruns, uint64_t n, uint64_t *d_run_off, v
 int sg_dev_gather_runs(const uint8_t *d_slab, const uint64_t *d_slab_off, const uint32_t *d_nruns,
                        const uint64_t *d_run_off, uint64_t n, uint8_t *d_runs, void *stream)
 {
+    return sg_dev_gather_runs_sized(d_slab, d_slab_off, d_nruns, d_run_off, n, d_runs, 0, stream);
+}
+
+int sg_dev_gather_runs_sized(const uint8_t *d_slab, const uint64_t *d_slab_off, const uint32_t *d_nruns,
+                             const uint64_t *d_run_off, uint64_t n, uint8_t *d_runs, uint64_t runs_per_alignment_hint, void *stream)
+{
     if (n == 0) return SG_OK;
     if (!d_slab || !d_slab_off || !d_nruns || !d_run_off || !d_runs)
         return fail(SG_ERR_BAD_ARG, "sg_dev_gather_runs: null pointer");
@@ -515,11 +521,17 @@ int sg_dev_gather_runs(const uint8_t *d_slab, const uint64_t *d_slab_off, const 
     int rc = device_info(&di);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    // a warp per alignment (long reads have thousands of runs; short reads a handful, where the gather is
-    // a negligible part of the step either way)
-    const uint64_t want = (n * 32ull + 255ull) / 256ull;
-    const unsigned blocks = (unsigned)std::min<uint64_t>(want, (uint64_t)di->sms * 32ull);
-    gather_runs_kernel<32><<<blocks, 256, 0, st>>>(d_slab, d_slab_off, d_nruns, d_run_off, n, d_runs);
+    // a warp per alignment when alignments have hundreds of runs or more (or nothing is known: hint 0); four lanes per
+    // alignment when they have a handful (10 M short reads: the warp-wide version leaves 28 of 32 lanes idle)
+    if (runs_per_alignment_hint != 0 && runs_per_alignment_hint <= 1024) {
+        const uint64_t want = (n * 4ull + 255ull) / 256ull;
+        const unsigned blocks = (unsigned)std::min<uint64_t>(want, (uint64_t)di->sms * 32ull);
+        gather_runs_kernel<4><<<blocks, 256, 0, st>>>(d_slab, d_slab_off, d_nruns, d_run_off, n, d_runs);
+    } else {
+        const uint64_t want = (n * 32ull + 255ull) / 256ull;
+        const unsigned blocks = (unsigned)std::min<uint64_t>(want, (uint64_t)di->sms * 32ull);
+        gather_runs_kernel<32><<<blocks, 256, 0, st>>>(d_slab, d_slab_off, d_nruns, d_run_off, n, d_runs);
+    }
     SG_CUDA(cudaGetLastError());
     return SG_OK;
 }

@@ -565,8 +565,9 @@ int stage_b(Slot &s, const Workload &w, sg_result *res)
         g_pool.release(s.piece);
         s.piece = {nullptr, 0};
         R(g_pool.acquire(s.total_runs + 16, &s.piece));
-        R(sg_dev_gather_runs(s.slab.as<uint8_t>(), s.desc.as<uint64_t>() + 4 * n, s.nruns.as<uint32_t>(), s.run_off.as<uint64_t>(), n,
-                             s.runs.as<uint8_t>(), st));
+        // the mean number of runs per alignment of this sub-batch is known by now: short alignments are gathered by four lanes
+        R(sg_dev_gather_runs_sized(s.slab.as<uint8_t>(), s.desc.as<uint64_t>() + 4 * n, s.nruns.as<uint32_t>(), s.run_off.as<uint64_t>(), n,
+                                   s.runs.as<uint8_t>(), std::max<uint64_t>(1, (s.total_runs + n - 1) / n), st));
         SG_CUDA(cudaMemcpyAsync(s.piece.p, s.runs.p, s.total_runs, cudaMemcpyDeviceToHost, st));
         SG_CUDA(cudaMemcpyAsync(res->run_off + s.a0, s.run_off.p, n * 8, cudaMemcpyDeviceToHost, st));  // sub-batch-local, rebased in finalize()
     }

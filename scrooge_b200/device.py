@@ -83,7 +83,10 @@ class DeviceAligner:
         if runs is None:
             total = int(self.run_off[-1].item())
             runs = torch.empty(max(total, 1), dtype=torch.uint8, device=self.device)
-        check(lib().sg_dev_gather_runs(_p(self.slab), _p(slab_off), _p(o.nruns), _p(self.run_off), self.n, _p(runs), _stream()))
+        # hint: the slab capacity per alignment (an upper bound of its runs); short alignments are gathered by four lanes
+        hint = int(self.slab.numel() // max(self.n, 1)) if self.slab is not None else 0
+        check(lib().sg_dev_gather_runs_sized(_p(self.slab), _p(slab_off), _p(o.nruns), _p(self.run_off), self.n, _p(runs), hint,
+                                             _stream()))
         return self.run_off, runs
 
 
