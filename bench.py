@@ -383,7 +383,8 @@ def main():
                            (n * stride + n * L) / 1e9, (words_t + words_q) * 4 / 1e9),
                        "step": "ingest(ASCII->2bit) + align(DC+TB+RLE) + compaction(scan+gather), inputs resident in HBM"},
             "gcups": value * L * L / 1e9, "mean_edit_distance": mean_ed, "runs_per_alignment": total_runs / n,
-            "gpu_launches": args.steps * 9,   # 2 x (bulk-staged ingest + its tail), alignment, 3 scan passes, gather "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+            # launches per step: 2 x (bulk-staged ingest + its tail), alignment, 3 scan passes, gather
+            "gpu_launches": args.steps * 9, "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
             "parity": parity}
     print(json.dumps(line))
     if world > 1:
