@@ -74,3 +74,19 @@ def test_odd_windows_model(oracle, W, O):
     for k in range(len(T)):
         ed, cg, rc, _ = align_delta_generic(T[k], Q[k], W, O)
         assert (ed, cg, rc) == (int(res.edit[k]), res.cigars[k], int(res.ref_consumed[k])), (W, O, T[k], Q[k])
+
+
+def test_random_windows_model(oracle):
+    """Thirty random (W, O) of the supported range: the general kernel's formulation (padded vectors, full-width planes, op
+    streams of 4 or 8 words, stream RLE) against the oracle."""
+    import random
+    from kernel_model import align_delta_generic
+    rng = random.Random(4711)
+    for _ in range(30):
+        W = rng.choice([rng.randint(2, 256), rng.choice([31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256])])
+        O = rng.randint(max(0, W - 128), W - 1)
+        T, Q = random_pairs(rng.randrange(1 << 30), 16, [0, 1, 2, W - 1, W, W + 1, 2 * W + 1, 300], [0, 0.05, 0.3, 0.6])
+        res = oracle.align_pairs(T, Q, W=W, O=O)
+        for k in range(len(T)):
+            ed, cg, rc, _ = align_delta_generic(T[k], Q[k], W, O)
+            assert (ed, cg, rc) == (int(res.edit[k]), res.cigars[k], int(res.ref_consumed[k])), (W, O, T[k], Q[k])
