@@ -1,5 +1,7 @@
 # Builds the product library (sm_100a only) in-tree:
 #   scrooge_b200/lib/libscrooge_b200.so   C ABI of include/scrooge_b200.h + C++ drop-in genasm_gpu::align_all
+#   scrooge_b200/lib/libscrooge_b200_rdc.a  the reference header's one exported kernel (src/genasm_gpu.hpp:9) as relocatable
+#                                           device code, for callers built like the reference (-rdc=true) that launch it
 #   build/library_example, build/sg_tests  (C++ programs mirroring the reference's library_example / tests binaries)
 # The oracle (test infrastructure) is built by oracle/Makefile.
 NVCC ?= /usr/local/cuda/bin/nvcc
@@ -12,7 +14,14 @@ LIB := scrooge_b200/lib/libscrooge_b200.so
 OBJS := build/sg_device_api.o build/sg_host_api.o build/genasm_gpu.o build/sg_host_pack.o build/sg_io.o
 HDRS := $(wildcard $(SRC)/*.cuh $(SRC)/*.h include/*.h include/*.hpp)
 
-all: $(LIB) build/library_example build/sg_tests
+RDC := scrooge_b200/lib/libscrooge_b200_rdc.a
+
+all: $(LIB) $(RDC) build/library_example build/sg_tests
+
+$(RDC): $(SRC)/sg_dropin_rdc.cu
+	@mkdir -p build scrooge_b200/lib
+	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -rdc=true -ccbin $(CCBIN) -Xcompiler -fPIC -c $< -o build/sg_dropin_rdc.o
+	rm -f $@ && ar rcs $@ build/sg_dropin_rdc.o
 
 build/%.o: $(SRC)/%.cu $(HDRS)
 	@mkdir -p build

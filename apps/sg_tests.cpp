@@ -10,7 +10,7 @@
 
 #include "genasm_gpu.hpp"
 #include "scrooge_b200.h"
-#include "util.hpp"
+#include "scrooge_io.hpp"
 
 using namespace std;
 

@@ -5,6 +5,12 @@
 // shared; the file-format readers the reference declares next to them (FASTA/FASTQ/MAF/PAF, SURVEY.md
 // section 8f-3) are outside this library.
 #pragma once
+// The reference's util.hpp defines the same names (it sets SEED_FILE_MAF, src/util.hpp:8): when it came first, its
+// definitions stand and this header adds nothing.
+#if !defined(SEED_FILE_MAF) || defined(SCROOGE_B200_TYPES)
+#ifndef SCROOGE_B200_TYPES
+#define SCROOGE_B200_TYPES 1
+#endif
 
 #include <chrono>
 #include <cstdint>
@@ -66,3 +72,5 @@ template <typename Fn> long long measure_ns(Fn fn)
     const auto t1 = std::chrono::high_resolution_clock::now();
     return std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
 }
+
+#endif  // the reference's util.hpp was not included first

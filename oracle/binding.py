@@ -50,6 +50,22 @@ def build(force: bool = False) -> None:
     if os.path.exists(src) and (force or not os.path.exists(out)
                                 or os.path.getmtime(out) < os.path.getmtime(os.path.join(HERE, "ref_gpu_shim.cpp"))):
         subprocess.check_call(["make", "-s", "-C", HERE, "refgpu"], stdout=subprocess.DEVNULL)
+    build_dropin(force)
+
+
+def build_dropin(force: bool = False) -> bool:
+    """The reference's own callers (src/library_example.cu, src/tests.cu), unmodified, linked against the product
+    library in place of src/genasm_gpu.cu (oracle/Makefile `dropin`).  Needs /root/reference and the built product
+    library; returns whether the binaries exist afterwards."""
+    outs = [os.path.join(REF_DIR, n) for n in ("dropin_library_example", "dropin_library_example_gxx", "dropin_tests")]
+    lib_dir = os.path.join(os.path.dirname(HERE), "scrooge_b200", "lib")
+    deps = [os.path.join(lib_dir, "libscrooge_b200.so"), os.path.join(lib_dir, "libscrooge_b200_rdc.a")]
+    if os.path.exists("/root/reference/src/library_example.cu") and all(os.path.exists(d) for d in deps):
+        stale = force or not all(os.path.exists(o) for o in outs) or \
+            min(os.path.getmtime(o) for o in outs) < os.path.getmtime(deps[1])
+        if stale:
+            subprocess.check_call(["make", "-s", "-C", HERE, "dropin"], stdout=subprocess.DEVNULL)
+    return all(os.path.exists(o) for o in outs)
 
 
 def _blob(strings: Sequence[str | bytes]) -> Tuple[bytes, np.ndarray]:
