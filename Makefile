@@ -2,6 +2,7 @@
 #   scrooge_b200/lib/libscrooge_b200.so   C ABI of include/scrooge_b200.h + C++ drop-in genasm_gpu::align_all
 #   scrooge_b200/lib/libscrooge_b200_rdc.a  the reference header's one exported kernel (src/genasm_gpu.hpp:9) as relocatable
 #                                           device code, for callers built like the reference (-rdc=true) that launch it
+#   scrooge_b200/lib/libscrooge_b200_bench.so  synthetic generators, peak probes, batch checker (bench.py / tests / apps only)
 #   build/library_example, build/sg_tests  (C++ programs mirroring the reference's library_example / tests binaries)
 # The oracle (test infrastructure) is built by oracle/Makefile.
 NVCC ?= /usr/local/cuda/bin/nvcc
@@ -15,8 +16,14 @@ OBJS := build/sg_device_api.o build/sg_host_api.o build/genasm_gpu.o build/sg_ho
 HDRS := $(wildcard $(SRC)/*.cuh $(SRC)/*.h include/*.h include/*.hpp)
 
 RDC := scrooge_b200/lib/libscrooge_b200_rdc.a
+# measurement / synthetic-data / checking helpers (include/scrooge_b200_bench.h): NOT in the product library
+BENCHLIB := scrooge_b200/lib/libscrooge_b200_bench.so
 
-all: $(LIB) $(RDC) build/library_example build/sg_tests
+all: $(LIB) $(RDC) $(BENCHLIB) build/library_example build/sg_tests
+
+$(BENCHLIB): build/sg_bench_api.o
+	@mkdir -p scrooge_b200/lib
+	$(NVCC) $(ARCH) -shared -ccbin $(CCBIN) -Xcompiler -fopenmp -o $@ build/sg_bench_api.o -lcudart -lgomp
 
 $(RDC): $(SRC)/sg_dropin_rdc.cu
 	@mkdir -p build scrooge_b200/lib
@@ -47,8 +54,8 @@ $(LIB): $(OBJS)
 build/library_example: examples/library_example.cpp $(LIB) $(HDRS)
 	$(CCBIN) -O2 -std=c++17 -Iinclude -o $@ $< -Lscrooge_b200/lib -lscrooge_b200 -Wl,-rpath,'$$ORIGIN/../scrooge_b200/lib'
 
-build/sg_tests: apps/sg_tests.cpp $(LIB) $(HDRS)
-	$(CCBIN) -O2 -std=c++17 -Wall -Iinclude -o $@ $< -Lscrooge_b200/lib -lscrooge_b200 -Wl,-rpath,'$$ORIGIN/../scrooge_b200/lib'
+build/sg_tests: apps/sg_tests.cpp $(LIB) $(BENCHLIB) $(HDRS)
+	$(CCBIN) -O2 -std=c++17 -Wall -Iinclude -o $@ $< -Lscrooge_b200/lib -lscrooge_b200 -lscrooge_b200_bench -Wl,-rpath,'$$ORIGIN/../scrooge_b200/lib'
 
 clean:
 	rm -rf build scrooge_b200/lib

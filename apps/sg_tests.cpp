@@ -10,6 +10,7 @@
 
 #include "genasm_gpu.hpp"
 #include "scrooge_b200.h"
+#include "scrooge_b200_bench.h"
 #include "scrooge_io.hpp"
 
 using namespace std;

@@ -68,6 +68,12 @@ SIGNATURES = {
     "sg_dev_gather_runs": (i32, [vp, vp, vp, vp, u64, vp, vp]),
     "sg_dev_gather_runs_sized": (i32, [vp, vp, vp, vp, u64, vp, u64, vp]),
     "sg_dev_align_geometry": (i32, [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+}
+
+# name -> (restype, argtypes); every symbol include/scrooge_b200_bench.h declares (libscrooge_b200_bench.so: synthetic
+# generators, peak probes, the batch checker -- measurement and test helpers, not part of the product library)
+BENCH_SIGNATURES = {
+    "sg_bench_last_error": (cp, []),
     "sg_dev_int32_peak": (i32, [i32, dbl, C.POINTER(dbl)]),
     "sg_synth_text_stride": (u64, [u32, u32]),
     "sg_dev_check_runs": (i32, [vp, vp, u64, vp, vp, vp, u32, vp, vp]),
@@ -78,6 +84,7 @@ SIGNATURES = {
 }
 
 _lib = None
+_bench = None
 
 
 class ScroogeError(RuntimeError):
@@ -106,6 +113,27 @@ def lib() -> C.CDLL:
             fn.argtypes = args
         _lib = l
     return _lib
+
+
+def bench_lib() -> C.CDLL:
+    """libscrooge_b200_bench.so (include/scrooge_b200_bench.h); independent of the product library."""
+    global _bench
+    if _bench is None:
+        path = os.environ.get("SG_BENCH_LIB") or os.path.join(os.path.dirname(LIB_PATH), "libscrooge_b200_bench.so")
+        if not os.path.exists(path):
+            raise ImportError(f"{path} is missing: run `make` (or __graft_entry__.build())")
+        l = C.CDLL(path)
+        for name, (res, args) in BENCH_SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _bench = l
+    return _bench
+
+
+def bench_check(rc: int) -> None:
+    if rc != SG_OK:
+        raise ScroogeError(rc, bench_lib().sg_bench_last_error().decode(errors="replace"))
 
 
 def check(rc: int) -> None:

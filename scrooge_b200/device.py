@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from ._lib import SG_FLAG_DISTANCE_ONLY, check, lib
+from ._lib import SG_FLAG_DISTANCE_ONLY, bench_check, bench_lib, check, lib
 
 U64_MAX = (1 << 64) - 1
 
@@ -96,7 +96,7 @@ def check_runs(runs: torch.Tensor, run_off: torch.Tensor, query_len: torch.Tenso
     distance (sg_dev_check_runs: the sequence-independent validateCigarString properties on the whole batch)."""
     n = query_len.numel()
     bad = torch.zeros(1, dtype=torch.int64, device=runs.device)
-    check(lib().sg_dev_check_runs(_p(runs), _p(run_off), n, _p(query_len), _p(out.edit), _p(out.ref_consumed),
+    bench_check(bench_lib().sg_dev_check_runs(_p(runs), _p(run_off), n, _p(query_len), _p(out.edit), _p(out.ref_consumed),
                                   W - (min(W // 2 + 1, W - 1) if O is None else O), _p(bad), _stream()))
     return int(bad.item())
 
@@ -109,17 +109,17 @@ def align_geometry(W: int, O: Optional[int] = None) -> Tuple[int, int, int]:
 
 def int32_peak(kind: int = 2, ms: float = 50.0) -> float:
     g = C.c_double()
-    check(lib().sg_dev_int32_peak(kind, ms, C.byref(g)))
+    bench_check(bench_lib().sg_dev_int32_peak(kind, ms, C.byref(g)))
     return g.value
 
 
 def synth_pairs_device(seed: int, first_pair: int, n_pairs: int, read_len: int, err: float, ratio: Tuple[int, int, int],
                        slack: int, device: torch.device):
     """Generates pairs on the device.  Returns (text uint8 [n, stride], text_len int64 [n], reads uint8 [n, L])."""
-    stride = int(lib().sg_synth_text_stride(read_len, slack))
+    stride = int(bench_lib().sg_synth_text_stride(read_len, slack))
     text = torch.empty((n_pairs, stride), dtype=torch.uint8, device=device)
     tlen = torch.empty(n_pairs, dtype=torch.int64, device=device)
     reads = torch.empty((n_pairs, read_len), dtype=torch.uint8, device=device)
-    check(lib().sg_dev_synth_pairs(seed, first_pair, n_pairs, read_len, float(err), ratio[0], ratio[1], ratio[2], slack,
+    bench_check(bench_lib().sg_dev_synth_pairs(seed, first_pair, n_pairs, read_len, float(err), ratio[0], ratio[1], ratio[2], slack,
                                    _p(text), stride, _p(tlen), _p(reads), _stream()))
     return text, tlen, reads

@@ -6,7 +6,7 @@ from typing import List, Optional, Tuple
 
 import numpy as np
 
-from ._lib import check, lib
+from ._lib import bench_check, bench_lib, check, lib
 
 PACBIO = (6, 50, 54)     # sub:ins:del, reference DATASETS.md:51 (--difference-ratio)
 ILLUMINA = (90, 5, 5)    # substitution dominated (our choice; the reference does not specify one)
@@ -47,7 +47,7 @@ WORKLOADS = {
 
 
 def text_stride(read_len: int, slack: int = 64) -> int:
-    return int(lib().sg_synth_text_stride(read_len, slack))
+    return int(bench_lib().sg_synth_text_stride(read_len, slack))
 
 
 def pairs_host(wl: Workload, first_pair: int, n_pairs: int):
@@ -56,7 +56,7 @@ def pairs_host(wl: Workload, first_pair: int, n_pairs: int):
     text = np.empty((n_pairs, stride), dtype=np.uint8)
     tlen = np.empty(n_pairs, dtype=np.uint64)
     reads = np.empty((n_pairs, wl.read_len), dtype=np.uint8)
-    check(lib().sg_synth_pairs_host(wl.seed, first_pair, n_pairs, wl.read_len, float(wl.err), wl.ratio[0], wl.ratio[1],
+    bench_check(bench_lib().sg_synth_pairs_host(wl.seed, first_pair, n_pairs, wl.read_len, float(wl.err), wl.ratio[0], wl.ratio[1],
                                     wl.ratio[2], wl.slack, text.ctypes.data, stride, tlen.ctypes.data, reads.ctypes.data))
     return text, tlen, reads
 

@@ -10,8 +10,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    src = open(os.path.join(ROOT, "include", "scrooge_b200.h")).read()
+def declared_symbols(header="scrooge_b200.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(sg_[a-z0-9_]+)\s*\(", src)))
 
@@ -24,6 +24,19 @@ def test_header_symbols_are_exported_and_bound(sglib):
         assert hasattr(sglib, n), f"{n} declared in the header but not exported"
         assert n in SIGNATURES, f"{n} has no ctypes signature"
     assert sorted(SIGNATURES) == names
+
+
+def test_bench_helpers_live_in_their_own_library(sglib):
+    """Synthetic generators, peak probes and the batch checker are not product code: they are declared in
+    scrooge_b200_bench.h, exported by libscrooge_b200_bench.so and absent from libscrooge_b200.so."""
+    import scrooge_b200
+    from scrooge_b200._lib import BENCH_SIGNATURES
+    bl = scrooge_b200.bench_lib()
+    names = declared_symbols("scrooge_b200_bench.h")
+    assert sorted(BENCH_SIGNATURES) == names and len(names) >= 7
+    for n in names:
+        assert hasattr(bl, n), f"{n} declared in scrooge_b200_bench.h but not exported"
+        assert not hasattr(sglib, n), f"{n} is a bench helper but libscrooge_b200.so exports it"
 
 
 def test_no_cpu_fallback(sglib):

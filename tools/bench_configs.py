@@ -165,10 +165,10 @@ def cmd_mapping(args, peak):
     seed = synth.BASE_SEED + 4
     t0 = time.time()
     genome = torch.empty(G, dtype=torch.uint8, device=dev)
-    scrooge_b200._lib.check(lib.sg_synth_genome(seed, 0, G, None, p(genome), stream()))
+    scrooge_b200._lib.check(scrooge_b200.bench_lib().sg_synth_genome(seed, 0, G, None, p(genome), stream()))
     reads = torch.empty((n_reads, L), dtype=torch.uint8, device=dev)
     pos = torch.empty(n_reads, dtype=torch.int64, device=dev)
-    scrooge_b200._lib.check(lib.sg_synth_reads(seed + 1, 0, n_reads, L, 0.10, 6, 50, 54, p(genome), G, p(reads), p(pos), 1, stream()))
+    scrooge_b200._lib.check(scrooge_b200.bench_lib().sg_synth_reads(seed + 1, 0, n_reads, L, 0.10, 6, 50, 54, p(genome), G, p(reads), p(pos), 1, stream()))
     pgenome, bad_g = device.pack_2bit(genome)   # one packed copy of the reference, resident in HBM
     preads, bad_r = device.pack_2bit(reads.view(-1))
     torch.cuda.synchronize()

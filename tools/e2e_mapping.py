@@ -29,10 +29,10 @@ st = int(torch.cuda.current_stream().cuda_stream)
 seed = synth.BASE_SEED + 4
 t0 = time.time()
 genome = torch.empty(G, dtype=torch.uint8, device=dev)
-check(lib.sg_synth_genome(seed, 0, G, None, p(genome), st))
+check(scrooge_b200.bench_lib().sg_synth_genome(seed, 0, G, None, p(genome), st))
 reads = torch.empty((n_reads, L), dtype=torch.uint8, device=dev)
 pos = torch.empty(n_reads, dtype=torch.int64, device=dev)
-check(lib.sg_synth_reads(seed + 1, 0, n_reads, L, 0.10, 6, 50, 54, p(genome), G, p(reads), p(pos), 1, st))
+check(scrooge_b200.bench_lib().sg_synth_reads(seed + 1, 0, n_reads, L, 0.10, 6, 50, 54, p(genome), G, p(reads), p(pos), 1, st))
 h_genome = torch.empty(G, dtype=torch.uint8, pin_memory=True).copy_(genome)
 h_reads = torch.empty((n_reads, L), dtype=torch.uint8, pin_memory=True).copy_(reads)
 gcpu = torch.Generator(device="cpu").manual_seed(7)
