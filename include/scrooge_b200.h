@@ -76,6 +76,11 @@ int sg_device_count(void);
 
 /* Create a context over n_devices GPUs (device_ids == NULL: devices 0..n_devices-1; n_devices == 0: all).
  * W is 64 (O=33) or 32 (O=17).  Replaces the reference's hard-wired GPU_ID 0 (src/genasm_gpu.cu:67). */
+/* Host threads: every GPU of a context gets a disjoint share of the CPUs the process may run on (its affinity mask, or
+ * SG_CPUS=<cpu list>), NUMA-local to the GPU where the machine says so, and a persistent team of packer threads bound to
+ * it (SG_HOST_THREADS=<n per GPU>, 0 = none: all input crosses PCIe as ASCII; SG_AFFINITY=0 = no binding).  During a call
+ * on a single-GPU context the calling thread is bound to that share too and restored on return; the caller's current
+ * CUDA device is restored likewise. */
 int sg_ctx_create(sg_ctx **out, const int *device_ids, int n_devices, int W);
 /* The same with an explicit window configuration: 2 <= W <= 256, 0 <= O < W, W-O <= 128.  Replaces a rebuild of the reference with -DCLI_W=<W> -DCLI_K=<W> -DCLI_O=<O>
  * (src/genasm_cpu.cpp:22-35, scripts/profile.py:29,132). */
@@ -136,6 +141,28 @@ int64_t sg_result_entries(const sg_result *r, uint64_t idx, sg_cigar_entry *out,
 uint64_t sg_result_render_all(const sg_result *r, char *blob, uint64_t blob_cap, uint64_t *text_off, int threads);
 void sg_result_free(sg_result *r);
 
+/* Where the time and the PCIe bytes of the call that produced r went (the end-to-end path is bound by the host, so this is
+ * what explains an end-to-end number).  Times are wall-clock; "max over GPUs" = the slowest GPU's worker thread. */
+typedef struct sg_call_stats {
+    int64_t total_ns;           /* the whole call */
+    int64_t kernel_ns;          /* alignment kernels only, max over GPUs (= sg_result_kernel_ns) */
+    int64_t upload_ns;          /* ingest phase of all sub-batches: host packing + queuing of the copies, max over GPUs */
+    int64_t pack_thread_ns;     /* time inside the packing loops, summed over all packer threads of all GPUs */
+    int64_t wait_ns;            /* blocked on the device (kernels, compaction, copies back), max over GPUs */
+    int64_t host_other_ns;      /* descriptors + result bookkeeping, max over GPUs */
+    uint64_t h2d_ascii_bytes;   /* crossed PCIe as ASCII (packed by the ingest kernel) */
+    uint64_t h2d_packed_bytes;  /* crossed PCIe at 2 bit/base (packed by the host threads) */
+    uint64_t h2d_other_bytes;   /* descriptors */
+    uint64_t d2h_bytes;         /* distances, consumed prefixes, run offsets, packed runs */
+    uint32_t n_devices, sub_batches, host_threads_per_device, reserved;
+} sg_call_stats;
+int sg_result_stats(const sg_result *r, sg_call_stats *out);
+
+/* Result blocks live in page-locked memory; freed blocks are kept for reuse in a per-process cache of at most
+ * min(RAM/32, 4 GB) (SG_PINNED_CACHE_GB=<n> overrides, 0 = keep nothing).  sg_trim_host_cache releases the cache now; the
+ * destruction of a process's last context does the same. */
+void sg_trim_host_cache(void);
+
 /* Page-locked host memory for input blobs: uploads from it run at full PCIe speed and overlap with compute
  * (pageable memory works too, but the driver then stages every copy).  NULL on failure. */
 void *sg_host_alloc(uint64_t bytes);
@@ -185,6 +212,17 @@ int sg_dev_align_wo(int W, int O, const uint32_t *d_text, const uint64_t *d_text
                     uint64_t n, uint32_t flags, uint8_t *d_slab, const uint64_t *d_slab_off,
                     uint64_t *d_counter, int64_t *d_edit, uint64_t *d_ref_consumed, uint32_t *d_nruns,
                     uint8_t *d_status, uint64_t *d_dc_entries, uint32_t *d_windows, void *stream);
+
+/* The same with a launch order: the kernel's work queue hands out alignment d_order[k] as its k-th item (d_order: a
+ * permutation of 0..n-1, n < 2^32; NULL = input order).  Results stay indexed by alignment.  With alignments of very
+ * different lengths in one launch, longest-first order keeps the last lanes from finishing long after the rest -- what
+ * the reference's callers do by sorting their reads before the call (src/tests.cu:377). */
+int sg_dev_align_ordered(int W, int O, const uint32_t *d_text, const uint64_t *d_text_start, const uint64_t *d_text_len,
+                         const uint32_t *d_query, const uint64_t *d_query_start, const uint64_t *d_query_len,
+                         uint64_t n, uint32_t flags, uint8_t *d_slab, const uint64_t *d_slab_off,
+                         uint64_t *d_counter, int64_t *d_edit, uint64_t *d_ref_consumed, uint32_t *d_nruns,
+                         uint8_t *d_status, uint64_t *d_dc_entries, uint32_t *d_windows, const uint32_t *d_order,
+                         void *stream);
 
 /* CIGAR compaction: exclusive scan of d_nruns into d_run_off[n+1] (d_scan_tmp: sg_scan_tmp_bytes(n)
  * bytes), then gather every alignment's runs from its slab slot into one dense array.

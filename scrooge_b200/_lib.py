@@ -54,6 +54,8 @@ SIGNATURES = {
     "sg_result_entries": (i64, [vp, u64, vp, u64]),
     "sg_result_render_all": (u64, [vp, vp, u64, vp, i32]),
     "sg_result_free": (None, [vp]),
+    "sg_result_stats": (i32, [vp, vp]),
+    "sg_trim_host_cache": (None, []),
     "sg_host_alloc": (vp, [u64]),
     "sg_host_free": (None, [vp]),
     "sg_host_pack_2bit": (u64, [vp, u64, vp, i32]),
@@ -62,6 +64,7 @@ SIGNATURES = {
     "sg_dev_pack_2bit": (i32, [vp, u64, vp, vp, vp]),
     "sg_dev_align": (i32, [i32, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "sg_dev_align_wo": (i32, [i32, i32, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "sg_dev_align_ordered": (i32, [i32, i32, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "sg_dev_align_geometry_wo": (i32, [i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
     "sg_scan_tmp_bytes": (u64, [u64]),
     "sg_dev_scan_runs": (i32, [vp, u64, vp, vp, vp]),
@@ -82,6 +85,13 @@ BENCH_SIGNATURES = {
     "sg_synth_genome": (i32, [u64, u64, u64, vp, vp, vp]),
     "sg_synth_reads": (i32, [u64, u64, u64, u32, dbl, u32, u32, u32, vp, u64, vp, vp, i32, vp]),
 }
+
+class CallStats(C.Structure):
+    """sg_call_stats (include/scrooge_b200.h)."""
+    _fields_ = [("total_ns", i64), ("kernel_ns", i64), ("upload_ns", i64), ("pack_thread_ns", i64), ("wait_ns", i64),
+                ("host_other_ns", i64), ("h2d_ascii_bytes", u64), ("h2d_packed_bytes", u64), ("h2d_other_bytes", u64),
+                ("d2h_bytes", u64), ("n_devices", u32), ("sub_batches", u32), ("host_threads_per_device", u32), ("reserved", u32)]
+
 
 _lib = None
 _bench = None

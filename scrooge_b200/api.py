@@ -77,6 +77,12 @@ class Result:
                 pass
             self._h = None
 
+    def stats(self) -> dict:
+        """sg_call_stats of the call that produced this result: where its time and its PCIe bytes went."""
+        st = _lib.CallStats()
+        check(lib().sg_result_stats(self._h, C.byref(st)))
+        return {name: int(getattr(st, name)) for name, _ in st._fields_ if name != "reserved"}
+
     def _arr(self, ptr, n, dtype):
         if not ptr or n == 0:
             return np.zeros(0, dtype=dtype)

@@ -4,6 +4,7 @@
 // sg_set_reference + sg_align_candidates, renders the packed runs to CIGAR text with all host threads
 // (the reference renders serially through a stringstream per alignment, src/genasm_gpu.cu:881-888,
 // 1049-1053 -- 20x its kernel time in its own README transcript, README.md:103-108).
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -26,8 +27,36 @@ namespace {
 struct Holder {
     sg_ctx *ctx = nullptr;
     int W = 0, O = 0, n_gpus = 0;
+    // the genome resident on the GPUs: (address, length, content hash) of the Genome_t::content it was packed from
+    const char *genome_ptr = nullptr;
+    uint64_t genome_len = 0, genome_hash = 0;
+    bool have_genome = false;
     ~Holder() { if (ctx) sg_ctx_destroy(ctx); }
 };
+
+// 64-bit content hash of a byte range, all host threads (a 3 Gbp genome at memory speed: ~30 ms, against ~100 ms per GPU
+// for uploading and packing it again).  Every byte takes part: a caller that edits the genome in place gets a new upload.
+uint64_t content_hash(const char *p, uint64_t n)
+{
+    const uint64_t blk = 1ull << 20, nblk = (n + blk - 1) / blk;
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ n;
+#pragma omp parallel for schedule(static) reduction(^ : h)
+    for (long long b = 0; b < (long long)nblk; b++) {
+        const uint64_t a0 = (uint64_t)b * blk, a1 = std::min(n, a0 + blk);
+        uint64_t x[4] = {0x243F6A8885A308D3ull + (uint64_t)b, 0x13198A2E03707344ull, 0xA4093822299F31D0ull, 0x082EFA98EC4E6C89ull};
+        uint64_t i = a0;
+        for (; i + 32 <= a1; i += 32) {
+            uint64_t w[4];
+            memcpy(w, p + i, 32);
+            for (int k = 0; k < 4; k++) { x[k] = (x[k] ^ w[k]) * 0xFF51AFD7ED558CCDull; x[k] ^= x[k] >> 29; }
+        }
+        for (; i < a1; i++) { x[0] = (x[0] ^ (uint8_t)p[i]) * 0xFF51AFD7ED558CCDull; x[0] ^= x[0] >> 29; }
+        uint64_t m = x[0] ^ (x[1] * 3) ^ (x[2] * 5) ^ (x[3] * 7);
+        m = (m ^ (m >> 33)) * 0xC4CEB9FE1A85EC53ull;
+        h ^= m + 0x9E3779B97F4A7C15ull * (uint64_t)(b + 1);
+    }
+    return h;
+}
 
 std::mutex g_mutex;  // calls are serialised per process (the reference is not re-entrant either)
 Holder g_holder;
@@ -46,6 +75,7 @@ sg_ctx *context()
     if (g_holder.ctx && (g_holder.W != W || g_holder.O != O || g_holder.n_gpus != n)) {
         sg_ctx_destroy(g_holder.ctx);
         g_holder.ctx = nullptr;
+        g_holder.have_genome = false;
     }
     if (!g_holder.ctx) {
         if (sg_ctx_create_wo(&g_holder.ctx, nullptr, n, W, O) != SG_OK)
@@ -70,14 +100,24 @@ std::vector<Alignment_t> collect(sg_result *res, Extra *extra, long long *core_a
     const int64_t *ed = sg_result_edit_distances(res);
     const uint64_t *rc = sg_result_ref_consumed(res);
     if (extra) extra->ref_consumed.resize(n);
-    // every string is sized and rendered in place, all host threads at once
-#pragma omp parallel for schedule(dynamic, 64)
-    for (long long i = 0; i < (long long)n; i++) {
-        const uint64_t len = sg_result_cigar_len(res, (uint64_t)i);
-        out[i].cigar.resize(len);
-        if (len) sg_result_render_cigar(res, (uint64_t)i, &out[i].cigar[0], len + 1);  // the string owns the NUL slot
-        out[i].edit_distance = ed[i];
-        if (extra) extra->ref_consumed[i] = rc[i];
+    // Every CIGAR is rendered into a per-thread scratch that stays in cache (3 characters per run at most) and copied
+    // into its string from there: the string's memory is written once (resize-then-render would zero-fill it first),
+    // all host threads at once.
+    const uint64_t *ro = sg_result_run_offsets(res);
+#pragma omp parallel
+    {
+        std::vector<char> scratch(4096);
+#pragma omp for schedule(dynamic, 64)
+        for (long long i = 0; i < (long long)n; i++) {
+            const uint64_t runs = ro ? ro[i + 1] - ro[i] : 0;
+            if (runs) {
+                if (scratch.size() < 4 * runs + 8) scratch.resize(4 * runs + 8);
+                const int64_t len = sg_result_render_cigar(res, (uint64_t)i, scratch.data(), scratch.size());
+                if (len > 0) out[i].cigar.assign(scratch.data(), (size_t)len);
+            }
+            out[i].edit_distance = ed[i];
+            if (extra) extra->ref_consumed[i] = rc[i];
+        }
     }
     const long long ns = sg_result_kernel_ns(res);
     if (core_algorithm_ns) *core_algorithm_ns = ns;
@@ -121,7 +161,18 @@ std::vector<Alignment_t> mapping_impl(Genome_t &reference, std::vector<Read_t> &
     std::lock_guard<std::mutex> lock(g_mutex);
     sg_ctx *ctx = context();
     if (enabled_algorithm_log) std::cerr << "Preparing data..." << std::endl;
-    check(sg_set_reference(ctx, reference.content.data(), reference.content.size()));
+    // the packed genome stays on the GPUs across calls: upload only when address, length or content changed
+    // (the reference converts and uploads it on every call, src/genasm_gpu.cu:692-748,903)
+    {
+        const char *gp = reference.content.data();
+        const uint64_t gl = reference.content.size(), gh = content_hash(gp, gl);
+        if (!(g_holder.have_genome && g_holder.genome_ptr == gp && g_holder.genome_len == gl && g_holder.genome_hash == gh)) {
+            g_holder.have_genome = false;
+            check(sg_set_reference(ctx, gp, gl));
+            g_holder.genome_ptr = gp; g_holder.genome_len = gl; g_holder.genome_hash = gh;
+            g_holder.have_genome = true;
+        }
+    }
     std::vector<const char *> rptr(reads.size());
     std::vector<uint64_t> rlen(reads.size());
     uint64_t n_cand = 0;

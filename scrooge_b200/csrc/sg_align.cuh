@@ -119,6 +119,7 @@ struct AlignParams {
     uint8_t *status;
     uint64_t *dc_entries;  // optional: sum over windows of (d_w+1)*(n+1), the early-termination-minimal DC work
     uint32_t *windows;     // optional: number of windows of the alignment
+    const uint32_t *order; // optional: the queue hands out alignment order[k] as its k-th item (a permutation of 0..n-1)
     uint32_t k_one, k_two; // the constants 1 and 2, opaque to the compiler (sg_align_delta.cuh: fma-pipe shifts and adds)
     uint32_t k_4, k_16, k_256;  // 4, 16, 256 likewise: the shifts of the bit gathers of the window setup as IMADs
     uint32_t k_sel[16];         // k_sel[c] = 1 << (30 - 2c): brings the base code of column c of a text word to bits 31:30
@@ -333,6 +334,7 @@ __global__ void __launch_bounds__(SmemLayout<W, TMEM>::WARPS_PER_CTA * 32, TMEM 
             while (true) {
                 uint64_t idx = atomicAdd(P.counter, 1ull);
                 if (idx >= P.n) { drained = true; break; }
+                if (P.order) idx = P.order[idx];   // longest-first launch order (reference src/tests.cu:377)
                 uint64_t ql = P.query_len[idx];
                 if (ql == 0) {  // zero windows: distance 0, empty CIGAR (src/tests.cu:243,246)
                     P.edit[idx] = 0;
@@ -576,7 +578,7 @@ __global__ void __launch_bounds__(SmemLayout<W, TMEM>::WARPS_PER_CTA * 32, TMEM 
         if (q_pos >= q_end) {
             P.edit[pair] = ed;
             P.ref_consumed[pair] = t_pos - t_begin;
-            P.nruns[pair] = nruns;
+            P.nruns[pair] = overflow ? 0u : nruns;   // nothing valid in the slot: the compaction must not read past it
             P.status[pair] = overflow ? 5 : 0;
             if (P.dc_entries) P.dc_entries[pair] = entries & (kWindowUnit - 1);
             if (P.windows) P.windows[pair] = (uint32_t)(entries >> 40);

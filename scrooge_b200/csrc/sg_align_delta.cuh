@@ -283,6 +283,7 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
             while (true) {
                 uint64_t idx = atomicAdd(P.counter, 1ull);
                 if (idx >= P.n) { drained = true; break; }
+                if (P.order) idx = P.order[idx];   // longest-first launch order (reference src/tests.cu:377)
                 uint64_t ql = P.query_len[idx];
                 if (ql == 0) {  // zero windows: distance 0, empty CIGAR (src/tests.cu:243,246)
                     P.edit[idx] = 0;
@@ -640,7 +641,7 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
         if (q_pos >= q_end) {
             P.edit[pair] = ed;
             P.ref_consumed[pair] = t_pos - t_begin;
-            P.nruns[pair] = nruns;
+            P.nruns[pair] = overflow ? 0u : nruns;   // nothing valid in the slot: the compaction must not read past it
             P.status[pair] = overflow ? 5 : 0;
             if (P.dc_entries) P.dc_entries[pair] = entries & (kWindowUnit - 1);
             if (P.windows) P.windows[pair] = (uint32_t)(entries >> 40);

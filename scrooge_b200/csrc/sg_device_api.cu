@@ -432,11 +432,22 @@ int sg_dev_align_wo(int W, int O, const uint32_t *d_text, const uint64_t *d_text
                     uint64_t *d_counter, int64_t *d_edit, uint64_t *d_ref_consumed, uint32_t *d_nruns,
                     uint8_t *d_status, uint64_t *d_dc_entries, uint32_t *d_windows, void *stream)
 {
+    return sg_dev_align_ordered(W, O, d_text, d_text_start, d_text_len, d_query, d_query_start, d_query_len, n, flags, d_slab, d_slab_off,
+                                d_counter, d_edit, d_ref_consumed, d_nruns, d_status, d_dc_entries, d_windows, nullptr, stream);
+}
+
+int sg_dev_align_ordered(int W, int O, const uint32_t *d_text, const uint64_t *d_text_start, const uint64_t *d_text_len,
+                         const uint32_t *d_query, const uint64_t *d_query_start, const uint64_t *d_query_len,
+                         uint64_t n, uint32_t flags, uint8_t *d_slab, const uint64_t *d_slab_off,
+                         uint64_t *d_counter, int64_t *d_edit, uint64_t *d_ref_consumed, uint32_t *d_nruns,
+                         uint8_t *d_status, uint64_t *d_dc_entries, uint32_t *d_windows, const uint32_t *d_order, void *stream)
+{
     {
         const int wrc = check_window(W, O);
         if (wrc) return wrc;
     }
     if (n == 0) return SG_OK;
+    if (d_order && n > 0xFFFFFFFFull) return fail(SG_ERR_BAD_ARG, "sg_dev_align_ordered: more than 2^32 alignments in one launch");
     if (!d_text || !d_text_start || !d_text_len || !d_query || !d_query_start || !d_query_len || !d_counter ||
         !d_edit || !d_ref_consumed || !d_nruns || !d_status)
         return fail(SG_ERR_BAD_ARG, "sg_dev_align: null pointer");
@@ -453,6 +464,7 @@ int sg_dev_align_wo(int W, int O, const uint32_t *d_text, const uint64_t *d_text
     P.n = n; P.flags = flags; P.slab = d_slab; P.slab_off = d_slab_off;
     P.counter = (unsigned long long *)d_counter;
     P.edit = d_edit; P.ref_consumed = d_ref_consumed; P.nruns = d_nruns; P.status = d_status; P.dc_entries = d_dc_entries; P.windows = d_windows;
+    P.order = d_order;
     P.k_one = 1u; P.k_two = 2u; P.k_4 = 4u; P.k_16 = 16u; P.k_256 = 256u;
     for (int c = 0; c < 16; c++) P.k_sel[c] = 1u << (30 - 2 * c);
     if (!tuned_config(W, O)) return launch_generic(*di, P, W, O, st);

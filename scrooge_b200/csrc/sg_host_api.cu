@@ -21,12 +21,14 @@
 #include <chrono>
 #include <algorithm>
 #include <memory>
+#include <atomic>
 #include <omp.h>
 #include <unistd.h>
 #include <cuda_runtime.h>
 
 #include "../../include/scrooge_b200.h"
 #include "sg_internal.h"
+#include "sg_host_threads.h"
 
 namespace sg {
 
@@ -86,13 +88,15 @@ struct PinnedPool {
     std::mutex mu;
     std::vector<Block> free_blocks;
     size_t cached = 0;
-    // how much pinned memory the pool keeps for reuse: a quarter of the machine's RAM, at most 64 GB (a read-mapping
-    // call over 8 M candidates returns 19 GB of runs; re-pinning that much costs seconds), SG_PINNED_CACHE_GB overrides
+    // How much page-locked memory the pool keeps for reuse after the results that used it were freed: 1/32 of the
+    // machine's RAM, at most 4 GB per process (enough for the result blocks of a 2 M x 10 kbp call; re-pinning costs
+    // ~0.3 s per GB) -- page-locked memory cannot be swapped, and every process has its own pool.  SG_PINNED_CACHE_GB
+    // overrides (0 = keep nothing); sg_trim_host_cache() and the destruction of the last context release it.
     const size_t kMaxCached = [] {
         if (const char *v = std::getenv("SG_PINNED_CACHE_GB")) return (size_t)std::max(0ll, std::atoll(v)) << 30;
         const long pages = sysconf(_SC_PHYS_PAGES), psz = sysconf(_SC_PAGE_SIZE);
         const size_t ram = pages > 0 && psz > 0 ? (size_t)pages * (size_t)psz : (size_t)64 << 30;
-        return std::min<size_t>(ram / 4, (size_t)64 << 30);
+        return std::min<size_t>(ram / 32, (size_t)4 << 30);
     }();
 
     int acquire(size_t bytes, Block *out)
@@ -143,9 +147,18 @@ struct PinnedPool {
 };
 static PinnedPool g_pool;
 
-// SG_DEBUG=1: where the host time of a call goes (printed by run_all)
-struct HostTimes { double pack = 0, wait = 0, desc = 0, copy_out = 0; };
-static HostTimes g_ht;
+// Where the host time and the PCIe bytes of a call go, per GPU of the context (one writer: the GPU's own worker thread;
+// the packer threads add their share through atomics).  Merged into sg_call_stats by run_all.
+struct ShardStats {
+    double upload = 0;      // wall time of the ingest phase: host packing + queuing of the copies, all sub-batches
+    double wait = 0;        // blocked on the device (alignment kernel, compaction, copies back)
+    double desc = 0;        // descriptor arithmetic
+    double out = 0;         // results into the caller-visible block
+    std::atomic<uint64_t> pack_thread_ns{0};   // summed over the packer threads: time inside the packing loop
+    std::atomic<uint64_t> h2d_packed{0};       // bytes that crossed PCIe packed by the host (2 bit/base)
+    uint64_t h2d_ascii = 0, h2d_other = 0, d2h = 0;
+    uint32_t sub_batches = 0;
+};
 static const bool g_debug = std::getenv("SG_DEBUG") != nullptr;
 struct ScopedT {
     double &acc; std::chrono::steady_clock::time_point t0;
@@ -175,8 +188,8 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_mid = nullptr, ev_end = nullptr;
     cudaEvent_t ev_dma[kMaxDmaDepth] = {};   // adaptive ingest: one per ASCII chunk copy in flight
-    DevBuf ascii_t, ascii_q, packed_t, packed_q, desc, slab, counter, edit, refc, nruns, status, run_off, scan_tmp, runs, bad;
-    PinBuf h_small, h_status, h_stage_t, h_stage_q, h_desc;
+    DevBuf ascii_t, ascii_q, packed_t, packed_q, desc, slab, counter, edit, refc, nruns, status, run_off, scan_tmp, runs, bad, order;
+    PinBuf h_small, h_status, h_stage_t, h_stage_q, h_desc, h_order;
     PinnedPool::Block piece{nullptr, 0};
     // the batch in flight
     bool busy = false, mid_done = false;
@@ -195,9 +208,9 @@ struct Slot {
     void destroy()
     {
         for (DevBuf *b : {&ascii_t, &ascii_q, &packed_t, &packed_q, &desc, &slab, &counter, &edit, &refc, &nruns, &status, &run_off,
-                          &scan_tmp, &runs, &bad})
+                          &scan_tmp, &runs, &bad, &order})
             b->release();
-        for (PinBuf *b : {&h_small, &h_status, &h_stage_t, &h_stage_q, &h_desc}) b->release();
+        for (PinBuf *b : {&h_small, &h_status, &h_stage_t, &h_stage_q, &h_desc, &h_order}) b->release();
         g_pool.release(piece);
         piece = {nullptr, 0};
         if (ev_k0) cudaEventDestroy(ev_k0);
@@ -214,8 +227,25 @@ struct Device {
     Slot slots[kMaxSlots];
     int n_slots = 3;
     DevBuf genome;  // packed reference, resident across calls
+    DevBuf piece_bad;   // sg_set_reference: one offending-base word per uploaded piece
     uint64_t genome_len = 0;
     bool has_genome = false;
+    std::vector<int> cpus;   // the CPUs this GPU's host threads run on (sg_host_threads.h)
+    ThreadTeam team;         // its packer threads: created with the context, asleep between jobs
+};
+
+// Devices own threads and streams: neither copied nor moved, so a fixed array instead of a std::vector.
+struct DeviceList {
+    std::unique_ptr<Device[]> p;
+    size_t n = 0;
+    void resize(size_t k) { p.reset(new Device[k]); n = k; }
+    size_t size() const { return n; }
+    Device &operator[](size_t k) { return p[k]; }
+    const Device &operator[](size_t k) const { return p[k]; }
+    Device *begin() { return p.get(); }
+    Device *end() { return p.get() + n; }
+    const Device *begin() const { return p.get(); }
+    const Device *end() const { return p.get() + n; }
 };
 
 }  // namespace sg
@@ -225,7 +255,7 @@ using namespace sg;
 struct sg_ctx {
     int W = 64;
     int O = 33;
-    std::vector<Device> devs;
+    DeviceList devs;
     // sub-batch rule: at least batch_bytes of ASCII AND at least min_batch_units alignments (one alignment
     // occupies one lane for its whole life -- 11 ms for a 10 kbp read with every lane busy -- so a launch needs an
     // alignment per lane to fill the device), but never more than max_batch_bytes (per-slot buffers)
@@ -251,6 +281,8 @@ struct sg_ctx {
     int dma_depth = 4;
     uint64_t ascii_min_bytes = 8ull << 20;   // blobs smaller than this are not split
     std::mutex mu;  // calls on one context are serialised
+    bool longest_first = true;   // SG_LONGEST_FIRST=0: launches take their alignments in input order
+    bool counted = false;   // fully created (sg_ctx_destroy also cleans up after a failed creation)
 };
 
 struct sg_result {
@@ -270,6 +302,7 @@ struct sg_result {
     std::vector<uint64_t> piece_runs;    // runs in each piece
     std::vector<uint8_t> flat;           // lazily flattened view for sg_result_runs
     int64_t kernel_ns = 0, total_ns = 0;
+    sg_call_stats stats;
     ~sg_result() { for (auto &b : pieces) g_pool.release(b); g_pool.release(store); }
 };
 
@@ -279,6 +312,7 @@ struct ShardOut {
     int rc = SG_OK;
     std::string err;
     double kernel_ms = 0;
+    ShardStats stats;
     std::vector<PinnedPool::Block> pieces;
     std::vector<uint64_t> piece_first, piece_runs;
     ~ShardOut() { for (auto &b : pieces) g_pool.release(b); }
@@ -309,165 +343,260 @@ int bad_base_error(const char *what, const char *unit, uint64_t index, uint64_t 
                                      std::to_string(pos));
 }
 
-// Adaptive ingest of one blob range (see sg_ctx::adaptive).  All copies go to `st` in issue order.
-int upload_blob_adaptive(sg_ctx *ctx, int dev_id, cudaStream_t st, cudaEvent_t *ev_dma, const char *src, uint64_t nbytes, DevBuf &d_ascii,
-                         DevBuf &d_packed, PinBuf &h_stage, uint64_t *d_bad, uint64_t *bad_pos, uint64_t *split_out)
+// One blob range of a sub-batch on its way to the device.
+struct Segment {
+    const char *src = nullptr; uint64_t nbytes = 0;
+    DevBuf *d_ascii = nullptr, *d_packed = nullptr; PinBuf *h_stage = nullptr; uint64_t *d_bad = nullptr;
+    long long chunk0 = 0, nch = 0;   // its chunks in the sub-batch's chunk list
+    uint64_t split = 0;              // out: [0, split) was packed by the host, [split, nbytes) crossed as ASCII
+};
+
+// Adaptive ingest of a sub-batch's blobs (see sg_ctx::adaptive): the blobs are cut into chunks, one list over all
+// segments.  The GPU's packer threads take chunks from the FRONT (pack to 2 bit/base into pinned staging, upload the
+// packed chunk right away); the calling thread -- the GPU's worker -- is the feeder: it keeps `dma_depth` ASCII chunk
+// copies from the BACK in flight, and the device packs whatever arrived as ASCII.  Whoever is faster takes more.
+// host_threads == 0: everything crosses as ASCII; dma_depth == 0: everything is packed by the host.
+int upload_adaptive(sg_ctx *ctx, Device &d, cudaStream_t st, cudaEvent_t *ev_dma, Segment *seg, int nseg, ShardStats &cs, uint64_t *bad_pos, int *bad_seg)
 {
-    const uint64_t words = sg_packed_words(nbytes);
-    R(d_packed.reserve(words * 4));
-    R(h_stage.reserve(words * 4 + 64));
-    R(d_ascii.reserve(nbytes + 64));
-    uint32_t *hp = h_stage.as<uint32_t>();
     const uint64_t C = ctx->chunk_bytes;   // a multiple of 256: chunks start on whole packed words and whole output cache lines
-    const long long nch = (long long)((nbytes + C - 1) / C);
-    const int depth = std::min(kMaxDmaDepth, std::max(1, ctx->dma_depth));
-    const int packers = std::max(1, ctx->host_threads);
+    long long nch = 0;
+    for (int k = 0; k < nseg; k++) {
+        Segment &g = seg[k];
+        const uint64_t words = sg_packed_words(g.nbytes);
+        R(g.d_packed->reserve(words * 4));
+        if (d.team.size() > 0) R(g.h_stage->reserve(words * 4 + 64));
+        if (ctx->dma_depth > 0 || d.team.size() == 0) R(g.d_ascii->reserve(g.nbytes + 64));
+        g.chunk0 = nch;
+        g.nch = (long long)((g.nbytes + C - 1) / C);
+        nch += g.nch;
+    }
+    const int depth = d.team.size() == 0 ? std::max(1, std::min(kMaxDmaDepth, ctx->dma_depth)) : std::min(kMaxDmaDepth, ctx->dma_depth);
+    auto locate = [&](long long c, uint64_t *off, uint64_t *len) -> Segment & {
+        int k = 0;
+        while (k + 1 < nseg && c >= seg[k + 1].chunk0) k++;
+        *off = (uint64_t)(c - seg[k].chunk0) * C;
+        *len = std::min(C, seg[k].nbytes - *off);
+        return seg[k];
+    };
     std::mutex mu;
-    long long front = 0, back = nch;   // host threads take chunk `front++`, the feeder chunk `--back`
+    long long front = 0, back = nch;   // packers take chunk `front++`, the feeder chunk `--back`
     auto take_front = [&]() -> long long { std::lock_guard<std::mutex> g(mu); return front < back ? front++ : -1; };
     auto take_back = [&]() -> long long { std::lock_guard<std::mutex> g(mu); return back > front ? --back : -1; };
-    uint64_t bad = ~0ull;
-    int cuda_rc = 0;   // shared; only ever set to 1
-    ScopedT t_pack(g_ht.pack);
-#pragma omp parallel num_threads(packers + 1) reduction(min : bad)
-    {
-        // the team may be smaller than asked for: the feeder role exists only when there is a second thread
-        const int tid = omp_get_thread_num(), team = omp_get_num_threads();
-        bool ok = cudaSetDevice(dev_id) == cudaSuccess;
-        if (ok && team > 1 && tid == 0) {
-            int issued = 0;
-            while (true) {
-                if (issued >= depth && cudaEventSynchronize(ev_dma[issued % depth]) != cudaSuccess) { ok = false; break; }
-                const long long c = take_back();
-                if (c < 0) break;
-                const uint64_t off = (uint64_t)c * C, len = std::min(C, nbytes - off);
-                if (cudaMemcpyAsync(d_ascii.as<char>() + off, src + off, len, cudaMemcpyHostToDevice, st) != cudaSuccess ||
-                    cudaEventRecord(ev_dma[issued % depth], st) != cudaSuccess) { ok = false; break; }
-                issued++;
+    std::atomic<uint64_t> bad{~0ull};      // (segment << 56) | position: the smallest wins
+    std::atomic<int> cuda_rc{0};
+    std::function<void(int)> job = [&](int) {
+        const auto t0 = std::chrono::steady_clock::now();
+        uint64_t sent = 0;
+        while (true) {
+            const long long c = take_front();
+            if (c < 0) break;
+            uint64_t off, len;
+            Segment &g = locate(c, &off, &len);
+            uint32_t *hp = g.h_stage->as<uint32_t>() + off / 16;
+            const uint64_t r = sg_host_pack_2bit_st(g.src + off, len, hp);
+            if (r != ~0ull) {
+                const uint64_t key = ((uint64_t)(&g - seg) << 56) | (off + r);
+                uint64_t cur = bad.load();
+                while (key < cur && !bad.compare_exchange_weak(cur, key)) {}
+                break;
             }
-        } else if (ok) {
-            while (true) {
-                const long long c = take_front();
-                if (c < 0) break;
-                const uint64_t off = (uint64_t)c * C, len = std::min(C, nbytes - off);
-                const uint64_t r = sg_host_pack_2bit_st(src + off, len, hp + off / 16);
-                if (r != ~0ull) { bad = std::min(bad, off + r); break; }
-                if (cudaMemcpyAsync(d_packed.as<uint32_t>() + off / 16, hp + off / 16, ((len + 15) / 16) * 4, cudaMemcpyHostToDevice, st) !=
-                    cudaSuccess) { ok = false; break; }
-            }
+            const uint64_t bytes = ((len + 15) / 16) * 4;
+            if (cudaMemcpyAsync(g.d_packed->as<uint32_t>() + off / 16, hp, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { cuda_rc = 1; break; }
+            sent += bytes;
         }
-        if (!ok) {
-#pragma omp atomic write
-            cuda_rc = 1;
+        cs.h2d_packed += sent;
+        cs.pack_thread_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    };
+    if (d.team.size() > 0) d.team.launch(job);
+    if (depth > 0) {
+        int issued = 0;
+        while (true) {
+            if (issued >= depth && cudaEventSynchronize(ev_dma[issued % depth]) != cudaSuccess) { cuda_rc = 1; break; }
+            const long long c = take_back();
+            if (c < 0) break;
+            uint64_t off, len;
+            Segment &g = locate(c, &off, &len);
+            if (cudaMemcpyAsync(g.d_ascii->as<char>() + off, g.src + off, len, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+                cudaEventRecord(ev_dma[issued % depth], st) != cudaSuccess) { cuda_rc = 1; break; }
+            cs.h2d_ascii += len;
+            issued++;
         }
     }
+    if (d.team.size() > 0) d.team.wait();
     if (cuda_rc) { cudaGetLastError(); return fail(SG_ERR_CUDA, "adaptive ingest: a CUDA call failed"); }
-    *bad_pos = bad;
-    if (bad != ~0ull) return SG_OK;   // the caller names the offender
-    const uint64_t split = std::min(nbytes, (uint64_t)back * C);   // [0, split) packed by the host, [split, nbytes) arrived as ASCII
-    *split_out = split;
-    if (split < nbytes) return sg_dev_pack_2bit(d_ascii.as<char>() + split, nbytes - split, d_packed.as<uint32_t>() + split / 16, d_bad, st);
-    const uint64_t used = (nbytes + 15) / 16;
-    SG_CUDA(cudaMemsetAsync(d_packed.as<uint32_t>() + used, 0, (words - used) * 4, st));  // padding words the aligner may read
+    if (bad.load() != ~0ull) {   // the caller names the offender
+        *bad_seg = (int)(bad.load() >> 56);
+        *bad_pos = bad.load() & ((1ull << 56) - 1);
+        return SG_OK;
+    }
+    *bad_pos = ~0ull;
+    for (int k = 0; k < nseg; k++) {   // chunks [0, back) were packed by the host, [back, nch) arrived as ASCII
+        Segment &g = seg[k];
+        const long long host_chunks = std::min(g.nch, std::max(0ll, back - g.chunk0));
+        g.split = std::min(g.nbytes, (uint64_t)host_chunks * C);
+        if (g.split < g.nbytes) {
+            R(sg_dev_pack_2bit(g.d_ascii->as<char>() + g.split, g.nbytes - g.split, g.d_packed->as<uint32_t>() + g.split / 16, g.d_bad, st));
+        } else {
+            const uint64_t words = sg_packed_words(g.nbytes), used = (g.nbytes + 15) / 16;
+            SG_CUDA(cudaMemsetAsync(g.d_packed->as<uint32_t>() + used, 0, (words - used) * 4, st));  // padding words the aligner may read
+        }
+    }
     return SG_OK;
 }
 
-// Strings [i0, i1) -> packed words on the device; start[k] receives the first base of string i0+k in the packed blob.
-//   host_pack: packed by the host threads straight into pinned staging (a blob as one stream, separate strings each
-//              at a word boundary), a quarter of the bytes cross PCIe;
-//   else:      ASCII crosses PCIe (a blob straight from the caller's memory, separate strings gathered into pinned
-//              staging first) and pack_2bit_kernel packs it; an offending base is then reported through d_bad.
-int upload_strings(sg_ctx *ctx, int dev_id, cudaStream_t st, cudaEvent_t *ev_dma, const Strings &S, uint64_t i0, uint64_t i1, const char *what, const char *unit,
-                   DevBuf &d_ascii, DevBuf &d_packed, PinBuf &h_stage, uint64_t *d_bad, uint64_t *start, uint64_t *bad_bias)
+// Separate strings [i0, i1) (pointer + length each, e.g. the std::strings of the C++ drop-in) -> packed words on the device,
+// every string at a word boundary; start[k] receives the first base of string i0+k in the packed blob.  The strings live in
+// pageable memory wherever the caller allocated them, so the copy engine cannot fetch them: the packer threads pack them
+// where they lie (reading a string once costs the same as gathering it into pinned staging would) in chunks of strings, and
+// every packed chunk is uploaded as soon as it is done.
+int upload_separate(sg_ctx *ctx, Device &d, cudaStream_t st, const Strings &S, uint64_t i0, uint64_t i1, const char *what, const char *unit,
+                    DevBuf &d_packed, PinBuf &h_stage, uint64_t *start, ShardStats &cs)
 {
-    *bad_bias = 0;
     const uint64_t n = i1 - i0;
-    const int threads = ctx->host_threads;
-    if (S.blob) {
-        const uint64_t base = S.off[i0], nbytes = S.off[i1] - base;
-        parallel_for(n, threads, [&](uint64_t k0, uint64_t k1) { for (uint64_t k = k0; k < k1; k++) start[k] = S.off[i0 + k] - base; });
-        const uint64_t words = sg_packed_words(nbytes);
+    uint64_t w = 0;
+    for (uint64_t k = 0; k < n; k++) { start[k] = w * 16; w += (S.len[i0 + k] + 15) / 16; }
+    const uint64_t words = w + 8;
+    R(d_packed.reserve(words * 4));
+    R(h_stage.reserve(words * 4));
+    uint32_t *hp = h_stage.as<uint32_t>();
+    memset(hp + w, 0, 8 * 4);   // padding words the aligner may read
+    // chunks of strings worth about chunk_bytes of ASCII each
+    std::vector<uint64_t> cut{0};
+    {
+        uint64_t acc = 0;
+        for (uint64_t k = 0; k < n; k++) {
+            acc += S.len[i0 + k];
+            if (acc >= ctx->chunk_bytes) { cut.push_back(k + 1); acc = 0; }
+        }
+        if (cut.back() != n) cut.push_back(n);
+    }
+    const long long nch = (long long)cut.size() - 1;
+    std::atomic<long long> next{0};
+    std::atomic<uint64_t> bad_k{~0ull};
+    std::atomic<int> cuda_rc{0};
+    std::function<void(int)> job = [&](int) {
+        const auto t0 = std::chrono::steady_clock::now();
+        uint64_t sent = 0;
+        while (true) {
+            const long long c = next.fetch_add(1);
+            if (c >= nch) break;
+            const uint64_t k0 = cut[c], k1 = cut[c + 1];
+            bool ok = true;
+            for (uint64_t k = k0; k < k1 && ok; k++)
+                if (sg_host_pack_2bit_st(S.ptr[i0 + k], S.len[i0 + k], hp + start[k] / 16) != ~0ull) {
+                    uint64_t cur = bad_k.load();
+                    while (k < cur && !bad_k.compare_exchange_weak(cur, k)) {}
+                    ok = false;
+                }
+            if (!ok) break;
+            const uint64_t w0 = start[k0] / 16, w1 = k1 < n ? start[k1] / 16 : words;
+            if (cudaMemcpyAsync(d_packed.as<uint32_t>() + w0, hp + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { cuda_rc = 1; break; }
+            sent += (w1 - w0) * 4;
+        }
+        cs.h2d_packed += sent;
+        cs.pack_thread_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    };
+    if (d.team.size() > 0) { d.team.launch(job); d.team.wait(); }
+    else job(0);
+    if (cuda_rc) { cudaGetLastError(); return fail(SG_ERR_CUDA, "ingest: a CUDA call failed"); }
+    if (bad_k.load() != ~0ull) {
+        const uint64_t k = bad_k.load();
+        std::vector<uint32_t> tmp((S.len[i0 + k] + 15) / 16 + 1);
+        return bad_base_error(what, unit, i0 + k, sg_host_pack_2bit_st(S.ptr[i0 + k], S.len[i0 + k], tmp.data()));
+    }
+    return SG_OK;
+}
+
+// Blob strings [i0, i1) of up to two inputs -> packed words on the device.
+//   adaptive (default): upload_adaptive over all segments at once;
+//   fixed policies (SG_INGEST=fixed, A/B experiments): host_pack = the packer threads pack the head of every blob and
+//   ascii_frac of its tail crosses as ASCII; else everything crosses as ASCII and pack_2bit_kernel packs it.
+// An offending base found on the device side is reported later through d_bad (+ bad_bias).
+struct BlobIn { const Strings *S; uint64_t i0, i1; const char *what, *unit; DevBuf *d_ascii, *d_packed; PinBuf *h_stage; uint64_t *d_bad, *start, *bad_bias; };
+
+int upload_blobs(sg_ctx *ctx, Device &d, cudaStream_t st, cudaEvent_t *ev_dma, BlobIn *in, int nin, ShardStats &cs)
+{
+    Segment seg[2];
+    int nseg = 0, seg_of[2] = {-1, -1};
+    for (int q = 0; q < nin; q++) {
+        BlobIn &b = in[q];
+        const Strings &S = *b.S;
+        const uint64_t n = b.i1 - b.i0, base = S.off[b.i0], nbytes = S.off[b.i1] - base;
+        *b.bad_bias = 0;
+        parallel_for(n, ctx->host_threads, [&](uint64_t k0, uint64_t k1) { for (uint64_t k = k0; k < k1; k++) b.start[k] = S.off[b.i0 + k] - base; });
         if (ctx->adaptive && nbytes >= ctx->ascii_min_bytes && nbytes >= 256) {
-            uint64_t bad = ~0ull, split = nbytes;
-            R(upload_blob_adaptive(ctx, dev_id, st, ev_dma, S.blob + base, nbytes, d_ascii, d_packed, h_stage, d_bad, &bad, &split));
-            if (bad != ~0ull) {
-                const uint64_t i = (uint64_t)(std::upper_bound(S.off + i0, S.off + i1 + 1, base + bad) - S.off) - 1;
-                return bad_base_error(what, unit, i, base + bad - S.off[i]);
-            }
-            *bad_bias = split < nbytes ? split : 0;
-            return SG_OK;
+            Segment &g = seg[nseg];
+            g.src = S.blob + base; g.nbytes = nbytes; g.d_ascii = b.d_ascii; g.d_packed = b.d_packed; g.h_stage = b.h_stage; g.d_bad = b.d_bad;
+            seg_of[nseg++] = q;
+            continue;
         }
-        R(d_packed.reserve(words * 4));
-        if (!ctx->host_pack) {
-            R(d_ascii.reserve(nbytes + 64));
-            SG_CUDA(cudaMemcpyAsync(d_ascii.p, S.blob + base, nbytes, cudaMemcpyHostToDevice, st));
-            return sg_dev_pack_2bit(d_ascii.as<char>(), nbytes, d_packed.as<uint32_t>(), d_bad, st);
+        const uint64_t words = sg_packed_words(nbytes);
+        R(b.d_packed->reserve(words * 4));
+        if (!ctx->host_pack || d.team.size() == 0) {
+            R(b.d_ascii->reserve(nbytes + 64));
+            SG_CUDA(cudaMemcpyAsync(b.d_ascii->p, S.blob + base, nbytes, cudaMemcpyHostToDevice, st));
+            cs.h2d_ascii += nbytes;
+            R(sg_dev_pack_2bit(b.d_ascii->as<char>(), nbytes, b.d_packed->as<uint32_t>(), b.d_bad, st));
+            continue;
         }
-        R(h_stage.reserve(words * 4));
-        uint32_t *hp = h_stage.as<uint32_t>();
+        R(b.h_stage->reserve(words * 4));
+        uint32_t *hp = b.h_stage->as<uint32_t>();
         // hybrid: bases [split, nbytes) travel as ASCII (the copy is queued first, so the copy engine works while the
         // host packs [0, split)) and are packed on the device into the words that follow the host's
         uint64_t split = nbytes;
         if (ctx->ascii_frac > 0 && nbytes >= ctx->ascii_min_bytes && nbytes >= 128) split = (uint64_t)((double)nbytes * (1.0 - ctx->ascii_frac)) & ~63ull;
         if (split < nbytes) {
-            R(d_ascii.reserve(nbytes - split + 64));
-            SG_CUDA(cudaMemcpyAsync(d_ascii.p, S.blob + base + split, nbytes - split, cudaMemcpyHostToDevice, st));
+            R(b.d_ascii->reserve(nbytes - split + 64));
+            SG_CUDA(cudaMemcpyAsync(b.d_ascii->p, S.blob + base + split, nbytes - split, cudaMemcpyHostToDevice, st));
+            cs.h2d_ascii += nbytes - split;
         }
         const uint64_t used = (split + 15) / 16;
         uint64_t bad;
-        { ScopedT t(g_ht.pack); bad = sg_host_pack_2bit(S.blob + base, split, hp, threads); }
+        {
+            const auto t0 = std::chrono::steady_clock::now();
+            bad = sg_host_pack_2bit(S.blob + base, split, hp, std::max(1, ctx->host_threads));
+            cs.pack_thread_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count() *
+                                 (uint64_t)std::max(1, ctx->host_threads);
+        }
         if (bad != ~0ull) {
-            const uint64_t i = (uint64_t)(std::upper_bound(S.off + i0, S.off + i1 + 1, base + bad) - S.off) - 1;
-            return bad_base_error(what, unit, i, base + bad - S.off[i]);
+            const uint64_t i = (uint64_t)(std::upper_bound(S.off + b.i0, S.off + b.i1 + 1, base + bad) - S.off) - 1;
+            return bad_base_error(b.what, b.unit, i, base + bad - S.off[i]);
         }
         if (split < nbytes) {
-            SG_CUDA(cudaMemcpyAsync(d_packed.p, hp, used * 4, cudaMemcpyHostToDevice, st));
-            *bad_bias = split;
-            return sg_dev_pack_2bit(d_ascii.as<char>(), nbytes - split, d_packed.as<uint32_t>() + used, d_bad, st);
+            SG_CUDA(cudaMemcpyAsync(b.d_packed->p, hp, used * 4, cudaMemcpyHostToDevice, st));
+            cs.h2d_packed += used * 4;
+            *b.bad_bias = split;
+            R(sg_dev_pack_2bit(b.d_ascii->as<char>(), nbytes - split, b.d_packed->as<uint32_t>() + used, b.d_bad, st));
+            continue;
         }
         memset(hp + used, 0, (words - used) * 4);  // padding words the aligner may read
-        SG_CUDA(cudaMemcpyAsync(d_packed.p, hp, words * 4, cudaMemcpyHostToDevice, st));
-        return SG_OK;
+        SG_CUDA(cudaMemcpyAsync(b.d_packed->p, hp, words * 4, cudaMemcpyHostToDevice, st));
+        cs.h2d_packed += words * 4;
     }
-    if (ctx->host_pack) {
-        uint64_t w = 0;
-        for (uint64_t k = 0; k < n; k++) { start[k] = w * 16; w += (S.len[i0 + k] + 15) / 16; }
-        const uint64_t words = w + 8;
-        R(d_packed.reserve(words * 4));
-        R(h_stage.reserve(words * 4));
-        uint32_t *hp = h_stage.as<uint32_t>();
-        uint64_t bad_k = ~0ull;
-#pragma omp parallel for schedule(dynamic, 16) num_threads(threads) reduction(min : bad_k)
-        for (long long k = 0; k < (long long)n; k++)
-            if (sg_host_pack_2bit_st(S.ptr[i0 + k], S.len[i0 + k], hp + start[k] / 16) != ~0ull) bad_k = std::min<uint64_t>(bad_k, (uint64_t)k);
-        if (bad_k != ~0ull) {
-            std::vector<uint32_t> tmp((S.len[i0 + bad_k] + 15) / 16 + 1);
-            return bad_base_error(what, unit, i0 + bad_k, sg_host_pack_2bit_st(S.ptr[i0 + bad_k], S.len[i0 + bad_k], tmp.data()));
+    if (nseg) {
+        uint64_t bad = ~0ull;
+        int bad_seg = 0;
+        R(upload_adaptive(ctx, d, st, ev_dma, seg, nseg, cs, &bad, &bad_seg));
+        if (bad != ~0ull) {
+            const BlobIn &b = in[seg_of[bad_seg]];
+            const Strings &S = *b.S;
+            const uint64_t base = S.off[b.i0];
+            const uint64_t i = (uint64_t)(std::upper_bound(S.off + b.i0, S.off + b.i1 + 1, base + bad) - S.off) - 1;
+            return bad_base_error(b.what, b.unit, i, base + bad - S.off[i]);
         }
-        memset(hp + w, 0, 8 * 4);
-        SG_CUDA(cudaMemcpyAsync(d_packed.p, hp, words * 4, cudaMemcpyHostToDevice, st));
-        return SG_OK;
+        for (int k = 0; k < nseg; k++) *in[seg_of[k]].bad_bias = seg[k].split < seg[k].nbytes ? seg[k].split : 0;
     }
-    uint64_t bytes = 0;
-    for (uint64_t k = 0; k < n; k++) { start[k] = bytes; bytes += S.len[i0 + k]; }
-    R(h_stage.reserve(bytes + 64));
-    R(d_ascii.reserve(bytes + 64));
-    R(d_packed.reserve(sg_packed_words(bytes) * 4));
-    char *ha = h_stage.as<char>();
-#pragma omp parallel for schedule(dynamic, 16) num_threads(threads)
-    for (long long k = 0; k < (long long)n; k++)
-        if (S.len[i0 + k]) memcpy(ha + start[k], S.ptr[i0 + k], S.len[i0 + k]);
-    SG_CUDA(cudaMemcpyAsync(d_ascii.p, ha, bytes, cudaMemcpyHostToDevice, st));
-    return sg_dev_pack_2bit(d_ascii.as<char>(), bytes, d_packed.as<uint32_t>(), d_bad, st);
+    return SG_OK;
 }
 
 // stage A: uploads, ingest, descriptors, alignment kernel, run-count scan; ends with ev_mid
-int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uint64_t a1, sg_result *res)
+int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uint64_t a1, sg_result *res, ShardStats &cs)
 {
     const uint64_t n = a1 - a0;
     const bool want_cigar = !(w.flags & SG_FLAG_DISTANCE_ONLY);
     cudaStream_t st = s.stream;
     s.a0 = a0; s.a1 = a1; s.busy = true; s.mid_done = false; s.total_runs = 0;
+    cs.sub_batches++;
     R(s.desc.reserve((5 * n + 1) * 8)); R(s.h_desc.reserve((5 * n + 1) * 8));
     R(s.counter.reserve(8)); R(s.edit.reserve(n * 8)); R(s.refc.reserve(n * 8));
     R(s.nruns.reserve(n * 4)); R(s.status.reserve(n)); R(s.run_off.reserve((n + 1) * 8));
@@ -478,9 +607,20 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
     uint64_t *h_tstart = s.h_desc.as<uint64_t>(), *h_tlen = h_tstart + n, *h_qstart = h_tlen + n, *h_qlen = h_qstart + n, *h_slab = h_qlen + n;
     uint64_t *d_tstart = s.desc.as<uint64_t>(), *d_tlen = d_tstart + n, *d_qstart = d_tlen + n, *d_qlen = d_qstart + n, *d_slab = d_qlen + n;
     const uint32_t *d_text;
+    s.bad_bias[0] = s.bad_bias[1] = 0;
     if (!w.mapping) {
-        R(upload_strings(ctx, d.id, st, s.ev_dma, w.text, a0, a1, "text", "pair", s.ascii_t, s.packed_t, s.h_stage_t, s.bad.as<uint64_t>(), h_tstart, &s.bad_bias[0]));
-        R(upload_strings(ctx, d.id, st, s.ev_dma, w.query, a0, a1, "query", "pair", s.ascii_q, s.packed_q, s.h_stage_q, s.bad.as<uint64_t>() + 1, h_qstart, &s.bad_bias[1]));
+        {
+            ScopedT t_up(cs.upload);
+            if (w.text.off) {
+                BlobIn in[2] = {{&w.text, a0, a1, "text", "pair", &s.ascii_t, &s.packed_t, &s.h_stage_t, s.bad.as<uint64_t>(), h_tstart, &s.bad_bias[0]},
+                                {&w.query, a0, a1, "query", "pair", &s.ascii_q, &s.packed_q, &s.h_stage_q, s.bad.as<uint64_t>() + 1, h_qstart, &s.bad_bias[1]}};
+                R(upload_blobs(ctx, d, st, s.ev_dma, in, 2, cs));
+            } else {
+                R(upload_separate(ctx, d, st, w.text, a0, a1, "text", "pair", s.packed_t, s.h_stage_t, h_tstart, cs));
+                R(upload_separate(ctx, d, st, w.query, a0, a1, "query", "pair", s.packed_q, s.h_stage_q, h_qstart, cs));
+            }
+        }
+        ScopedT t_desc(cs.desc);
         parallel_for(n, ctx->host_threads, [&](uint64_t k0, uint64_t k1) {
             for (uint64_t k = k0; k < k1; k++) { h_tlen[k] = w.text.size(a0 + k); h_qlen[k] = w.query.size(a0 + k); }
         });
@@ -490,36 +630,76 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
         // range is tight; each read is uploaded and packed once and shared by its candidates, cf. reference
         // twobit_reads, src/genasm_gpu.cu:784-796)
         uint32_t r0 = w.cand_read[a0], r1 = w.cand_read[a0];
-        for (uint64_t c = a0; c < a1; c++) { r0 = std::min(r0, w.cand_read[c]); r1 = std::max(r1, w.cand_read[c]); }
-        std::vector<uint64_t> rstart((uint64_t)r1 - r0 + 1);
-        R(upload_strings(ctx, d.id, st, s.ev_dma, w.query, r0, (uint64_t)r1 + 1, "content", "read", s.ascii_q, s.packed_q, s.h_stage_q,
-                         s.bad.as<uint64_t>() + 1, rstart.data(), &s.bad_bias[1]));
-        for (uint64_t k = 0; k < n; k++) {
-            const uint64_t cs = w.cand_start[a0 + k];
-            const uint32_t r = w.cand_read[a0 + k];
-            h_tstart[k] = cs;
-            h_tlen[k] = d.genome_len - cs;  // the text runs to the end of the genome (src/genasm_cpu.cpp:512-514)
-            h_qstart[k] = rstart[r - r0];
-            h_qlen[k] = w.query.size(r);
+        {
+            ScopedT t_desc(cs.desc);
+            std::mutex mu;
+            parallel_for(n, ctx->host_threads, [&](uint64_t k0, uint64_t k1) {
+                uint32_t lo = w.cand_read[a0 + k0], hi = lo;
+                for (uint64_t c = a0 + k0; c < a0 + k1; c++) { lo = std::min(lo, w.cand_read[c]); hi = std::max(hi, w.cand_read[c]); }
+                std::lock_guard<std::mutex> g(mu);
+                r0 = std::min(r0, lo); r1 = std::max(r1, hi);
+            });
         }
+        std::vector<uint64_t> rstart((uint64_t)r1 - r0 + 1);
+        {
+            ScopedT t_up(cs.upload);
+            if (w.query.off) {
+                BlobIn in[1] = {{&w.query, r0, (uint64_t)r1 + 1, "content", "read", &s.ascii_q, &s.packed_q, &s.h_stage_q, s.bad.as<uint64_t>() + 1,
+                                 rstart.data(), &s.bad_bias[1]}};
+                R(upload_blobs(ctx, d, st, s.ev_dma, in, 1, cs));
+            } else {
+                R(upload_separate(ctx, d, st, w.query, r0, (uint64_t)r1 + 1, "content", "read", s.packed_q, s.h_stage_q, rstart.data(), cs));
+            }
+        }
+        ScopedT t_desc(cs.desc);
+        parallel_for(n, ctx->host_threads, [&](uint64_t k0, uint64_t k1) {
+            for (uint64_t k = k0; k < k1; k++) {
+                const uint64_t cstart = w.cand_start[a0 + k];
+                const uint32_t r = w.cand_read[a0 + k];
+                h_tstart[k] = cstart;
+                h_tlen[k] = d.genome_len - cstart;  // the text runs to the end of the genome (src/genasm_cpu.cpp:512-514)
+                h_qstart[k] = rstart[r - r0];
+                h_qlen[k] = w.query.size(r);
+            }
+        });
         d_text = d.genome.as<uint32_t>();
     }
-    ScopedT t_desc(g_ht.desc);
     uint64_t slab_bytes = 0;
-    if (!w.mapping && w.query.blob) {   // capacity 2*|query|+8 per alignment: the prefix sum is a difference of offsets
-        const uint64_t *qo = w.query.off + a0;
-        parallel_for(n + 1, ctx->host_threads, [&](uint64_t k0, uint64_t k1) { for (uint64_t k = k0; k < k1; k++) h_slab[k] = 2ull * (qo[k] - qo[0]) + 8ull * k; });
-        slab_bytes = h_slab[n];
-    } else {
-        for (uint64_t k = 0; k < n; k++) { h_slab[k] = slab_bytes; slab_bytes += 2ull * h_qlen[k] + 8ull; }
-        h_slab[n] = slab_bytes;
+    {
+        ScopedT t_desc(cs.desc);
+        if (!w.mapping && w.query.off) {   // capacity 2*|query|+8 per alignment: the prefix sum is a difference of offsets
+            const uint64_t *qo = w.query.off + a0;
+            parallel_for(n + 1, ctx->host_threads, [&](uint64_t k0, uint64_t k1) { for (uint64_t k = k0; k < k1; k++) h_slab[k] = 2ull * (qo[k] - qo[0]) + 8ull * k; });
+            slab_bytes = h_slab[n];
+        } else {
+            for (uint64_t k = 0; k < n; k++) { h_slab[k] = slab_bytes; slab_bytes += 2ull * h_qlen[k] + 8ull; }
+            h_slab[n] = slab_bytes;
+        }
     }
     SG_CUDA(cudaMemcpyAsync(s.desc.p, s.h_desc.p, (5 * n + 1) * 8, cudaMemcpyHostToDevice, st));
+    cs.h2d_other += (5 * n + 1) * 8;
+    // Mixed lengths in one launch: the kernel's queue hands the alignments out longest first (the reference's callers sort
+    // their reads by descending length before the call for the same reason, src/tests.cu:377), results stay in input order.
+    const uint32_t *d_order = nullptr;
+    if (ctx->longest_first && n > 1 && n <= 0xFFFFFFFFull) {
+        ScopedT t_desc(cs.desc);
+        uint64_t lo = h_qlen[0], hi = h_qlen[0];
+        for (uint64_t k = 1; k < n; k++) { lo = std::min(lo, h_qlen[k]); hi = std::max(hi, h_qlen[k]); }
+        if (hi > lo + lo / 4 + 64) {
+            R(s.order.reserve(n * 4)); R(s.h_order.reserve(n * 4));
+            uint32_t *ho = s.h_order.as<uint32_t>();
+            for (uint64_t k = 0; k < n; k++) ho[k] = (uint32_t)k;
+            std::stable_sort(ho, ho + n, [&](uint32_t a, uint32_t b) { return h_qlen[a] > h_qlen[b]; });
+            SG_CUDA(cudaMemcpyAsync(s.order.p, ho, n * 4, cudaMemcpyHostToDevice, st));
+            cs.h2d_other += n * 4;
+            d_order = s.order.as<uint32_t>();
+        }
+    }
     if (want_cigar) R(s.slab.reserve(slab_bytes + 16));
     SG_CUDA(cudaEventRecord(s.ev_k0, st));
-    R(sg_dev_align_wo(ctx->W, ctx->O, d_text, d_tstart, d_tlen, s.packed_q.as<uint32_t>(), d_qstart, d_qlen, n, w.flags, s.slab.as<uint8_t>(), d_slab,
-                   s.counter.as<uint64_t>(), s.edit.as<int64_t>(), s.refc.as<uint64_t>(), s.nruns.as<uint32_t>(), s.status.as<uint8_t>(),
-                   nullptr, nullptr, st));
+    R(sg_dev_align_ordered(ctx->W, ctx->O, d_text, d_tstart, d_tlen, s.packed_q.as<uint32_t>(), d_qstart, d_qlen, n, w.flags, s.slab.as<uint8_t>(), d_slab,
+                           s.counter.as<uint64_t>(), s.edit.as<int64_t>(), s.refc.as<uint64_t>(), s.nruns.as<uint32_t>(), s.status.as<uint8_t>(),
+                           nullptr, nullptr, d_order, st));
     SG_CUDA(cudaEventRecord(s.ev_k1, st));
     uint64_t *h = s.h_small.as<uint64_t>();
     SG_CUDA(cudaMemcpyAsync(h, s.bad.p, 16, cudaMemcpyDeviceToHost, st));
@@ -530,18 +710,19 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
     SG_CUDA(cudaMemcpyAsync(res->edit + a0, s.edit.p, n * 8, cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaMemcpyAsync(res->refc + a0, s.refc.p, n * 8, cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaMemcpyAsync(s.h_status.p, s.status.p, n, cudaMemcpyDeviceToHost, st));
+    cs.d2h += 17 * n + 24;
     SG_CUDA(cudaEventRecord(s.ev_mid, st));
     return SG_OK;
 }
 
 // stage B: once the run total is known, gather the runs and send everything home; ends with ev_end
-int stage_b(Slot &s, const Workload &w, sg_result *res)
+int stage_b(Slot &s, const Workload &w, sg_result *res, ShardStats &cs)
 {
     if (!s.busy || s.mid_done) return SG_OK;
     const uint64_t n = s.a1 - s.a0;
     const bool want_cigar = !(w.flags & SG_FLAG_DISTANCE_ONLY);
     cudaStream_t st = s.stream;
-    { ScopedT t(g_ht.wait); SG_CUDA(cudaEventSynchronize(s.ev_mid)); }
+    { ScopedT t(cs.wait); SG_CUDA(cudaEventSynchronize(s.ev_mid)); }
     s.mid_done = true;
     const uint64_t *h = s.h_small.as<uint64_t>();
     if (h[0] != ~0ull || h[1] != ~0ull) {
@@ -559,6 +740,10 @@ int stage_b(Slot &s, const Workload &w, sg_result *res)
             if (hd[2 * n + k] <= pos && hd[2 * n + k] >= best_start) { best_start = hd[2 * n + k]; best = w.cand_read[s.a0 + k]; }
         return bad_base_error("content", "read", best, pos - best_start);
     }
+    // an alignment that ran out of slab capacity: stop here, before anything is gathered from the slab
+    if (const void *hit = n ? memchr(s.h_status.p, SG_ERR_CIGAR_OVERFLOW, n) : nullptr)
+        return fail(SG_ERR_CIGAR_OVERFLOW, "alignment " + std::to_string(s.a0 + (uint64_t)((const uint8_t *)hit - s.h_status.as<uint8_t>())) +
+                                               " exceeded its run capacity");
     if (want_cigar) {
         s.total_runs = h[2];
         R(s.runs.reserve(s.total_runs + 16));
@@ -570,6 +755,7 @@ int stage_b(Slot &s, const Workload &w, sg_result *res)
                                    s.runs.as<uint8_t>(), std::max<uint64_t>(1, (s.total_runs + n - 1) / n), st));
         SG_CUDA(cudaMemcpyAsync(s.piece.p, s.runs.p, s.total_runs, cudaMemcpyDeviceToHost, st));
         SG_CUDA(cudaMemcpyAsync(res->run_off + s.a0, s.run_off.p, n * 8, cudaMemcpyDeviceToHost, st));  // sub-batch-local, rebased in finalize()
+        cs.d2h += s.total_runs + n * 8;
     }
     SG_CUDA(cudaEventRecord(s.ev_end, st));
     return SG_OK;
@@ -579,15 +765,11 @@ int stage_b(Slot &s, const Workload &w, sg_result *res)
 int stage_c(Slot &s, const Workload &w, sg_result *res, ShardOut &so)
 {
     if (!s.busy) return SG_OK;
-    const uint64_t n = s.a1 - s.a0;
     const bool want_cigar = !(w.flags & SG_FLAG_DISTANCE_ONLY);
-    R(stage_b(s, w, res));
-    { ScopedT t(g_ht.wait); SG_CUDA(cudaEventSynchronize(s.ev_end)); }
+    R(stage_b(s, w, res, so.stats));
+    { ScopedT t(so.stats.wait); SG_CUDA(cudaEventSynchronize(s.ev_end)); }
     s.busy = false;
-    ScopedT t_out(g_ht.copy_out);
-    const uint8_t *status = s.h_status.as<uint8_t>();
-    if (const void *hit = n ? memchr(status, SG_ERR_CIGAR_OVERFLOW, n) : nullptr)
-        return fail(SG_ERR_CIGAR_OVERFLOW, "alignment " + std::to_string(s.a0 + (uint64_t)((const uint8_t *)hit - status)) + " exceeded its run capacity");
+    ScopedT t_out(so.stats.out);
     float ms = 0;
     SG_CUDA(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
     so.kernel_ms += ms;
@@ -600,9 +782,38 @@ int stage_c(Slot &s, const Workload &w, sg_result *res, ShardOut &so)
     return SG_OK;
 }
 
-// The pipeline over one device's share [c0, c1): weight prefix `woff` decides the sub-batch cuts.
-void run_shard(sg_ctx *ctx, Device &d, const Workload &w, const uint64_t *woff, uint64_t per_unit_extra, uint64_t c0, uint64_t c1,
-               sg_result *res, ShardOut &so)
+// Sub-batch cuts of the alignment range [c0, c1): a sub-batch grows while it stays under max_batch_bytes and is either
+// still small in bytes or still short of min_batch_units alignments.  Both stop conditions are monotone in the end:
+// binary search for the first end in (a, c1) that stops (a batch always takes at least one alignment).
+std::vector<uint64_t> sub_batch_cuts(uint64_t batch_bytes, uint64_t max_batch_bytes, uint64_t min_batch_units, const uint64_t *woff,
+                                     uint64_t per_unit_extra, uint64_t c0, uint64_t c1)
+{
+    std::vector<uint64_t> cuts{c0};
+    while (cuts.back() < c1) {
+        const uint64_t a = cuts.back();
+        auto stops = [&](uint64_t b) {
+            const uint64_t bytes = (woff[b + 1] - woff[a]) + per_unit_extra * (b + 1 - a);
+            return bytes > max_batch_bytes || (bytes > batch_bytes && b - a >= min_batch_units);
+        };
+        uint64_t lo = a + 1, hi = c1;
+        while (lo < hi) {
+            const uint64_t mid = lo + (hi - lo) / 2;
+            if (stops(mid)) hi = mid; else lo = mid + 1;
+        }
+        cuts.push_back(lo);
+    }
+    return cuts;
+}
+
+// One GPU's worker: a three-slot pipeline over the sub-batches it takes from the call's shared queue.  The queue is
+// the list of sub-batch cuts of the whole call in order; a GPU that finishes early simply takes more of them (dynamic
+// balance across GPUs, like the reference's atomic pair counter does across thread blocks, src/genasm_gpu.cu:602-622).
+struct BatchQueue {
+    std::vector<uint64_t> cuts;
+    std::atomic<size_t> next{0};
+};
+
+void run_shard(sg_ctx *ctx, Device &d, const Workload &w, BatchQueue &q, sg_result *res, ShardOut &so)
 {
     auto bail = [&](int rc) {
         so.rc = rc;
@@ -614,54 +825,23 @@ void run_shard(sg_ctx *ctx, Device &d, const Workload &w, const uint64_t *woff, 
         cudaGetLastError();
     };
     if (cudaSetDevice(d.id) != cudaSuccess) { cudaGetLastError(); fail(SG_ERR_CUDA, "cudaSetDevice failed"); bail(SG_ERR_CUDA); return; }
-    std::vector<uint64_t> cuts{c0};
-    while (cuts.back() < c1) {
-        // the sub-batch [a, b): b grows while the batch stays under max_batch_bytes and is either still small in bytes or
-        // still short of min_batch_units alignments.  Both stop conditions are monotone in b: binary search for the
-        // first b in (a, c1) that stops (a batch always takes at least one alignment).
-        const uint64_t a = cuts.back();
-        auto stops = [&](uint64_t b) {
-            const uint64_t bytes = (woff[b + 1] - woff[a]) + per_unit_extra * (b + 1 - a);
-            return bytes > ctx->max_batch_bytes || (bytes > ctx->batch_bytes && b - a >= ctx->min_batch_units);
-        };
-        uint64_t lo = a + 1, hi = c1;
-        while (lo < hi) {
-            const uint64_t mid = lo + (hi - lo) / 2;
-            if (stops(mid)) hi = mid; else lo = mid + 1;
-        }
-        cuts.push_back(lo);
-    }
-    const int nb = (int)cuts.size() - 1;
+    const size_t nb = q.cuts.size() - 1;
     const int kSlots = d.n_slots;
-    for (int k = 0; k < nb; k++) {
+    int k = 0;   // sub-batches this GPU has taken
+    while (true) {
+        const size_t b = q.next.fetch_add(1);
+        if (b >= nb) break;
         Slot &s = d.slots[k % kSlots];
-        int rc = stage_c(s, w, res, so);                       // frees the slot used by batch k - kSlots
-        if (!rc) rc = stage_a(ctx, d, s, w, cuts[k], cuts[k + 1], res);
-        if (!rc && k >= 1) rc = stage_b(d.slots[(k - 1) % kSlots], w, res);
+        int rc = stage_c(s, w, res, so);                       // frees the slot used by this GPU's batch k - kSlots
+        if (!rc) rc = stage_a(ctx, d, s, w, q.cuts[b], q.cuts[b + 1], res, so.stats);
+        if (!rc && k >= 1) rc = stage_b(d.slots[(k - 1) % kSlots], w, res, so.stats);
+        if (rc) { bail(rc); return; }
+        k++;
+    }
+    for (int j = std::max(0, k - kSlots); j < k; j++) {
+        int rc = stage_c(d.slots[j % kSlots], w, res, so);
         if (rc) { bail(rc); return; }
     }
-    for (int k = std::max(0, nb - kSlots); k < nb; k++) {
-        int rc = stage_c(d.slots[k % kSlots], w, res, so);
-        if (rc) { bail(rc); return; }
-    }
-}
-
-// splits [0,n) into contiguous parts with about equal weight, weight prefix given by off (n+1 entries)
-std::vector<uint64_t> split_by_weight(const uint64_t *off, uint64_t n, int parts)
-{
-    std::vector<uint64_t> cut(parts + 1, n);
-    cut[0] = 0;
-    const uint64_t total = off[n] - off[0] + n;  // +1 per alignment so that empty queries still spread
-    for (int k = 1; k < parts; k++) {
-        const uint64_t target = total / parts * k;
-        uint64_t lo = cut[k - 1], hi = n;
-        while (lo < hi) {
-            uint64_t mid = (lo + hi) / 2;
-            if (off[mid] - off[0] + mid < target) lo = mid + 1; else hi = mid;
-        }
-        cut[k] = lo;
-    }
-    return cut;
 }
 
 void finalize(sg_result *res, std::vector<ShardOut> &shards)
@@ -670,17 +850,23 @@ void finalize(sg_result *res, std::vector<ShardOut> &shards)
     for (ShardOut &so : shards) kms = std::max(kms, so.kernel_ms);
     res->kernel_ns = (int64_t)(kms * 1e6);
     if (!res->has_cigar) return;
-    // pieces are in alignment order once the shards are concatenated; rebase per-piece offsets to global ones
-    uint64_t run0 = 0;
+    // every processed sub-batch left one piece; with several GPUs taking sub-batches from one queue the pieces of a
+    // shard are ordered but interleaved with the other shards': sort all by first alignment, then rebase the
+    // per-piece run offsets to global ones
+    struct Piece { PinnedPool::Block blk; uint64_t first, runs; };
+    std::vector<Piece> all;
     for (ShardOut &so : shards) {
-        for (size_t k = 0; k < so.pieces.size(); k++) {
-            res->piece_first.push_back(so.piece_first[k]);
-            res->piece_run0.push_back(run0);
-            res->piece_runs.push_back(so.piece_runs[k]);
-            run0 += so.piece_runs[k];
-            res->pieces.push_back(so.pieces[k]);
-        }
+        for (size_t k = 0; k < so.pieces.size(); k++) all.push_back({so.pieces[k], so.piece_first[k], so.piece_runs[k]});
         so.pieces.clear();
+    }
+    std::sort(all.begin(), all.end(), [](const Piece &a, const Piece &b) { return a.first < b.first; });
+    uint64_t run0 = 0;
+    for (const Piece &pc : all) {
+        res->piece_first.push_back(pc.first);
+        res->piece_run0.push_back(run0);
+        res->piece_runs.push_back(pc.runs);
+        res->pieces.push_back(pc.blk);
+        run0 += pc.runs;
     }
     for (size_t k = 0; k < res->pieces.size(); k++) {
         const uint64_t a0 = res->piece_first[k];
@@ -702,9 +888,17 @@ const uint8_t *runs_of(const sg_result *r, uint64_t idx, uint64_t *count)
     return r->pieces[k].p + (r->run_off[idx] - r->piece_run0[k]);
 }
 
+// Restores the caller's current CUDA device when a public entry point returns.
+struct ScopedDevice {
+    int saved = -1;
+    ScopedDevice() { if (cudaGetDevice(&saved) != cudaSuccess) { cudaGetLastError(); saved = -1; } }
+    ~ScopedDevice() { if (saved >= 0) cudaSetDevice(saved); }
+};
+
 int run_all(sg_ctx *ctx, const Workload &w, const uint64_t *woff, uint64_t per_unit_extra, uint64_t n, sg_result **out)
 {
     auto t_begin = std::chrono::steady_clock::now();
+    ScopedDevice keep_device;
     std::unique_ptr<sg_result> res(new sg_result);
     res->n = n;
     res->has_cigar = !(w.flags & SG_FLAG_DISTANCE_ONLY);
@@ -718,13 +912,23 @@ int run_all(sg_ctx *ctx, const Workload &w, const uint64_t *woff, uint64_t per_u
     const int nd = (int)ctx->devs.size();
     std::vector<ShardOut> shards(nd);
     if (n) {
-        const std::vector<uint64_t> cut = split_by_weight(woff, n, nd);
+        BatchQueue q;
+        q.cuts = sub_batch_cuts(ctx->batch_bytes, ctx->max_batch_bytes, ctx->min_batch_units, woff, per_unit_extra, 0, n);
+        // a call with fewer than two sub-batches per GPU would leave GPUs idle or without anything to overlap: cut finer
+        if (nd > 1 && q.cuts.size() - 1 < (size_t)nd * 2) {
+            const uint64_t total = woff[n] - woff[0] + per_unit_extra * n;
+            q.cuts = sub_batch_cuts(std::max<uint64_t>(1, total / ((uint64_t)nd * 2)), ctx->max_batch_bytes, 1, woff, per_unit_extra, 0, n);
+        }
         if (nd == 1) {
-            run_shard(ctx, ctx->devs[0], w, woff, per_unit_extra, cut[0], cut[1], res.get(), shards[0]);
+            ScopedAffinity bound(ctx->devs[0].cpus);   // the caller's thread is this GPU's worker for the call
+            run_shard(ctx, ctx->devs[0], w, q, res.get(), shards[0]);
         } else {
             std::vector<std::thread> th;
             for (int k = 0; k < nd; k++)
-                th.emplace_back([&, k]() { run_shard(ctx, ctx->devs[k], w, woff, per_unit_extra, cut[k], cut[k + 1], res.get(), shards[k]); });
+                th.emplace_back([&, k]() {
+                    bind_this_thread(ctx->devs[k].cpus);
+                    run_shard(ctx, ctx->devs[k], w, q, res.get(), shards[k]);
+                });
             for (auto &t : th) t.join();
         }
         for (ShardOut &so : shards)
@@ -732,11 +936,29 @@ int run_all(sg_ctx *ctx, const Workload &w, const uint64_t *woff, uint64_t per_u
     }
     finalize(res.get(), shards);
     res->total_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_begin).count();
-    if (g_debug) {
-        fprintf(stderr, "[sg] call %.1f ms: host pack %.1f, waits %.1f, results out %.1f, descriptors %.1f\n", res->total_ns / 1e6,
-                g_ht.pack * 1e3, g_ht.wait * 1e3, g_ht.copy_out * 1e3, g_ht.desc * 1e3);
-        g_ht = HostTimes();
+    sg_call_stats &S = res->stats;
+    memset(&S, 0, sizeof S);
+    S.total_ns = res->total_ns;
+    S.kernel_ns = res->kernel_ns;
+    S.n_devices = (uint32_t)nd;
+    S.host_threads_per_device = (uint32_t)ctx->host_threads;
+    for (ShardOut &so : shards) {
+        const ShardStats &c = so.stats;
+        S.upload_ns = std::max<int64_t>(S.upload_ns, (int64_t)(c.upload * 1e9));
+        S.wait_ns = std::max<int64_t>(S.wait_ns, (int64_t)(c.wait * 1e9));
+        S.host_other_ns = std::max<int64_t>(S.host_other_ns, (int64_t)((c.desc + c.out) * 1e9));
+        S.pack_thread_ns += (int64_t)c.pack_thread_ns.load();
+        S.h2d_ascii_bytes += c.h2d_ascii;
+        S.h2d_packed_bytes += c.h2d_packed.load();
+        S.h2d_other_bytes += c.h2d_other;
+        S.d2h_bytes += c.d2h;
+        S.sub_batches += c.sub_batches;
     }
+    if (g_debug)
+        fprintf(stderr, "[sg] call %.1f ms on %d GPU(s): ingest %.1f (packer threads busy %.1f thread-ms), waits %.1f, other host %.1f; "
+                        "H2D %.1f MB ASCII + %.1f MB packed + %.1f MB descriptors, D2H %.1f MB, %u sub-batches\n",
+                S.total_ns / 1e6, nd, S.upload_ns / 1e6, S.pack_thread_ns / 1e6, S.wait_ns / 1e6, S.host_other_ns / 1e6, S.h2d_ascii_bytes / 1e6,
+                S.h2d_packed_bytes / 1e6, S.h2d_other_bytes / 1e6, S.d2h_bytes / 1e6, S.sub_batches);
     *out = res.release();
     return SG_OK;
 }
@@ -754,9 +976,12 @@ int sg_ctx_create(sg_ctx **out, const int *device_ids, int n_devices, int W)
 int sg_ctx_window(const sg_ctx *ctx) { return ctx ? ctx->W : 0; }
 int sg_ctx_overlap(const sg_ctx *ctx) { return ctx ? ctx->O : 0; }
 
+static std::atomic<int> g_live_contexts{0};
+
 int sg_ctx_create_wo(sg_ctx **out, const int *device_ids, int n_devices, int W, int O)
 {
     if (!out) return fail(SG_ERR_BAD_ARG, "sg_ctx_create: null out");
+    ScopedDevice keep_device;
     if (W < 2 || W > 256 || O < 0 || O >= W || W - O > 128)
         return fail(SG_ERR_BAD_ARG, "window configuration out of range: need 2 <= W <= 256, 0 <= O < W, W - O <= 128");
     const int avail = sg_device_count();
@@ -772,10 +997,12 @@ int sg_ctx_create_wo(sg_ctx **out, const int *device_ids, int n_devices, int W, 
         if (mb > 0) ctx->batch_bytes = (uint64_t)mb << 20;
     }
     {
-        // host threads this context may use for packing: SG_HOST_THREADS, else all hardware threads shared by its GPUs
-        int hw = (int)std::thread::hardware_concurrency();
-        if (const char *v = std::getenv("SG_HOST_THREADS")) hw = std::max(1, std::atoi(v));
-        ctx->host_threads = std::max(1, hw / n_devices);
+        // Host threads per GPU for packing: the CPUs this process may use (its affinity mask, or SG_CPUS=<list>) divided
+        // among the context's GPUs; SG_HOST_THREADS=<n> sets the count per GPU directly (0: no packer threads, every blob
+        // crosses PCIe as ASCII).  One of a GPU's CPUs is left to its worker thread (the feeder of the adaptive ingest).
+        const std::vector<int> allowed = allowed_cpus();
+        ctx->host_threads = std::max(1, (int)allowed.size() / n_devices - (allowed.size() / n_devices >= 4 ? 1 : 0));
+        if (const char *v = std::getenv("SG_HOST_THREADS")) ctx->host_threads = std::max(0, std::atoi(v));
         ctx->host_pack = ctx->host_threads >= 10;   // ~7-10 GB/s of ASCII per thread against ~47 GB/s of PCIe per GPU
         if (const char *v = std::getenv("SG_HOST_PACK")) ctx->host_pack = std::atoi(v) != 0;
         if (const char *v = std::getenv("SG_ASCII_MIN_BYTES")) ctx->ascii_min_bytes = (uint64_t)std::max(0ll, std::atoll(v));
@@ -785,7 +1012,21 @@ int sg_ctx_create_wo(sg_ctx **out, const int *device_ids, int n_devices, int W, 
         ctx->adaptive = !std::getenv("SG_HOST_PACK") && !std::getenv("SG_ASCII_PCT");
         if (const char *v = std::getenv("SG_INGEST")) ctx->adaptive = std::string(v) == "adaptive";
         if (const char *v = std::getenv("SG_CHUNK_KB")) ctx->chunk_bytes = std::max<uint64_t>(256, ((uint64_t)std::max(1ll, std::atoll(v)) << 10) & ~255ull);
-        if (const char *v = std::getenv("SG_DMA_DEPTH")) ctx->dma_depth = std::min(kMaxDmaDepth, std::max(1, std::atoi(v)));
+        // SG_DMA_DEPTH=<n>: ASCII chunk copies the feeder keeps in flight (0: none -- the host packs everything)
+        if (const char *v = std::getenv("SG_DMA_DEPTH")) ctx->dma_depth = std::min(kMaxDmaDepth, std::max(0, std::atoi(v)));
+        if (ctx->host_threads == 0) ctx->dma_depth = std::max(1, ctx->dma_depth);
+    }
+    // which CPUs serve which GPU (sg_host_threads.h); SG_AFFINITY=0 leaves every thread where the scheduler puts it
+    std::vector<std::vector<int>> cpu_sets(n_devices);
+    if (!(std::getenv("SG_AFFINITY") && std::atoi(std::getenv("SG_AFFINITY")) == 0)) {
+        std::vector<std::vector<int>> local(n_devices);
+        for (int k = 0; k < n_devices; k++) {
+            char bus[32] = {0};
+            const int id = device_ids ? device_ids[k] : k;
+            if (id >= 0 && id < avail && cudaDeviceGetPCIBusId(bus, sizeof bus, id) == cudaSuccess) local[k] = pci_local_cpus(bus);
+            cudaGetLastError();
+        }
+        cpu_sets = assign_cpus(allowed_cpus(), local);
     }
     if (const char *v = std::getenv("SG_MAX_BATCH_MB")) {
         const long mb = std::atol(v);
@@ -796,14 +1037,28 @@ int sg_ctx_create_wo(sg_ctx **out, const int *device_ids, int n_devices, int W, 
         d.id = device_ids ? device_ids[k] : k;
         if (d.id < 0 || d.id >= avail) return fail(SG_ERR_BAD_ARG, "device id out of range");
         SG_CUDA(cudaSetDevice(d.id));
+        d.cpus = cpu_sets[k];
         if (const char *v = std::getenv("SG_SLOTS")) d.n_slots = std::min(kMaxSlots, std::max(2, std::atoi(v)));
         for (int q = 0; q < d.n_slots; q++) R(d.slots[q].create());
+        if (ctx->host_threads > 0) {
+            const int dev_id = d.id;
+            d.team.start(ctx->host_threads, d.cpus, [dev_id](int) { cudaSetDevice(dev_id); });
+        }
         int wps = 0, sms = 0;
         R(sg_dev_align_geometry_wo(W, O, &wps, nullptr, &sms));
         // one alignment per resident lane fills the device (104 192 lanes on a B200 at W=64)
         ctx->min_batch_units = std::max<uint64_t>(ctx->min_batch_units, 32ull * (uint64_t)wps * (uint64_t)sms);
     }
+    if (const char *v = std::getenv("SG_LONGEST_FIRST")) ctx->longest_first = std::atoi(v) != 0;
     if (const char *v = std::getenv("SG_MIN_BATCH_UNITS")) ctx->min_batch_units = (uint64_t)std::max(1ll, std::atoll(v));
+    if (g_debug)
+        for (const Device &d : ctx->devs) {
+            std::string l;
+            for (int c : d.cpus) l += (l.empty() ? "" : ",") + std::to_string(c);
+            fprintf(stderr, "[sg] GPU %d: %d packer threads on CPUs {%s}\n", d.id, ctx->host_threads, l.c_str());
+        }
+    g_live_contexts++;
+    ctx->counted = true;
     *out = ctx.release();
     return SG_OK;
 }
@@ -811,24 +1066,73 @@ int sg_ctx_create_wo(sg_ctx **out, const int *device_ids, int n_devices, int W, 
 void sg_ctx_destroy(sg_ctx *ctx)
 {
     if (!ctx) return;
-    for (Device &d : ctx->devs) {
-        cudaSetDevice(d.id);
-        for (Slot &s : d.slots) s.destroy();
-        d.genome.release();
+    {
+        ScopedDevice keep_device;
+        for (Device &d : ctx->devs) {
+            d.team.stop();
+            cudaSetDevice(d.id);
+            for (Slot &s : d.slots) s.destroy();
+            d.genome.release();
+            d.piece_bad.release();
+        }
     }
+    const bool counted = ctx->counted;
     delete ctx;
+    // the page-locked blocks the pool kept for reuse go back to the system with the last context
+    if (counted && --g_live_contexts == 0) g_pool.trim(0);
+}
+
+void sg_trim_host_cache(void) { g_pool.trim(0); }
+
+int sg_result_stats(const sg_result *r, sg_call_stats *out)
+{
+    if (!r || !out) return fail(SG_ERR_BAD_ARG, "sg_result_stats: null argument");
+    *out = r->stats;
+    return SG_OK;
 }
 
 int sg_ctx_num_devices(const sg_ctx *ctx) { return ctx ? (int)ctx->devs.size() : 0; }
 
+// n+1 offsets must not decrease, and a blob that holds bytes must exist: otherwise sizes wrap to ~2^64 further down
+static int check_blob(const char *name, const char *blob, const uint64_t *off, uint64_t n, int threads)
+{
+    std::atomic<uint64_t> first_bad{~0ull};
+    parallel_for(n, threads, [&](uint64_t k0, uint64_t k1) {
+        for (uint64_t k = k0; k < k1; k++)
+            if (off[k + 1] < off[k]) {
+                uint64_t cur = first_bad.load();
+                while (k < cur && !first_bad.compare_exchange_weak(cur, k)) {}
+                return;
+            }
+    });
+    if (first_bad.load() != ~0ull)
+        return fail(SG_ERR_BAD_ARG, std::string(name) + " offsets decrease at entry " + std::to_string(first_bad.load() + 1));
+    if (!blob && off[n] > off[0]) return fail(SG_ERR_BAD_ARG, std::string(name) + " blob is NULL but its offsets span " + std::to_string(off[n] - off[0]) + " bytes");
+    return SG_OK;
+}
+
+static int check_separate(const char *name, const char *const *ptr, const uint64_t *len, uint64_t n)
+{
+    for (uint64_t k = 0; k < n; k++)
+        if (!ptr[k] && len[k]) return fail(SG_ERR_BAD_ARG, std::string(name) + " " + std::to_string(k) + " is NULL with a non-zero length");
+    return SG_OK;
+}
+
 static int align_pairs_common(sg_ctx *ctx, const Strings &text, const Strings &query, uint64_t n_pairs, uint32_t flags, sg_result **out)
 {
     std::lock_guard<std::mutex> lock(ctx->mu);
+    if (text.off) {
+        R(check_blob("text", text.blob, text.off, n_pairs, ctx->host_threads));
+        R(check_blob("query", query.blob, query.off, n_pairs, ctx->host_threads));
+    } else {
+        R(check_separate("text", text.ptr, text.len, n_pairs));
+        R(check_separate("query", query.ptr, query.len, n_pairs));
+    }
     Workload w;
     w.text = text; w.query = query; w.flags = flags;
     // sub-batches are cut by uploaded bytes (text + query), shards by the same weight
     std::unique_ptr<uint64_t[]> woff(new uint64_t[n_pairs + 1]);
-    if (text.blob && query.blob) {   // a prefix sum of sizes is a difference of offsets: no serial pass over the pairs
+    if (text.off && query.off) {   // a prefix sum of sizes is a difference of offsets: no serial pass over the pairs
         const uint64_t t0 = text.off[0], q0 = query.off[0];
         parallel_for(n_pairs + 1, ctx->host_threads, [&](uint64_t p0, uint64_t p1) {
             for (uint64_t p = p0; p < p1; p++) woff[p] = (text.off[p] - t0) + (query.off[p] - q0);
@@ -877,28 +1181,39 @@ int sg_set_reference(sg_ctx *ctx, const char *genome_ascii, uint64_t genome_len)
         SG_CUDA(cudaSetDevice(d.id));
         d.has_genome = false;
         R(d.genome.reserve(sg_packed_words(genome_len) * 4 + 64));
-        R(s.bad.reserve(16));
-        R(s.h_small.reserve(64));
-        SG_CUDA(cudaMemsetAsync(s.bad.p, 0xFF, 16, s.stream));
-        // upload in 256 Mbase pieces (a multiple of 16 bases, so every piece packs to whole words), alternating
-        // between two staging buffers so that the copy of piece k+1 can overlap the packing of piece k
+        // upload in 256 Mbase pieces (a multiple of 16 bases, so every piece packs to whole words) through two staging
+        // buffers: copies go to a copy stream, packing kernels to the slot's stream, chained by events -- the copy of
+        // piece k+1 overlaps the packing of piece k, a buffer is reused only after the kernel that read it.  The
+        // offending-base word is checked once, after the last piece (the kernel keeps the smallest position).
         const uint64_t piece = 256ull << 20;
         DevBuf *stage[2] = {&s.ascii_t, &s.ascii_q};
         R(stage[0]->reserve(std::min<uint64_t>(piece, genome_len) + 64));
         if (genome_len > piece) R(stage[1]->reserve(std::min<uint64_t>(piece, genome_len - piece) + 64));
-        uint64_t pos = 0, first_bad = ~0ull;
-        uint64_t *h = s.h_small.as<uint64_t>();
+        cudaStream_t copy_st = d.slots[1].stream;
+        cudaEvent_t copied[2] = {s.ev_dma[0], s.ev_dma[1]}, packed[2] = {s.ev_dma[2], s.ev_dma[3]};
+        R(d.piece_bad.reserve(16 * (genome_len / piece + 1)));
+        SG_CUDA(cudaMemsetAsync(d.piece_bad.p, 0xFF, 16 * (genome_len / piece + 1), s.stream));
+        SG_CUDA(cudaEventRecord(packed[0], s.stream));
+        SG_CUDA(cudaEventRecord(packed[1], s.stream));
+        uint64_t pos = 0, first_bad = ~0ull, npieces = 0;
         int k2 = 0;
-        do {
+        while (pos < genome_len) {
             const uint64_t len = std::min<uint64_t>(piece, genome_len - pos);
-            SG_CUDA(cudaMemcpyAsync(stage[k2]->p, genome_ascii + pos, len, cudaMemcpyHostToDevice, s.stream));
-            R(sg_dev_pack_2bit(stage[k2]->as<char>(), len, d.genome.as<uint32_t>() + pos / 16, s.bad.as<uint64_t>(), s.stream));
-            SG_CUDA(cudaMemcpyAsync(h, s.bad.p, 8, cudaMemcpyDeviceToHost, s.stream));
-            SG_CUDA(cudaStreamSynchronize(s.stream));
-            if (h[0] != ~0ull) { first_bad = pos + h[0]; break; }
+            SG_CUDA(cudaStreamWaitEvent(copy_st, packed[k2], 0));
+            SG_CUDA(cudaMemcpyAsync(stage[k2]->p, genome_ascii + pos, len, cudaMemcpyHostToDevice, copy_st));
+            SG_CUDA(cudaEventRecord(copied[k2], copy_st));
+            SG_CUDA(cudaStreamWaitEvent(s.stream, copied[k2], 0));
+            R(sg_dev_pack_2bit(stage[k2]->as<char>(), len, d.genome.as<uint32_t>() + pos / 16, d.piece_bad.as<uint64_t>() + 2 * npieces, s.stream));
+            SG_CUDA(cudaEventRecord(packed[k2], s.stream));
             pos += len;
+            npieces++;
             k2 ^= 1;
-        } while (pos < genome_len);
+        }
+        std::vector<uint64_t> hbad(2 * std::max<uint64_t>(npieces, 1), ~0ull);
+        if (npieces) SG_CUDA(cudaMemcpyAsync(hbad.data(), d.piece_bad.p, 16 * npieces, cudaMemcpyDeviceToHost, s.stream));
+        SG_CUDA(cudaStreamSynchronize(s.stream));
+        for (uint64_t q = 0; q < npieces && first_bad == ~0ull; q++)
+            if (hbad[2 * q] != ~0ull) first_bad = q * piece + hbad[2 * q];
         if (first_bad != ~0ull) return fail(SG_ERR_BAD_BASE, "non-ACGT character in reference at position " + std::to_string(first_bad));
         d.genome_len = genome_len;
         d.has_genome = true;
@@ -918,11 +1233,36 @@ static int align_candidates_common(sg_ctx *ctx, const Strings &reads, uint64_t n
     for (Device &d : ctx->devs)
         if (!d.has_genome) return fail(SG_ERR_NO_REFERENCE, "sg_align_candidates: call sg_set_reference first");
     const uint64_t genome_len = ctx->devs[0].genome_len;
-    std::vector<uint64_t> woff(n_cand + 1, 0);  // weight of a candidate = its read's length
-    for (uint64_t c = 0; c < n_cand; c++) {
-        if (cand_read[c] >= n_reads) return fail(SG_ERR_BAD_ARG, "candidate " + std::to_string(c) + ": read index out of range");
-        if (cand_start[c] > genome_len) return fail(SG_ERR_BAD_ARG, "candidate " + std::to_string(c) + ": start beyond the reference");
-        woff[c + 1] = woff[c] + reads.size(cand_read[c]);
+    if (reads.off) R(check_blob("read", reads.blob, reads.off, n_reads, ctx->host_threads));
+    else R(check_separate("read", reads.ptr, reads.len, n_reads));
+    // weight of a candidate = its read's length: every thread validates and prefix-sums its own range, the ranges are
+    // then rebased by the totals of the ranges before them
+    std::vector<uint64_t> woff(n_cand + 1, 0);
+    {
+        std::atomic<uint64_t> bad_read{~0ull}, bad_start{~0ull};
+        auto note = [](std::atomic<uint64_t> &a, uint64_t c) { uint64_t cur = a.load(); while (c < cur && !a.compare_exchange_weak(cur, c)) {} };
+        std::mutex mu;
+        std::vector<std::pair<uint64_t, uint64_t>> ranges;   // (first candidate of a range, its total weight)
+        parallel_for(n_cand, ctx->host_threads, [&](uint64_t c0, uint64_t c1) {
+            uint64_t acc = 0;
+            for (uint64_t c = c0; c < c1; c++) {
+                if (cand_read[c] >= n_reads) { note(bad_read, c); continue; }
+                if (cand_start[c] > genome_len) note(bad_start, c);
+                acc += reads.size(cand_read[c]);
+                woff[c + 1] = acc;
+            }
+            std::lock_guard<std::mutex> g(mu);
+            ranges.emplace_back(c0, acc);
+        });
+        if (bad_read.load() != ~0ull) return fail(SG_ERR_BAD_ARG, "candidate " + std::to_string(bad_read.load()) + ": read index out of range");
+        if (bad_start.load() != ~0ull) return fail(SG_ERR_BAD_ARG, "candidate " + std::to_string(bad_start.load()) + ": start beyond the reference");
+        std::sort(ranges.begin(), ranges.end());
+        uint64_t base = 0;
+        for (size_t r = 0; r < ranges.size(); r++) {
+            const uint64_t c0 = ranges[r].first, c1 = r + 1 < ranges.size() ? ranges[r + 1].first : n_cand;
+            if (base) parallel_for(c1 - c0, ctx->host_threads, [&](uint64_t k0, uint64_t k1) { for (uint64_t k = k0; k < k1; k++) woff[c0 + k + 1] += base; });
+            base += ranges[r].second;
+        }
     }
     Workload w;
     w.mapping = true;

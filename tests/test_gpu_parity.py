@@ -273,7 +273,8 @@ def test_multi_gpu_context_matches_single(oracle, sglib):
 
 
 @pytest.mark.parametrize("dc,forefront,host_pack", [("delta", "smem", "0"), ("delta", "smem", "1"), ("delta", "smem", "hybrid"),
-                                                    ("delta", "smem", "adaptive"),
+                                                    ("delta", "smem", "adaptive"), ("delta", "smem", "adaptive_dma"),
+                                                    ("delta", "smem", "adaptive_host"),
                                                     ("rows", "smem", "0"), ("rows", "tmem", "1"), ("rows", "smem", "1"),
                                                     ("rows", "tmem", "0")])
 def test_kernel_and_ingest_variants(dc, forefront, host_pack):
@@ -331,8 +332,12 @@ def test_kernel_and_ingest_variants(dc, forefront, host_pack):
     )
     import os
     env = dict(os.environ, SG_DC=dc, SG_FOREFRONT=forefront)
-    if host_pack == "adaptive":   # the default for large blobs, forced here on the small test inputs with 1 KB chunks
+    if host_pack.startswith("adaptive"):   # the default for large blobs, forced here on the small test inputs with 1 KB chunks
         env.update(SG_INGEST="adaptive", SG_ASCII_MIN_BYTES="0", SG_CHUNK_KB="1")
+        if host_pack == "adaptive_dma":    # no packer threads: every chunk crosses as ASCII
+            env.update(SG_HOST_THREADS="0")
+        if host_pack == "adaptive_host":   # no ASCII copies: the packer threads take every chunk
+            env.update(SG_DMA_DEPTH="0")
     else:
         env.update(SG_HOST_PACK="1" if host_pack == "hybrid" else host_pack)
     if host_pack == "hybrid":

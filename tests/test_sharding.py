@@ -27,6 +27,23 @@ def test_rank_shard_partitions():
         sharding.rank_shard(4, 4, 10)
 
 
+def test_rank_cpus_are_disjoint_and_numa_local():
+    allowed = list(range(32))
+    # unknown locality: 8 ranks share 32 CPUs in equal slices
+    sets = [sharding.rank_cpus(r, 8, allowed, [[]] * 8) for r in range(8)]
+    assert all(len(s) == 4 for s in sets) and sorted(c for s in sets for c in s) == allowed
+    # two NUMA nodes, four GPUs each: every rank stays on its GPU's node
+    local = [list(range(0, 16))] * 4 + [list(range(16, 32))] * 4
+    sets = [sharding.rank_cpus(r, 8, allowed, local) for r in range(8)]
+    assert sorted(c for s in sets for c in s) == allowed
+    assert all(set(sets[r]) <= set(local[r]) for r in range(8))
+    # a restricted affinity mask wins over the machine's list; a GPU whose node is outside the mask falls back to the mask
+    sets = [sharding.rank_cpus(r, 2, [0, 1, 2, 3], [[0, 1, 2, 3, 4, 5], [16, 17]]) for r in range(2)]
+    assert all(s and set(s) <= {0, 1, 2, 3} for s in sets)
+    assert sharding.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert sharding.format_cpulist([4, 5, 9]) == "4,5,9"
+
+
 def _worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
