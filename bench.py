@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU per step")
     ap.add_argument("--e2e-pairs", type=int, default=524_288, help="pairs per GPU per end-to-end step (host buffers)")
     ap.add_argument("--cpu-sample", type=int, default=32_768, help="pairs of the CPU baseline / parity sample")
+    ap.add_argument("--pipeline", type=int, default=1, help="1: ingest / align / compaction of consecutive passes overlap on three streams; "
+                                                            "0: one stream, stages back to back")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs legs (configs[1] short reads, configs[3] mapping)")
@@ -263,41 +265,84 @@ def main():
     qlen = torch.full((n,), L, dtype=torch.int64, device=dev)
     cap = 2 * L + 8  # runs per alignment (reference: 2*|query| entries, src/genasm_gpu.cu:995-1001)
     slab_off = torch.arange(n + 1, dtype=torch.int64, device=dev) * cap
-    da = device.DeviceAligner(W, n, dev, slab_bytes=n * cap)
+    # Two buffer sets: while the alignment kernel works on pass k (high-priority stream), the ingest of pass k+1 and the
+    # compaction of pass k-1 run beside it on two more streams -- both are HBM-bound and small (2 x 2.0 ms and 1.2 ms
+    # against 36.5 ms of integer-issue-bound alignment), and the alignment kernel leaves a CTA slot per SM free for them
+    # (csrc/sg_device_api.cu: setup_delta_kernel).  --pipeline 0 runs the three stages of a pass back to back on one stream.
+    nset = 2 if args.pipeline else 1
+    das = [device.DeviceAligner(W, n, dev, slab_bytes=n * cap) for _ in range(nset)]
     words_t, words_q = int(lib.sg_packed_words(n * stride)), int(lib.sg_packed_words(n * L))
-    ptext = torch.empty(words_t, dtype=torch.int32, device=dev)
-    pquery = torch.empty(words_q, dtype=torch.int32, device=dev)
+    ptexts = [torch.empty(words_t, dtype=torch.int32, device=dev) for _ in range(nset)]
+    pquerys = [torch.empty(words_q, dtype=torch.int32, device=dev) for _ in range(nset)]
     bad = torch.full((2,), -1, dtype=torch.int64, device=dev)
-    runs = None  # dense run array, sized exactly by the first (untimed) step: the batch is the same every step
-    stream = int(torch.cuda.current_stream().cuda_stream)
+    runs_sets = [None] * nset  # dense run arrays, sized exactly by the first (untimed) pass: the batch is the same every pass
     p = lambda t: int(t.data_ptr())
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+    main = torch.cuda.current_stream()
+    s_align = torch.cuda.Stream(device=dev, priority=-1) if args.pipeline else main
+    s_in = torch.cuda.Stream(device=dev) if args.pipeline else main
+    s_out = torch.cuda.Stream(device=dev) if args.pipeline else main
+    e_ingested = [torch.cuda.Event() for _ in range(nset)]
+    e_aligned = [torch.cuda.Event() for _ in range(nset)]
+    e_compacted = [torch.cuda.Event() for _ in range(nset)]
 
-    def step(k=None):
-        scrooge_b200._lib.check(lib.sg_dev_pack_2bit(p(text), n * stride, p(ptext), p(bad), stream))
-        scrooge_b200._lib.check(lib.sg_dev_pack_2bit(p(reads), n * L, p(pquery), p(bad) + 8, stream))
-        if k is not None:
-            ev[k][0].record()
-        da.align(ptext, tstart, tlen, pquery, qstart, qlen, slab_off)
-        if k is not None:
-            ev[k][1].record()
-        return da.compact(slab_off, runs)[1]
+    def ingest(b):
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(e_aligned[b])      # the alignment that read this set's packed buffers is done
+            st = int(s_in.cuda_stream)
+            side = 1 if args.pipeline else 0   # SG_PACK_SIDE: CTAs that fit beside the alignment kernel
+            scrooge_b200._lib.check(lib.sg_dev_pack_2bit_ex(p(text), n * stride, p(ptexts[b]), p(bad), side, st))
+            scrooge_b200._lib.check(lib.sg_dev_pack_2bit_ex(p(reads), n * L, p(pquerys[b]), p(bad) + 8, side, st))
+            e_ingested[b].record(s_in)
+
+    def align(b, k=None):
+        with torch.cuda.stream(s_align):
+            s_align.wait_event(e_ingested[b])
+            s_align.wait_event(e_compacted[b])  # this set's slab and run counts have been gathered
+            if k is not None:
+                ev[k][0].record(s_align)
+            das[b].align(ptexts[b], tstart, tlen, pquerys[b], qstart, qlen, slab_off)
+            if k is not None:
+                ev[k][1].record(s_align)
+            e_aligned[b].record(s_align)
+
+    def compact(b):
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(e_aligned[b])
+            runs_sets[b] = das[b].compact(slab_off, runs_sets[b])[1]
+            e_compacted[b].record(s_out)
+
+    def run_steps(K, timed):
+        """K complete passes (K ingests, K alignments, K compactions), software-pipelined over the buffer sets."""
+        for st_ in (s_align, s_in, s_out):
+            st_.wait_stream(main)
+        for b in range(nset):
+            for e in (e_ingested[b], e_aligned[b], e_compacted[b]):
+                e.record(main)
+        ingest(0)
+        for k in range(K):
+            b = k % nset
+            align(b, k if timed else None)
+            if k + 1 < K:
+                ingest((k + 1) % nset)
+            compact(b)
+        for st_ in (s_align, s_in, s_out):
+            main.wait_stream(st_)
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
 
-    runs = step()  # untimed: also allocates the dense run array
-    for _ in range(args.warmup):
-        step()
+    run_steps(nset, False)  # untimed: also allocates the dense run arrays
+    torch.cuda.synchronize()
+    run_steps(max(args.warmup, 1), False)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_begin.record()
-    for k in range(args.steps):
-        step(k)
-    t_end.record()
+    t_begin.record(main)
+    run_steps(args.steps, True)
+    t_end.record(main)
     barrier()
     clocks = sampler.stop() if sampler else None
     ms_total = t_begin.elapsed_time(t_end)
@@ -306,6 +351,14 @@ def main():
     ms_kernel = sharding.max_over_ranks(ms_kernel)
     ms_step = ms_total / args.steps
     value = world * n / (ms_step / 1e3)
+    da, runs, ptext, pquery = das[0], runs_sets[0], ptexts[0], pquerys[0]
+    if nset > 1:   # both sets hold the same batch: the second must have produced the same bytes
+        assert torch.equal(das[1].out.edit, da.out.edit) and torch.equal(das[1].run_off, da.run_off), "buffer sets disagree"
+        n_cmp = min(int(da.run_off[-1]), 1 << 28)
+        assert torch.equal(runs_sets[1][:n_cmp], runs[:n_cmp]), "buffer sets disagree (runs)"
+        das[1] = None
+        runs_sets[1] = ptexts[1] = pquerys[1] = None
+        torch.cuda.empty_cache()
 
     assert int(bad[0]) == -1 and int(bad[1]) == -1, "ingest flagged a non-ACGT base"
     assert int(da.out.status.max()) == 0, "a CIGAR slab overflowed"
@@ -513,6 +566,7 @@ def main():
     extra = None
     if world == 1 and not args.no_extra:
         del text, reads, ptext, pquery, runs, da, slab_off
+        das.clear(); runs_sets.clear(); ptexts.clear(); pquerys.clear()
         torch.cuda.empty_cache()
         import bench_extra
         extra = []
@@ -537,7 +591,9 @@ def main():
                        "O": 33 if W == 64 else 17, "pairs_per_gpu_per_step": n, "cigar": "full", "seed": wl.seed,
                        "l2": "inputs larger than L2 (ASCII %.1f GB + packed %.1f GB per step)" % (
                            (n * stride + n * L) / 1e9, (words_t + words_q) * 4 / 1e9),
-                       "step": "ingest(ASCII->2bit) + align(DC+TB+RLE) + compaction(scan+gather), inputs resident in HBM"},
+                       "step": "ingest(ASCII->2bit) + align(DC+TB+RLE) + compaction(scan+gather), inputs resident in HBM",
+                       "pipeline": ("the three stages of consecutive passes overlap on three streams (two buffer sets); the timed region "
+                                    "holds exactly `steps` ingests, alignments and compactions") if args.pipeline else "one stream, stages back to back"},
             "gcups": value * L * L / 1e9, "mean_edit_distance": mean_ed, "runs_per_alignment": total_runs / n,
             # launches per step: 2 x (bulk-staged ingest + its tail), alignment, 3 scan passes, gather
             "gpu_launches": args.steps * 9, "clocks": clocks, "e2e": e2e, "e2e_rendered": e2e_rendered, "roofline": roofline,

@@ -185,6 +185,11 @@ int sg_host_pack_isa(void);
 uint64_t sg_packed_words(uint64_t n_bases);
 int sg_dev_pack_2bit(const char *d_ascii, uint64_t n_bases, uint32_t *d_packed, uint64_t *d_bad_pos,
                      void *stream);
+/* The same with flags.  SG_PACK_SIDE: the launch is meant to run BESIDE the alignment kernel of another batch (other
+ * stream): CTAs of 32 KB shared memory that fit the slot sg_dev_align leaves free on every SM, instead of 96 KB ones. */
+#define SG_PACK_SIDE 1u
+int sg_dev_pack_2bit_ex(const char *d_ascii, uint64_t n_bases, uint32_t *d_packed, uint64_t *d_bad_pos, uint32_t flags,
+                        void *stream);
 
 /* The alignment kernel (DC + TB + per-window RLE), one launch over n alignments.
  *   d_text / d_query    packed blobs (may be the same blob)

@@ -62,6 +62,7 @@ SIGNATURES = {
     "sg_host_pack_isa": (i32, []),
     "sg_packed_words": (u64, [u64]),
     "sg_dev_pack_2bit": (i32, [vp, u64, vp, vp, vp]),
+    "sg_dev_pack_2bit_ex": (i32, [vp, u64, vp, vp, u32, vp]),
     "sg_dev_align": (i32, [i32, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "sg_dev_align_wo": (i32, [i32, i32, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "sg_dev_align_ordered": (i32, [i32, i32, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

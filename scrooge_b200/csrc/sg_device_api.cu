@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <mutex>
 #include <cuda_runtime.h>
 
 #include "../../include/scrooge_b200.h"
@@ -76,7 +77,19 @@ template <int W> static int setup_delta_kernel(int *ctas_per_sm)
         fprintf(stderr, "[sg] delta W=%d: occupancy %d CTAs/SM, %d regs, %d dyn smem, %d threads/CTA\n", W, *ctas_per_sm, fa.numRegs,
                 L::BYTES_PER_CTA, L::WARPS_PER_CTA * 32);
     }
-    if (const char *e = std::getenv("SG_DELTA_CTAS")) *ctas_per_sm = std::min(*ctas_per_sm, std::max(1, atoi(e)));  // experiment knob
+    // Leave one CTA slot per SM to the HBM-bound kernels around the aligner (ingest of the next batch, compaction of the
+    // previous one run beside it on other streams): 256 threads and 40 KB of shared memory.  The aligner does not need the
+    // slot -- W=64: 12 / 16 / 20 / 24 warps per SM run 1 M pairs in 40.6 / 38.2 / 36.49 / 36.48 ms (the alu pipe saturates at 20).
+    {
+        int dev = 0, smem_sm = 0;
+        SG_CUDA(cudaGetDevice(&dev));
+        SG_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+        // the side geometry of the ingest kernel: 32 KB of tiles + its barriers + the 1 KB the system takes per CTA
+        const int side = kPackSideTile * kPackSideStages + 1024 + 256;
+        const int by_smem = (smem_sm - side) / (L::BYTES_PER_CTA + 1024), by_threads = (2048 - 256) / (L::WARPS_PER_CTA * 32);
+        *ctas_per_sm = std::max(1, std::min(*ctas_per_sm, std::min(by_smem, by_threads)));
+    }
+    if (const char *e = std::getenv("SG_DELTA_CTAS")) *ctas_per_sm = std::max(1, atoi(e));  // experiment knob (the launch fails if it does not fit)
     if (*ctas_per_sm < 1) return fail(SG_ERR_CUDA, "alignment kernel does not fit on this device");
     return SG_OK;
 }
@@ -316,6 +329,27 @@ template <int W, bool TMEM> static int launch_align(const DeviceInfo &di, const 
     return SG_OK;
 }
 
+template <int TILE, int STAGES>
+static int launch_pack_bulk(const DeviceInfo &di, const char *d_ascii, uint64_t n_bases, uint32_t *d_packed, uint64_t *d_bad_pos, cudaStream_t st,
+                            uint64_t *done_bases)
+{
+    static std::once_flag attr_once[64];
+    int dev = 0;
+    SG_CUDA(cudaGetDevice(&dev));
+    constexpr int smem = TILE * STAGES;
+    cudaError_t attr_rc = cudaSuccess;
+    if (dev >= 0 && dev < 64)
+        std::call_once(attr_once[dev], [&] { attr_rc = cudaFuncSetAttribute(pack_2bit_bulk_kernel<TILE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+    SG_CUDA(attr_rc);
+    const uint64_t n_tiles = n_bases / (uint64_t)TILE;
+    const int per_sm = std::max(1, (227 * 1024) / (smem + 1024));
+    const int blocks = (int)std::min<uint64_t>(n_tiles, (uint64_t)di.sms * (uint64_t)per_sm);
+    pack_2bit_bulk_kernel<TILE, STAGES><<<blocks, 256, smem, st>>>(d_ascii, n_tiles, d_packed, (unsigned long long *)d_bad_pos);
+    SG_CUDA(cudaGetLastError());
+    *done_bases = n_tiles * (uint64_t)TILE;
+    return SG_OK;
+}
+
 }  // namespace sg
 
 using namespace sg;
@@ -340,32 +374,26 @@ uint64_t sg_packed_words(uint64_t n_bases) { return (n_bases + 15ull) / 16ull + 
 
 int sg_dev_pack_2bit(const char *d_ascii, uint64_t n_bases, uint32_t *d_packed, uint64_t *d_bad_pos, void *stream)
 {
+    return sg_dev_pack_2bit_ex(d_ascii, n_bases, d_packed, d_bad_pos, 0, stream);
+}
+
+int sg_dev_pack_2bit_ex(const char *d_ascii, uint64_t n_bases, uint32_t *d_packed, uint64_t *d_bad_pos, uint32_t flags, void *stream)
+{
     if (!d_packed || !d_bad_pos || (!d_ascii && n_bases)) return fail(SG_ERR_BAD_ARG, "sg_dev_pack_2bit: null pointer");
     if (((uintptr_t)d_ascii & 15u) != 0) return fail(SG_ERR_BAD_ARG, "sg_dev_pack_2bit: d_ascii must be 16-byte aligned");
     DeviceInfo *di;
     int rc = device_info(&di);
     if (rc) return rc;
     const uint64_t n_words = sg_packed_words(n_bases);  // includes zeroed padding words the aligner may read
-    // the whole 16 KB tiles of the blob through the bulk-copy-staged kernel, the tail through the plain one (SG_PACK=plain:
+    // the whole tiles of the blob through the bulk-copy-staged kernel, the tail through the plain one (SG_PACK=plain:
     // everything through the plain one)
     static const bool bulk = [] { const char *e = std::getenv("SG_PACK"); return !(e && std::string(e) == "plain"); }();
     uint64_t done_bases = 0;
-    if (bulk && n_bases >= (uint64_t)kPackTile) {
-        static bool attr_set[64] = {};
-        int dev = 0;
-        SG_CUDA(cudaGetDevice(&dev));
-        const int smem = kPackTile * kPackStages;
-        if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-            SG_CUDA(cudaFuncSetAttribute(pack_2bit_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_set[dev] = true;
-        }
-        const uint64_t n_tiles = n_bases / (uint64_t)kPackTile;
-        const int per_sm = std::max(1, (227 * 1024) / (smem + 1024));
-        const int blocks = (int)std::min<uint64_t>(n_tiles, (uint64_t)di->sms * (uint64_t)per_sm);
-        pack_2bit_bulk_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(d_ascii, n_tiles, d_packed, (unsigned long long *)d_bad_pos);
-        SG_CUDA(cudaGetLastError());
-        done_bases = n_tiles * (uint64_t)kPackTile;
-    }
+    if (bulk && (flags & SG_PACK_SIDE) && n_bases >= (uint64_t)kPackSideTile)
+        rc = launch_pack_bulk<kPackSideTile, kPackSideStages>(*di, d_ascii, n_bases, d_packed, d_bad_pos, (cudaStream_t)stream, &done_bases);
+    else if (bulk && n_bases >= (uint64_t)kPackTile)
+        rc = launch_pack_bulk<kPackTile, kPackStages>(*di, d_ascii, n_bases, d_packed, d_bad_pos, (cudaStream_t)stream, &done_bases);
+    if (rc) return rc;
     const uint64_t rest_words = n_words - done_bases / 16ull;
     const uint64_t want = (rest_words + 255ull) / 256ull;
     const int blocks = (int)std::min<uint64_t>(want, (uint64_t)di->sms * 16ull);

@@ -435,7 +435,7 @@ int upload_adaptive(sg_ctx *ctx, Device &d, cudaStream_t st, cudaEvent_t *ev_dma
         const long long host_chunks = std::min(g.nch, std::max(0ll, back - g.chunk0));
         g.split = std::min(g.nbytes, (uint64_t)host_chunks * C);
         if (g.split < g.nbytes) {
-            R(sg_dev_pack_2bit(g.d_ascii->as<char>() + g.split, g.nbytes - g.split, g.d_packed->as<uint32_t>() + g.split / 16, g.d_bad, st));
+            R(sg_dev_pack_2bit_ex(g.d_ascii->as<char>() + g.split, g.nbytes - g.split, g.d_packed->as<uint32_t>() + g.split / 16, g.d_bad, SG_PACK_SIDE, st));
         } else {
             const uint64_t words = sg_packed_words(g.nbytes), used = (g.nbytes + 15) / 16;
             SG_CUDA(cudaMemsetAsync(g.d_packed->as<uint32_t>() + used, 0, (words - used) * 4, st));  // padding words the aligner may read
