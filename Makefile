@@ -12,7 +12,7 @@ NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -ccbin $(CCBIN) -Xcompiler -fPIC,-fo
            -Xptxas -v -Iinclude
 SRC := scrooge_b200/csrc
 LIB := scrooge_b200/lib/libscrooge_b200.so
-OBJS := build/sg_device_api.o build/sg_host_api.o build/genasm_gpu.o build/sg_host_pack.o build/sg_io.o
+OBJS := build/sg_device_api.o build/sg_host_api.o build/genasm_gpu.o build/sg_host_pack.o build/sg_host_render.o build/sg_io.o
 HDRS := $(wildcard $(SRC)/*.cuh $(SRC)/*.h include/*.h include/*.hpp)
 
 RDC := scrooge_b200/lib/libscrooge_b200_rdc.a
@@ -38,6 +38,10 @@ build/%.o: $(SRC)/%.cu $(HDRS)
 build/sg_host_pack.o: $(SRC)/sg_host_pack.cpp
 	@mkdir -p build
 	$(CCBIN) -O3 -std=c++17 -fPIC -fopenmp -Wall -c $< -o $@
+
+build/sg_host_render.o: $(SRC)/sg_host_render.cpp
+	@mkdir -p build
+	$(CCBIN) -O3 -std=c++17 -fPIC -Wall -c $< -o $@
 
 build/sg_io.o: $(SRC)/sg_io.cpp include/scrooge_io.hpp include/scrooge_types.hpp
 	@mkdir -p build

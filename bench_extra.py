@@ -139,7 +139,9 @@ def pairs_e2e(wl, n, steps=2, render=False):
     del text, reads
     tb_pin, qb_pin = torch.from_numpy(tb).pin_memory(), torch.from_numpy(qb).pin_memory()
     al = scrooge_b200.Aligner(W=wl.W, O=wl.overlap, device_ids=[torch.cuda.current_device()])
-    res = al.align_pairs_blob(tb_pin, toff, qb_pin, qoff)
+    res = None
+    for _ in range(2):   # two untimed calls: the second one still allocates result blocks (the first result is alive while it runs)
+        res = al.align_pairs_blob(tb_pin, toff, qb_pin, qoff)
     t0 = time.perf_counter()
     for _ in range(steps):
         res = al.align_pairs_blob(tb_pin, toff, qb_pin, qoff)
@@ -287,7 +289,7 @@ def mapping_point(G, n_reads, stress, peak, sub_batch=1_000_000, steps=2, e2e_re
         sg_check(lib().sg_set_reference(al._h, p(h_genome), G))
         t_ref = time.perf_counter() - t0
         res, best = None, 1e9
-        for _ in range(1 + steps):
+        for _ in range(2 + steps):   # best of: the first two calls allocate the page-locked result blocks
             h = C.c_void_p()
             t0 = time.perf_counter()
             sg_check(lib().sg_align_candidates(al._h, p(h_reads), roff.ctypes.data, ne, h_cstart.ctypes.data, h_cread.ctypes.data, ne * ncand, 0, C.byref(h)))

@@ -88,16 +88,28 @@ struct PinnedPool {
     std::mutex mu;
     std::vector<Block> free_blocks;
     size_t cached = 0;
-    // How much page-locked memory the pool keeps for reuse after the results that used it were freed: 1/32 of the
-    // machine's RAM, at most 4 GB per process (enough for the result blocks of a 2 M x 10 kbp call; re-pinning costs
-    // ~0.3 s per GB) -- page-locked memory cannot be swapped, and every process has its own pool.  SG_PINNED_CACHE_GB
-    // overrides (0 = keep nothing); sg_trim_host_cache() and the destruction of the last context release it.
-    const size_t kMaxCached = [] {
-        if (const char *v = std::getenv("SG_PINNED_CACHE_GB")) return (size_t)std::max(0ll, std::atoll(v)) << 30;
+    // How much page-locked memory the pool keeps for reuse after the results that used it were freed.  Page-locked memory
+    // cannot be swapped and every process has its own pool, so the cache follows what the recent calls actually used:
+    // limit = max(base, peak of the bytes handed out at the same time over the recent calls), never more than a quarter
+    // of the machine's RAM; the peak halves with every call that does not reach it, so one large call does not pin its
+    // footprint for the life of the process.  base = min(RAM/32, 4 GB).  Re-pinning is what the cache avoids: ~0.3 s per
+    // GB, i.e. more than the whole call for a read-mapping batch that returns 4 GB of runs.  SG_PINNED_CACHE_GB=<n> fixes
+    // the limit (0 = keep nothing); sg_trim_host_cache() and the destruction of the last context release everything.
+    size_t ram_bytes() const
+    {
         const long pages = sysconf(_SC_PHYS_PAGES), psz = sysconf(_SC_PAGE_SIZE);
-        const size_t ram = pages > 0 && psz > 0 ? (size_t)pages * (size_t)psz : (size_t)64 << 30;
-        return std::min<size_t>(ram / 32, (size_t)4 << 30);
-    }();
+        return pages > 0 && psz > 0 ? (size_t)pages * (size_t)psz : (size_t)64 << 30;
+    }
+    const long long kFixedCap = [] { const char *v = std::getenv("SG_PINNED_CACHE_GB"); return v ? std::max(0ll, std::atoll(v)) << 30 : -1ll; }();
+    const size_t kBaseCap = std::min<size_t>(ram_bytes() / 32, (size_t)4 << 30);
+    const size_t kHardCap = ram_bytes() / 4;
+    size_t live = 0, peak_live = 0;   // bytes handed out now / their recent peak (under mu)
+    size_t limit() const { return kFixedCap >= 0 ? (size_t)kFixedCap : std::min(kHardCap, std::max(kBaseCap, peak_live)); }
+    void call_done()   // once per call: let the peak decay towards what is in use
+    {
+        std::lock_guard<std::mutex> g(mu);
+        peak_live = std::max(live, peak_live / 2);
+    }
 
     int acquire(size_t bytes, Block *out)
     {
@@ -110,6 +122,8 @@ struct PinnedPool {
                 *out = free_blocks[best];
                 cached -= out->cap;
                 free_blocks.erase(free_blocks.begin() + best);
+                live += out->cap;
+                peak_live = std::max(peak_live, live);
                 return SG_OK;
             }
         }
@@ -125,13 +139,17 @@ struct PinnedPool {
         }
         out->p = (uint8_t *)p;
         out->cap = want;
+        std::lock_guard<std::mutex> g(mu);
+        live += want;
+        peak_live = std::max(peak_live, live);
         return SG_OK;
     }
     void release(Block b)
     {
         if (!b.p) return;
         std::lock_guard<std::mutex> g(mu);
-        if (cached + b.cap > kMaxCached) { cudaFreeHost(b.p); return; }
+        live -= std::min(live, b.cap);
+        if (cached + b.cap > limit()) { cudaFreeHost(b.p); return; }
         free_blocks.push_back(b);
         cached += b.cap;
     }
@@ -181,7 +199,7 @@ template <class F> void parallel_for(uint64_t n, int threads, F &&fn)
 extern "C" uint64_t sg_host_pack_2bit_st(const char *ascii, uint64_t n_bases, uint32_t *packed);
 
 constexpr int kMaxSlots = 8;
-constexpr int kMaxDmaDepth = 8;
+constexpr int kMaxDmaDepth = 16;
 
 // One pipeline stage's worth of buffers: a sub-batch lives in a slot from upload to download.
 struct Slot {
@@ -202,7 +220,9 @@ struct Slot {
         SG_CUDA(cudaEventCreate(&ev_k1));
         SG_CUDA(cudaEventCreateWithFlags(&ev_mid, cudaEventDisableTiming));
         SG_CUDA(cudaEventCreateWithFlags(&ev_end, cudaEventDisableTiming));
-        for (cudaEvent_t &e : ev_dma) SG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
+        // polled by the feeder of the adaptive ingest (a blocking wait costs an interrupt and a wake-up per chunk, which a
+        // virtual machine turns into gaps on the PCIe link)
+        for (cudaEvent_t &e : ev_dma) SG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         return SG_OK;
     }
     void destroy()
@@ -278,9 +298,10 @@ struct sg_ctx {
     // tuned fraction, and it degrades gracefully when several ranks share the host's threads.
     bool adaptive = true;
     uint64_t chunk_bytes = 8ull << 20;
-    int dma_depth = 4;
+    int dma_depth = 8;
     uint64_t ascii_min_bytes = 8ull << 20;   // blobs smaller than this are not split
     std::mutex mu;  // calls on one context are serialised
+    bool taper = true;           // SG_TAPER=0: the last sub-batch of a call is not cut finer
     bool longest_first = true;   // SG_LONGEST_FIRST=0: launches take their alignments in input order
     bool counted = false;   // fully created (sg_ctx_destroy also cleans up after a failed creation)
 };
@@ -411,7 +432,12 @@ int upload_adaptive(sg_ctx *ctx, Device &d, cudaStream_t st, cudaEvent_t *ev_dma
     if (depth > 0) {
         int issued = 0;
         while (true) {
-            if (issued >= depth && cudaEventSynchronize(ev_dma[issued % depth]) != cudaSuccess) { cuda_rc = 1; break; }
+            if (issued >= depth) {   // the oldest copy in flight must be done before another is queued
+                cudaError_t q;
+                while ((q = cudaEventQuery(ev_dma[issued % depth])) == cudaErrorNotReady)
+                    for (int spin = 0; spin < 64; spin++) __builtin_ia32_pause();
+                if (q != cudaSuccess) { cuda_rc = 1; break; }
+            }
             const long long c = take_back();
             if (c < 0) break;
             uint64_t off, len;
@@ -805,6 +831,33 @@ std::vector<uint64_t> sub_batch_cuts(uint64_t batch_bytes, uint64_t max_batch_by
     return cuts;
 }
 
+// The end of a call is exposed: after the last upload nothing overlaps the last sub-batch's kernel, compaction and copy
+// back.  So the tail of the call is cut finer -- the last full sub-batch is replaced by pieces of 1/2, 1/4, 1/8, 1/8 of
+// its weight -- and the exposed remainder shrinks eightfold (measured on 524 288 x 10 kbp pairs: 21 ms of a 110 ms call
+// were spent waiting for the last sub-batch).  Small launches do not fill the device, but at that point there is nothing
+// else for it to do.
+void taper_tail(std::vector<uint64_t> &cuts, const uint64_t *woff, uint64_t per_unit_extra, uint64_t min_piece_bytes)
+{
+    if (cuts.size() < 2) return;
+    size_t k = cuts.size() - 2;   // the last sub-batch [cuts[k], cuts[k+1])
+    auto weight = [&](uint64_t a, uint64_t b) { return (woff[b] - woff[a]) + per_unit_extra * (b - a); };
+    // a short last sub-batch is joined with the one before it, so that the taper always works on a full one
+    if (k > 0 && weight(cuts[k], cuts[k + 1]) * 2 < weight(cuts[k - 1], cuts[k])) { cuts.erase(cuts.begin() + (long)k); k--; }
+    const uint64_t a = cuts[k], b = cuts[k + 1], total = weight(a, b);
+    if (total < 8 * min_piece_bytes || b - a < 16) return;
+    std::vector<uint64_t> inner;
+    for (uint64_t num : {4ull, 6ull, 7ull}) {   // boundaries at 1/2, 3/4, 7/8 of the weight
+        const uint64_t target = total / 8 * num;
+        uint64_t lo = a + 1, hi = b - 1;
+        while (lo < hi) {
+            const uint64_t mid = lo + (hi - lo) / 2;
+            if (weight(a, mid) < target) lo = mid + 1; else hi = mid;
+        }
+        if ((inner.empty() ? a : inner.back()) < lo && lo < b) inner.push_back(lo);
+    }
+    cuts.insert(cuts.begin() + (long)k + 1, inner.begin(), inner.end());
+}
+
 // One GPU's worker: a three-slot pipeline over the sub-batches it takes from the call's shared queue.  The queue is
 // the list of sub-batch cuts of the whole call in order; a GPU that finishes early simply takes more of them (dynamic
 // balance across GPUs, like the reference's atomic pair counter does across thread blocks, src/genasm_gpu.cu:602-622).
@@ -919,6 +972,7 @@ int run_all(sg_ctx *ctx, const Workload &w, const uint64_t *woff, uint64_t per_u
             const uint64_t total = woff[n] - woff[0] + per_unit_extra * n;
             q.cuts = sub_batch_cuts(std::max<uint64_t>(1, total / ((uint64_t)nd * 2)), ctx->max_batch_bytes, 1, woff, per_unit_extra, 0, n);
         }
+        if (ctx->taper) taper_tail(q.cuts, woff, per_unit_extra, 4ull << 20);
         if (nd == 1) {
             ScopedAffinity bound(ctx->devs[0].cpus);   // the caller's thread is this GPU's worker for the call
             run_shard(ctx, ctx->devs[0], w, q, res.get(), shards[0]);
@@ -935,6 +989,7 @@ int run_all(sg_ctx *ctx, const Workload &w, const uint64_t *woff, uint64_t per_u
             if (so.rc) return fail(so.rc, so.err);
     }
     finalize(res.get(), shards);
+    g_pool.call_done();
     res->total_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_begin).count();
     sg_call_stats &S = res->stats;
     memset(&S, 0, sizeof S);
@@ -1050,6 +1105,7 @@ int sg_ctx_create_wo(sg_ctx **out, const int *device_ids, int n_devices, int W, 
         ctx->min_batch_units = std::max<uint64_t>(ctx->min_batch_units, 32ull * (uint64_t)wps * (uint64_t)sms);
     }
     if (const char *v = std::getenv("SG_LONGEST_FIRST")) ctx->longest_first = std::atoi(v) != 0;
+    if (const char *v = std::getenv("SG_TAPER")) ctx->taper = std::atoi(v) != 0;
     if (const char *v = std::getenv("SG_MIN_BATCH_UNITS")) ctx->min_batch_units = (uint64_t)std::max(1ll, std::atoll(v));
     if (g_debug)
         for (const Device &d : ctx->devs) {
@@ -1312,47 +1368,11 @@ const uint8_t *sg_result_runs(const sg_result *r)
 int64_t sg_result_kernel_ns(const sg_result *r) { return r ? r->kernel_ns : 0; }
 int64_t sg_result_total_ns(const sg_result *r) { return r ? r->total_ns : 0; }
 
-// "%d%c" of one packed run (reference src/genasm_gpu.cu:881-888) from a 256-entry table: the text of run byte b padded
-// to 4 characters, and its length (2 or 3; count 0 never occurs).  A run is rendered with one 4-byte store.
-struct RunText {
-    uint32_t text[256];
-    uint8_t len[256];
-    RunText()
-    {
-        static const char ops[4] = {'=', 'X', 'I', 'D'};
-        for (unsigned b = 0; b < 256; b++) {
-            const unsigned c = SG_RUN_COUNT(b);
-            char t[4] = {0, 0, 0, 0};
-            unsigned l = 0;
-            if (c >= 10) t[l++] = (char)('0' + c / 10);
-            t[l++] = (char)('0' + c % 10);
-            t[l++] = ops[SG_RUN_OP(b)];
-            memcpy(&text[b], t, 4);
-            len[b] = (uint8_t)l;
-        }
-    }
-};
-static const RunText g_run_text;
-
-static inline uint64_t runs_text_len(const uint8_t *p, uint64_t cnt)
-{
-    uint64_t len = 0;
-    for (uint64_t k = 0; k < cnt; k++) len += g_run_text.len[p[k]];
-    return len;
-}
-
-// renders cnt runs at o; the caller guarantees room for the text (+ nothing else): the last run is written byte by byte
-static inline char *runs_render(const uint8_t *p, uint64_t cnt, char *o)
-{
-    if (!cnt) return o;
-    for (uint64_t k = 0; k + 1 < cnt; k++) {   // a 4-byte store may spill 1-2 bytes into the next run's place: fine
-        memcpy(o, &g_run_text.text[p[k]], 4);
-        o += g_run_text.len[p[k]];
-    }
-    const uint8_t b = p[cnt - 1];
-    memcpy(o, &g_run_text.text[b], g_run_text.len[b]);
-    return o + g_run_text.len[b];
-}
+// "%d%c" per packed run (reference src/genasm_gpu.cu:881-888): sg_host_render.cpp, 64 runs per step with AVX-512 VBMI2
+extern "C" uint64_t sg_host_runs_text_len(const uint8_t *runs, uint64_t cnt);
+extern "C" char *sg_host_runs_render(const uint8_t *runs, uint64_t cnt, char *out);
+static inline uint64_t runs_text_len(const uint8_t *p, uint64_t cnt) { return cnt ? sg_host_runs_text_len(p, cnt) : 0; }
+static inline char *runs_render(const uint8_t *p, uint64_t cnt, char *o) { return cnt ? sg_host_runs_render(p, cnt, o) : o; }
 
 // Window configurations with W - O > 63: a run longer than 63 arrives as bytes with count 0 ("63 more of this op") followed
 // by the byte with the rest.  fn(count, op) is called once per run, the pieces summed.

@@ -97,3 +97,24 @@ def test_window_configuration_arguments(sglib):
         assert sglib.sg_ctx_create_wo(C.byref(h), None, 1, W, O) == 3, (W, O)
         assert b"window configuration" in sglib.sg_last_error()
     assert sglib.sg_ctx_create(C.byref(h), None, 1, 48) == 3
+
+
+def test_host_renderer_matches_python(sglib):
+    """CIGAR text from packed runs (sg_host_render.cpp: AVX-512 VBMI2 when the CPU has it, scalar otherwise): exact text,
+    exact length, nothing written outside it -- around the 64-run block boundaries in particular."""
+    sglib.sg_host_runs_text_len.restype = C.c_uint64
+    sglib.sg_host_runs_text_len.argtypes = [C.c_void_p, C.c_uint64]
+    sglib.sg_host_runs_render.restype = C.c_void_p
+    sglib.sg_host_runs_render.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    rng = np.random.default_rng(1)
+    for cnt in [1, 2, 21, 22, 42, 43, 63, 64, 65, 127, 128, 129, 191, 192, 193, 1000, 2113]:
+        for hi in (64, 10, 32):   # all counts / one-digit counts only / the 64/33 window's range
+            runs = ((rng.integers(0, 4, cnt) << 6) | rng.integers(1, hi, cnt)).astype(np.uint8)
+            want = "".join(f"{int(b) & 63}{'=XID'[int(b) >> 6]}" for b in runs)
+            n = sglib.sg_host_runs_text_len(runs.ctypes.data, cnt)
+            assert n == len(want), (cnt, hi)
+            out = np.full(n + 160, 0x7E, dtype=np.uint8)
+            end = sglib.sg_host_runs_render(runs.ctypes.data, cnt, out.ctypes.data + 80)
+            assert end == out.ctypes.data + 80 + n
+            assert bytes(out[80:80 + n]).decode() == want, (cnt, hi)
+            assert (out[:80] == 0x7E).all() and (out[80 + n:] == 0x7E).all(), ("wrote outside the text", cnt, hi)

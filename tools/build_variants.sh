@@ -11,6 +11,6 @@ while [ $# -ge 2 ]; do
       -Xcompiler -fPIC,-fopenmp,-Wall,-Wno-unknown-pragmas -Iinclude $flags -c scrooge_b200/csrc/sg_device_api.cu -o build/variants/dev_$name.o
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -ccbin /usr/bin/g++ -Xcompiler -fopenmp \
       -o scrooge_b200/lib/variants/libscrooge_b200_$name.so build/variants/dev_$name.o build/sg_host_api.o build/genasm_gpu.o \
-      build/sg_host_pack.o build/sg_io.o -lcudart -lgomp
+      build/sg_host_pack.o build/sg_host_render.o build/sg_io.o -lcudart -lgomp
   echo "built variant $name ($flags)"
 done
