@@ -154,7 +154,9 @@ typedef struct sg_call_stats {
     uint64_t h2d_packed_bytes;  /* crossed PCIe at 2 bit/base (packed by the host threads) */
     uint64_t h2d_other_bytes;   /* descriptors */
     uint64_t d2h_bytes;         /* distances, consumed prefixes, run offsets, packed runs */
-    uint32_t n_devices, sub_batches, host_threads_per_device, reserved;
+    uint32_t n_devices, sub_batches, host_threads_per_device;
+    uint32_t packers_in_use;    /* packer threads per GPU the ingest used for its last sub-batch (chosen from measured rates:
+                                 * all, half or none of host_threads_per_device; SG_PACKERS=<n> fixes it, SG_TUNE=0 = all) */
 } sg_call_stats;
 int sg_result_stats(const sg_result *r, sg_call_stats *out);
 

@@ -91,7 +91,7 @@ class CallStats(C.Structure):
     """sg_call_stats (include/scrooge_b200.h)."""
     _fields_ = [("total_ns", i64), ("kernel_ns", i64), ("upload_ns", i64), ("pack_thread_ns", i64), ("wait_ns", i64),
                 ("host_other_ns", i64), ("h2d_ascii_bytes", u64), ("h2d_packed_bytes", u64), ("h2d_other_bytes", u64),
-                ("d2h_bytes", u64), ("n_devices", u32), ("sub_batches", u32), ("host_threads_per_device", u32), ("reserved", u32)]
+                ("d2h_bytes", u64), ("n_devices", u32), ("sub_batches", u32), ("host_threads_per_device", u32), ("packers_in_use", u32)]
 
 
 _lib = None

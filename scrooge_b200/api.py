@@ -81,7 +81,7 @@ class Result:
         """sg_call_stats of the call that produced this result: where its time and its PCIe bytes went."""
         st = _lib.CallStats()
         check(lib().sg_result_stats(self._h, C.byref(st)))
-        return {name: int(getattr(st, name)) for name, _ in st._fields_ if name != "reserved"}
+        return {name: int(getattr(st, name)) for name, _ in st._fields_}
 
     def _arr(self, ptr, n, dtype):
         if not ptr or n == 0:

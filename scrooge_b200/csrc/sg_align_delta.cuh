@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
     uint32_t *tb_s = smem + L::PM_WORDS + lane * 2;
 
     const bool want_cigar = !(P.flags & 1u);
+    const bool want_stats = P.dc_entries != nullptr || P.windows != nullptr;
 
     bool have = false, drained = false;
     uint64_t pair = 0, t_pos = 0, t_begin = 0, t_end = 0, q_pos = 0, q_end = 0;
@@ -451,7 +452,8 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
 
         if (!have) continue;
 
-        {   // window distance d_w = D(0,0) = sum of the vertical deltas of column 0 (src/genasm_cpu.cpp:278-283)
+        if (want_stats) {   // window distance d_w = D(0,0) = sum of the vertical deltas of column 0 (src/genasm_cpu.cpp:278-283);
+                            // nothing the path returns needs it: only the work counters of the measurement interface do
             int dw = 0;
 #pragma unroll
             for (int k = 0; k < NW; k++) dw += __popc(Pv[k]) - __popc(Mv[k]);

@@ -77,10 +77,14 @@ template <int W> static int setup_delta_kernel(int *ctas_per_sm)
         fprintf(stderr, "[sg] delta W=%d: occupancy %d CTAs/SM, %d regs, %d dyn smem, %d threads/CTA\n", W, *ctas_per_sm, fa.numRegs,
                 L::BYTES_PER_CTA, L::WARPS_PER_CTA * 32);
     }
-    // Leave one CTA slot per SM to the HBM-bound kernels around the aligner (ingest of the next batch, compaction of the
-    // previous one run beside it on other streams): 256 threads and 40 KB of shared memory.  The aligner does not need the
-    // slot -- W=64: 12 / 16 / 20 / 24 warps per SM run 1 M pairs in 40.6 / 38.2 / 36.49 / 36.48 ms (the alu pipe saturates at 20).
-    {
+    // SG_DELTA_RESERVE=1 leaves one CTA slot per SM to the HBM-bound kernels around the aligner (ingest of the next batch,
+    // compaction of the previous one run beside it on other streams; bench.py --pipeline 1).  The aligner does not need the
+    // slot -- W=64: 12 / 16 / 20 / 24 warps per SM run 1 M pairs in 40.6 / 38.2 / 36.49 / 36.48 ms -- but the overlap buys
+    // nothing either: beside the ingest the alignment kernel slows from 36.4 to 40.0 ms (both want the alu pipe; the
+    // ingest's SWAR conversion alone is ~2 ms of it) and a pipelined pass takes 42.8 ms against 41.8 ms back to back
+    // (profiles/r02_pipeline_ab.md).  Off by default.
+    static const bool reserve = [] { const char *e = std::getenv("SG_DELTA_RESERVE"); return e && atoi(e) != 0; }();
+    if (reserve) {
         int dev = 0, smem_sm = 0;
         SG_CUDA(cudaGetDevice(&dev));
         SG_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));

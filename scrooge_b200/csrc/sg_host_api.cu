@@ -176,6 +176,7 @@ struct ShardStats {
     std::atomic<uint64_t> h2d_packed{0};       // bytes that crossed PCIe packed by the host (2 bit/base)
     uint64_t h2d_ascii = 0, h2d_other = 0, d2h = 0;
     uint32_t sub_batches = 0;
+    uint32_t packers_in_use = 0;   // packer threads the ingest tuner used for the last sub-batch
 };
 static const bool g_debug = std::getenv("SG_DEBUG") != nullptr;
 struct ScopedT {
@@ -242,8 +243,48 @@ struct Slot {
     }
 };
 
+// How many of a GPU's packer threads the adaptive ingest uses.  Copy engines and packers read the same host DRAM: on a
+// box where PCIe is the narrow link (one GPU, many cores) every packer helps, on a box where DRAM is (eight GPUs pulling
+// ASCII over eight links) a packed byte costs 1.5 bytes of DRAM traffic against 1.0 for a copied one and the packers
+// only take bandwidth from the copy engines.  Instead of a rule in terms of core counts the context measures: the first
+// large sub-batches run with all, half and none of the packers, the ingest rate (ASCII bytes per second of upload
+// phase) of each is recorded, and the best setting is kept (SG_PACKERS=<n> fixes it, SG_TUNE=0 keeps all).
+struct IngestTuner {
+    static constexpr uint64_t kMinBytes = 96ull << 20;   // smaller sub-batches say little about a rate
+    int fixed = -1;        // SG_PACKERS
+    bool enabled = true;   // SG_TUNE
+    int candidates[3] = {0, 0, 0};
+    double rate[3] = {0, 0, 0};
+    int tried = 0, best = 0, current = 0;
+    void init(int threads)
+    {
+        candidates[0] = threads; candidates[1] = threads / 2; candidates[2] = 0;
+        if (const char *v = std::getenv("SG_PACKERS")) fixed = std::max(0, std::min(threads, std::atoi(v)));
+        if (const char *v = std::getenv("SG_TUNE")) enabled = std::atoi(v) != 0;
+        if (threads < 2) enabled = false;
+    }
+    int packers(int threads, uint64_t bytes)
+    {
+        if (fixed >= 0) return fixed;
+        if (!enabled) return threads;
+        current = (tried < 3 && bytes >= kMinBytes) ? tried : best;
+        return candidates[current];
+    }
+    void report(uint64_t bytes, double seconds)
+    {
+        if (fixed >= 0 || !enabled || tried >= 3 || bytes < kMinBytes || current != tried || seconds <= 0) return;
+        rate[tried] = (double)bytes / seconds;
+        tried++;
+        if (tried == 3) {
+            best = 0;
+            for (int k = 1; k < 3; k++) if (rate[k] > rate[best] * 1.03) best = k;   // a setting has to win clearly
+        }
+    }
+};
+
 struct Device {
     int id = 0;
+    IngestTuner tuner;
     Slot slots[kMaxSlots];
     int n_slots = 3;
     DevBuf genome;  // packed reference, resident across calls
@@ -405,7 +446,13 @@ int upload_adaptive(sg_ctx *ctx, Device &d, cudaStream_t st, cudaEvent_t *ev_dma
     auto take_back = [&]() -> long long { std::lock_guard<std::mutex> g(mu); return back > front ? --back : -1; };
     std::atomic<uint64_t> bad{~0ull};      // (segment << 56) | position: the smallest wins
     std::atomic<int> cuda_rc{0};
-    std::function<void(int)> job = [&](int) {
+    uint64_t total_bytes = 0;
+    for (int k = 0; k < nseg; k++) total_bytes += seg[k].nbytes;
+    const int active = ctx->dma_depth > 0 ? d.tuner.packers(d.team.size(), total_bytes) : d.team.size();
+    cs.packers_in_use = (uint32_t)std::max(0, active);
+    const auto t_ingest = std::chrono::steady_clock::now();
+    std::function<void(int)> job = [&](int tid) {
+        if (tid >= active) return;
         const auto t0 = std::chrono::steady_clock::now();
         uint64_t sent = 0;
         while (true) {
@@ -449,6 +496,7 @@ int upload_adaptive(sg_ctx *ctx, Device &d, cudaStream_t st, cudaEvent_t *ev_dma
         }
     }
     if (d.team.size() > 0) d.team.wait();
+    d.tuner.report(total_bytes, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_ingest).count());
     if (cuda_rc) { cudaGetLastError(); return fail(SG_ERR_CUDA, "adaptive ingest: a CUDA call failed"); }
     if (bad.load() != ~0ull) {   // the caller names the offender
         *bad_seg = (int)(bad.load() >> 56);
@@ -864,7 +912,35 @@ void taper_tail(std::vector<uint64_t> &cuts, const uint64_t *woff, uint64_t per_
 struct BatchQueue {
     std::vector<uint64_t> cuts;
     std::atomic<size_t> next{0};
+    // the largest sub-batch of the call: alignments, uploaded text / query bytes, slab bytes (0 = unknown: grow on demand)
+    uint64_t max_n = 0, max_text = 0, max_query = 0, max_slab = 0;
+    bool blobs = false, mapping = false;
 };
+
+int presize_slot(sg_ctx *ctx, Device &d, Slot &s, const BatchQueue &q)
+{
+    const uint64_t n = q.max_n;
+    if (!n) return SG_OK;
+    R(s.desc.reserve((5 * n + 1) * 8)); R(s.h_desc.reserve((5 * n + 1) * 8));
+    R(s.counter.reserve(8)); R(s.edit.reserve(n * 8)); R(s.refc.reserve(n * 8));
+    R(s.nruns.reserve(n * 4)); R(s.status.reserve(n)); R(s.run_off.reserve((n + 1) * 8));
+    R(s.scan_tmp.reserve(sg_scan_tmp_bytes(n))); R(s.bad.reserve(16)); R(s.h_small.reserve(64));
+    R(s.h_status.reserve(n));
+    if (q.max_slab) R(s.slab.reserve(q.max_slab + 16));
+    if (!q.blobs) return SG_OK;
+    const bool stage = d.team.size() > 0, ascii = ctx->dma_depth > 0 || d.team.size() == 0 || !ctx->adaptive;
+    if (!q.mapping && q.max_text) {
+        R(s.packed_t.reserve(sg_packed_words(q.max_text) * 4));
+        if (stage) R(s.h_stage_t.reserve(sg_packed_words(q.max_text) * 4 + 64));
+        if (ascii) R(s.ascii_t.reserve(q.max_text + 64));
+    }
+    if (q.max_query) {
+        R(s.packed_q.reserve(sg_packed_words(q.max_query) * 4));
+        if (stage) R(s.h_stage_q.reserve(sg_packed_words(q.max_query) * 4 + 64));
+        if (ascii) R(s.ascii_q.reserve(q.max_query + 64));
+    }
+    return SG_OK;
+}
 
 void run_shard(sg_ctx *ctx, Device &d, const Workload &w, BatchQueue &q, sg_result *res, ShardOut &so)
 {
@@ -880,6 +956,17 @@ void run_shard(sg_ctx *ctx, Device &d, const Workload &w, BatchQueue &q, sg_resu
     if (cudaSetDevice(d.id) != cudaSuccess) { cudaGetLastError(); fail(SG_ERR_CUDA, "cudaSetDevice failed"); bail(SG_ERR_CUDA); return; }
     const size_t nb = q.cuts.size() - 1;
     const int kSlots = d.n_slots;
+    // Which sub-batch lands in which slot of which GPU changes from call to call (one queue, several takers), and a slot
+    // whose buffers have to grow pays for it with cudaFree / cudaMallocHost in the middle of the pipeline (page-locking
+    // the staging of a 2 GB sub-batch: ~0.2 s).  So every slot this call can use is sized for the call's largest
+    // sub-batch up front; buffers only ever grow, a second call of the same shape allocates nothing.
+    {
+        const int used = (int)std::min<size_t>((size_t)kSlots, nb);
+        for (int k = 0; k < used; k++) {
+            const int rc = presize_slot(ctx, d, d.slots[k], q);
+            if (rc) { bail(rc); return; }
+        }
+    }
     int k = 0;   // sub-batches this GPU has taken
     while (true) {
         const size_t b = q.next.fetch_add(1);
@@ -973,6 +1060,17 @@ int run_all(sg_ctx *ctx, const Workload &w, const uint64_t *woff, uint64_t per_u
             q.cuts = sub_batch_cuts(std::max<uint64_t>(1, total / ((uint64_t)nd * 2)), ctx->max_batch_bytes, 1, woff, per_unit_extra, 0, n);
         }
         if (ctx->taper) taper_tail(q.cuts, woff, per_unit_extra, 4ull << 20);
+        q.mapping = w.mapping;
+        q.blobs = w.query.off != nullptr && (w.mapping || w.text.off != nullptr);
+        const bool want_cigar = !(w.flags & SG_FLAG_DISTANCE_ONLY);
+        for (size_t b = 0; b + 1 < q.cuts.size(); b++) {
+            const uint64_t a0 = q.cuts[b], a1 = q.cuts[b + 1];
+            q.max_n = std::max(q.max_n, a1 - a0);
+            if (!q.blobs || w.mapping) continue;   // mapping: the reads of a sub-batch are known only after a scan of its candidates
+            q.max_text = std::max(q.max_text, w.text.off[a1] - w.text.off[a0]);
+            q.max_query = std::max(q.max_query, w.query.off[a1] - w.query.off[a0]);
+            if (want_cigar) q.max_slab = std::max<uint64_t>(q.max_slab, 2 * (w.query.off[a1] - w.query.off[a0]) + 8 * (a1 - a0));
+        }
         if (nd == 1) {
             ScopedAffinity bound(ctx->devs[0].cpus);   // the caller's thread is this GPU's worker for the call
             run_shard(ctx, ctx->devs[0], w, q, res.get(), shards[0]);
@@ -1008,6 +1106,7 @@ int run_all(sg_ctx *ctx, const Workload &w, const uint64_t *woff, uint64_t per_u
         S.h2d_other_bytes += c.h2d_other;
         S.d2h_bytes += c.d2h;
         S.sub_batches += c.sub_batches;
+        S.packers_in_use = std::max(S.packers_in_use, c.packers_in_use);
     }
     if (g_debug)
         fprintf(stderr, "[sg] call %.1f ms on %d GPU(s): ingest %.1f (packer threads busy %.1f thread-ms), waits %.1f, other host %.1f; "
@@ -1099,6 +1198,7 @@ int sg_ctx_create_wo(sg_ctx **out, const int *device_ids, int n_devices, int W, 
             const int dev_id = d.id;
             d.team.start(ctx->host_threads, d.cpus, [dev_id](int) { cudaSetDevice(dev_id); });
         }
+        d.tuner.init(ctx->host_threads);
         int wps = 0, sms = 0;
         R(sg_dev_align_geometry_wo(W, O, &wps, nullptr, &sms));
         // one alignment per resident lane fills the device (104 192 lanes on a B200 at W=64)

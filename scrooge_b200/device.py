@@ -68,9 +68,16 @@ class DeviceAligner:
 
     def align(self, text: torch.Tensor, text_start: torch.Tensor, text_len: torch.Tensor, query: torch.Tensor,
               query_start: torch.Tensor, query_len: torch.Tensor, slab_off: Optional[torch.Tensor] = None,
-              distance_only: bool = False) -> AlignOut:
+              distance_only: bool = False, stats: bool = True) -> AlignOut:
+        """stats=False: the optional work counters (dc_entries, windows) are not requested, as in the host API's launches;
+        the kernel then skips the window-distance bookkeeping they need."""
         flags = SG_FLAG_DISTANCE_ONLY if distance_only else 0
         o = self.out
+        if not stats:
+            check(lib().sg_dev_align_wo(self.W, self.O, _p(text), _p(text_start), _p(text_len), _p(query), _p(query_start), _p(query_len),
+                                        self.n, flags, _p(self.slab), _p(slab_off), _p(self.counter), _p(o.edit),
+                                        _p(o.ref_consumed), _p(o.nruns), _p(o.status), None, None, _stream()))
+            return o
         check(lib().sg_dev_align_wo(self.W, self.O, _p(text), _p(text_start), _p(text_len), _p(query), _p(query_start), _p(query_len),
                                     self.n, flags, _p(self.slab), _p(slab_off), _p(self.counter), _p(o.edit),
                                     _p(o.ref_consumed), _p(o.nruns), _p(o.status), _p(o.dc_entries), _p(o.windows), _stream()))
