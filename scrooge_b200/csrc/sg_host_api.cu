@@ -286,7 +286,7 @@ struct Device {
     int id = 0;
     IngestTuner tuner;
     Slot slots[kMaxSlots];
-    int n_slots = 3;
+    int n_slots = 4;
     DevBuf genome;  // packed reference, resident across calls
     DevBuf piece_bad;   // sg_set_reference: one offending-base word per uploaded piece
     uint64_t genome_len = 0;
@@ -968,17 +968,38 @@ void run_shard(sg_ctx *ctx, Device &d, const Workload &w, BatchQueue &q, sg_resu
         }
     }
     int k = 0;   // sub-batches this GPU has taken
+    // The worker never blocks on the device while there is something to upload: a sub-batch's second stage (it needs the
+    // run total from the device) is started as soon as a poll finds its kernel finished -- after an upload, or when its
+    // slot is needed again -- and only the end of the call waits.  (Blocking here after every upload cost nothing with
+    // 2 GB sub-batches, whose kernel is long done when the next upload ends, but it stalled the feeder and the packers
+    // behind the kernels of the small sub-batches at the tapered end of a call.)
+    auto poll_second_stages = [&](int upto) -> int {
+        for (int j = std::max(0, upto - kSlots + 1); j <= upto; j++) {
+            Slot &sj = d.slots[j % kSlots];
+            if (!sj.busy || sj.mid_done) continue;
+            const cudaError_t qe = cudaEventQuery(sj.ev_mid);
+            if (qe == cudaErrorNotReady) break;   // second stages start in order: their copies back land in order
+            if (qe != cudaSuccess) { cudaGetLastError(); return fail(SG_ERR_CUDA, "cudaEventQuery failed"); }
+            const int rc = stage_b(sj, w, res, so.stats);
+            if (rc) return rc;
+        }
+        return SG_OK;
+    };
     while (true) {
         const size_t b = q.next.fetch_add(1);
         if (b >= nb) break;
         Slot &s = d.slots[k % kSlots];
         int rc = stage_c(s, w, res, so);                       // frees the slot used by this GPU's batch k - kSlots
         if (!rc) rc = stage_a(ctx, d, s, w, q.cuts[b], q.cuts[b + 1], res, so.stats);
-        if (!rc && k >= 1) rc = stage_b(d.slots[(k - 1) % kSlots], w, res, so.stats);
+        if (!rc) rc = poll_second_stages(k);
         if (rc) { bail(rc); return; }
         k++;
     }
-    for (int j = std::max(0, k - kSlots); j < k; j++) {
+    for (int j = std::max(0, k - kSlots); j < k; j++) {       // the end of the call: second stages first, all of them ...
+        int rc = stage_b(d.slots[j % kSlots], w, res, so.stats);
+        if (rc) { bail(rc); return; }
+    }
+    for (int j = std::max(0, k - kSlots); j < k; j++) {       // ... then the results
         int rc = stage_c(d.slots[j % kSlots], w, res, so);
         if (rc) { bail(rc); return; }
     }
