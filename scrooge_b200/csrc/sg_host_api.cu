@@ -179,6 +179,16 @@ struct ShardStats {
     uint32_t packers_in_use = 0;   // packer threads the ingest tuner used for the last sub-batch
 };
 static const bool g_debug = std::getenv("SG_DEBUG") != nullptr;
+// SG_TRACE=1: one line per pipeline event on stderr (milliseconds since the call began) -- where a call's time goes
+static const bool g_trace = std::getenv("SG_TRACE") != nullptr;
+static std::chrono::steady_clock::time_point g_trace_t0;
+static void trace(int dev, uint64_t first, uint64_t count, const char *what, double extra = -1)
+{
+    if (!g_trace) return;
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g_trace_t0).count();
+    if (extra >= 0) fprintf(stderr, "[sg-trace] %9.3f ms  gpu %d  batch %llu+%llu  %s %.3f\n", ms, dev, (unsigned long long)first, (unsigned long long)count, what, extra);
+    else fprintf(stderr, "[sg-trace] %9.3f ms  gpu %d  batch %llu+%llu  %s\n", ms, dev, (unsigned long long)first, (unsigned long long)count, what);
+}
 struct ScopedT {
     double &acc; std::chrono::steady_clock::time_point t0;
     explicit ScopedT(double &a) : acc(a), t0(std::chrono::steady_clock::now()) {}
@@ -671,6 +681,7 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
     cudaStream_t st = s.stream;
     s.a0 = a0; s.a1 = a1; s.busy = true; s.mid_done = false; s.total_runs = 0;
     cs.sub_batches++;
+    trace(d.id, a0, n, "upload begins");
     R(s.desc.reserve((5 * n + 1) * 8)); R(s.h_desc.reserve((5 * n + 1) * 8));
     R(s.counter.reserve(8)); R(s.edit.reserve(n * 8)); R(s.refc.reserve(n * 8));
     R(s.nruns.reserve(n * 4)); R(s.status.reserve(n)); R(s.run_off.reserve((n + 1) * 8));
@@ -689,6 +700,7 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
                 BlobIn in[2] = {{&w.text, a0, a1, "text", "pair", &s.ascii_t, &s.packed_t, &s.h_stage_t, s.bad.as<uint64_t>(), h_tstart, &s.bad_bias[0]},
                                 {&w.query, a0, a1, "query", "pair", &s.ascii_q, &s.packed_q, &s.h_stage_q, s.bad.as<uint64_t>() + 1, h_qstart, &s.bad_bias[1]}};
                 R(upload_blobs(ctx, d, st, s.ev_dma, in, 2, cs));
+                trace(d.id, a0, n, "upload queued");
             } else {
                 R(upload_separate(ctx, d, st, w.text, a0, a1, "text", "pair", s.packed_t, s.h_stage_t, h_tstart, cs));
                 R(upload_separate(ctx, d, st, w.query, a0, a1, "query", "pair", s.packed_q, s.h_stage_q, h_qstart, cs));
@@ -786,6 +798,7 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
     SG_CUDA(cudaMemcpyAsync(s.h_status.p, s.status.p, n, cudaMemcpyDeviceToHost, st));
     cs.d2h += 17 * n + 24;
     SG_CUDA(cudaEventRecord(s.ev_mid, st));
+    trace(d.id, a0, n, "first stage queued");
     return SG_OK;
 }
 
@@ -796,7 +809,9 @@ int stage_b(Slot &s, const Workload &w, sg_result *res, ShardStats &cs)
     const uint64_t n = s.a1 - s.a0;
     const bool want_cigar = !(w.flags & SG_FLAG_DISTANCE_ONLY);
     cudaStream_t st = s.stream;
+    trace(-1, s.a0, n, "second stage: waiting for the kernel");
     { ScopedT t(cs.wait); SG_CUDA(cudaEventSynchronize(s.ev_mid)); }
+    trace(-1, s.a0, n, "second stage: kernel done");
     s.mid_done = true;
     const uint64_t *h = s.h_small.as<uint64_t>();
     if (h[0] != ~0ull || h[1] != ~0ull) {
@@ -832,6 +847,7 @@ int stage_b(Slot &s, const Workload &w, sg_result *res, ShardStats &cs)
         cs.d2h += s.total_runs + n * 8;
     }
     SG_CUDA(cudaEventRecord(s.ev_end, st));
+    trace(-1, s.a0, n, "second stage queued, runs", (double)s.total_runs);
     return SG_OK;
 }
 
@@ -841,12 +857,14 @@ int stage_c(Slot &s, const Workload &w, sg_result *res, ShardOut &so)
     if (!s.busy) return SG_OK;
     const bool want_cigar = !(w.flags & SG_FLAG_DISTANCE_ONLY);
     R(stage_b(s, w, res, so.stats));
+    trace(-1, s.a0, s.a1 - s.a0, "results: waiting for the copies back");
     { ScopedT t(so.stats.wait); SG_CUDA(cudaEventSynchronize(s.ev_end)); }
     s.busy = false;
     ScopedT t_out(so.stats.out);
     float ms = 0;
     SG_CUDA(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
     so.kernel_ms += ms;
+    trace(-1, s.a0, s.a1 - s.a0, "results in place; kernel ms", ms);
     if (want_cigar) {
         so.pieces.push_back(s.piece);
         so.piece_first.push_back(s.a0);
@@ -1059,6 +1077,7 @@ struct ScopedDevice {
 int run_all(sg_ctx *ctx, const Workload &w, const uint64_t *woff, uint64_t per_unit_extra, uint64_t n, sg_result **out)
 {
     auto t_begin = std::chrono::steady_clock::now();
+    g_trace_t0 = t_begin;
     ScopedDevice keep_device;
     std::unique_ptr<sg_result> res(new sg_result);
     res->n = n;
