@@ -215,6 +215,7 @@ constexpr int kMaxDmaDepth = 16;
 // One pipeline stage's worth of buffers: a sub-batch lives in a slot from upload to download.
 struct Slot {
     cudaStream_t stream = nullptr;
+    cudaEvent_t ev_copied = nullptr;   // recorded in the device's host-to-device stream after the sub-batch's last copy
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_mid = nullptr, ev_end = nullptr;
     cudaEvent_t ev_dma[kMaxDmaDepth] = {};   // adaptive ingest: one per ASCII chunk copy in flight
     DevBuf ascii_t, ascii_q, packed_t, packed_q, desc, slab, counter, edit, refc, nruns, status, run_off, scan_tmp, runs, bad, order;
@@ -227,6 +228,7 @@ struct Slot {
     int create()
     {
         SG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        SG_CUDA(cudaEventCreateWithFlags(&ev_copied, cudaEventDisableTiming));
         SG_CUDA(cudaEventCreate(&ev_k0));
         SG_CUDA(cudaEventCreate(&ev_k1));
         SG_CUDA(cudaEventCreateWithFlags(&ev_mid, cudaEventDisableTiming));
@@ -249,6 +251,7 @@ struct Slot {
         if (ev_mid) cudaEventDestroy(ev_mid);
         if (ev_end) cudaEventDestroy(ev_end);
         for (cudaEvent_t e : ev_dma) if (e) cudaEventDestroy(e);
+        if (ev_copied) cudaEventDestroy(ev_copied);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -294,6 +297,15 @@ struct IngestTuner {
 
 struct Device {
     int id = 0;
+    // EVERY host-to-device copy of this GPU goes through this one stream, whatever sub-batch it belongs to.  The copy
+    // engine serves the channel of a stream that keeps it busy and does not switch away while that channel has work: with
+    // the ASCII chunk copies of sub-batch k+1 back to back in one stream, a host-to-device copy queued in ANOTHER stream
+    // (the descriptors or the last packed chunks of sub-batch k, in front of its kernels) was not executed until the
+    // host stopped feeding -- measured with tools/ce_probe.cu: "H2D 8 MB in B, then kernel in B" is not ready after 400 ms
+    // of flooding stream A, while the same copy queued in A with an event for B's kernel is ready after 6.4 ms
+    // (profiles/r02_copy_engine_probe.txt).  Kernels and device-to-host copies of other streams are not affected.  One
+    // stream = one FIFO: sub-batches hand over to their own (compute) stream through ev_copied.
+    cudaStream_t h2d = nullptr;
     IngestTuner tuner;
     Slot slots[kMaxSlots];
     int n_slots = 4;
@@ -428,8 +440,10 @@ struct Segment {
 // packed chunk right away); the calling thread -- the GPU's worker -- is the feeder: it keeps `dma_depth` ASCII chunk
 // copies from the BACK in flight, and the device packs whatever arrived as ASCII.  Whoever is faster takes more.
 // host_threads == 0: everything crosses as ASCII; dma_depth == 0: everything is packed by the host.
-int upload_adaptive(sg_ctx *ctx, Device &d, cudaStream_t st, cudaEvent_t *ev_dma, Segment *seg, int nseg, ShardStats &cs, uint64_t *bad_pos, int *bad_seg)
+int upload_adaptive(sg_ctx *ctx, Device &d, cudaStream_t st, cudaEvent_t ev_copied, cudaEvent_t *ev_dma, Segment *seg, int nseg,
+                    ShardStats &cs, uint64_t *bad_pos, int *bad_seg)
 {
+    cudaStream_t hst = d.h2d;   // every host-to-device copy of the GPU: see Device::h2d
     const uint64_t C = ctx->chunk_bytes;   // a multiple of 256: chunks start on whole packed words and whole output cache lines
     long long nch = 0;
     for (int k = 0; k < nseg; k++) {
@@ -479,7 +493,7 @@ int upload_adaptive(sg_ctx *ctx, Device &d, cudaStream_t st, cudaEvent_t *ev_dma
                 break;
             }
             const uint64_t bytes = ((len + 15) / 16) * 4;
-            if (cudaMemcpyAsync(g.d_packed->as<uint32_t>() + off / 16, hp, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { cuda_rc = 1; break; }
+            if (cudaMemcpyAsync(g.d_packed->as<uint32_t>() + off / 16, hp, bytes, cudaMemcpyHostToDevice, hst) != cudaSuccess) { cuda_rc = 1; break; }
             sent += bytes;
         }
         cs.h2d_packed += sent;
@@ -499,13 +513,15 @@ int upload_adaptive(sg_ctx *ctx, Device &d, cudaStream_t st, cudaEvent_t *ev_dma
             if (c < 0) break;
             uint64_t off, len;
             Segment &g = locate(c, &off, &len);
-            if (cudaMemcpyAsync(g.d_ascii->as<char>() + off, g.src + off, len, cudaMemcpyHostToDevice, st) != cudaSuccess ||
-                cudaEventRecord(ev_dma[issued % depth], st) != cudaSuccess) { cuda_rc = 1; break; }
+            if (cudaMemcpyAsync(g.d_ascii->as<char>() + off, g.src + off, len, cudaMemcpyHostToDevice, hst) != cudaSuccess ||
+                cudaEventRecord(ev_dma[issued % depth], hst) != cudaSuccess) { cuda_rc = 1; break; }
             cs.h2d_ascii += len;
             issued++;
         }
     }
     if (d.team.size() > 0) d.team.wait();
+    // the sub-batch's own stream (the device packs its ASCII part there) continues once its last chunk has arrived
+    if (cudaEventRecord(ev_copied, hst) != cudaSuccess || cudaStreamWaitEvent(st, ev_copied, 0) != cudaSuccess) cuda_rc = 1;
     d.tuner.report(total_bytes, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_ingest).count());
     if (cuda_rc) { cudaGetLastError(); return fail(SG_ERR_CUDA, "adaptive ingest: a CUDA call failed"); }
     if (bad.load() != ~0ull) {   // the caller names the offender
@@ -574,7 +590,7 @@ int upload_separate(sg_ctx *ctx, Device &d, cudaStream_t st, const Strings &S, u
                 }
             if (!ok) break;
             const uint64_t w0 = start[k0] / 16, w1 = k1 < n ? start[k1] / 16 : words;
-            if (cudaMemcpyAsync(d_packed.as<uint32_t>() + w0, hp + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { cuda_rc = 1; break; }
+            if (cudaMemcpyAsync(d_packed.as<uint32_t>() + w0, hp + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, d.h2d) != cudaSuccess) { cuda_rc = 1; break; }
             sent += (w1 - w0) * 4;
         }
         cs.h2d_packed += sent;
@@ -598,8 +614,14 @@ int upload_separate(sg_ctx *ctx, Device &d, cudaStream_t st, const Strings &S, u
 // An offending base found on the device side is reported later through d_bad (+ bad_bias).
 struct BlobIn { const Strings *S; uint64_t i0, i1; const char *what, *unit; DevBuf *d_ascii, *d_packed; PinBuf *h_stage; uint64_t *d_bad, *start, *bad_bias; };
 
-int upload_blobs(sg_ctx *ctx, Device &d, cudaStream_t st, cudaEvent_t *ev_dma, BlobIn *in, int nin, ShardStats &cs)
+int upload_blobs(sg_ctx *ctx, Device &d, cudaStream_t st, cudaEvent_t ev_copied, cudaEvent_t *ev_dma, BlobIn *in, int nin, ShardStats &cs)
 {
+    cudaStream_t hst = d.h2d;
+    auto handover = [&]() -> int {   // st continues after everything queued in hst so far
+        SG_CUDA(cudaEventRecord(ev_copied, hst));
+        SG_CUDA(cudaStreamWaitEvent(st, ev_copied, 0));
+        return SG_OK;
+    };
     Segment seg[2];
     int nseg = 0, seg_of[2] = {-1, -1};
     for (int q = 0; q < nin; q++) {
@@ -618,8 +640,9 @@ int upload_blobs(sg_ctx *ctx, Device &d, cudaStream_t st, cudaEvent_t *ev_dma, B
         R(b.d_packed->reserve(words * 4));
         if (!ctx->host_pack || d.team.size() == 0) {
             R(b.d_ascii->reserve(nbytes + 64));
-            SG_CUDA(cudaMemcpyAsync(b.d_ascii->p, S.blob + base, nbytes, cudaMemcpyHostToDevice, st));
+            SG_CUDA(cudaMemcpyAsync(b.d_ascii->p, S.blob + base, nbytes, cudaMemcpyHostToDevice, hst));
             cs.h2d_ascii += nbytes;
+            R(handover());
             R(sg_dev_pack_2bit(b.d_ascii->as<char>(), nbytes, b.d_packed->as<uint32_t>(), b.d_bad, st));
             continue;
         }
@@ -631,7 +654,7 @@ int upload_blobs(sg_ctx *ctx, Device &d, cudaStream_t st, cudaEvent_t *ev_dma, B
         if (ctx->ascii_frac > 0 && nbytes >= ctx->ascii_min_bytes && nbytes >= 128) split = (uint64_t)((double)nbytes * (1.0 - ctx->ascii_frac)) & ~63ull;
         if (split < nbytes) {
             R(b.d_ascii->reserve(nbytes - split + 64));
-            SG_CUDA(cudaMemcpyAsync(b.d_ascii->p, S.blob + base + split, nbytes - split, cudaMemcpyHostToDevice, st));
+            SG_CUDA(cudaMemcpyAsync(b.d_ascii->p, S.blob + base + split, nbytes - split, cudaMemcpyHostToDevice, hst));
             cs.h2d_ascii += nbytes - split;
         }
         const uint64_t used = (split + 15) / 16;
@@ -647,20 +670,21 @@ int upload_blobs(sg_ctx *ctx, Device &d, cudaStream_t st, cudaEvent_t *ev_dma, B
             return bad_base_error(b.what, b.unit, i, base + bad - S.off[i]);
         }
         if (split < nbytes) {
-            SG_CUDA(cudaMemcpyAsync(b.d_packed->p, hp, used * 4, cudaMemcpyHostToDevice, st));
+            SG_CUDA(cudaMemcpyAsync(b.d_packed->p, hp, used * 4, cudaMemcpyHostToDevice, hst));
             cs.h2d_packed += used * 4;
             *b.bad_bias = split;
+            R(handover());
             R(sg_dev_pack_2bit(b.d_ascii->as<char>(), nbytes - split, b.d_packed->as<uint32_t>() + used, b.d_bad, st));
             continue;
         }
         memset(hp + used, 0, (words - used) * 4);  // padding words the aligner may read
-        SG_CUDA(cudaMemcpyAsync(b.d_packed->p, hp, words * 4, cudaMemcpyHostToDevice, st));
+        SG_CUDA(cudaMemcpyAsync(b.d_packed->p, hp, words * 4, cudaMemcpyHostToDevice, hst));
         cs.h2d_packed += words * 4;
     }
     if (nseg) {
         uint64_t bad = ~0ull;
         int bad_seg = 0;
-        R(upload_adaptive(ctx, d, st, ev_dma, seg, nseg, cs, &bad, &bad_seg));
+        R(upload_adaptive(ctx, d, st, ev_copied, ev_dma, seg, nseg, cs, &bad, &bad_seg));
         if (bad != ~0ull) {
             const BlobIn &b = in[seg_of[bad_seg]];
             const Strings &S = *b.S;
@@ -699,7 +723,7 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
             if (w.text.off) {
                 BlobIn in[2] = {{&w.text, a0, a1, "text", "pair", &s.ascii_t, &s.packed_t, &s.h_stage_t, s.bad.as<uint64_t>(), h_tstart, &s.bad_bias[0]},
                                 {&w.query, a0, a1, "query", "pair", &s.ascii_q, &s.packed_q, &s.h_stage_q, s.bad.as<uint64_t>() + 1, h_qstart, &s.bad_bias[1]}};
-                R(upload_blobs(ctx, d, st, s.ev_dma, in, 2, cs));
+                R(upload_blobs(ctx, d, st, s.ev_copied, s.ev_dma, in, 2, cs));
                 trace(d.id, a0, n, "upload queued");
             } else {
                 R(upload_separate(ctx, d, st, w.text, a0, a1, "text", "pair", s.packed_t, s.h_stage_t, h_tstart, cs));
@@ -732,7 +756,7 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
             if (w.query.off) {
                 BlobIn in[1] = {{&w.query, r0, (uint64_t)r1 + 1, "content", "read", &s.ascii_q, &s.packed_q, &s.h_stage_q, s.bad.as<uint64_t>() + 1,
                                  rstart.data(), &s.bad_bias[1]}};
-                R(upload_blobs(ctx, d, st, s.ev_dma, in, 1, cs));
+                R(upload_blobs(ctx, d, st, s.ev_copied, s.ev_dma, in, 1, cs));
             } else {
                 R(upload_separate(ctx, d, st, w.query, r0, (uint64_t)r1 + 1, "content", "read", s.packed_q, s.h_stage_q, rstart.data(), cs));
             }
@@ -762,7 +786,7 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
             h_slab[n] = slab_bytes;
         }
     }
-    SG_CUDA(cudaMemcpyAsync(s.desc.p, s.h_desc.p, (5 * n + 1) * 8, cudaMemcpyHostToDevice, st));
+    SG_CUDA(cudaMemcpyAsync(s.desc.p, s.h_desc.p, (5 * n + 1) * 8, cudaMemcpyHostToDevice, d.h2d));
     cs.h2d_other += (5 * n + 1) * 8;
     // Mixed lengths in one launch: the kernel's queue hands the alignments out longest first (the reference's callers sort
     // their reads by descending length before the call for the same reason, src/tests.cu:377), results stay in input order.
@@ -776,12 +800,15 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
             uint32_t *ho = s.h_order.as<uint32_t>();
             for (uint64_t k = 0; k < n; k++) ho[k] = (uint32_t)k;
             std::stable_sort(ho, ho + n, [&](uint32_t a, uint32_t b) { return h_qlen[a] > h_qlen[b]; });
-            SG_CUDA(cudaMemcpyAsync(s.order.p, ho, n * 4, cudaMemcpyHostToDevice, st));
+            SG_CUDA(cudaMemcpyAsync(s.order.p, ho, n * 4, cudaMemcpyHostToDevice, d.h2d));
             cs.h2d_other += n * 4;
             d_order = s.order.as<uint32_t>();
         }
     }
     if (want_cigar) R(s.slab.reserve(slab_bytes + 16));
+    // everything this sub-batch needs from the host is queued in the GPU's host-to-device stream: hand over to its own
+    SG_CUDA(cudaEventRecord(s.ev_copied, d.h2d));
+    SG_CUDA(cudaStreamWaitEvent(st, s.ev_copied, 0));
     SG_CUDA(cudaEventRecord(s.ev_k0, st));
     R(sg_dev_align_ordered(ctx->W, ctx->O, d_text, d_tstart, d_tlen, s.packed_q.as<uint32_t>(), d_qstart, d_qlen, n, w.flags, s.slab.as<uint8_t>(), d_slab,
                            s.counter.as<uint64_t>(), s.edit.as<int64_t>(), s.refc.as<uint64_t>(), s.nruns.as<uint32_t>(), s.status.as<uint8_t>(),
@@ -965,6 +992,7 @@ void run_shard(sg_ctx *ctx, Device &d, const Workload &w, BatchQueue &q, sg_resu
     auto bail = [&](int rc) {
         so.rc = rc;
         so.err = g_last_error;
+        if (d.h2d) cudaStreamSynchronize(d.h2d);
         for (Slot &s : d.slots) {  // let the device drain before the buffers are reused
             if (s.stream) cudaStreamSynchronize(s.stream);
             s.busy = false;
@@ -1232,6 +1260,7 @@ int sg_ctx_create_wo(sg_ctx **out, const int *device_ids, int n_devices, int W, 
         if (d.id < 0 || d.id >= avail) return fail(SG_ERR_BAD_ARG, "device id out of range");
         SG_CUDA(cudaSetDevice(d.id));
         d.cpus = cpu_sets[k];
+        SG_CUDA(cudaStreamCreateWithFlags(&d.h2d, cudaStreamNonBlocking));
         if (const char *v = std::getenv("SG_SLOTS")) d.n_slots = std::min(kMaxSlots, std::max(2, std::atoi(v)));
         for (int q = 0; q < d.n_slots; q++) R(d.slots[q].create());
         if (ctx->host_threads > 0) {
@@ -1268,6 +1297,8 @@ void sg_ctx_destroy(sg_ctx *ctx)
             d.team.stop();
             cudaSetDevice(d.id);
             for (Slot &s : d.slots) s.destroy();
+            if (d.h2d) cudaStreamDestroy(d.h2d);
+            d.h2d = nullptr;
             d.genome.release();
             d.piece_bad.release();
         }
@@ -1385,7 +1416,7 @@ int sg_set_reference(sg_ctx *ctx, const char *genome_ascii, uint64_t genome_len)
         DevBuf *stage[2] = {&s.ascii_t, &s.ascii_q};
         R(stage[0]->reserve(std::min<uint64_t>(piece, genome_len) + 64));
         if (genome_len > piece) R(stage[1]->reserve(std::min<uint64_t>(piece, genome_len - piece) + 64));
-        cudaStream_t copy_st = d.slots[1].stream;
+        cudaStream_t copy_st = d.h2d;
         cudaEvent_t copied[2] = {s.ev_dma[0], s.ev_dma[1]}, packed[2] = {s.ev_dma[2], s.ev_dma[3]};
         R(d.piece_bad.reserve(16 * (genome_len / piece + 1)));
         SG_CUDA(cudaMemsetAsync(d.piece_bad.p, 0xFF, 16 * (genome_len / piece + 1), s.stream));
