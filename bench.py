@@ -447,38 +447,45 @@ def main():
             lib.sg_host_pack_2bit(qb_pin.data_ptr(), qb.nbytes, h_packed.data_ptr() + (tb.nbytes // 16 + 16) * 4, max(1, host_threads))
         h2d_s, _ = timed(h2d_only)
         pack_s, _ = timed(pack_only)
-        h2d_gbs = world * ascii_bytes * args.steps / h2d_s / 1e9        # all ranks' copy engines at once
-        pack_gbs = world * ascii_bytes * args.steps / pack_s / 1e9      # all ranks' packer threads at once
-        # adaptive ingest at its best: the copy engines run flat out, and every byte the host packs still crosses PCIe at a
-        # quarter of its size: ASCII bytes/s <= h2d + 0.75 * pack
-        ceiling = (h2d_gbs + 0.75 * pack_gbs) * 1e9 / (ascii_bytes / ne)
-        # The two do not add up on a real host: copy engines and packers read the same DRAM.  Both AT THE SAME TIME (the
-        # copy engine takes the first half of every blob, the packers the second), all ranks at once:
+        h2d_gbs = world * ascii_bytes * args.steps / h2d_s / 1e9        # all ranks' copy engines at once, nothing else running
+        pack_gbs = world * ascii_bytes * args.steps / pack_s / 1e9      # all ranks' packer threads at once, nothing else running
+        # The two do not add up on a real host: copy engines and packers read the same DRAM.  Both AT THE SAME TIME for half
+        # a second, all ranks at once: a thread keeps the copy engine busy with the first half of the blobs while the
+        # packers work through the second half again and again; bytes moved by each over the common window.
+        import threading
         ht, hq = (tb.nbytes // 2) & ~63, (qb.nbytes // 2) & ~63
-        cev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        both_t = {"h2d": 0.0, "pack": 0.0}
+        side = torch.cuda.Stream(device=dev)
+        stop, moved = threading.Event(), [0]
 
-        def both():
-            cev[0].record()
-            d_buf[:ht].copy_(tb_pin[:ht], non_blocking=True)
-            d_buf[ht:ht + hq].copy_(qb_pin[:hq], non_blocking=True)
-            cev[1].record()
-            t0 = time.perf_counter()
+        def copier():
+            torch.cuda.set_device(dev)
+            with torch.cuda.stream(side):
+                while not stop.is_set():
+                    d_buf[:ht].copy_(tb_pin[:ht], non_blocking=True)
+                    d_buf[ht:ht + hq].copy_(qb_pin[:hq], non_blocking=True)
+                    side.synchronize()
+                    moved[0] += ht + hq
+        barrier()
+        th = threading.Thread(target=copier)
+        t0 = time.perf_counter()
+        th.start()
+        packed_bytes = 0
+        while time.perf_counter() - t0 < 0.5:
             lib.sg_host_pack_2bit(tb_pin.data_ptr() + ht, tb.nbytes - ht, h_packed.data_ptr(), max(1, host_threads))
             lib.sg_host_pack_2bit(qb_pin.data_ptr() + hq, qb.nbytes - hq, h_packed.data_ptr() + (tb.nbytes // 16 + 16) * 4, max(1, host_threads))
-            both_t["pack"] += time.perf_counter() - t0
-            torch.cuda.synchronize()
-            both_t["h2d"] += cev[0].elapsed_time(cev[1]) / 1e3
-        for _ in range(2):
-            both()
-        both_t["h2d"] = both_t["pack"] = 0.0
-        barrier()
-        for _ in range(args.steps):
-            both()
-        conc_h2d_gbs = world * (ht + hq) * args.steps / sharding.max_over_ranks(both_t["h2d"]) / 1e9
-        conc_pack_gbs = world * (ascii_bytes - ht - hq) * args.steps / sharding.max_over_ranks(both_t["pack"]) / 1e9
-        ceiling_conc = (conc_h2d_gbs + 0.75 * conc_pack_gbs) * 1e9 / (ascii_bytes / ne)
+            packed_bytes += ascii_bytes - ht - hq
+        t_pack = time.perf_counter() - t0
+        stop.set()
+        th.join()
+        t_copy = time.perf_counter() - t0
+        conc_h2d_gbs = world * moved[0] / sharding.max_over_ranks(t_copy) / 1e9
+        conc_pack_gbs = world * packed_bytes / sharding.max_over_ranks(t_pack) / 1e9
         del d_buf, h_packed
+        # What the host can deliver at best, in ASCII bytes per second: either the copy engines alone (every byte crosses as
+        # ASCII; best when DRAM, not PCIe, is the narrow link: many GPUs on one host) or copy engines and packers together,
+        # where every byte the host packs still crosses PCIe at a quarter of its size.
+        ceil_gbs = max(h2d_gbs, conc_h2d_gbs + 0.75 * conc_pack_gbs)
+        ceiling = ceil_gbs * 1e9 / (ascii_bytes / ne)
 
         def gather(x):
             if world == 1:
@@ -497,15 +504,12 @@ def main():
                "d2h_bytes_per_step": st["d2h_bytes"], "input_ascii_bytes_per_step": ascii_bytes,
                "h2d_split": {"ascii": st["h2d_ascii_bytes"], "packed_2bit": st["h2d_packed_bytes"], "descriptors": st["h2d_other_bytes"]},
                "pairs_per_step": ne, "ms_per_step": e2e_s / args.steps * 1e3, "host_threads_per_gpu": host_threads,
-               "ceiling": {"value": ceiling, "unit": "alignments/s", "h2d_ascii_gbs": h2d_gbs, "host_pack_gbs": pack_gbs,
-                           "rule": "(h2d + 0.75 * pack) bytes/s / ASCII bytes per pair; both rates measured in this run with all "
-                                   "ranks at once, ONE AFTER THE OTHER: pinned ASCII -> device copies only, then sg_host_pack_2bit only"},
+               "ceiling": {"value": ceiling, "unit": "alignments/s", "ascii_gbs": ceil_gbs, "copy_engines_alone_gbs": h2d_gbs,
+                           "packers_alone_gbs": pack_gbs, "concurrent_copy_engines_gbs": conc_h2d_gbs, "concurrent_packers_gbs": conc_pack_gbs,
+                           "rule": "max(copy engines alone, concurrent copy engines + 0.75 x concurrent packers) ASCII bytes/s over the "
+                                   "ASCII bytes per pair; all rates measured in this run on this run's pinned input with all ranks at "
+                                   "once (pinned ASCII -> device copies only; sg_host_pack_2bit only; both at the same time for 0.5 s)"},
                "frac_of_ceiling": value_e2e / ceiling,
-               "ceiling_concurrent": {"value": ceiling_conc, "unit": "alignments/s", "h2d_ascii_gbs": conc_h2d_gbs, "host_pack_gbs": conc_pack_gbs,
-                                      "rule": "the same rule with both rates measured AT THE SAME TIME on disjoint halves of the blobs "
-                                              "(copy engines and packer threads share the host's DRAM bandwidth: this is the ceiling "
-                                              "the host can actually deliver)"},
-               "frac_of_ceiling_concurrent": value_e2e / ceiling_conc,
                "breakdown_per_rank": per_rank,
                "api": "sg_align_pairs (C ABI, pinned host ASCII blobs in, distances + packed CIGAR runs out); adaptive ingest: a "
                       "persistent team of packer threads per GPU (bound to the GPU's CPUs) packs chunks to 2 bit/base (AVX-512) from "

@@ -314,6 +314,10 @@ struct Device {
     uint64_t genome_len = 0;
     bool has_genome = false;
     std::vector<int> cpus;   // the CPUs this GPU's host threads run on (sg_host_threads.h)
+    // The worker (the feeder of the adaptive ingest: it keeps the copy engine's queue full and polls for finished kernels)
+    // gets a CPU of its own, the packers share the rest: with packers on every CPU the feeder was descheduled for
+    // milliseconds at a time and the PCIe link ran dry (13 GB/s of ASCII chunk copies where 24 GB/s fit).
+    std::vector<int> worker_cpus, packer_cpus;
     ThreadTeam team;         // its packer threads: created with the context, asleep between jobs
 };
 
@@ -361,7 +365,7 @@ struct sg_ctx {
     // tuned fraction, and it degrades gracefully when several ranks share the host's threads.
     bool adaptive = true;
     uint64_t chunk_bytes = 8ull << 20;
-    int dma_depth = 8;
+    int dma_depth = 12;
     uint64_t ascii_min_bytes = 8ull << 20;   // blobs smaller than this are not split
     std::mutex mu;  // calls on one context are serialised
     bool taper = true;           // SG_TAPER=0: the last sub-batch of a call is not cut finer
@@ -1140,13 +1144,13 @@ int run_all(sg_ctx *ctx, const Workload &w, const uint64_t *woff, uint64_t per_u
             if (want_cigar) q.max_slab = std::max<uint64_t>(q.max_slab, 2 * (w.query.off[a1] - w.query.off[a0]) + 8 * (a1 - a0));
         }
         if (nd == 1) {
-            ScopedAffinity bound(ctx->devs[0].cpus);   // the caller's thread is this GPU's worker for the call
+            ScopedAffinity bound(ctx->devs[0].worker_cpus);   // the caller's thread is this GPU's worker for the call
             run_shard(ctx, ctx->devs[0], w, q, res.get(), shards[0]);
         } else {
             std::vector<std::thread> th;
             for (int k = 0; k < nd; k++)
                 th.emplace_back([&, k]() {
-                    bind_this_thread(ctx->devs[k].cpus);
+                    bind_this_thread(ctx->devs[k].worker_cpus);
                     run_shard(ctx, ctx->devs[k], w, q, res.get(), shards[k]);
                 });
             for (auto &t : th) t.join();
@@ -1260,12 +1264,17 @@ int sg_ctx_create_wo(sg_ctx **out, const int *device_ids, int n_devices, int W, 
         if (d.id < 0 || d.id >= avail) return fail(SG_ERR_BAD_ARG, "device id out of range");
         SG_CUDA(cudaSetDevice(d.id));
         d.cpus = cpu_sets[k];
+        d.worker_cpus = d.packer_cpus = d.cpus;
+        if (d.cpus.size() >= 2 && ctx->host_threads > 0) {
+            d.worker_cpus.assign(1, d.cpus.back());
+            d.packer_cpus.assign(d.cpus.begin(), d.cpus.end() - 1);
+        }
         SG_CUDA(cudaStreamCreateWithFlags(&d.h2d, cudaStreamNonBlocking));
         if (const char *v = std::getenv("SG_SLOTS")) d.n_slots = std::min(kMaxSlots, std::max(2, std::atoi(v)));
         for (int q = 0; q < d.n_slots; q++) R(d.slots[q].create());
         if (ctx->host_threads > 0) {
             const int dev_id = d.id;
-            d.team.start(ctx->host_threads, d.cpus, [dev_id](int) { cudaSetDevice(dev_id); });
+            d.team.start(ctx->host_threads, d.packer_cpus, [dev_id](int) { cudaSetDevice(dev_id); });
         }
         d.tuner.init(ctx->host_threads);
         int wps = 0, sms = 0;
@@ -1280,7 +1289,7 @@ int sg_ctx_create_wo(sg_ctx **out, const int *device_ids, int n_devices, int W, 
         for (const Device &d : ctx->devs) {
             std::string l;
             for (int c : d.cpus) l += (l.empty() ? "" : ",") + std::to_string(c);
-            fprintf(stderr, "[sg] GPU %d: %d packer threads on CPUs {%s}\n", d.id, ctx->host_threads, l.c_str());
+            fprintf(stderr, "[sg] GPU %d: %d packer threads on CPUs {%s}, the last one for the worker\n", d.id, ctx->host_threads, l.c_str());
         }
     g_live_contexts++;
     ctx->counted = true;

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <thread>
 #include <atomic>
+#include <vector>
 #include <cuda_runtime.h>
 
 #define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
@@ -84,6 +85,32 @@ int main()
         else printf("%-64s NOT ready after 400 ms of flooding (flood %.1f GB/s)\n", name, flood_gbs);
     };
 
+    // ---- how fast does ONE stream move back-to-back copies of a given size, issued by 1 or 8 host threads?
+    for (int nthreads : {1, 8}) {
+        for (size_t sz : {(size_t)1 << 20, (size_t)2 << 20, (size_t)4 << 20, (size_t)8 << 20, (size_t)32 << 20}) {
+            const size_t total = (size_t)2 << 30;
+            const size_t ncopies = total / sz;
+            CU(cudaDeviceSynchronize());
+            const double t0 = now_ms();
+            std::atomic<size_t> next{0};
+            std::vector<std::thread> ths;
+            for (int t = 0; t < nthreads; t++)
+                ths.emplace_back([&]() {
+                    while (true) {
+                        const size_t k = next.fetch_add(1);
+                        if (k >= ncopies) break;
+                        const size_t off = (k * sz) % (chunk * nchunk - sz + 1);
+                        cudaMemcpyAsync(d_a + off, h_src + off, sz, cudaMemcpyHostToDevice, A);
+                    }
+                });
+            for (auto &t : ths) t.join();
+            const double t_issued = now_ms();
+            CU(cudaStreamSynchronize(A));
+            const double t1 = now_ms();
+            printf("one stream, %d issuing thread(s), %4zu MB copies: %6.1f GB/s  (issue %.1f ms, total %.1f ms, %.1f us per copy)\n", nthreads, sz >> 20,
+                   total / ((t1 - t0) * 1e-3) / 1e9, t_issued - t0, t1 - t0, (t1 - t0) * 1e3 / ncopies);
+        }
+    }
     for (int depth : {0, 8}) {
         printf("---- stream A flood depth %d\n", depth);
         scenario("kernel(5ms) in B", depth, [&] { spin_kernel<<<148, 128, 0, B>>>(ms5, d_flag); cudaEventRecord(done, B); });

@@ -46,7 +46,7 @@ for step in "$@"; do
         timeout 900 ./build/sg_e2e_probe --gpus $GPUS --layout $layout ${PROBE_ARGS:-} > gpurun_out/${TAG}_probe_$layout.jsonl 2> gpurun_out/${TAG}_probe_$layout.err
         echo "probe $layout rc=$?"; cut -c1-600 gpurun_out/${TAG}_probe_$layout.jsonl
       done ;;
-    configs) timeout 2400 python tools/bench_configs.py all > gpurun_out/${TAG}_configs.jsonl 2> gpurun_out/${TAG}_configs.err; echo "configs rc=$?" ;;
+    configs) for what in short mapping sweep; do timeout 2400 python tools/bench_configs.py $what >> gpurun_out/${TAG}_configs.jsonl 2>> gpurun_out/${TAG}_configs.err; echo "configs $what rc=$?"; done ;;
     cmd:*) k=$((k+1)); timeout 2400 bash -c "${step#cmd:}" > gpurun_out/${TAG}_cmd$k.log 2>&1; echo "cmd$k rc=$?"; tail -5 gpurun_out/${TAG}_cmd$k.log ;;
     *) echo "unknown step $step" ;;
   esac
