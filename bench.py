@@ -427,7 +427,7 @@ def main():
         # threads inside the timed region -- what the reference's CPU arm produces (sprintf, src/genasm_cpu.cpp:387-403)
         def rendered():
             r = al.align_pairs_blob(tb_pin, toff, qb_pin, qoff)
-            rendered.text = r.cigar_text()
+            rendered.text = r.cigar_text(out=getattr(rendered, "text", None))   # the text buffer is the caller's and is reused
             return r
         ren_s, res_r = timed(rendered)
         text_blob, text_off = rendered.text

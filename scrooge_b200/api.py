@@ -116,12 +116,19 @@ class Result:
             raise ScroogeError(_lib.SG_ERR_BAD_ARG, "render_cigar failed")
         return buf.value.decode()
 
-    def cigar_text(self, threads: int = 0):
-        """All CIGAR texts as one uint8 array + offsets (count+1), rendered by the library's host threads."""
-        off = np.zeros(self.count + 1, dtype=np.uint64)
+    def cigar_text(self, threads: int = 0, out: Optional[Tuple[np.ndarray, np.ndarray]] = None):
+        """All CIGAR texts as one uint8 array + offsets (count+1), rendered by the library's host threads.  `out` = a
+        (blob, offsets) pair from an earlier call to reuse (a caller that renders batch after batch keeps its buffer:
+        fresh pages for gigabytes of text cost more than the rendering)."""
+        off = out[1] if out is not None and len(out[1]) == self.count + 1 else np.zeros(self.count + 1, dtype=np.uint64)
+        blob = out[0].base if out is not None and out[0].base is not None else (out[0] if out is not None else None)
+        if blob is not None:   # one pass when the buffer is large enough
+            total = int(lib().sg_result_render_all(self._h, blob.ctypes.data, blob.size, off.ctypes.data, threads))
+            if total <= blob.size:
+                return blob[:total], off
         total = int(lib().sg_result_render_all(self._h, None, 0, off.ctypes.data, threads))
-        blob = np.empty(max(total, 1), dtype=np.uint8)
-        lib().sg_result_render_all(self._h, blob.ctypes.data, total, off.ctypes.data, threads)
+        blob = np.empty(max(total + total // 16, 1), dtype=np.uint8)
+        lib().sg_result_render_all(self._h, blob.ctypes.data, blob.size, off.ctypes.data, threads)
         return blob[:total], off
 
     def cigars(self) -> List[str]:
