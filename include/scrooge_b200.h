@@ -165,6 +165,15 @@ int sg_result_stats(const sg_result *r, sg_call_stats *out);
  * destruction of a process's last context does the same. */
 void sg_trim_host_cache(void);
 
+/* How a call over n alignments would be cut into sub-batches (the unit of the per-GPU pipeline and of the queue the GPUs
+ * of a context share): weight_off = n+1 prefix sums of the bytes an alignment uploads, per_unit_extra = descriptor bytes
+ * per alignment; a sub-batch grows while it is under max_batch_bytes and either under batch_bytes or short of
+ * min_batch_units alignments; with taper the last full sub-batch is cut into 1/2, 1/4, 1/8, 1/8 of its weight (the end of
+ * a call is exposed).  Writes up to cuts_cap cut points (first 0, last n) and returns how many there are.  No device
+ * needed: planning and tests. */
+uint64_t sg_plan_sub_batches(const uint64_t *weight_off, uint64_t n, uint64_t per_unit_extra, uint64_t batch_bytes,
+                             uint64_t max_batch_bytes, uint64_t min_batch_units, int taper, uint64_t *cuts, uint64_t cuts_cap);
+
 /* Page-locked host memory for input blobs: uploads from it run at full PCIe speed and overlap with compute
  * (pageable memory works too, but the driver then stages every copy).  NULL on failure. */
 void *sg_host_alloc(uint64_t bytes);

@@ -56,6 +56,7 @@ SIGNATURES = {
     "sg_result_free": (None, [vp]),
     "sg_result_stats": (i32, [vp, vp]),
     "sg_trim_host_cache": (None, []),
+    "sg_plan_sub_batches": (u64, [vp, u64, u64, u64, u64, u64, i32, vp, u64]),
     "sg_host_alloc": (vp, [u64]),
     "sg_host_free": (None, [vp]),
     "sg_host_pack_2bit": (u64, [vp, u64, vp, i32]),

@@ -1320,6 +1320,16 @@ void sg_ctx_destroy(sg_ctx *ctx)
 
 void sg_trim_host_cache(void) { g_pool.trim(0); }
 
+uint64_t sg_plan_sub_batches(const uint64_t *weight_off, uint64_t n, uint64_t per_unit_extra, uint64_t batch_bytes, uint64_t max_batch_bytes,
+                             uint64_t min_batch_units, int taper, uint64_t *cuts, uint64_t cuts_cap)
+{
+    if (!weight_off || !n) return 0;
+    std::vector<uint64_t> c = sub_batch_cuts(batch_bytes, max_batch_bytes, min_batch_units, weight_off, per_unit_extra, 0, n);
+    if (taper) taper_tail(c, weight_off, per_unit_extra, 4ull << 20);
+    for (uint64_t k = 0; k < c.size() && cuts && k < cuts_cap; k++) cuts[k] = c[k];
+    return c.size();
+}
+
 int sg_result_stats(const sg_result *r, sg_call_stats *out)
 {
     if (!r || !out) return fail(SG_ERR_BAD_ARG, "sg_result_stats: null argument");

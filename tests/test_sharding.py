@@ -88,3 +88,44 @@ def test_two_ranks_over_gloo(oracle):
     assert [g[1:3] for g in got] == [(0, 40), (40, 80)]
     assert got[0][3] + got[1][3] == want
     assert all(g[4] == 2.0 for g in got)
+
+
+def _plan(sglib, sizes, extra, batch, max_batch, min_units, taper):
+    off = np.zeros(len(sizes) + 1, dtype=np.uint64)
+    np.cumsum(np.asarray(sizes, dtype=np.uint64), out=off[1:])
+    cuts = np.zeros(len(sizes) + 2, dtype=np.uint64)
+    k = sglib.sg_plan_sub_batches(off.ctypes.data, len(sizes), extra, batch, max_batch, min_units, taper, cuts.ctypes.data, len(cuts))
+    return [int(c) for c in cuts[:k]], off
+
+
+def test_sub_batch_plan_rules_and_taper(sglib):
+    """The cuts of a call (sg_plan_sub_batches = what run_all uses): cover [0, n) in order, respect the byte and unit rules,
+    and with taper end in pieces of about 1/2, 1/4, 1/8, 1/8 of a full sub-batch."""
+    MB = 1 << 20
+    n, per = 524_288, 20_102                       # the end-to-end bench call: 10 kbp pairs
+    cuts, off = _plan(sglib, [per] * n, 48, 256 * MB, 3072 * MB, 113_664, 0)
+    assert cuts[0] == 0 and cuts[-1] == n and cuts == sorted(set(cuts))
+    sizes = np.diff(cuts)
+    assert all(s == 113_664 for s in sizes[:-1]) and sizes[-1] == n - 4 * 113_664   # the unit rule decides for 20 KB pairs
+    tap, _ = _plan(sglib, [per] * n, 48, 256 * MB, 3072 * MB, 113_664, 1)
+    assert tap[0] == 0 and tap[-1] == n and tap == sorted(set(tap))
+    ts = np.diff(tap)
+    # the last sub-batch (69 632 pairs: more than half a full one, so it is not joined with its predecessor) is cut into
+    # 1/2, 1/4, 1/8, 1/8
+    last = n - 4 * 113_664
+    assert list(ts[:4]) == [113_664] * 4 and len(ts) == 8
+    assert abs(ts[4] - last / 2) <= 2 and abs(ts[5] - last / 4) <= 2 and abs(ts[6] - last / 8) <= 2 and abs(ts[7] - last / 8) <= 3
+    # a short last sub-batch is joined with the one before it first
+    tap2, _ = _plan(sglib, [per] * (4 * 113_664 + 1000), 48, 256 * MB, 3072 * MB, 113_664, 1)
+    t2 = np.diff(tap2)
+    assert list(t2[:3]) == [113_664] * 3 and len(t2) == 7 and abs(t2[3] - (113_664 + 1000) / 2) <= 2
+    # short reads: the byte rule decides; nothing exceeds the maximum
+    cuts, off = _plan(sglib, [300] * 2_000_000, 48, 256 * MB, 3072 * MB, 113_664, 1)
+    w = np.diff(off[cuts].astype(np.int64)) + 48 * np.diff(cuts)
+    assert w.max() <= 256 * MB + 348 and cuts[-1] == 2_000_000
+    # one huge alignment per sub-batch when a single one exceeds the maximum; empty strings still advance
+    cuts, _ = _plan(sglib, [4000 * MB, 0, 0, 5], 48, 256 * MB, 3072 * MB, 4, 0)
+    assert cuts[0] == 0 and cuts[1] == 1 and cuts[-1] == 4
+    # a tiny call is not tapered
+    cuts, _ = _plan(sglib, [100] * 10, 48, 256 * MB, 3072 * MB, 4, 1)
+    assert cuts == [0, 10]
