@@ -87,6 +87,11 @@
 #ifndef SG_DELTA_RLE2
 #define SG_DELTA_RLE2 1
 #endif
+//   SG_DELTA_SHORTFAST  windows with fewer than W-O pattern characters take the unchecked walk too and have their op streams
+//                   cut where the pattern ran out (see the traceback).  ON.
+#ifndef SG_DELTA_SHORTFAST
+#define SG_DELTA_SHORTFAST 1
+#endif
 
 namespace sg {
 
@@ -355,9 +360,18 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
             sts_vec<NW>(pm_s + 4 * PMS, hm);   // a character that matches nothing: columns i >= n
         }
         const bool uniform = __all_sync(0xFFFFFFFFu, !have || n == W);
-        // the first TB_LIMIT steps of a traceback cannot end it when the window holds at least TB_LIMIT pattern characters
-        // (after k steps i <= k and j <= k): warps whose lanes all have such a window walk them without any end test
+        // The first TB_LIMIT steps of a traceback cannot end a window that holds at least TB_LIMIT pattern characters
+        // (after k steps i <= k and j <= k), so they are walked without any end test.  A window with fewer pattern
+        // characters (the last window of a read) walks them unchecked too: the only limit it can overrun is j == m, the
+        // steps beyond that point read whatever the planes hold below the pattern (in bounds: at most TB_LIMIT columns
+        // and TB_LIMIT mask shifts) and are cut off afterwards, where the m-th pattern-consuming step is found in the
+        // op streams.  (Before, one short window among a warp's 32 sent the whole warp through the checked loop: with
+        // 150 bp reads that was nearly every iteration -- SG_DELTA_SHORTFAST=0 restores it.)
+#if SG_DELTA_SHORTFAST
+        const bool tb_fast = true;
+#else
         const bool tb_fast = __all_sync(0xFFFFFFFFu, !have || m >= TBL);
+#endif
 #ifdef SG_STATS
         if (lane == 0) {
             atomicAdd(&g_delta_stats[uniform ? 0 : 1], 1ull);
@@ -526,6 +540,30 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
 #endif
             }
             bit0 = TBL < 32 ? 1u << (TBL & 31) : 0u;
+#if SG_DELTA_SHORTFAST
+            if (m < TBL) {
+                constexpr uint32_t kWalked = TBL < 32 ? (1u << (TBL & 31)) - 1u : 0xFFFFFFFFu;
+                const uint32_t nd = ~(h0 & l0) & kWalked;          // steps that consumed a pattern character (all but 'D')
+                if (__popc(nd) >= m) {
+                    // the pattern ran out within these steps: the position of the m-th set bit of nd, by halving
+                    uint32_t pos = 0u;
+                    int r = m;
+#pragma unroll
+                    for (int half = 16; half >= 1; half >>= 1) {
+                        const int c = __popc((nd >> pos) & ((1u << half) - 1u));
+                        if (c < r) { r -= c; pos += (uint32_t)half; }
+                    }
+                    const uint32_t keep = (2u << pos) - 1u;        // steps 0..pos are the walk (pos <= TBL-1 <= 30)
+                    h0 &= keep;
+                    l0 &= keep;
+                    const int took_text = __popc(~(h0 & ~l0) & keep);   // every step but an 'I' consumed a text character
+                    tcol = tb_begin + (uint32_t)took_text * (uint32_t)(TBS * 4);
+                    mask = mask_end;                               // j == m: the checked loop below has nothing left to do
+                }
+                // else: fewer than m pattern characters consumed so far (deletions): the state is that of a checked walk
+                // after TB_LIMIT steps, and the loop below goes on from it
+            }
+#endif
         }
 #pragma unroll
         for (int w = 0; w < SW; w++) {

@@ -291,3 +291,64 @@ def rle_streams(hs: List[int], ls: List[int], j: int):
             ew &= ew - 1
         st -= 32
     return runs, edits
+
+
+def walk_checked(A: List[int], B: List[int], m: int, TBL: int):
+    """The traceback walk with its end tests (reference src/genasm_cpu.cpp:307-310): op planes A/B per column, pattern
+    position j at bit 31-j, op = 2A+B (0 '=', 1 'X', 2 'I', 3 'D').  Returns (ops, i, j)."""
+    i = j = 0
+    ops: List[int] = []
+    jmax = min(m, TBL)
+    while j < jmax and i < TBL and len(ops) < 2 * TBL:
+        op = 2 * ((A[i] >> (31 - j)) & 1) + ((B[i] >> (31 - j)) & 1)
+        ops.append(op)
+        if op != 2:
+            i += 1
+        if op != 3:
+            j += 1
+    return ops, i, j
+
+
+def walk_unchecked_then_cut(A: List[int], B: List[int], m: int, TBL: int):
+    """What genasm_delta_kernel does (SG_DELTA_SHORTFAST): TB_LIMIT steps without any end test -- also for a window with
+    m < TB_LIMIT pattern characters, whose steps beyond j == m read whatever the planes hold below the pattern -- then,
+    for such a window, the op streams are cut at the m-th step that consumed a pattern character (every op but 'D'),
+    found by halving with popcounts; a walk that is not over after TB_LIMIT steps goes on with the end tests."""
+    i = j = 0
+    h = l = 0
+    for k in range(TBL):
+        a, b = (A[i] >> (31 - j)) & 1, (B[i] >> (31 - j)) & 1
+        h |= a << k
+        l |= b << k
+        if not (a and not b):
+            i += 1
+        if not (a and b):
+            j += 1
+    steps = TBL
+    if m < TBL:
+        walked = (1 << TBL) - 1
+        nd = ~(h & l) & walked
+        if bin(nd).count("1") >= m:
+            pos, r = 0, m
+            for half in (16, 8, 4, 2, 1):
+                c = bin((nd >> pos) & ((1 << half) - 1)).count("1")
+                if c < r:
+                    r -= c
+                    pos += half
+            keep = (2 << pos) - 1
+            h &= keep
+            l &= keep
+            i = bin(~(h & ~l) & keep).count("1")
+            j = m
+            steps = pos + 1
+            return [2 * ((h >> k) & 1) + ((l >> k) & 1) for k in range(steps)], i, j
+    ops = [2 * ((h >> k) & 1) + ((l >> k) & 1) for k in range(steps)]
+    jmax = min(m, TBL)
+    while j < jmax and i < TBL and len(ops) < 2 * TBL:
+        op = 2 * ((A[i] >> (31 - j)) & 1) + ((B[i] >> (31 - j)) & 1)
+        ops.append(op)
+        if op != 2:
+            i += 1
+        if op != 3:
+            j += 1
+    return ops, i, j

@@ -90,3 +90,19 @@ def test_random_windows_model(oracle):
         for k in range(len(T)):
             ed, cg, rc, _ = align_delta_generic(T[k], Q[k], W, O)
             assert (ed, cg, rc) == (int(res.edit[k]), res.cigars[k], int(res.ref_consumed[k])), (W, O, T[k], Q[k])
+
+
+def test_unchecked_walk_with_cut_equals_checked_walk():
+    """The short-window walk of genasm_delta_kernel: TB_LIMIT unchecked steps + cutting the op streams where the pattern
+    ran out gives the checked walk's ops, i and j -- for ANY plane contents (random planes: whatever lies below the
+    pattern cannot matter), every m, both tuned window configurations."""
+    import random
+    from kernel_model import walk_checked, walk_unchecked_then_cut
+    rng = random.Random(2024)
+    for TBL in (31, 15):
+        for trial in range(4000):
+            m = rng.randrange(1, TBL + 8)
+            bias = rng.choice([0.02, 0.2, 0.5, 0.9])     # from almost all '=' to mostly edits (long walks, many 'D')
+            A = [sum((rng.random() < bias) << b for b in range(32)) for _ in range(TBL + 1)]
+            B = [rng.getrandbits(32) for _ in range(TBL + 1)]
+            assert walk_unchecked_then_cut(A, B, m, TBL) == walk_checked(A, B, m, TBL), (TBL, m, trial)
