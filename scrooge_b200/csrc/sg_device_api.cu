@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <cuda_runtime.h>
 
@@ -140,16 +141,24 @@ static int device_info(DeviceInfo **out)
     SG_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return fail(SG_ERR_BAD_ARG, "device index out of range");
     DeviceInfo &di = g_dev_info[dev];
-    if (!di.ready) {
-        SG_CUDA(cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, dev));
-        int rc = setup_kernel<64, false>(&di.ctas_per_sm[0][0]);
-        if (!rc) rc = setup_kernel<64, true>(&di.ctas_per_sm[0][1]);
-        if (!rc) rc = setup_kernel<32, false>(&di.ctas_per_sm[1][0]);
-        if (!rc) rc = setup_kernel<32, true>(&di.ctas_per_sm[1][1]);
-        if (!rc) rc = setup_delta_kernel<64>(&di.delta_ctas_per_sm[0]);
-        if (!rc) rc = setup_delta_kernel<32>(&di.delta_ctas_per_sm[1]);
-        if (rc) return rc;
-        di.ready = true;
+    // set up once per device, whichever thread or context comes first (two contexts on one device, or device-API calls
+    // from several threads, must not race on the occupancy fields); a failed set-up is retried by the next call
+    static std::mutex setup_mu[64];
+    static std::atomic<bool> ready[64];
+    if (!ready[dev].load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> g(setup_mu[dev]);
+        if (!ready[dev].load(std::memory_order_relaxed)) {
+            SG_CUDA(cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, dev));
+            int rc = setup_kernel<64, false>(&di.ctas_per_sm[0][0]);
+            if (!rc) rc = setup_kernel<64, true>(&di.ctas_per_sm[0][1]);
+            if (!rc) rc = setup_kernel<32, false>(&di.ctas_per_sm[1][0]);
+            if (!rc) rc = setup_kernel<32, true>(&di.ctas_per_sm[1][1]);
+            if (!rc) rc = setup_delta_kernel<64>(&di.delta_ctas_per_sm[0]);
+            if (!rc) rc = setup_delta_kernel<32>(&di.delta_ctas_per_sm[1]);
+            if (rc) return rc;
+            di.ready = true;
+            ready[dev].store(true, std::memory_order_release);
+        }
     }
     *out = &di;
     return SG_OK;
@@ -256,17 +265,16 @@ static int launch_generic(const DeviceInfo &di, const AlignParams &P, int W, int
     G.W = W; G.TBL = W - O; G.NWT = (G.TBL + 31) / 32; G.planes = nullptr;
     const unsigned ctas = (unsigned)balanced_ctas(P.n, (uint64_t)di.sms * (uint64_t)per_sm, 32ull);
     if (gp) {   // stream-ordered scratch: launches on different streams of one device never share it
-        static bool pool_kept[64] = {};
+        static std::atomic<bool> pool_kept[64];
         int dev = 0;
         SG_CUDA(cudaGetDevice(&dev));
-        if (dev >= 0 && dev < 64 && !pool_kept[dev]) {
+        if (dev >= 0 && dev < 64 && !pool_kept[dev].exchange(true)) {
             // keep freed scratch in the device's pool across synchronisations (the default threshold of 0 hands it back to
             // the driver at every sync, and each launch would pay a real allocation)
             cudaMemPool_t pool;
             unsigned long long keep = ~0ull;
             if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
             cudaGetLastError();
-            pool_kept[dev] = true;
         }
         void *scratch = nullptr;
         SG_CUDA(cudaMallocAsync(&scratch, (size_t)ctas * (size_t)generic_plane_words(G.TBL) * 4, st));

@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
 #include <immintrin.h>
 #include <omp.h>
 
@@ -111,7 +112,7 @@ __attribute__((target("avx2"))) uint64_t pack_avx2(const uint8_t *a, uint64_t n,
     return first_bad_block;
 }
 
-int g_isa = -1;  // 2 avx512, 1 avx2, 0 scalar
+std::atomic<int> g_isa{-1};  // 2 avx512, 1 avx2, 0 scalar (every thread that finds -1 computes the same value)
 
 }  // namespace
 
@@ -121,10 +122,11 @@ extern "C" {
 // untouched).  Bases past n in the last word are zero.  Returns the smallest offending position or UINT64_MAX.
 uint64_t sg_host_pack_2bit(const char *ascii, uint64_t n_bases, uint32_t *packed, int threads)
 {
-    if (g_isa < 0) {
+    if (g_isa.load(std::memory_order_relaxed) < 0) {
         __builtin_cpu_init();
-        g_isa = __builtin_cpu_supports("avx512bw") ? 2 : (__builtin_cpu_supports("avx2") ? 1 : 0);
-        if (const char *e = getenv("SG_HOST_ISA")) g_isa = std::min(g_isa, atoi(e));
+        int isa = __builtin_cpu_supports("avx512bw") ? 2 : (__builtin_cpu_supports("avx2") ? 1 : 0);
+        if (const char *e = getenv("SG_HOST_ISA")) isa = std::min(isa, atoi(e));
+        g_isa.store(isa, std::memory_order_relaxed);
     }
     const uint8_t *a = (const uint8_t *)ascii;
     uint8_t *out = (uint8_t *)packed;

@@ -9,7 +9,9 @@
 // (tens, ones, op) characters by byte permutes, the absent tens digits are squeezed out with VPCOMPRESSB, and the
 // three pieces are stored with byte masks (nothing is written past an alignment's text: neighbouring alignments are
 // rendered by other threads).  Compiled by g++ with per-function targets; the scalar path is the fallback.
+#include <atomic>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <immintrin.h>
 
@@ -118,18 +120,18 @@ SG_TGT char *render_avx512(const uint8_t *p, uint64_t cnt, char *o)
     return render_scalar(p + k, cnt - k, o);
 }
 
-int g_isa = -1;   // 1: AVX-512 VBMI2 path, 0: scalar
+std::atomic<int> g_isa{-1};   // 1: AVX-512 VBMI2 path, 0: scalar (every thread that finds -1 computes the same value)
 
 inline int isa()
 {
-    if (g_isa < 0) {
+    if (g_isa.load(std::memory_order_relaxed) < 0) {
         __builtin_cpu_init();
         int v = __builtin_cpu_supports("avx512vbmi2") && __builtin_cpu_supports("avx512vbmi") && __builtin_cpu_supports("avx512bw") &&
                 __builtin_cpu_supports("bmi2");
         if (const char *e = getenv("SG_HOST_ISA")) if (atoi(e) < 2) v = 0;
-        g_isa = v;
+        g_isa.store(v, std::memory_order_relaxed);
     }
-    return g_isa;
+    return g_isa.load(std::memory_order_relaxed);
 }
 
 }  // namespace
