@@ -623,7 +623,8 @@ def main():
                       "value": m["alignments_per_s_step"], "unit": "alignments/s", "kernel_alignments_per_s": m["alignments_per_s_kernel"],
                       "ms_per_step": m["step_ms"], "kernel_ms": m["kernel_ms"], "roofline_frac": m["int32_frac"], "gcups": m["gcups_kernel"],
                       "e2e": m.get("e2e"), "parity": m["parity"]})
-        m = bench_extra.mapping_point(3_000_000_000, 262_144, True, peak_gops, steps=1, sub_batch=262_144 * 8)
+        # launches of 1 M alignments: with 2 M per launch (a 42 GB run slab) the same kernel runs 15 % slower on this workload
+        m = bench_extra.mapping_point(3_000_000_000, 262_144, True, peak_gops, steps=1, sub_batch=1_048_576)
         extra.append({"workload": m["workload"], "config": {k: m[k] for k in ("genome_bases", "reads", "candidates_per_read", "read_len", "W")},
                       "value": m["alignments_per_s_step"], "unit": "alignments/s", "kernel_alignments_per_s": m["alignments_per_s_kernel"],
                       "ms_per_step": m["step_ms"], "kernel_ms": m["kernel_ms"], "roofline_frac": m["int32_frac"], "gcups": m["gcups_kernel"],
