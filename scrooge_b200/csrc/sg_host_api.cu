@@ -308,7 +308,7 @@ struct Device {
     cudaStream_t h2d = nullptr;
     IngestTuner tuner;
     Slot slots[kMaxSlots];
-    int n_slots = 4;
+    int n_slots = 5;
     DevBuf genome;  // packed reference, resident across calls
     DevBuf piece_bad;   // sg_set_reference: one offending-base word per uploaded piece
     uint64_t genome_len = 0;
@@ -318,6 +318,10 @@ struct Device {
     // gets a CPU of its own, the packers share the rest: with packers on every CPU the feeder was descheduled for
     // milliseconds at a time and the PCIe link ran dry (13 GB/s of ASCII chunk copies where 24 GB/s fit).
     std::vector<int> worker_cpus, packer_cpus;
+    // set by the worker for the duration of a call: starts the second stage of earlier sub-batches whose kernels are done.
+    // The feeder calls it between chunk copies, so that a sub-batch's runs are on their way back while the next one is
+    // still being uploaded (and its slot is free when the pipeline comes round to it).
+    std::function<int()> idle_poll;
     ThreadTeam team;         // its packer threads: created with the context, asleep between jobs
 };
 
@@ -521,12 +525,14 @@ int upload_adaptive(sg_ctx *ctx, Device &d, cudaStream_t st, cudaEvent_t ev_copi
                 cudaEventRecord(ev_dma[issued % depth], hst) != cudaSuccess) { cuda_rc = 1; break; }
             cs.h2d_ascii += len;
             issued++;
+            if (d.idle_poll && (issued & 7) == 0 && d.idle_poll() != SG_OK) { cuda_rc = 2; break; }
         }
     }
     if (d.team.size() > 0) d.team.wait();
     // the sub-batch's own stream (the device packs its ASCII part there) continues once its last chunk has arrived
     if (cudaEventRecord(ev_copied, hst) != cudaSuccess || cudaStreamWaitEvent(st, ev_copied, 0) != cudaSuccess) cuda_rc = 1;
     d.tuner.report(total_bytes, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_ingest).count());
+    if (cuda_rc == 2) return SG_ERR_CUDA;   // a second stage failed inside the poll: its message stands
     if (cuda_rc) { cudaGetLastError(); return fail(SG_ERR_CUDA, "adaptive ingest: a CUDA call failed"); }
     if (bad.load() != ~0ull) {   // the caller names the offender
         *bad_seg = (int)(bad.load() >> 56);
@@ -1024,7 +1030,7 @@ void run_shard(sg_ctx *ctx, Device &d, const Workload &w, BatchQueue &q, sg_resu
     // 2 GB sub-batches, whose kernel is long done when the next upload ends, but it stalled the feeder and the packers
     // behind the kernels of the small sub-batches at the tapered end of a call.)
     auto poll_second_stages = [&](int upto) -> int {
-        for (int j = std::max(0, upto - kSlots + 1); j <= upto; j++) {
+        for (int j = std::max(0, k - kSlots + 1); j <= upto; j++) {   // never the slot being filled (j == k only after stage_a(k))
             Slot &sj = d.slots[j % kSlots];
             if (!sj.busy || sj.mid_done) continue;
             const cudaError_t qe = cudaEventQuery(sj.ev_mid);
@@ -1035,16 +1041,24 @@ void run_shard(sg_ctx *ctx, Device &d, const Workload &w, BatchQueue &q, sg_resu
         }
         return SG_OK;
     };
+    int poll_rc = SG_OK;
+    d.idle_poll = [&]() -> int {   // between chunk copies of sub-batch k: the sub-batches before it
+        const int rc = poll_second_stages(k - 1);
+        if (rc) poll_rc = rc;
+        return rc;
+    };
     while (true) {
         const size_t b = q.next.fetch_add(1);
         if (b >= nb) break;
         Slot &s = d.slots[k % kSlots];
         int rc = stage_c(s, w, res, so);                       // frees the slot used by this GPU's batch k - kSlots
         if (!rc) rc = stage_a(ctx, d, s, w, q.cuts[b], q.cuts[b + 1], res, so.stats);
+        if (!rc) rc = poll_rc;
         if (!rc) rc = poll_second_stages(k);
-        if (rc) { bail(rc); return; }
+        if (rc) { d.idle_poll = nullptr; bail(rc); return; }
         k++;
     }
+    d.idle_poll = nullptr;
     for (int j = std::max(0, k - kSlots); j < k; j++) {       // the end of the call: second stages first, all of them ...
         int rc = stage_b(d.slots[j % kSlots], w, res, so.stats);
         if (rc) { bail(rc); return; }
