@@ -630,6 +630,11 @@ def main():
                       "ms_per_step": m["step_ms"], "kernel_ms": m["kernel_ms"], "roofline_frac": m["int32_frac"], "gcups": m["gcups_kernel"],
                       "e2e": None, "parity": m["parity"]})
 
+    if world > 1 and cpu is not None:
+        # the CPU baseline is a figure of the N=1 line (all host cores); under torchrun rank 0 owns a share of the CPUs only,
+        # so the sample above served as the parity check and its rate is reported as what it is
+        cpu["note"] = "rank 0's CPU share only (%d threads): parity check, not the box's CPU baseline -- see the N=1 line" % cpu["cores"]
+
     line = {"metric": "alignments_per_second", "value": value, "unit": "alignments/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",

@@ -256,45 +256,6 @@ struct Slot {
     }
 };
 
-// How many of a GPU's packer threads the adaptive ingest uses.  Copy engines and packers read the same host DRAM: on a
-// box where PCIe is the narrow link (one GPU, many cores) every packer helps, on a box where DRAM is (eight GPUs pulling
-// ASCII over eight links) a packed byte costs 1.5 bytes of DRAM traffic against 1.0 for a copied one and the packers
-// only take bandwidth from the copy engines.  Instead of a rule in terms of core counts the context measures: the first
-// large sub-batches run with all, half and none of the packers, the ingest rate (ASCII bytes per second of upload
-// phase) of each is recorded, and the best setting is kept (SG_PACKERS=<n> fixes it, SG_TUNE=0 keeps all).
-struct IngestTuner {
-    static constexpr uint64_t kMinBytes = 96ull << 20;   // smaller sub-batches say little about a rate
-    int fixed = -1;        // SG_PACKERS
-    bool enabled = true;   // SG_TUNE
-    int candidates[3] = {0, 0, 0};
-    double rate[3] = {0, 0, 0};
-    int tried = 0, best = 0, current = 0;
-    void init(int threads)
-    {
-        candidates[0] = threads; candidates[1] = threads / 2; candidates[2] = 0;
-        if (const char *v = std::getenv("SG_PACKERS")) fixed = std::max(0, std::min(threads, std::atoi(v)));
-        if (const char *v = std::getenv("SG_TUNE")) enabled = std::atoi(v) != 0;
-        if (threads < 2) enabled = false;
-    }
-    int packers(int threads, uint64_t bytes)
-    {
-        if (fixed >= 0) return fixed;
-        if (!enabled) return threads;
-        current = (tried < 3 && bytes >= kMinBytes) ? tried : best;
-        return candidates[current];
-    }
-    void report(uint64_t bytes, double seconds)
-    {
-        if (fixed >= 0 || !enabled || tried >= 3 || bytes < kMinBytes || current != tried || seconds <= 0) return;
-        rate[tried] = (double)bytes / seconds;
-        tried++;
-        if (tried == 3) {
-            best = 0;
-            for (int k = 1; k < 3; k++) if (rate[k] > rate[best] * 1.03) best = k;   // a setting has to win clearly
-        }
-    }
-};
-
 struct Device {
     int id = 0;
     // EVERY host-to-device copy of this GPU goes through this one stream, whatever sub-batch it belongs to.  The copy
