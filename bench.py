@@ -548,7 +548,7 @@ def main():
     # of one launch), scaled from that launch's pair count to this one's
     traffic, traffic_src = None, None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
         if tr["workload"] == wl.name and delta:
             traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["pairs_in_launch"] * n
             traffic_src = tr["source"]
