@@ -375,7 +375,6 @@ struct ShardOut {
 struct Strings {
     const char *blob = nullptr; const uint64_t *off = nullptr;
     const char *const *ptr = nullptr; const uint64_t *len = nullptr;
-    const char *data(uint64_t i) const { return ptr ? ptr[i] : blob + off[i]; }
     uint64_t size(uint64_t i) const { return ptr ? len[i] : off[i + 1] - off[i]; }
 };
 
