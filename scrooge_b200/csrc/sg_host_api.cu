@@ -3,14 +3,21 @@
 // Replaces the host side of the reference GPU library (src/genasm_gpu.cu:692-1065): cudaMallocManaged
 // blobs, per-string descriptor loops, one synchronous kernel over everything and a linked-list walk per
 // alignment become
-//   * a host-side scatter over the context's GPUs: alignments are independent
-//     (src/genasm_cpu.cpp:451-455), so each GPU gets a contiguous share balanced by query bases and there
-//     is no inter-GPU exchange of any kind.  In mapping mode every GPU holds its own packed reference;
-//   * per GPU, a three-slot software pipeline over sub-batches: while batch k is being aligned, batch
-//     k+1's ASCII is on its way over PCIe (one contiguous copy, packed to 2 bit/base on the device) and
-//     batch k-1's distances and compacted CIGAR runs are on their way back into pinned host memory;
-//   * descriptors derived on the device from the offset arrays, a run slab with per-alignment capacity
-//     2*|query|+8 (reference: 2*|query| entries, src/genasm_gpu.cu:995-1001) compacted on the device.
+//   * a call cut into sub-batches that form ONE queue; every GPU of the context has a worker thread that takes
+//     sub-batches from it (alignments are independent, src/genasm_cpu.cpp:451-455: no inter-GPU exchange of any
+//     kind; a GPU that finishes early takes more, like the reference's atomic pair counter across thread blocks,
+//     src/genasm_gpu.cu:602-622).  In mapping mode every GPU holds its own packed reference;
+//   * per GPU, a five-slot software pipeline: while sub-batch k is being aligned, k+1 is on its way over PCIe and
+//     the distances and compacted CIGAR runs of k-1 are on their way back into pinned host memory.  The worker never
+//     blocks on the device while there is something to upload;
+//   * ingest shared between the GPU's packer threads (a persistent team bound to the GPU's CPUs: chunks packed to
+//     2 bit/base on the host, a quarter of the bytes cross PCIe) and its copy engine (chunks cross as ASCII, the device
+//     packs them), as many packers as the measured ingest rate says.  EVERY host-to-device copy of a GPU goes through
+//     one stream: a flooded copy-engine channel starves the host-to-device copies of other streams (Device::h2d);
+//   * descriptors built on the host, a run slab with per-alignment capacity 2*|query|+8 (reference: 2*|query| entries,
+//     src/genasm_gpu.cu:995-1001) compacted on the device; launches of mixed lengths handed out longest first.
+// The end-to-end path is bound by the host's memory system; sg_result_stats and SG_TRACE=1 say
+// where a call's time went.
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
