@@ -1020,7 +1020,8 @@ void run_shard(sg_ctx *ctx, Device &d, const Workload &w, BatchQueue &q, sg_resu
         Slot &s = d.slots[k % kSlots];
         int rc = stage_c(s, w, res, so);                       // frees the slot used by this GPU's batch k - kSlots
         if (!rc) rc = stage_a(ctx, d, s, w, q.cuts[b], q.cuts[b + 1], res, so.stats);
-        if (!rc) rc = poll_rc;
+        if (poll_rc) rc = poll_rc;   // a second stage failed inside the feeder's poll (e.g. the device found a bad base in an
+                                     // earlier sub-batch): its code and message are the call's
         if (!rc) rc = poll_second_stages(k);
         if (rc) { d.idle_poll = nullptr; bail(rc); return; }
         k++;

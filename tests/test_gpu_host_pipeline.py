@@ -173,3 +173,36 @@ def test_pinned_cache_is_bounded_and_trimmable(sglib):
     assert list(r2.edit_distances) == ed
     del r2
     a.close()
+
+
+def test_bad_base_in_an_early_sub_batch_of_a_long_call():
+    """A non-ACGT base that only the DEVICE sees (copies-only ingest), in the first of many sub-batches: whichever pipeline
+    step notices it -- the feeder's poll during a later upload, the slot's reuse, the end of the call -- the call fails
+    with SG_ERR_BAD_BASE and names the pair."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, '.'); sys.path.insert(0, 'tests')\n"
+        "import random, scrooge_b200\n"
+        "from conftest import rand_seq, mutate\n"
+        "rng = random.Random(4)\n"
+        "T = [rand_seq(rng, 1300) for _ in range(3000)]\n"
+        "Q = [mutate(rng, t, 1000, 0.05) for t in T]\n"
+        "for bad_pair, where in ((100, 'query'), (2900, 'text')):\n"
+        "    T2, Q2 = list(T), list(Q)\n"
+        "    if where == 'query': Q2[bad_pair] = Q2[bad_pair][:500] + 'N' + Q2[bad_pair][501:]\n"
+        "    else: T2[bad_pair] = T2[bad_pair][:77] + 'n' + T2[bad_pair][78:]\n"
+        "    al = scrooge_b200.Aligner(W=64, n_gpus=1)\n"
+        "    try:\n"
+        "        al.align_pairs(T2, Q2)\n"
+        "        raise SystemExit('bad base not detected')\n"
+        "    except scrooge_b200.ScroogeError as e:\n"
+        "        assert e.code == 2 and f'pair {bad_pair}' in str(e) and where in str(e), str(e)\n"
+        "    ok = al.align_pairs(T, Q)   # the context is usable afterwards\n"
+        "    assert ok.count == 3000\n"
+        "    al.close()\n"
+        "print('bad base ok')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SG_BATCH_MB="1", SG_MIN_BATCH_UNITS="64", SG_ASCII_MIN_BYTES="0", SG_CHUNK_KB="16", SG_HOST_THREADS="0")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "bad base ok" in r.stdout, r.stderr[-2000:] + r.stdout[-500:]
