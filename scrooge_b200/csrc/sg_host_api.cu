@@ -204,13 +204,25 @@ struct ScopedT {
 
 // Per-alignment host loops (descriptor arithmetic): serial up to a quarter of a million alignments -- a sub-batch of long reads --
 // and split over plain threads (131 072 alignments each) above that (batches of short reads).  Deliberately not OpenMP: an OpenMP
-// team that fits the cores spin-waits after its region and delays the CUDA calls that follow.
+// team that fits the cores spin-waits after its region and delays the CUDA calls that follow.  The threads run on every CPU
+// the process may use: a new thread inherits the affinity of its creator, and the creator is a GPU's worker, which is
+// bound to ONE CPU for the duration of a call -- without the reset all of them would share that CPU.
+static const std::vector<int> &process_cpus()
+{
+    static const std::vector<int> cpus = allowed_cpus();   // first use is in sg_ctx_create, before any worker is bound
+    return cpus;
+}
+
 template <class F> void parallel_for(uint64_t n, int threads, F &&fn)
 {
     const int nt = (int)std::min<uint64_t>((uint64_t)std::max(1, threads), n >> 17);
     if (nt <= 1) { fn((uint64_t)0, n); return; }
     std::vector<std::thread> th;
-    for (int t = 0; t < nt; t++) th.emplace_back([&fn, n, t, nt]() { fn(n * (uint64_t)t / nt, n * (uint64_t)(t + 1) / nt); });
+    for (int t = 0; t < nt; t++)
+        th.emplace_back([&fn, n, t, nt]() {
+            bind_this_thread(process_cpus());
+            fn(n * (uint64_t)t / nt, n * (uint64_t)(t + 1) / nt);
+        });
     for (auto &x : th) x.join();
 }
 
@@ -306,6 +318,18 @@ struct DeviceList {
     const Device *begin() const { return p.get(); }
     const Device *end() const { return p.get() + n; }
 };
+
+// The same split over the GPU's packer team: its threads exist, are bound to the GPU's CPUs and are idle whenever the
+// worker runs descriptor loops (creating and joining plain threads cost ~0.3 ms per loop, five loops per sub-batch:
+// a quarter of a 10 M x 150 bp call).
+template <class F> void team_for(Device &d, uint64_t n, F &&fn)
+{
+    const int nt = d.team.size();
+    if (nt <= 1 || n < (1u << 16)) { fn((uint64_t)0, n); return; }
+    std::function<void(int)> job = [&](int t) { fn(n * (uint64_t)t / (uint64_t)nt, n * (uint64_t)(t + 1) / (uint64_t)nt); };
+    d.team.launch(job);
+    d.team.wait();
+}
 
 }  // namespace sg
 
@@ -476,13 +500,31 @@ int upload_adaptive(sg_ctx *ctx, Device &d, cudaStream_t st, cudaEvent_t ev_copi
     };
     if (d.team.size() > 0) d.team.launch(job);
     if (depth > 0) {
-        int issued = 0;
+        // The feeder claims a chunk for the copy engine only while that does not take work the packers would finish
+        // sooner: a claimed chunk waits behind the copies already in flight (~0.3 ms each) while `active` packers get
+        // through ~one chunk per millisecond each.  With 2 GB sub-batches the rule never binds; with the 256 MB
+        // sub-batches of short reads a feeder that queued its 12 copies up front left the packers idle two thirds of
+        // the time (10 M x 150 bp: ingest 53 ms with 275 of 795 packer thread-ms busy).
+        const long long guard = std::max<long long>(1, active / 4);
+        long long issued = 0, completed = 0;
+        int polls = 0;
+        auto pause = [] { for (int spin = 0; spin < 64; spin++) __builtin_ia32_pause(); };
         while (true) {
-            if (issued >= depth) {   // the oldest copy in flight must be done before another is queued
-                cudaError_t q;
-                while ((q = cudaEventQuery(ev_dma[issued % depth])) == cudaErrorNotReady)
-                    for (int spin = 0; spin < 64; spin++) __builtin_ia32_pause();
-                if (q != cudaSuccess) { cuda_rc = 1; break; }
+            while (completed < issued) {   // retire finished copies (events are reused modulo depth, oldest first)
+                const cudaError_t qe = cudaEventQuery(ev_dma[completed % depth]);
+                if (qe == cudaErrorNotReady) break;
+                if (qe != cudaSuccess) { cuda_rc = 1; break; }
+                completed++;
+            }
+            if (cuda_rc) break;
+            const long long inflight = issued - completed;
+            long long remaining;
+            { std::lock_guard<std::mutex> g(mu); remaining = back - front; }
+            if (remaining <= 0) break;
+            if (inflight >= depth || (active > 0 && inflight > 0 && remaining < guard * (inflight + 1))) {
+                if (d.idle_poll && (++polls & 63) == 0 && d.idle_poll() != SG_OK) { cuda_rc = 2; break; }
+                pause();
+                continue;
             }
             const long long c = take_back();
             if (c < 0) break;
@@ -606,7 +648,7 @@ int upload_blobs(sg_ctx *ctx, Device &d, cudaStream_t st, cudaEvent_t ev_copied,
         const Strings &S = *b.S;
         const uint64_t n = b.i1 - b.i0, base = S.off[b.i0], nbytes = S.off[b.i1] - base;
         *b.bad_bias = 0;
-        parallel_for(n, ctx->host_threads, [&](uint64_t k0, uint64_t k1) { for (uint64_t k = k0; k < k1; k++) b.start[k] = S.off[b.i0 + k] - base; });
+        team_for(d, n, [&](uint64_t k0, uint64_t k1) { for (uint64_t k = k0; k < k1; k++) b.start[k] = S.off[b.i0 + k] - base; });
         if (ctx->adaptive && nbytes >= ctx->ascii_min_bytes && nbytes >= 256) {
             Segment &g = seg[nseg];
             g.src = S.blob + base; g.nbytes = nbytes; g.d_ascii = b.d_ascii; g.d_packed = b.d_packed; g.h_stage = b.h_stage; g.d_bad = b.d_bad;
@@ -708,7 +750,7 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
             }
         }
         ScopedT t_desc(cs.desc);
-        parallel_for(n, ctx->host_threads, [&](uint64_t k0, uint64_t k1) {
+        team_for(d, n, [&](uint64_t k0, uint64_t k1) {
             for (uint64_t k = k0; k < k1; k++) { h_tlen[k] = w.text.size(a0 + k); h_qlen[k] = w.query.size(a0 + k); }
         });
         d_text = s.packed_t.as<uint32_t>();
@@ -720,7 +762,8 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
         {
             ScopedT t_desc(cs.desc);
             std::mutex mu;
-            parallel_for(n, ctx->host_threads, [&](uint64_t k0, uint64_t k1) {
+            team_for(d, n, [&](uint64_t k0, uint64_t k1) {
+                if (k0 >= k1) return;
                 uint32_t lo = w.cand_read[a0 + k0], hi = lo;
                 for (uint64_t c = a0 + k0; c < a0 + k1; c++) { lo = std::min(lo, w.cand_read[c]); hi = std::max(hi, w.cand_read[c]); }
                 std::lock_guard<std::mutex> g(mu);
@@ -739,7 +782,7 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
             }
         }
         ScopedT t_desc(cs.desc);
-        parallel_for(n, ctx->host_threads, [&](uint64_t k0, uint64_t k1) {
+        team_for(d, n, [&](uint64_t k0, uint64_t k1) {
             for (uint64_t k = k0; k < k1; k++) {
                 const uint64_t cstart = w.cand_start[a0 + k];
                 const uint32_t r = w.cand_read[a0 + k];
@@ -756,7 +799,7 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
         ScopedT t_desc(cs.desc);
         if (!w.mapping && w.query.off) {   // capacity 2*|query|+8 per alignment: the prefix sum is a difference of offsets
             const uint64_t *qo = w.query.off + a0;
-            parallel_for(n + 1, ctx->host_threads, [&](uint64_t k0, uint64_t k1) { for (uint64_t k = k0; k < k1; k++) h_slab[k] = 2ull * (qo[k] - qo[0]) + 8ull * k; });
+            team_for(d, n + 1, [&](uint64_t k0, uint64_t k1) { for (uint64_t k = k0; k < k1; k++) h_slab[k] = 2ull * (qo[k] - qo[0]) + 8ull * k; });
             slab_bytes = h_slab[n];
         } else {
             for (uint64_t k = 0; k < n; k++) { h_slab[k] = slab_bytes; slab_bytes += 2ull * h_qlen[k] + 8ull; }
@@ -771,7 +814,16 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
     if (ctx->longest_first && n > 1 && n <= 0xFFFFFFFFull) {
         ScopedT t_desc(cs.desc);
         uint64_t lo = h_qlen[0], hi = h_qlen[0];
-        for (uint64_t k = 1; k < n; k++) { lo = std::min(lo, h_qlen[k]); hi = std::max(hi, h_qlen[k]); }
+        {
+            std::mutex mm;
+            team_for(d, n, [&](uint64_t k0, uint64_t k1) {
+                if (k0 >= k1) return;
+                uint64_t l = h_qlen[k0], h = l;
+                for (uint64_t k = k0 + 1; k < k1; k++) { l = std::min(l, h_qlen[k]); h = std::max(h, h_qlen[k]); }
+                std::lock_guard<std::mutex> g(mm);
+                lo = std::min(lo, l); hi = std::max(hi, h);
+            });
+        }
         if (hi > lo + lo / 4 + 64) {
             R(s.order.reserve(n * 4)); R(s.h_order.reserve(n * 4));
             uint32_t *ho = s.h_order.as<uint32_t>();
@@ -1208,7 +1260,7 @@ int sg_ctx_create_wo(sg_ctx **out, const int *device_ids, int n_devices, int W, 
         // Host threads per GPU for packing: the CPUs this process may use (its affinity mask, or SG_CPUS=<list>) divided
         // among the context's GPUs; SG_HOST_THREADS=<n> sets the count per GPU directly (0: no packer threads, every blob
         // crosses PCIe as ASCII).  One of a GPU's CPUs is left to its worker thread (the feeder of the adaptive ingest).
-        const std::vector<int> allowed = allowed_cpus();
+        const std::vector<int> allowed = process_cpus();
         ctx->host_threads = std::max(1, (int)allowed.size() / n_devices - (allowed.size() / n_devices >= 4 ? 1 : 0));
         if (const char *v = std::getenv("SG_HOST_THREADS")) ctx->host_threads = std::max(0, std::atoi(v));
         ctx->host_pack = ctx->host_threads >= 10;   // ~7-10 GB/s of ASCII per thread against ~47 GB/s of PCIe per GPU
@@ -1234,7 +1286,7 @@ int sg_ctx_create_wo(sg_ctx **out, const int *device_ids, int n_devices, int W, 
             if (id >= 0 && id < avail && cudaDeviceGetPCIBusId(bus, sizeof bus, id) == cudaSuccess) local[k] = pci_local_cpus(bus);
             cudaGetLastError();
         }
-        cpu_sets = assign_cpus(allowed_cpus(), local);
+        cpu_sets = assign_cpus(process_cpus(), local);
     }
     if (const char *v = std::getenv("SG_MAX_BATCH_MB")) {
         const long mb = std::atol(v);
