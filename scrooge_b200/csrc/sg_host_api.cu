@@ -1595,6 +1595,8 @@ int64_t sg_result_total_ns(const sg_result *r) { return r ? r->total_ns : 0; }
 // "%d%c" per packed run (reference src/genasm_gpu.cu:881-888): sg_host_render.cpp, 64 runs per step with AVX-512 VBMI2
 extern "C" uint64_t sg_host_runs_text_len(const uint8_t *runs, uint64_t cnt);
 extern "C" char *sg_host_runs_render(const uint8_t *runs, uint64_t cnt, char *out);
+extern "C" char *sg_host_runs_render_stream(const uint8_t *runs, uint64_t cnt, char *out, char *scratch);
+extern "C" void sg_host_stream_fence(void);
 static inline uint64_t runs_text_len(const uint8_t *p, uint64_t cnt) { return cnt ? sg_host_runs_text_len(p, cnt) : 0; }
 static inline char *runs_render(const uint8_t *p, uint64_t cnt, char *o) { return cnt ? sg_host_runs_render(p, cnt, o) : o; }
 
@@ -1702,13 +1704,20 @@ uint64_t sg_result_render_all(const sg_result *r, char *blob, uint64_t blob_cap,
     for (uint64_t a = 0; a < n; a++) text_off[a + 1] += text_off[a];
     const uint64_t total = text_off[n];
     if (!blob || blob_cap < total) return total;  // sizes only: call again with a big enough blob
+    // a blob of a few megabytes stays in the caches and is rendered in place; a large one is written around them
+    const bool stream = total >= (64ull << 20);
     parallel([&](uint64_t a0, uint64_t a1) {
+        std::vector<char> scratch;
         for (uint64_t a = a0; a < a1; a++) {
             uint64_t cnt;
             const uint8_t *p = runs_of(r, a, &cnt);
             if (r->wide_runs) wide_render(p, cnt, blob + text_off[a]);
-            else runs_render(p, cnt, blob + text_off[a]);
+            else if (stream && cnt) {
+                if (scratch.size() < 3 * cnt + 192) scratch.resize(3 * cnt + 4096);
+                sg_host_runs_render_stream(p, cnt, blob + text_off[a], scratch.data());
+            } else runs_render(p, cnt, blob + text_off[a]);
         }
+        if (stream) sg_host_stream_fence();
     });
     return total;
 }

@@ -144,6 +144,33 @@ uint64_t sg_host_runs_text_len(const uint8_t *runs, uint64_t cnt) { return isa()
 // renders cnt packed runs at out (exactly sg_host_runs_text_len bytes are written); returns the end
 char *sg_host_runs_render(const uint8_t *runs, uint64_t cnt, char *out) { return isa() ? render_avx512(runs, cnt, out) : render_scalar(runs, cnt, out); }
 
+// The same into memory that will not be read again soon (the text blob of a whole batch: gigabytes): rendered into
+// `scratch` first (cache resident; at least 3 * cnt + 192 bytes), then copied out with non-temporal stores for the whole
+// 64-byte lines of the destination and plain stores for its edges -- a plain store to a line that is not in cache
+// makes the core read it first, which for a 2.4 GB blob is 2.4 GB of DRAM traffic the host does not have to spare.
+// The caller issues the store fence (sg_host_stream_fence) before other threads read the text.
+__attribute__((target("avx512f"))) static char *stream_out(const char *s0, size_t len, char *out)
+{
+    // s0 has the same misalignment as out: whole lines of out are whole lines of s0
+    const size_t mis = (uintptr_t)out & 63u;
+    size_t i = mis ? (64 - mis < len ? 64 - mis : len) : 0;
+    memcpy(out, s0, i);
+    for (; i + 64 <= len; i += 64) _mm512_stream_si512((__m512i *)(out + i), _mm512_load_si512((const void *)(s0 + i)));
+    memcpy(out + i, s0 + i, len - i);
+    return out + len;
+}
+
+char *sg_host_runs_render_stream(const uint8_t *runs, uint64_t cnt, char *out, char *scratch)
+{
+    if (!isa()) return render_scalar(runs, cnt, out);
+    char *base = (char *)(((uintptr_t)scratch + 63u) & ~(uintptr_t)63u);
+    char *s0 = base + ((uintptr_t)out & 63u);
+    char *send = render_avx512(runs, cnt, s0);
+    return stream_out(s0, (size_t)(send - s0), out);
+}
+
+void sg_host_stream_fence(void) { _mm_sfence(); }
+
 int sg_host_render_isa(void) { return isa(); }
 
 }  // extern "C"

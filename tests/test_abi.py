@@ -118,3 +118,24 @@ def test_host_renderer_matches_python(sglib):
             assert end == out.ctypes.data + 80 + n
             assert bytes(out[80:80 + n]).decode() == want, (cnt, hi)
             assert (out[:80] == 0x7E).all() and (out[80 + n:] == 0x7E).all(), ("wrote outside the text", cnt, hi)
+
+
+def test_streaming_renderer_is_exact_at_every_alignment(sglib):
+    """sg_host_runs_render_stream (what sg_result_render_all uses for large blobs: rendered into a cache-resident scratch,
+    copied out with non-temporal stores for whole destination lines): exact text, nothing outside it, at every
+    misalignment of the destination."""
+    sglib.sg_host_runs_render_stream.restype = C.c_void_p
+    sglib.sg_host_runs_render_stream.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(3)
+    for cnt in [1, 5, 21, 22, 43, 64, 65, 200, 2113]:
+        runs = ((rng.integers(0, 4, cnt) << 6) | rng.integers(1, 64, cnt)).astype(np.uint8)
+        want = "".join(f"{int(b) & 63}{'=XID'[int(b) >> 6]}" for b in runs).encode()
+        scratch = np.zeros(3 * cnt + 4096, dtype=np.uint8)
+        for mis in range(64):
+            out = np.full(len(want) + 256, 0x7E, dtype=np.uint8)
+            dst = ((out.ctypes.data + 63) & ~63) + mis
+            end = sglib.sg_host_runs_render_stream(runs.ctypes.data, cnt, dst, scratch.ctypes.data + (mis % 5))
+            o0 = dst - out.ctypes.data
+            assert end == dst + len(want)
+            assert bytes(out[o0:o0 + len(want)]) == want, (cnt, mis)
+            assert (out[:o0] == 0x7E).all() and (out[o0 + len(want):] == 0x7E).all(), ("wrote outside the text", cnt, mis)
