@@ -431,6 +431,10 @@ def main():
             return r
         ren_s, res_r = timed(rendered)
         text_blob, text_off = rendered.text
+        # the bulk renderer (64 runs per step, text written around the caches) against the per-alignment one, spread over the batch
+        for k in list(range(0, ne, max(1, ne // 61))) + [ne - 1]:
+            if bytes(text_blob[int(text_off[k]):int(text_off[k + 1])]).decode() != res_r.cigar(k):
+                raise SystemExit(f"PARITY FAILURE: rendered CIGAR text of alignment {k} differs")
         del res_r
 
         # ---- what the host could deliver at best: copy-only and pack-only rates, all ranks at the same time ----------
