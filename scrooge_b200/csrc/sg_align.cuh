@@ -75,6 +75,7 @@ template <int W, bool TMEM = false> struct SmemLayout {
     static constexpr int BYTES_PER_CTA = BYTES_PER_WARP * WARPS_PER_CTA + (TMEM ? 16 : 0);
 };
 
+#ifndef SG_SIM   // the host simulation (tests/sim) runs the delta kernel only: tensor-memory PTX has no host twin
 // ---- tensor memory as per-lane scratch (sm_100a tcgen05) ----------------------------------------------
 template <int NW> __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[NW]);
 template <> __device__ __forceinline__ void tmem_ld<1>(uint32_t taddr, uint32_t (&v)[1])
@@ -96,6 +97,8 @@ template <> __device__ __forceinline__ void tmem_st<2>(uint32_t taddr, const uin
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+#endif  // !SG_SIM
 
 // The per-lane work counter carries the DC entries in its low 40 bits and the window count above them (one
 // accumulator, no extra register): good for reads up to ~500 Mbp.
@@ -201,6 +204,7 @@ template <> __device__ __forceinline__ void sts_vec<2>(uint32_t *p, const uint32
     *reinterpret_cast<uint2 *>(p) = make_uint2(v[0], v[1]);
 }
 
+#ifndef SG_SIM   // row-wise formulation (SG_DC=rows): not simulated
 // G rows of one column: entries and their << 1
 template <int NW> struct RowSet {
     static constexpr int G = WinCfg<NW * 32>::G;
@@ -596,5 +600,6 @@ __global__ void __launch_bounds__(SmemLayout<W, TMEM>::WARPS_PER_CTA * 32, TMEM 
         }
     }
 }
+#endif  // !SG_SIM
 
 }  // namespace sg

@@ -122,15 +122,39 @@ template <> __device__ __forceinline__ void add_vec<2>(const uint32_t (&a)[2], c
     s[1] = (uint32_t)(r >> 32);
 }
 
+// The host simulation (tests/sim, -DSG_SIM) compiles this file with g++: every inline-PTX block below has a C++ twin next
+// to it, and SG_SIM_COUNT feeds the simulation's event counters (nothing in the product build).
+#ifdef SG_SIM
+#define SG_SIM_COUNT(k, v) (sim::counters[k] += (uint64_t)(v))
+#else
+#define SG_SIM_COUNT(k, v) ((void)0)
+#endif
+
+// two consecutive words at shared-window address addr
+__device__ __forceinline__ void lds_pair(uint32_t addr, uint32_t &a, uint32_t &b)
+{
+#ifdef SG_SIM
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(sim::smem_base + addr);
+    a = p[0];
+    b = p[1];
+#else
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr));
+#endif
+}
+
 // Odd bits of x (bit 2k+1, k = 0..15) gathered into bits 16+k of the result; its low half is garbage.  x1 = x << 1.
 // Each stage keeps the upper of two neighbouring groups where it is and takes the lower one from a shifted copy -- a
 // bit select, so the garbage never carries into the payload -- and the shifted copies are IMADs (k4, k16, k256 are the
 // opaque constants 4, 16, 256): 4 alu-pipe + 3 fma-pipe instructions.
 __device__ __forceinline__ uint32_t bit_select(uint32_t a, uint32_t b, uint32_t m)   // (a & m) | (b & ~m) as ONE LOP3
 {
+#ifdef SG_SIM
+    return (a & m) | (b & ~m);
+#else
     uint32_t d;
     asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
     return d;
+#endif
 }
 __device__ __forceinline__ uint32_t gather_odd_hi(uint32_t x, uint32_t x1, uint32_t k4, uint32_t k16, uint32_t k256)
 {
@@ -249,7 +273,15 @@ __device__ __forceinline__ void delta_column_fma(uint32_t (&Pv)[NW], uint32_t (&
     }
 }
 
-template <int W>
+// EMIT selects how the runs of a window reach the alignment's slab slot:
+//   0  one byte store per run (the default: cheapest in instructions -- 6.4 runs per window at 10 % error);
+//   1  runs collected in a register and stored as whole 32-bit words (one PRMT per run, one store per four runs, the
+//      pending bytes carried across windows and flushed with the alignment's last window).  Needs slots that start and end
+//      on 4-byte boundaries (SG_FLAG_SLOTS_ALIGNED4: a promise of the caller).  For windows that are mostly edits -- a
+//      spurious candidate location of read mapping walks ~45 one-step runs per window -- the byte stores are what the
+//      kernel waits for: every lane's store is a separate 32-byte sector write in L1 and L2 (32 wavefronts per
+//      instruction), 45 x 32 per window and warp against the ~1 000 cycles a window's arithmetic takes.
+template <int W, int EMIT = 0>
 __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_delta_kernel(const AlignParams P)
 {
     using L = DeltaLayout<W>;
@@ -276,6 +308,7 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
     int64_t ed = 0;
     uint8_t *out = nullptr, *out_end = nullptr;
     uint32_t nruns = 0;
+    uint32_t acc = 0u;             // EMIT == 1: the runs not yet stored, newest in the top byte
     uint64_t entries = 0;
     bool overflow = false;
     int n = -1, m = 0;
@@ -483,7 +516,7 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
         uint32_t mask = 0x80000000u;                     // pattern position j, one-hot from the top
         uint32_t hs[SW], ls[SW];
         uint32_t ca, cb;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ca), "=r"(cb) : "r"(tcol));
+        lds_pair(tcol, ca, cb);
         uint32_t h0 = 0u, l0 = 0u, bit0 = 1u;
         if (tb_fast) {
 #pragma unroll
@@ -491,7 +524,16 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
                 // one step, written out as predicated instructions (the compiler's version spends selects on them):
                 //   hi/lo = the op's two bits; every op but 'I' (hi & !lo) consumes a text character (next column),
                 //   every op but 'D' (hi & lo) consumes a pattern character (mask >>= 1)
-#if SG_DELTA_TBFMA
+#if defined(SG_SIM)
+                {
+                    const bool hi = (ca & mask) != 0u, lo = (cb & mask) != 0u;
+                    if (hi) h0 |= 1u << k;
+                    if (lo) l0 |= 1u << k;
+                    if (!(hi && !lo)) tcol += TBS * 4;
+                    if (!(hi && lo)) mask >>= 1;
+                    lds_pair(tcol, ca, cb);
+                }
+#elif SG_DELTA_TBFMA
                 // the same step with the three accumulations (two stream bits, the column address) as predicated IMADs
                 // on the idle fma pipe: x += k_one * constant, k_one == 1 being a kernel parameter ptxas cannot fold
                 asm volatile(
@@ -578,7 +620,7 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
                     bit <<= 1;
                     if (!(hi && !lo)) tcol += TBS * 4;
                     if (!(hi && lo)) mask >>= 1;
-                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ca), "=r"(cb) : "r"(tcol));
+                    lds_pair(tcol, ca, cb);
                 } while (bit != 0u && mask != mask_end && tcol != tb_end);
             }
             hs[w] = h;
@@ -654,7 +696,19 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
                     const int p = __ffs((int)ew) - 1;
                     const uint32_t rh = __funnelshift_r(h7, h7, p), rl = __funnelshift_r(l6, l6, p);
                     const uint32_t t = (rh & 0x80u) | (rl & ~0x80u);
-                    *o++ = (uint8_t)((t & 0xC0u) | (uint32_t)(p - st));
+                    if constexpr (EMIT == 1) {
+                        // the run's byte enters the accumulator from the top (bytes 3..1 move down one place); the slot is
+                        // 4-byte aligned, so the pointer's low bits say how many bytes are pending, and the fourth completes a word
+                        acc = __byte_perm(acc, (t & 0xC0u) | (uint32_t)(p - st), 0x4321);
+                        o++;
+                        if (((uint32_t)(uintptr_t)o & 3u) == 0u) {
+                            *reinterpret_cast<uint32_t *>(o - 4) = acc;
+                            SG_SIM_COUNT(1, 1);
+                        }
+                    } else {
+                        *o++ = (uint8_t)((t & 0xC0u) | (uint32_t)(p - st));
+                        SG_SIM_COUNT(0, 1);
+                    }
                     st = p;
                     ew &= ew - 1u;
                 }
@@ -679,6 +733,15 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
         nruns += nb;
         ed += edits;
         if (q_pos >= q_end) {
+            if constexpr (EMIT == 1) {
+                // the pending 1..3 runs: moved down to the low bytes and stored as a word that ends inside the slot (its end is
+                // 4-byte aligned); the bytes above them are padding nobody reads
+                const uint32_t pend = (uint32_t)(uintptr_t)out & 3u;
+                if (want_cigar && pend != 0u) {
+                    *reinterpret_cast<uint32_t *>(out - pend) = acc >> (32u - 8u * pend);
+                    SG_SIM_COUNT(1, 1);
+                }
+            }
             P.edit[pair] = ed;
             P.ref_consumed[pair] = t_pos - t_begin;
             P.nruns[pair] = overflow ? 0u : nruns;   // nothing valid in the slot: the compaction must not read past it

@@ -1,0 +1,166 @@
+"""The alignment kernel's own SOURCE (scrooge_b200/csrc/sg_align_delta.cuh) run on the CPU-only box: tests/sim compiles it
+for the host (every CUDA thread a fiber, warp votes as rendezvous, shared memory a host array) and this file checks what
+it writes -- distances, consumed prefixes, run bytes, status -- against the oracle, bit for bit, for both window
+configurations and both run-emission variants.  tests/kernel_model.py models the ALGORITHM in Python; this runs the CODE.
+The GPU parity tests (tests/test_gpu_parity.py) remain the proof for the hardware; the few inline-PTX blocks have C++ twins
+under SG_SIM that only this simulation executes."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, random_pairs
+
+SIM_DIR = os.path.join(ROOT, "tests", "sim")
+SIM_LIB = os.path.join(SIM_DIR, "_build", "libsgsim.so")
+SIM_SRC = [os.path.join(SIM_DIR, "sim_kernels.cpp"), os.path.join(SIM_DIR, "sim_runtime.cpp")]
+SIM_DEPS = SIM_SRC + [os.path.join(SIM_DIR, "sim_runtime.h"), os.path.join(SIM_DIR, "shim", "cuda_runtime.h"),
+                      os.path.join(ROOT, "scrooge_b200", "csrc", "sg_align.cuh"),
+                      os.path.join(ROOT, "scrooge_b200", "csrc", "sg_align_delta.cuh")]
+CODE = np.full(256, 255, dtype=np.uint8)
+for _k, _c in enumerate("ACGT"):
+    CODE[ord(_c)] = _k
+    CODE[ord(_c.lower())] = _k
+
+
+@pytest.fixture(scope="module")
+def sim():
+    os.makedirs(os.path.dirname(SIM_LIB), exist_ok=True)
+    if not os.path.exists(SIM_LIB) or any(os.path.getmtime(d) > os.path.getmtime(SIM_LIB) for d in SIM_DEPS):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-w", "-shared", "-fPIC", "-DSG_SIM", "-I" + os.path.join(SIM_DIR, "shim"),
+                        "-I" + SIM_DIR] + SIM_SRC + ["-o", SIM_LIB], check=True)
+    lib = C.CDLL(SIM_LIB)
+    lib.sim_delta_align.restype = C.c_int
+    lib.sim_delta_align.argtypes = [C.c_int, C.c_int, C.c_uint] + [C.c_void_p] * 6 + [C.c_uint64, C.c_uint32] + [C.c_void_p] * 10
+    return lib
+
+
+def pack_blob(strings):
+    """2 bit/base, 16 bases per little-endian word, base k of a word in bits 2k+1:2k, strings concatenated without
+    alignment, 8 zero words of padding."""
+    lens = np.array([len(s) for s in strings], dtype=np.uint64)
+    start = np.zeros(len(strings), dtype=np.uint64)
+    if len(strings) > 1:
+        start[1:] = np.cumsum(lens)[:-1]
+    codes = CODE[np.frombuffer("".join(strings).encode(), dtype=np.uint8)].astype(np.uint32)
+    assert (codes < 4).all()
+    n = len(codes)
+    words = np.zeros((n + 15) // 16 + 8, dtype=np.uint32)
+    padded = np.zeros(((n + 15) // 16) * 16, dtype=np.uint32)
+    padded[:n] = codes
+    sh = (2 * np.arange(16, dtype=np.uint32))[None, :]
+    words[: (n + 15) // 16] = np.bitwise_or.reduce(padded.reshape(-1, 16) << sh, axis=1)
+    return words, start, lens
+
+
+def p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def run_sim(sim, W, emit, texts, queries, ctas=2, distance_only=False, order=None, cap_of=None, want_stats=True):
+    n = len(texts)
+    tw, ts, tl = pack_blob(texts)
+    qw, qs, ql = pack_blob(queries)
+    cap = np.array([cap_of(len(q)) if cap_of else 2 * len(q) + 8 for q in queries], dtype=np.uint64)
+    if emit == 1:
+        cap = (cap + np.uint64(3)) & ~np.uint64(3)          # SG_FLAG_SLOTS_ALIGNED4: slots start and end on 4-byte boundaries
+    slab_off = np.zeros(n + 1, dtype=np.uint64)
+    slab_off[1:] = np.cumsum(cap)
+    slab = np.full(int(slab_off[-1]) + 16, 0xEE, dtype=np.uint8)
+    assert slab.ctypes.data % 16 == 0
+    edit = np.full(n, -7, dtype=np.int64)
+    rc = np.full(n, 2**63, dtype=np.uint64)
+    nruns = np.full(n, 0xFFFFFFFF, dtype=np.uint32)
+    status = np.full(n, 0xFF, dtype=np.uint8)
+    dce = np.zeros(n, dtype=np.uint64) if want_stats else None
+    win = np.zeros(n, dtype=np.uint32) if want_stats else None
+    counters = np.zeros(8, dtype=np.uint64)
+    ordr = None if order is None else np.asarray(order, dtype=np.uint32)
+    r = sim.sim_delta_align(W, emit, ctas, p(tw), p(ts), p(tl), p(qw), p(qs), p(ql), n, (1 if distance_only else 0) | (2 if emit else 0),
+                            p(slab), p(slab_off), p(edit), p(rc), p(nruns), p(status), p(dce), p(win), p(ordr), p(counters))
+    assert r == 0
+    assert (slab[int(slab_off[-1]):] == 0xEE).all(), "write past the end of the slab"
+    return dict(edit=edit, rc=rc, nruns=nruns, status=status, slab=slab, slab_off=slab_off, dc_entries=dce, windows=win,
+                counters=counters)
+
+
+def cigar_of(out, a):
+    b = out["slab"][int(out["slab_off"][a]): int(out["slab_off"][a]) + int(out["nruns"][a])]
+    return "".join(f"{int(x) & 63}{'=XID'[int(x) >> 6]}" for x in b)
+
+
+def check(out, res, n, cigars=True):
+    assert (out["status"] == 0).all()
+    assert (out["edit"] == np.asarray(res.edit[:n], dtype=np.int64)).all()
+    assert (out["rc"] == np.asarray(res.ref_consumed[:n], dtype=np.uint64)).all()
+    if cigars:
+        for a in range(n):
+            assert cigar_of(out, a) == res.cigars[a], a
+
+
+@pytest.mark.parametrize("emit", [0, 1])
+@pytest.mark.parametrize("W", [64, 32])
+def test_sim_matches_oracle_mixed(sim, oracle, W, emit):
+    """Mixed bag (empty / 1-base / W+-1 lengths, exhausted texts, unrelated pairs, up to 40-80 % error) over several warps
+    and CTAs, so that lanes refill from the queue at different times."""
+    T, Q = random_pairs(101 + W + emit, 420, [0, 1, 2, 15, 16, 17, 31, 32, 33, 63, 64, 65, 100, 200, 500, 1200],
+                        [0, 0.05, 0.15, 0.4, 0.8])
+    res = oracle.align_pairs(T, Q, W=W)
+    out = run_sim(sim, W, emit, T, Q, ctas=2)
+    check(out, res, len(T))
+    assert int(out["dc_entries"].sum()) == res.stats["dc_entries"]
+    # runs are stored once each: as bytes (variant 0) or inside words (variant 1: one store per four runs + one flush)
+    total = int(out["nruns"].sum())
+    if emit == 0:
+        assert int(out["counters"][0]) == total and int(out["counters"][1]) == 0
+    else:
+        assert int(out["counters"][0]) == 0
+        assert int(out["counters"][1]) == int(((out["nruns"].astype(np.int64) + 3) // 4).sum())
+
+
+@pytest.mark.parametrize("emit", [0, 1])
+@pytest.mark.parametrize("W", [64, 32])
+def test_sim_golden_vectors(sim, golden, W, emit):
+    for group, items in golden[W]["groups"].items():
+        T = [x["text"] for x in items]
+        Q = [x["query"] for x in items]
+        out = run_sim(sim, W, emit, T, Q, ctas=1)
+        for a, x in enumerate(items):
+            assert int(out["edit"][a]) == x["edit"] and cigar_of(out, a) == x["cigar"], (group, a)
+
+
+@pytest.mark.parametrize("emit", [0, 1])
+def test_sim_order_distance_only_and_overflow(sim, oracle, emit):
+    T, Q = random_pairs(7, 150, [10, 100, 300, 700], [0.05, 0.3])
+    res = oracle.align_pairs(T, Q, W=64)
+    order = np.argsort([-len(q) for q in Q], kind="stable")
+    out = run_sim(sim, 64, emit, T, Q, ctas=1, order=order)
+    check(out, res, len(T))
+    out = run_sim(sim, 64, emit, T, Q, ctas=3, distance_only=True, want_stats=False)
+    check(out, res, len(T), cigars=False)
+    # slots too small for some alignments: those report status 5 and 0 runs, the others are intact, nothing is
+    # written outside a slot
+    out = run_sim(sim, 64, emit, T, Q, ctas=1, cap_of=lambda L: 8)
+    for a in range(len(T)):
+        want_runs = sum(1 for c in res.cigars[a] if c in "=XID")
+        if want_runs <= 8:
+            assert out["status"][a] == 0 and cigar_of(out, a) == res.cigars[a]
+        else:
+            assert out["status"][a] == 5 and out["nruns"][a] == 0
+    assert (out["edit"] == np.asarray(res.edit, dtype=np.int64)).all()
+
+
+def test_sim_unrelated_candidates_store_counts(sim, oracle):
+    """Windows that are mostly edits (a read against a random locus: the 7 spurious candidates of the stress mapping
+    workload): the word variant issues a quarter of the run stores."""
+    T, Q = random_pairs(99, 64, [600], [0.0], unrelated=1.0, short_text=0.0)
+    res = oracle.align_pairs(T, Q, W=64)
+    a = run_sim(sim, 64, 0, T, Q, ctas=1)
+    b = run_sim(sim, 64, 1, T, Q, ctas=1)
+    check(a, res, len(T))
+    check(b, res, len(T))
+    runs_per_window = a["nruns"].sum() / a["windows"].sum()
+    assert runs_per_window > 15          # 6.4 at 10 % error
+    assert int(b["counters"][1]) * 3.9 < int(a["counters"][0])
