@@ -211,40 +211,50 @@ def mapping_point(G, n_reads, stress, peak, sub_batch=1_000_000, steps=2, e2e_re
     slab_off = torch.arange(sub + 1, dtype=torch.int64, device=dev) * cap
     da = device.DeviceAligner(W, sub, dev, slab_bytes=sub * cap)
     runs = torch.empty(sub * (12000 if stress else 3000), dtype=torch.uint8, device=dev)
-    kev = []
-    keep = {}
+    assert cap % 4 == 0   # SG_FLAG_RUN_WORDS: slots on 4-byte boundaries
 
-    def step(record=False):
-        for b0 in range(0, n, sub):
-            b1 = min(n, b0 + sub)
-            assert b1 - b0 == sub, "reads x candidates must be a multiple of the sub-batch"
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            da.align(pgenome, cstart[b0:b1], tlen[b0:b1], preads, qstart[b0:b1], qlen[b0:b1], slab_off)
-            e1.record()
-            da.compact(slab_off, runs)
-            if record:
-                kev.append((e0, e1))
-            if b0 == 0 and not keep:
-                torch.cuda.synchronize()
-                keep["edit"] = da.out.edit[:2048].cpu().numpy().copy()
-                keep["refc"] = da.out.ref_consumed[:2048].cpu().numpy().astype(np.uint64).copy()
-                keep["ro"] = da.run_off[:2049].cpu().numpy().copy()
-                keep["runs"] = runs[: int(keep["ro"][-1])].cpu().numpy().copy()
-                keep["entries"] = int(da.out.dc_entries.sum())
-                keep["windows"] = int(da.out.windows.sum())
-                assert int(da.run_off[-1]) <= runs.numel() and int(da.out.status.max()) == 0
+    def timed(words):
+        """The whole candidate list, `steps` times, with the kernel storing its runs as bytes (False) or as whole words (True,
+        SG_FLAG_RUN_WORDS -- what sg_align_candidates launches); the first pass is untimed and keeps a sample."""
+        kev, keep = [], {}
 
-    step()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        step(record=True)
-    e1.record()
-    torch.cuda.synchronize()
-    ms_step = e0.elapsed_time(e1) / steps
-    ms_kernel = sum(a.elapsed_time(b) for a, b in kev) / steps
+        def step(record=False):
+            for b0 in range(0, n, sub):
+                b1 = min(n, b0 + sub)
+                assert b1 - b0 == sub, "reads x candidates must be a multiple of the sub-batch"
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                da.align(pgenome, cstart[b0:b1], tlen[b0:b1], preads, qstart[b0:b1], qlen[b0:b1], slab_off, run_words=words)
+                e1.record()
+                da.compact(slab_off, runs)
+                if record:
+                    kev.append((e0, e1))
+                if b0 == 0 and not keep:
+                    torch.cuda.synchronize()
+                    keep["edit"] = da.out.edit[:2048].cpu().numpy().copy()
+                    keep["refc"] = da.out.ref_consumed[:2048].cpu().numpy().astype(np.uint64).copy()
+                    keep["ro"] = da.run_off[:2049].cpu().numpy().copy()
+                    keep["runs"] = runs[: int(keep["ro"][-1])].cpu().numpy().copy()
+                    keep["entries"] = int(da.out.dc_entries.sum())
+                    keep["windows"] = int(da.out.windows.sum())
+                    assert int(da.run_off[-1]) <= runs.numel() and int(da.out.status.max()) == 0
+
+        step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(record=True)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, sum(a.elapsed_time(b) for a, b in kev) / steps, keep
+
+    # both ways of storing runs, each checked below; the entry's value is the better one and says which it is
+    by_emit = {"bytes": timed(False), "words": timed(True)}
+    emit = min(by_emit, key=lambda k: by_emit[k][1])
+    ms_step, ms_kernel, keep = by_emit[emit]
+    other = by_emit["words" if emit == "bytes" else "bytes"][2]
+    same = all(np.array_equal(keep[k], other[k]) for k in ("edit", "refc", "ro", "runs")) and keep["entries"] == other["entries"]
     assert int(bad_g) == -1 and int(bad_r) == -1
     # parity: the first 32 reads x 8 candidates against the oracle, on a window of the genome that contains them
     k_reads = 32
@@ -272,7 +282,8 @@ def mapping_point(G, n_reads, stress, peak, sub_batch=1_000_000, steps=2, e2e_re
            "reference_formulation_ratio": entries_per * n * OPS[W] / (ms_kernel / 1e3) / 1e9 / peak, "packed_genome_mb": pgenome.numel() * 4 / 1e6,
            "generate_and_pack_s": gen_s, "windows_per_alignment": keep["windows"] / sub,
            "mean_edit_distance_first_2048": float(np.mean(keep["edit"])), "true_start_mean_edit": float(np.mean(keep["edit"][0::ncand])),
-           "parity": {"checked": k_reads * ncand, "bit_exact": ok}}
+           "run_emission": emit, "kernel_ms_by_run_emission": {k: v[1] for k, v in by_emit.items()},
+           "parity": {"checked": k_reads * ncand, "bit_exact": ok and same, "both_run_emissions_identical_on": 2048}}
     del da, runs, slab_off, pgenome, preads
     if e2e_reads:
         # ---- end to end: host genome + host reads -> sg_set_reference (packed copy resident per GPU) + sg_align_candidates

@@ -52,6 +52,14 @@ extern "C" {
 
 /* flags */
 #define SG_FLAG_DISTANCE_ONLY 1u /* skip CIGAR storage and writeback (traceback still runs) */
+/* device API only: the caller promises that d_slab and every d_slab_off[a] are multiples of 4.  The tuned kernels (64/33,
+ * 32/17) then collect the runs of an alignment in a register and store them as whole 32-bit words -- a quarter of the
+ * store instructions and L2 sector writes of the default one-byte-per-run stores; the up to 3 bytes between an
+ * alignment's last run and the next 4-byte boundary of its slot are written as padding.  Pays when windows are mostly
+ * edits (read mapping with spurious candidate locations: ~20 runs per window against 6.4 at 10 % error), which is why
+ * sg_align_candidates uses it (SG_EMIT=bytes|words overrides for every host-API call).  Ignored by other window
+ * configurations. */
+#define SG_FLAG_RUN_WORDS 2u
 
 /* A CIGAR run as the kernels store it: one byte, (op << 6) | count, count in 1..W-O.  Window configurations with
  * W-O > 63 split a longer run: bytes with count 0 each stand for 63 more of the same op and the byte that follows them

@@ -21,6 +21,7 @@ SG_ERR_OOM = 4
 SG_ERR_CIGAR_OVERFLOW = 5
 SG_ERR_NO_REFERENCE = 6
 SG_FLAG_DISTANCE_ONLY = 1
+SG_FLAG_RUN_WORDS = 2
 
 u64, i64, u32, i32, vp, cp = C.c_uint64, C.c_int64, C.c_uint32, C.c_int, C.c_void_p, C.c_char_p
 dbl = C.c_double

@@ -35,7 +35,7 @@ int cuda_fail(cudaError_t e, const char *what)
 struct DeviceInfo {
     int sms = 0;
     int ctas_per_sm[2][2] = {{0, 0}, {0, 0}};  // row-wise kernel: [W=64 | W=32][smem forefront | TMEM forefront]
-    int delta_ctas_per_sm[2] = {0, 0};         // delta kernel: [W=64 | W=32]
+    int delta_ctas_per_sm[2][2] = {{0, 0}, {0, 0}};   // delta kernel: [W=64 | W=32][runs stored as bytes | as words]
     bool ready = false;
 };
 static DeviceInfo g_dev_info[64];
@@ -65,17 +65,17 @@ static bool use_delta()
     return v;
 }
 
-template <int W> static int setup_delta_kernel(int *ctas_per_sm)
+template <int W, int EMIT> static int setup_delta_kernel(int *ctas_per_sm)
 {
     using L = DeltaLayout<W>;
-    auto kern = genasm_delta_kernel<W>;
+    auto kern = genasm_delta_kernel<W, EMIT>;
     SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES_PER_CTA));
     SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kern, L::WARPS_PER_CTA * 32, L::BYTES_PER_CTA));
     if (std::getenv("SG_DEBUG")) {
         cudaFuncAttributes fa;
         cudaFuncGetAttributes(&fa, kern);
-        fprintf(stderr, "[sg] delta W=%d: occupancy %d CTAs/SM, %d regs, %d dyn smem, %d threads/CTA\n", W, *ctas_per_sm, fa.numRegs,
+        fprintf(stderr, "[sg] delta W=%d emit=%d: occupancy %d CTAs/SM, %d regs, %d dyn smem, %d threads/CTA\n", W, EMIT, *ctas_per_sm, fa.numRegs,
                 L::BYTES_PER_CTA, L::WARPS_PER_CTA * 32);
     }
     // SG_DELTA_RESERVE=1 leaves one CTA slot per SM to the HBM-bound kernels around the aligner (ingest of the next batch,
@@ -153,8 +153,10 @@ static int device_info(DeviceInfo **out)
             if (!rc) rc = setup_kernel<64, true>(&di.ctas_per_sm[0][1]);
             if (!rc) rc = setup_kernel<32, false>(&di.ctas_per_sm[1][0]);
             if (!rc) rc = setup_kernel<32, true>(&di.ctas_per_sm[1][1]);
-            if (!rc) rc = setup_delta_kernel<64>(&di.delta_ctas_per_sm[0]);
-            if (!rc) rc = setup_delta_kernel<32>(&di.delta_ctas_per_sm[1]);
+            if (!rc) rc = setup_delta_kernel<64, 0>(&di.delta_ctas_per_sm[0][0]);
+            if (!rc) rc = setup_delta_kernel<64, 1>(&di.delta_ctas_per_sm[0][1]);
+            if (!rc) rc = setup_delta_kernel<32, 0>(&di.delta_ctas_per_sm[1][0]);
+            if (!rc) rc = setup_delta_kernel<32, 1>(&di.delta_ctas_per_sm[1][1]);
             if (rc) return rc;
             di.ready = true;
             ready[dev].store(true, std::memory_order_release);
@@ -313,12 +315,12 @@ static uint64_t balanced_ctas(uint64_t n, uint64_t max_ctas, uint64_t lanes_per_
     return ctas;
 }
 
-template <int W> static int launch_delta(const DeviceInfo &di, const AlignParams &P, cudaStream_t st)
+template <int W, int EMIT> static int launch_delta(const DeviceInfo &di, const AlignParams &P, cudaStream_t st)
 {
     using L = DeltaLayout<W>;
-    const uint64_t max_ctas = (uint64_t)di.sms * (uint64_t)di.delta_ctas_per_sm[W == 64 ? 0 : 1];
+    const uint64_t max_ctas = (uint64_t)di.sms * (uint64_t)di.delta_ctas_per_sm[W == 64 ? 0 : 1][EMIT];
     const uint64_t ctas = balanced_ctas(P.n, max_ctas, 32ull * L::WARPS_PER_CTA);
-    genasm_delta_kernel<W><<<(unsigned)ctas, L::WARPS_PER_CTA * 32, L::BYTES_PER_CTA, st>>>(P);
+    genasm_delta_kernel<W, EMIT><<<(unsigned)ctas, L::WARPS_PER_CTA * 32, L::BYTES_PER_CTA, st>>>(P);
     SG_CUDA(cudaGetLastError());
     return SG_OK;
 }
@@ -441,7 +443,7 @@ int sg_dev_align_geometry_wo(int W, int O, int *warps_per_sm, int *smem_per_warp
         return SG_OK;
     }
     if (use_delta()) {
-        if (warps_per_sm) *warps_per_sm = di->delta_ctas_per_sm[W == 64 ? 0 : 1] * DeltaLayout<64>::WARPS_PER_CTA;
+        if (warps_per_sm) *warps_per_sm = di->delta_ctas_per_sm[W == 64 ? 0 : 1][0] * DeltaLayout<64>::WARPS_PER_CTA;
         if (smem_per_warp) *smem_per_warp = W == 64 ? DeltaLayout<64>::BYTES_PER_WARP : DeltaLayout<32>::BYTES_PER_WARP;
         if (num_sms) *num_sms = di->sms;
         return SG_OK;
@@ -508,7 +510,13 @@ int sg_dev_align_ordered(int W, int O, const uint32_t *d_text, const uint64_t *d
     P.k_one = 1u; P.k_two = 2u; P.k_4 = 4u; P.k_16 = 16u; P.k_256 = 256u;
     for (int c = 0; c < 16; c++) P.k_sel[c] = 1u << (30 - 2 * c);
     if (!tuned_config(W, O)) return launch_generic(*di, P, W, O, st);
-    if (use_delta()) return W == 64 ? launch_delta<64>(*di, P, st) : launch_delta<32>(*di, P, st);
+    if (use_delta()) {
+        // runs as whole words: only with CIGAR output, and only on the caller's promise of 4-byte aligned slots
+        const bool words = (flags & SG_FLAG_RUN_WORDS) && !(flags & SG_FLAG_DISTANCE_ONLY);
+        if (words && ((uintptr_t)d_slab & 3u) != 0) return fail(SG_ERR_BAD_ARG, "sg_dev_align: SG_FLAG_RUN_WORDS needs a 4-byte aligned d_slab (and slab offsets)");
+        if (words) return W == 64 ? launch_delta<64, 1>(*di, P, st) : launch_delta<32, 1>(*di, P, st);
+        return W == 64 ? launch_delta<64, 0>(*di, P, st) : launch_delta<32, 0>(*di, P, st);
+    }
     if (use_tmem(W)) return W == 64 ? launch_align<64, true>(*di, P, st) : launch_align<32, true>(*di, P, st);
     return W == 64 ? launch_align<64, false>(*di, P, st) : launch_align<32, false>(*di, P, st);
 }

@@ -366,6 +366,8 @@ struct sg_ctx {
     std::mutex mu;  // calls on one context are serialised
     bool taper = true;           // SG_TAPER=0: the last sub-batch of a call is not cut finer
     bool longest_first = true;   // SG_LONGEST_FIRST=0: launches take their alignments in input order
+    int emit = -1;               // how the kernel stores runs (SG_FLAG_RUN_WORDS): -1 = words for candidate locations, bytes for
+                                 // pairs; SG_EMIT=bytes|words forces one for every call
     bool counted = false;   // fully created (sg_ctx_destroy also cleans up after a failed creation)
 };
 
@@ -795,9 +797,16 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
         d_text = d.genome.as<uint32_t>();
     }
     uint64_t slab_bytes = 0;
+    // Candidate locations of read mapping are mostly spurious in practice (the reference's callers hand over every seed hit,
+    // src/tests.cu:335-409), and a read against an unrelated locus walks ~20 one- or two-step runs per window: the kernel
+    // then stores its runs as whole words (SG_FLAG_RUN_WORDS), which needs slots on 4-byte boundaries.
+    const bool run_words = want_cigar && (ctx->emit >= 0 ? ctx->emit == 1 : w.mapping);
     {
         ScopedT t_desc(cs.desc);
-        if (!w.mapping && w.query.off) {   // capacity 2*|query|+8 per alignment: the prefix sum is a difference of offsets
+        if (run_words) {
+            for (uint64_t k = 0; k < n; k++) { h_slab[k] = slab_bytes; slab_bytes += (2ull * h_qlen[k] + 8ull + 3ull) & ~3ull; }
+            h_slab[n] = slab_bytes;
+        } else if (!w.mapping && w.query.off) {   // capacity 2*|query|+8 per alignment: the prefix sum is a difference of offsets
             const uint64_t *qo = w.query.off + a0;
             team_for(d, n + 1, [&](uint64_t k0, uint64_t k1) { for (uint64_t k = k0; k < k1; k++) h_slab[k] = 2ull * (qo[k] - qo[0]) + 8ull * k; });
             slab_bytes = h_slab[n];
@@ -839,7 +848,8 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
     SG_CUDA(cudaEventRecord(s.ev_copied, d.h2d));
     SG_CUDA(cudaStreamWaitEvent(st, s.ev_copied, 0));
     SG_CUDA(cudaEventRecord(s.ev_k0, st));
-    R(sg_dev_align_ordered(ctx->W, ctx->O, d_text, d_tstart, d_tlen, s.packed_q.as<uint32_t>(), d_qstart, d_qlen, n, w.flags, s.slab.as<uint8_t>(), d_slab,
+    R(sg_dev_align_ordered(ctx->W, ctx->O, d_text, d_tstart, d_tlen, s.packed_q.as<uint32_t>(), d_qstart, d_qlen, n,
+                           w.flags | (run_words ? SG_FLAG_RUN_WORDS : 0u), s.slab.as<uint8_t>(), d_slab,
                            s.counter.as<uint64_t>(), s.edit.as<int64_t>(), s.refc.as<uint64_t>(), s.nruns.as<uint32_t>(), s.status.as<uint8_t>(),
                            nullptr, nullptr, d_order, st));
     SG_CUDA(cudaEventRecord(s.ev_k1, st));
@@ -1175,7 +1185,7 @@ int run_all(sg_ctx *ctx, const Workload &w, const uint64_t *woff, uint64_t per_u
             if (!q.blobs || w.mapping) continue;   // mapping: the reads of a sub-batch are known only after a scan of its candidates
             q.max_text = std::max(q.max_text, w.text.off[a1] - w.text.off[a0]);
             q.max_query = std::max(q.max_query, w.query.off[a1] - w.query.off[a0]);
-            if (want_cigar) q.max_slab = std::max<uint64_t>(q.max_slab, 2 * (w.query.off[a1] - w.query.off[a0]) + 8 * (a1 - a0));
+            if (want_cigar) q.max_slab = std::max<uint64_t>(q.max_slab, 2 * (w.query.off[a1] - w.query.off[a0]) + (ctx->emit == 1 ? 11 : 8) * (a1 - a0));
         }
         if (nd == 1) {
             ScopedAffinity bound(ctx->devs[0].worker_cpus);   // the caller's thread is this GPU's worker for the call
@@ -1317,6 +1327,7 @@ int sg_ctx_create_wo(sg_ctx **out, const int *device_ids, int n_devices, int W, 
         ctx->min_batch_units = std::max<uint64_t>(ctx->min_batch_units, 32ull * (uint64_t)wps * (uint64_t)sms);
     }
     if (const char *v = std::getenv("SG_LONGEST_FIRST")) ctx->longest_first = std::atoi(v) != 0;
+    if (const char *v = std::getenv("SG_EMIT")) ctx->emit = std::string(v) == "words" ? 1 : std::string(v) == "bytes" ? 0 : -1;
     if (const char *v = std::getenv("SG_TAPER")) ctx->taper = std::atoi(v) != 0;
     if (const char *v = std::getenv("SG_MIN_BATCH_UNITS")) ctx->min_batch_units = (uint64_t)std::max(1ll, std::atoll(v));
     if (g_debug)
@@ -1409,7 +1420,7 @@ static int align_pairs_common(sg_ctx *ctx, const Strings &text, const Strings &q
         R(check_separate("query", query.ptr, query.len, n_pairs));
     }
     Workload w;
-    w.text = text; w.query = query; w.flags = flags;
+    w.text = text; w.query = query; w.flags = flags & ~SG_FLAG_RUN_WORDS;   // the slab layout is this layer's business
     // sub-batches are cut by uploaded bytes (text + query), shards by the same weight
     std::unique_ptr<uint64_t[]> woff(new uint64_t[n_pairs + 1]);
     if (text.off && query.off) {   // a prefix sum of sizes is a difference of offsets: no serial pass over the pairs
@@ -1546,7 +1557,7 @@ static int align_candidates_common(sg_ctx *ctx, const Strings &reads, uint64_t n
     }
     Workload w;
     w.mapping = true;
-    w.query = reads; w.cand_start = cand_start; w.cand_read = cand_read; w.flags = flags;
+    w.query = reads; w.cand_start = cand_start; w.cand_read = cand_read; w.flags = flags & ~SG_FLAG_RUN_WORDS;
     return run_all(ctx, w, woff.data(), 64, n_cand, out);
 }
 

@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from ._lib import SG_FLAG_DISTANCE_ONLY, bench_check, bench_lib, check, lib
+from ._lib import SG_FLAG_DISTANCE_ONLY, SG_FLAG_RUN_WORDS, bench_check, bench_lib, check, lib
 
 U64_MAX = (1 << 64) - 1
 
@@ -68,10 +68,11 @@ class DeviceAligner:
 
     def align(self, text: torch.Tensor, text_start: torch.Tensor, text_len: torch.Tensor, query: torch.Tensor,
               query_start: torch.Tensor, query_len: torch.Tensor, slab_off: Optional[torch.Tensor] = None,
-              distance_only: bool = False, stats: bool = True) -> AlignOut:
+              distance_only: bool = False, stats: bool = True, run_words: bool = False) -> AlignOut:
         """stats=False: the optional work counters (dc_entries, windows) are not requested, as in the host API's launches;
-        the kernel then skips the window-distance bookkeeping they need."""
-        flags = SG_FLAG_DISTANCE_ONLY if distance_only else 0
+        the kernel then skips the window-distance bookkeeping they need.  run_words=True: SG_FLAG_RUN_WORDS (runs stored as
+        whole words; every slab offset must be a multiple of 4)."""
+        flags = (SG_FLAG_DISTANCE_ONLY if distance_only else 0) | (SG_FLAG_RUN_WORDS if run_words else 0)
         o = self.out
         if not stats:
             check(lib().sg_dev_align_wo(self.W, self.O, _p(text), _p(text_start), _p(text_len), _p(query), _p(query_start), _p(query_len),

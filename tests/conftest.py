@@ -85,3 +85,23 @@ def random_pairs(seed, count, lengths, errors, unrelated=0.1, short_text=0.2):
         T.append(t)
         Q.append(q)
     return T, Q
+
+
+def mapping_case(seed, n_reads=300, genome_len=60000):
+    """A small read-mapping case: per read the true locus, two jittered ones and an unrelated one (candidates may run into
+    the end of the genome).  Returns (genome, reads, cand_start, cand_read)."""
+    rng = random.Random(seed)
+    genome = rand_seq(rng, genome_len)
+    reads, cs, cr = [], [], []
+    for r in range(n_reads):
+        L = rng.choice([1, 40, 150, 900])
+        p0 = rng.randrange(0, len(genome) - L - 10)
+        rd = list(genome[p0:p0 + L])
+        for k in range(len(rd)):
+            if rng.random() < 0.08:
+                rd[k] = rng.choice("ACGT")
+        reads.append("".join(rd))
+        for c in (p0, max(0, p0 - 3), min(len(genome) - 1, p0 + 5), rng.randrange(0, len(genome))):
+            cs.append(c)
+            cr.append(r)
+    return genome, reads, cs, cr
