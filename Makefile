@@ -19,7 +19,7 @@ RDC := scrooge_b200/lib/libscrooge_b200_rdc.a
 # measurement / synthetic-data / checking helpers (include/scrooge_b200_bench.h): NOT in the product library
 BENCHLIB := scrooge_b200/lib/libscrooge_b200_bench.so
 
-all: $(LIB) $(RDC) $(BENCHLIB) build/library_example build/sg_tests build/sg_e2e_probe
+all: $(LIB) $(RDC) $(BENCHLIB) build/library_example build/sg_tests build/sg_e2e_probe build/sg_variant_ab
 
 $(BENCHLIB): build/sg_bench_api.o
 	@mkdir -p scrooge_b200/lib
@@ -66,6 +66,11 @@ CUDA_HOME ?= /usr/local/cuda
 build/sg_e2e_probe: apps/sg_e2e_probe.cpp $(LIB) $(BENCHLIB) $(HDRS)
 	$(CCBIN) -O2 -std=c++17 -Wall -fopenmp -Iinclude -I$(CUDA_HOME)/include -o $@ $< -Lscrooge_b200/lib -lscrooge_b200 -lscrooge_b200_bench \
 	    -L$(CUDA_HOME)/lib64 -lcudart -lpthread -Wl,-rpath,'$$ORIGIN/../scrooge_b200/lib'
+
+# A/B of the kernel's run-emission variants on device-resident synthetic workloads (apps/sg_variant_ab.cpp)
+build/sg_variant_ab: apps/sg_variant_ab.cpp $(LIB) $(BENCHLIB) $(HDRS)
+	$(CCBIN) -O2 -std=c++17 -Wall -Iinclude -I$(CUDA_HOME)/include -o $@ $< -Lscrooge_b200/lib -lscrooge_b200 -lscrooge_b200_bench \
+	    -L$(CUDA_HOME)/lib64 -lcudart -Wl,-rpath,'$$ORIGIN/../scrooge_b200/lib'
 
 clean:
 	rm -rf build scrooge_b200/lib
