@@ -268,7 +268,8 @@ def main():
     idx = torch.arange(n, dtype=torch.int64, device=dev)
     tstart, qstart = idx * stride, idx * L
     qlen = torch.full((n,), L, dtype=torch.int64, device=dev)
-    cap = 2 * L + 8  # runs per alignment (reference: 2*|query| entries, src/genasm_gpu.cu:995-1001)
+    cap = (2 * L + 8 + 3) & ~3  # runs per alignment (reference: 2*|query| entries, src/genasm_gpu.cu:995-1001); slots on 4-byte boundaries:
+    # the launches store runs as whole words (SG_FLAG_RUN_WORDS), as the host API's do
     slab_off = torch.arange(n + 1, dtype=torch.int64, device=dev) * cap
     # Two buffer sets: while the alignment kernel works on pass k (high-priority stream), the ingest of pass k+1 and the
     # compaction of pass k-1 run beside it on two more streams -- both are HBM-bound and small (2 x 2.0 ms and 1.2 ms
@@ -308,7 +309,7 @@ def main():
                 ev[k][0].record(s_align)
             # the work counters (dc_entries, windows) are collected by the untimed passes only: the timed launches are the
             # ones the host API makes (no counters)
-            das[b].align(ptexts[b], tstart, tlen, pquerys[b], qstart, qlen, slab_off, stats=not timed_now[0])
+            das[b].align(ptexts[b], tstart, tlen, pquerys[b], qstart, qlen, slab_off, stats=not timed_now[0], run_words=True)
             if k is not None:
                 ev[k][1].record(s_align)
             e_aligned[b].record(s_align)
@@ -647,6 +648,7 @@ def main():
                        "l2": "inputs larger than L2 (ASCII %.1f GB + packed %.1f GB per step)" % (
                            (n * stride + n * L) / 1e9, (words_t + words_q) * 4 / 1e9),
                        "step": "ingest(ASCII->2bit) + align(DC+TB+RLE) + compaction(scan+gather), inputs resident in HBM",
+                       "run_emission": "whole words (SG_FLAG_RUN_WORDS, the host API's launch; apps/sg_variant_ab compares it with byte stores)",
                        "pipeline": ("the three stages of consecutive passes overlap on three streams (two buffer sets); the timed region "
                                     "holds exactly `steps` ingests, alignments and compactions") if args.pipeline else "one stream, stages back to back"},
             "gcups": value * L * L / 1e9, "mean_edit_distance": mean_ed, "runs_per_alignment": total_runs / n,

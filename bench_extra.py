@@ -78,14 +78,14 @@ def pairs_point(wl, n, distance_only, peak_gops, check=256):
     idx = torch.arange(n, dtype=torch.int64, device=dev)
     tstart, qstart = idx * stride, idx * L
     qlen = torch.full((n,), L, dtype=torch.int64, device=dev)
-    cap = 2 * L + 8
+    cap = (2 * L + 8 + 3) & ~3   # slots on 4-byte boundaries: runs stored as whole words (SG_FLAG_RUN_WORDS), as the host API's launches do
     slab_off = None if distance_only else torch.arange(n + 1, dtype=torch.int64, device=dev) * cap
     da = device.DeviceAligner(W, n, dev, slab_bytes=0 if distance_only else n * cap, O=O)
     ptext, bad_t = device.pack_2bit(text.view(-1))
     pquery, bad_q = device.pack_2bit(reads.view(-1))
 
     def kernel():
-        da.align(ptext, tstart, tlen, pquery, qstart, qlen, slab_off, distance_only=distance_only)
+        da.align(ptext, tstart, tlen, pquery, qstart, qlen, slab_off, distance_only=distance_only, run_words=not distance_only)
 
     kernel()
     runs = None

@@ -55,10 +55,11 @@ extern "C" {
 /* device API only: the caller promises that d_slab and every d_slab_off[a] are multiples of 4.  The tuned kernels (64/33,
  * 32/17) then collect the runs of an alignment in a register and store them as whole 32-bit words -- a quarter of the
  * store instructions and L2 sector writes of the default one-byte-per-run stores; the up to 3 bytes between an
- * alignment's last run and the next 4-byte boundary of its slot are written as padding.  Pays when windows are mostly
- * edits (read mapping with spurious candidate locations: ~20 runs per window against 6.4 at 10 % error), which is why
- * sg_align_candidates uses it (SG_EMIT=bytes|words overrides for every host-API call).  Ignored by other window
- * configurations. */
+ * alignment's last run and the next 4-byte boundary of its slot are written as padding.  Same results, bit for bit.
+ * Measured on a B200 (apps/sg_variant_ab, profiles/r02_variant_ab.jsonl): 10 kbp pairs at 10 % 1.02 x, candidate lists
+ * with 7 of 8 loci spurious (~20 runs per window instead of 6.4) 1.42 x, 150 bp reads 1.04 x at 32/17 and 1.00 x at 64/33.
+ * The host API lays its slab out accordingly and always launches this way (SG_EMIT=bytes restores byte stores).
+ * Ignored by other window configurations and with SG_FLAG_DISTANCE_ONLY. */
 #define SG_FLAG_RUN_WORDS 2u
 
 /* A CIGAR run as the kernels store it: one byte, (op << 6) | count, count in 1..W-O.  Window configurations with

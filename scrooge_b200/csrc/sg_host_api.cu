@@ -366,8 +366,7 @@ struct sg_ctx {
     std::mutex mu;  // calls on one context are serialised
     bool taper = true;           // SG_TAPER=0: the last sub-batch of a call is not cut finer
     bool longest_first = true;   // SG_LONGEST_FIRST=0: launches take their alignments in input order
-    int emit = -1;               // how the kernel stores runs (SG_FLAG_RUN_WORDS): -1 = words for candidate locations, bytes for
-                                 // pairs; SG_EMIT=bytes|words forces one for every call
+    int emit = 1;                // how the kernel stores runs: 1 = as whole words (SG_FLAG_RUN_WORDS), 0 = as bytes (SG_EMIT=bytes)
     bool counted = false;   // fully created (sg_ctx_destroy also cleans up after a failed creation)
 };
 
@@ -797,21 +796,27 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
         d_text = d.genome.as<uint32_t>();
     }
     uint64_t slab_bytes = 0;
-    // Candidate locations of read mapping are mostly spurious in practice (the reference's callers hand over every seed hit,
-    // src/tests.cu:335-409), and a read against an unrelated locus walks ~20 one- or two-step runs per window: the kernel
-    // then stores its runs as whole words (SG_FLAG_RUN_WORDS), which needs slots on 4-byte boundaries.
-    const bool run_words = want_cigar && (ctx->emit >= 0 ? ctx->emit == 1 : w.mapping);
+    // The kernel stores an alignment's runs as whole 32-bit words (SG_FLAG_RUN_WORDS) unless SG_EMIT=bytes: a quarter of the
+    // store instructions and L2 sector writes.  Measured with apps/sg_variant_ab on a B200 (profiles/r02_variant_ab.jsonl):
+    // 10 kbp pairs 11.87 -> 11.65 ms per 303 104, candidate lists with 7 of 8 loci spurious (~20 runs per window: what the
+    // reference's callers produce by handing over every seed hit, src/tests.cu:335-409) 18.04 -> 12.74 ms, 150 bp reads
+    // 1.674 -> 1.613 ms per 4 M at 32/17 and unchanged at 64/33.  Slots therefore start and end on 4-byte boundaries.
+    const bool run_words = want_cigar && ctx->emit != 0;
     {
         ScopedT t_desc(cs.desc);
-        if (run_words) {
-            for (uint64_t k = 0; k < n; k++) { h_slab[k] = slab_bytes; slab_bytes += (2ull * h_qlen[k] + 8ull + 3ull) & ~3ull; }
-            h_slab[n] = slab_bytes;
-        } else if (!w.mapping && w.query.off) {   // capacity 2*|query|+8 per alignment: the prefix sum is a difference of offsets
+        if (!w.mapping && w.query.off) {
+            // capacity >= 2*|query|+8 per alignment (the reference reserves 2*|query| entries, src/genasm_gpu.cu:995-1001): the
+            // prefix sum is a difference of offsets; with 12 instead of 8 bytes of slack per alignment every offset can be
+            // rounded up to the next multiple of 4 on its own without a slot dropping under 2*|query|+8
             const uint64_t *qo = w.query.off + a0;
-            team_for(d, n + 1, [&](uint64_t k0, uint64_t k1) { for (uint64_t k = k0; k < k1; k++) h_slab[k] = 2ull * (qo[k] - qo[0]) + 8ull * k; });
+            if (run_words)
+                team_for(d, n + 1, [&](uint64_t k0, uint64_t k1) { for (uint64_t k = k0; k < k1; k++) h_slab[k] = (2ull * (qo[k] - qo[0]) + 12ull * k + 3ull) & ~3ull; });
+            else
+                team_for(d, n + 1, [&](uint64_t k0, uint64_t k1) { for (uint64_t k = k0; k < k1; k++) h_slab[k] = 2ull * (qo[k] - qo[0]) + 8ull * k; });
             slab_bytes = h_slab[n];
         } else {
-            for (uint64_t k = 0; k < n; k++) { h_slab[k] = slab_bytes; slab_bytes += 2ull * h_qlen[k] + 8ull; }
+            const uint64_t round = run_words ? 3ull : 0ull;
+            for (uint64_t k = 0; k < n; k++) { h_slab[k] = slab_bytes; slab_bytes += (2ull * h_qlen[k] + 8ull + round) & ~round; }
             h_slab[n] = slab_bytes;
         }
     }
@@ -1185,7 +1190,7 @@ int run_all(sg_ctx *ctx, const Workload &w, const uint64_t *woff, uint64_t per_u
             if (!q.blobs || w.mapping) continue;   // mapping: the reads of a sub-batch are known only after a scan of its candidates
             q.max_text = std::max(q.max_text, w.text.off[a1] - w.text.off[a0]);
             q.max_query = std::max(q.max_query, w.query.off[a1] - w.query.off[a0]);
-            if (want_cigar) q.max_slab = std::max<uint64_t>(q.max_slab, 2 * (w.query.off[a1] - w.query.off[a0]) + (ctx->emit == 1 ? 11 : 8) * (a1 - a0));
+            if (want_cigar) q.max_slab = std::max<uint64_t>(q.max_slab, 2 * (w.query.off[a1] - w.query.off[a0]) + (ctx->emit ? 12 : 8) * (a1 - a0) + 4);
         }
         if (nd == 1) {
             ScopedAffinity bound(ctx->devs[0].worker_cpus);   // the caller's thread is this GPU's worker for the call
@@ -1327,7 +1332,7 @@ int sg_ctx_create_wo(sg_ctx **out, const int *device_ids, int n_devices, int W, 
         ctx->min_batch_units = std::max<uint64_t>(ctx->min_batch_units, 32ull * (uint64_t)wps * (uint64_t)sms);
     }
     if (const char *v = std::getenv("SG_LONGEST_FIRST")) ctx->longest_first = std::atoi(v) != 0;
-    if (const char *v = std::getenv("SG_EMIT")) ctx->emit = std::string(v) == "words" ? 1 : std::string(v) == "bytes" ? 0 : -1;
+    if (const char *v = std::getenv("SG_EMIT")) ctx->emit = std::string(v) == "bytes" ? 0 : 1;
     if (const char *v = std::getenv("SG_TAPER")) ctx->taper = std::atoi(v) != 0;
     if (const char *v = std::getenv("SG_MIN_BATCH_UNITS")) ctx->min_batch_units = (uint64_t)std::max(1ll, std::atoll(v));
     if (g_debug)

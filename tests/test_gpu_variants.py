@@ -1,6 +1,6 @@
-"""GPU parity of the run-emission variants of the tuned kernels (SG_FLAG_RUN_WORDS: runs stored as whole 32-bit words, the
-default of sg_align_candidates; bytes: the default of sg_align_pairs) against the oracle and against each other, through
-the device API and through the host API with SG_EMIT forcing either variant.  The same kernel source is checked against the
+"""GPU parity of the run-emission variants of the tuned kernels (SG_FLAG_RUN_WORDS: runs stored as whole 32-bit words, what
+the host API launches; bytes: the device API's default) against the oracle and against each other, through the device API
+and through the host API with SG_EMIT forcing either variant.  The same kernel source is checked against the
 oracle on the CPU-only box by tests/test_kernel_sim.py."""
 import os
 import subprocess
@@ -89,8 +89,8 @@ print(json.dumps(out))
 
 @pytest.mark.parametrize("W", [64, 32])
 def test_host_api_emit_policies_agree(oracle, W):
-    """sg_align_pairs / sg_align_candidates with SG_EMIT=bytes, SG_EMIT=words and the default policy (words for candidate
-    locations, bytes for pairs): identical results, equal to the oracle's."""
+    """sg_align_pairs / sg_align_candidates with SG_EMIT=bytes, SG_EMIT=words and the default (words): identical results,
+    equal to the oracle's."""
     outs = {}
     for emit in ("bytes", "words", None):
         env = dict(os.environ)
