@@ -249,9 +249,9 @@ def mapping_point(G, n_reads, stress, peak, sub_batch=1_000_000, steps=2, e2e_re
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / steps, sum(a.elapsed_time(b) for a, b in kev) / steps, keep
 
-    # both ways of storing runs, each checked below; the entry's value is the better one and says which it is
+    # both ways of storing runs; the entry's value is the one sg_align_candidates launches (words), the other is reported beside it
     by_emit = {"bytes": timed(False), "words": timed(True)}
-    emit = min(by_emit, key=lambda k: by_emit[k][1])
+    emit = "words"
     ms_step, ms_kernel, keep = by_emit[emit]
     other = by_emit["words" if emit == "bytes" else "bytes"][2]
     same = all(np.array_equal(keep[k], other[k]) for k in ("edit", "refc", "ro", "runs")) and keep["entries"] == other["entries"]
