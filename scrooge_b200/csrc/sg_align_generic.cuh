@@ -48,6 +48,7 @@ __host__ __device__ inline int generic_smem_words(int NW, int W, int TBL, bool g
 
 // NW-word addition with carry propagation for any NW: one add.cc / addc.cc chain (a single asm statement, so that nothing
 // can come between the carry-setting and the carry-using instructions)
+#ifndef SG_SIM   // the host simulation (tests/sim) adds with a plain carry loop, see add_vec_any
 template <int NW> struct AddChain;
 template <> struct AddChain<1> {
     static __device__ __forceinline__ void run(const uint32_t (&a)[1], const uint32_t (&b)[1], uint32_t (&s)[1])
@@ -113,10 +114,20 @@ template <> struct AddChain<8> {
             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
     }
 };
+#endif  // !SG_SIM
 template <int NW>
 __device__ __forceinline__ void add_vec_any(const uint32_t (&a)[NW], const uint32_t (&b)[NW], uint32_t (&s)[NW])
 {
+#ifdef SG_SIM
+    uint64_t c = 0;
+    for (int k = 0; k < NW; k++) {
+        c += (uint64_t)a[k] + (uint64_t)b[k];
+        s[k] = (uint32_t)c;
+        c >>= 32;
+    }
+#else
     AddChain<NW>::run(a, b, s);
+#endif
 }
 
 // delta_column (sg_align_delta.cuh) for any NW

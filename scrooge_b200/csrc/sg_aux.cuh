@@ -106,6 +106,7 @@ constexpr int kPackStages = SG_PACK_STAGES;  // 6 x 16 KB = 96 KB of shared memo
 constexpr int kPackSideTile = 8192;
 constexpr int kPackSideStages = 4;
 
+#ifndef SG_SIM   // mbarrier / cp.async.bulk have no host twin: the simulation (tests/sim) runs the plain ingest kernel only
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase)
 {
     asm volatile(
@@ -166,6 +167,8 @@ __global__ void __launch_bounds__(256) pack_2bit_bulk_kernel(const char *__restr
         }
     }
 }
+
+#endif  // !SG_SIM
 
 // ---- CIGAR run compaction -----------------------------------------------------------------------------
 // The aligner writes each alignment's runs into its own slab slot (capacity known in advance, no device

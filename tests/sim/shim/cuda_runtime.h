@@ -76,6 +76,8 @@ static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh)
     return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31u));
 }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
+static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+static inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
 static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; if (v < o) *p = v; return o; }

@@ -16,9 +16,8 @@ from conftest import ROOT, random_pairs
 SIM_DIR = os.path.join(ROOT, "tests", "sim")
 SIM_LIB = os.path.join(SIM_DIR, "_build", "libsgsim.so")
 SIM_SRC = [os.path.join(SIM_DIR, "sim_kernels.cpp"), os.path.join(SIM_DIR, "sim_runtime.cpp")]
-SIM_DEPS = SIM_SRC + [os.path.join(SIM_DIR, "sim_runtime.h"), os.path.join(SIM_DIR, "shim", "cuda_runtime.h"),
-                      os.path.join(ROOT, "scrooge_b200", "csrc", "sg_align.cuh"),
-                      os.path.join(ROOT, "scrooge_b200", "csrc", "sg_align_delta.cuh")]
+SIM_DEPS = SIM_SRC + [os.path.join(SIM_DIR, "sim_runtime.h"), os.path.join(SIM_DIR, "shim", "cuda_runtime.h")] + [
+    os.path.join(ROOT, "scrooge_b200", "csrc", f) for f in ("sg_align.cuh", "sg_align_delta.cuh", "sg_align_generic.cuh", "sg_aux.cuh")]
 CODE = np.full(256, 255, dtype=np.uint8)
 for _k, _c in enumerate("ACGT"):
     CODE[ord(_c)] = _k
@@ -34,6 +33,11 @@ def sim():
     lib = C.CDLL(SIM_LIB)
     lib.sim_delta_align.restype = C.c_int
     lib.sim_delta_align.argtypes = [C.c_int, C.c_int, C.c_uint] + [C.c_void_p] * 6 + [C.c_uint64, C.c_uint32] + [C.c_void_p] * 10
+    lib.sim_generic_align.restype = C.c_int
+    lib.sim_generic_align.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint] + [C.c_void_p] * 6 + [C.c_uint64, C.c_uint32] + [C.c_void_p] * 9
+    lib.sim_pack_2bit.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint]
+    lib.sim_scan_runs.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.sim_gather_runs.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_uint64, C.c_void_p, C.c_uint]
     return lib
 
 
@@ -59,7 +63,9 @@ def p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def run_sim(sim, W, emit, texts, queries, ctas=2, distance_only=False, order=None, cap_of=None, want_stats=True):
+def run_sim(sim, W, emit, texts, queries, ctas=2, distance_only=False, order=None, cap_of=None, want_stats=True, generic=None):
+    """One simulated launch.  generic = None: genasm_delta_kernel<W, emit>; generic = (O, gp): genasm_generic_kernel at window
+    configuration (W, O), op planes in shared (gp = 0) or global (gp = 1) memory."""
     n = len(texts)
     tw, ts, tl = pack_blob(texts)
     qw, qs, ql = pack_blob(queries)
@@ -79,17 +85,33 @@ def run_sim(sim, W, emit, texts, queries, ctas=2, distance_only=False, order=Non
     win = np.zeros(n, dtype=np.uint32) if want_stats else None
     counters = np.zeros(8, dtype=np.uint64)
     ordr = None if order is None else np.asarray(order, dtype=np.uint32)
-    r = sim.sim_delta_align(W, emit, ctas, p(tw), p(ts), p(tl), p(qw), p(qs), p(ql), n, (1 if distance_only else 0) | (2 if emit else 0),
-                            p(slab), p(slab_off), p(edit), p(rc), p(nruns), p(status), p(dce), p(win), p(ordr), p(counters))
+    if generic is None:
+        r = sim.sim_delta_align(W, emit, ctas, p(tw), p(ts), p(tl), p(qw), p(qs), p(ql), n, (1 if distance_only else 0) | (2 if emit else 0),
+                                p(slab), p(slab_off), p(edit), p(rc), p(nruns), p(status), p(dce), p(win), p(ordr), p(counters))
+    else:
+        r = sim.sim_generic_align(W, generic[0], generic[1], ctas, p(tw), p(ts), p(tl), p(qw), p(qs), p(ql), n, 1 if distance_only else 0,
+                                  p(slab), p(slab_off), p(edit), p(rc), p(nruns), p(status), p(dce), p(win), p(ordr))
     assert r == 0
     assert (slab[int(slab_off[-1]):] == 0xEE).all(), "write past the end of the slab"
     return dict(edit=edit, rc=rc, nruns=nruns, status=status, slab=slab, slab_off=slab_off, dc_entries=dce, windows=win,
                 counters=counters)
 
 
+def runs_text(b):
+    """CIGAR text of packed runs; a byte with count 0 stands for 63 more of its op (windows with W - O > 63)."""
+    s, carry = [], 0
+    for x in b:
+        c = int(x) & 63
+        if c == 0:
+            carry += 63
+            continue
+        s.append(f"{carry + c}{'=XID'[int(x) >> 6]}")
+        carry = 0
+    return "".join(s)
+
+
 def cigar_of(out, a):
-    b = out["slab"][int(out["slab_off"][a]): int(out["slab_off"][a]) + int(out["nruns"][a])]
-    return "".join(f"{int(x) & 63}{'=XID'[int(x) >> 6]}" for x in b)
+    return runs_text(out["slab"][int(out["slab_off"][a]): int(out["slab_off"][a]) + int(out["nruns"][a])])
 
 
 def check(out, res, n, cigars=True):
@@ -169,3 +191,80 @@ def test_sim_unrelated_candidates_store_counts(sim, oracle):
     runs_per_window = a["nruns"].sum() / a["windows"].sum()
     assert runs_per_window > 15          # 6.4 at 10 % error
     assert int(b["counters"][1]) * 3.9 < int(a["counters"][0])
+
+
+def _generic_cases():
+    from oracle.binding import EXTRA_CONFIGS
+    odd = [(2, 1), (5, 0), (33, 2), (65, 3), (100, 40), (127, 64), (192, 97), (255, 127), (256, 250), (200, 72)]
+    return [(W, O, gp) for (W, O) in list(EXTRA_CONFIGS) + [(64, 33), (32, 17)] + odd for gp in (0, 1)]
+
+
+@pytest.mark.parametrize("W,O,gp", _generic_cases())
+def test_sim_generic_kernel_matches_oracle(sim, oracle, W, O, gp):
+    """genasm_generic_kernel (any window configuration at run time) on every configuration the reference was rebuilt for, the
+    two tuned ones and ten odd shapes, op planes in shared and in global memory: against the oracle (which is pinned to the
+    unmodified reference at these configurations, tests/test_oracle.py)."""
+    T, Q = random_pairs(1000 + 7 * W + O, 96, [0, 1, 2, W // 2, W - 1, W, W + 1, 2 * W + 1, 100, 300, 700], [0, 0.05, 0.15, 0.4, 0.8])
+    res = oracle.align_pairs(T, Q, W=W, O=O)
+    out = run_sim(sim, W, 0, T, Q, ctas=2, generic=(O, gp))
+    check(out, res, len(T))
+    assert int(out["dc_entries"].sum()) == res.stats["dc_entries"] and int(out["windows"].sum()) == res.stats["windows"]
+
+
+def test_sim_generic_kernel_golden_vectors(sim, golden_wo):
+    for (W, O), g in golden_wo.items():
+        for group, items in g["groups"].items():
+            T = [x["text"] for x in items]
+            Q = [x["query"] for x in items]
+            out = run_sim(sim, W, 0, T, Q, ctas=1, generic=(O, 0))
+            for a, x in enumerate(items):
+                assert int(out["edit"][a]) == x["edit"] and cigar_of(out, a) == x["cigar"], (W, O, group, a)
+
+
+def test_sim_ingest_kernel_matches_numpy(sim):
+    """pack_2bit_kernel: SWAR conversion, case folding, tail words, padding words, and the smallest offending position."""
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 15, 16, 17, 1000, 4099, 70001):
+        letters = np.frombuffer(b"ACGTacgt", dtype=np.uint8)
+        a = letters[rng.integers(0, 8, n)].copy()
+        buf = np.zeros(n + 64, dtype=np.uint8)     # 16-byte aligned source with room for the last vector load
+        buf[:n] = a
+        n_words = (n + 15) // 16 + 8
+        packed = np.full(n_words, 0xDEADBEEF, dtype=np.uint32)
+        bad = np.full(1, 2**64 - 1, dtype=np.uint64)
+        sim.sim_pack_2bit(p(buf), n, p(packed), n_words, p(bad), 0, 3)
+        want, _, _ = pack_blob([a.tobytes().decode()])
+        assert np.array_equal(packed, want) and int(bad[0]) == 2**64 - 1, n
+        if n >= 17:
+            for pos in (0, 16, n - 1, n // 2):
+                b2 = buf.copy()
+                b2[pos] = ord("N")
+                b2[min(n - 1, pos + 5)] = ord("x")
+                bad[0] = 2**64 - 1
+                sim.sim_pack_2bit(p(b2), n, p(packed), n_words, p(bad), 0, 2)
+                assert int(bad[0]) == pos, (n, pos)
+
+
+@pytest.mark.parametrize("group", [32, 4])
+def test_sim_scan_and_gather_match_numpy(sim, group):
+    """scan_* + gather_runs_kernel: exclusive scan of the run counts and the gather of every slot into the dense array, at
+    every relative misalignment of source and destination (byte-granular slots, word-granular copies)."""
+    rng = np.random.default_rng(9 + group)
+    for n, hi in ((1, 5), (7, 40), (2049, 9), (5000, 70)):
+        nruns = rng.integers(0, hi, n).astype(np.uint32)
+        cap = nruns.astype(np.uint64) + rng.integers(0, 6, n).astype(np.uint64)
+        slab_off = np.zeros(n + 1, dtype=np.uint64)
+        slab_off[1:] = np.cumsum(cap)
+        slab = rng.integers(0, 256, int(slab_off[-1]) + 16).astype(np.uint8)
+        run_off = np.full(n + 1, 2**63, dtype=np.uint64)
+        tmp = np.zeros(n // 2048 + 4, dtype=np.uint64)
+        sim.sim_scan_runs(p(nruns), n, p(run_off), p(tmp))
+        want_off = np.zeros(n + 1, dtype=np.uint64)
+        want_off[1:] = np.cumsum(nruns.astype(np.uint64))
+        assert np.array_equal(run_off, want_off)
+        total = int(want_off[-1])
+        runs = np.full(total + 16, 0x5A, dtype=np.uint8)
+        sim.sim_gather_runs(group, p(slab), p(slab_off), p(nruns), p(run_off), n, p(runs), 3)
+        want = np.concatenate([slab[int(slab_off[a]): int(slab_off[a]) + int(nruns[a])] for a in range(n)] + [np.zeros(0, np.uint8)])
+        assert np.array_equal(runs[:total], want)
+        assert (runs[total:] == 0x5A).all(), "wrote past the dense array"
