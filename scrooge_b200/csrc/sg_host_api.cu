@@ -805,18 +805,12 @@ int stage_a(sg_ctx *ctx, Device &d, Slot &s, const Workload &w, uint64_t a0, uin
     {
         ScopedT t_desc(cs.desc);
         if (!w.mapping && w.query.off) {
-            // capacity >= 2*|query|+8 per alignment (the reference reserves 2*|query| entries, src/genasm_gpu.cu:995-1001): the
-            // prefix sum is a difference of offsets; with 12 instead of 8 bytes of slack per alignment every offset can be
-            // rounded up to the next multiple of 4 on its own without a slot dropping under 2*|query|+8
+            // the prefix sum of the capacities is a difference of query offsets (slab_offset_blob, sg_host_threads.h)
             const uint64_t *qo = w.query.off + a0;
-            if (run_words)
-                team_for(d, n + 1, [&](uint64_t k0, uint64_t k1) { for (uint64_t k = k0; k < k1; k++) h_slab[k] = (2ull * (qo[k] - qo[0]) + 12ull * k + 3ull) & ~3ull; });
-            else
-                team_for(d, n + 1, [&](uint64_t k0, uint64_t k1) { for (uint64_t k = k0; k < k1; k++) h_slab[k] = 2ull * (qo[k] - qo[0]) + 8ull * k; });
+            team_for(d, n + 1, [&](uint64_t k0, uint64_t k1) { for (uint64_t k = k0; k < k1; k++) h_slab[k] = slab_offset_blob(qo[k] - qo[0], k, run_words); });
             slab_bytes = h_slab[n];
         } else {
-            const uint64_t round = run_words ? 3ull : 0ull;
-            for (uint64_t k = 0; k < n; k++) { h_slab[k] = slab_bytes; slab_bytes += (2ull * h_qlen[k] + 8ull + round) & ~round; }
+            for (uint64_t k = 0; k < n; k++) { h_slab[k] = slab_bytes; slab_bytes += slab_capacity(h_qlen[k], run_words); }
             h_slab[n] = slab_bytes;
         }
     }

@@ -28,6 +28,24 @@
 
 namespace sg {
 
+// ---- run slab layout ---------------------------------------------------------------------------------------------------
+// Alignment k of a sub-batch owns slab bytes [off[k], off[k+1]) for its CIGAR runs, at least 2*|query|+8 of them (the
+// reference reserves 2*|query| entries, src/genasm_gpu.cu:995-1001).  When the kernel stores runs as whole words
+// (SG_FLAG_RUN_WORDS) every offset is a multiple of 4.
+//   slab_capacity      one alignment's slot when the offsets are accumulated one by one (separate strings, candidates)
+//   slab_offset_blob   off[k] when the queries are one blob: q_prefix = bases of queries 0..k-1.  A difference of offsets,
+//                      so all n+1 of them are computed in parallel; with 12 instead of 8 bytes of slack per alignment each
+//                      offset can be rounded up on its own and no slot drops under 2*|query|+8.
+inline uint64_t slab_capacity(uint64_t query_len, bool words)
+{
+    const uint64_t c = 2ull * query_len + 8ull;
+    return words ? (c + 3ull) & ~3ull : c;
+}
+inline uint64_t slab_offset_blob(uint64_t q_prefix, uint64_t k, bool words)
+{
+    return words ? (2ull * q_prefix + 12ull * k + 3ull) & ~3ull : 2ull * q_prefix + 8ull * k;
+}
+
 // "0-3,8,10-11" -> sorted CPU numbers; empty on a malformed list
 inline std::vector<int> parse_cpulist(const char *s)
 {

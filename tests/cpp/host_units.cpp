@@ -112,6 +112,24 @@ int main()
         CHECK(o.packers(8, big) == 8);
         unsetenv("SG_TUNE");
     }
+    // ---- run slab layout: slots of at least 2*|query|+8 bytes, on 4-byte boundaries when runs are stored as words
+    {
+        uint64_t lens[] = {0, 1, 2, 3, 150, 151, 1000, 9999, 10000, 7, 0, 0, 5, 100001};
+        for (int words = 0; words < 2; words++) {
+            uint64_t prefix = 0, serial = 0;
+            for (uint64_t k = 0; k < sizeof lens / sizeof *lens; k++) {
+                const uint64_t o0 = slab_offset_blob(prefix, k, words), o1 = slab_offset_blob(prefix + lens[k], k + 1, words);
+                CHECK(o1 - o0 >= 2 * lens[k] + 8 && o1 - o0 <= 2 * lens[k] + 16);
+                CHECK(!words || (o0 % 4 == 0 && o1 % 4 == 0));
+                const uint64_t c = slab_capacity(lens[k], words);
+                CHECK(c >= 2 * lens[k] + 8 && c <= 2 * lens[k] + 11 && (!words || c % 4 == 0) && (words || c == 2 * lens[k] + 8));
+                CHECK(!words || serial % 4 == 0);
+                serial += c;
+                prefix += lens[k];
+            }
+            CHECK(slab_offset_blob(0, 0, words) == 0);
+        }
+    }
     std::printf("host units ok\n");
     return 0;
 }
