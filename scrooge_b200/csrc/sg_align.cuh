@@ -123,9 +123,6 @@ struct AlignParams {
     uint64_t *dc_entries;  // optional: sum over windows of (d_w+1)*(n+1), the early-termination-minimal DC work
     uint32_t *windows;     // optional: number of windows of the alignment
     const uint32_t *order; // optional: the queue hands out alignment order[k] as its k-th item (a permutation of 0..n-1)
-    uint32_t k_one, k_two; // the constants 1 and 2, opaque to the compiler (sg_align_delta.cuh: fma-pipe shifts and adds)
-    uint32_t k_4, k_16, k_256;  // 4, 16, 256 likewise: the shifts of the bit gathers of the window setup as IMADs
-    uint32_t k_sel[16];         // k_sel[c] = 1 << (30 - 2c): brings the base code of column c of a text word to bits 31:30
 };
 
 // ---- small helpers -------------------------------------------------------------------------------

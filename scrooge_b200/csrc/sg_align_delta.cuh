@@ -38,60 +38,34 @@
 #pragma once
 #include "sg_align.cuh"
 
-// Compile-time switches for A/B builds (tools/build_variants.sh).  Measured on a B200 against the plain version
-// (1 M x 10 kbp pairs, alignment kernel alone, +-0.01 ms run to run); only RLE2 and GATHER=2 pay and are on:
-//   SG_DELTA_PFPM   pattern masks of column i-1 fetched from shared memory while column i is computed: 37.0 -> 37.8 ms (the
-//                   short-scoreboard stalls the ncu source view shows at the first use of an LDS are already covered
-//                   by the other warps of the scheduler, and two more registers are live)
-//   SG_DELTA_FMA    the 64-bit addition and/or the two shifts of a column on the fma pipe (IMAD / IMAD.WIDE.U32 with
-//                   run-time multipliers 1 and 2 that ptxas cannot turn back into alu-pipe instructions; a column drops
-//                   from 18 to 15 alu-pipe instructions).  1 = both: 39.8 ms; 2 = addition only: 36.6 -> 39.8 ms;
-//                   3 = shifts only: 36.6 -> 38.0 ms.  IMAD.WIDE costs about 6 issue cycles more than the IADD3 it replaces.
-//   SG_DELTA_EARLY  the next window's text and pattern words requested right after the traceback, so that their L2
-//                   latency is covered by the run-length encoding: 37.0 -> 37.9 ms (69 registers instead of 62)
-//   SG_DELTA_TBFMA  fast traceback steps accumulate their stream bits (and, with 1, the column address) with predicated
-//                   IMADs instead of the 89 VIADDs per window the compiler emits: no change at all (36.59 vs 36.59 ms) --
-//                   VIADD does not compete with LOP3/SHF for the alu pipe, and the traceback is not what that pipe
-//                   waits for.
-//   SG_DELTA_RLE2   leaner run-emission loop (op bits rotated into place, one output pointer): 36.90 -> 36.59 ms.  ON.
-//                   2 = the same loop handling two runs per iteration: 36.46 -> 37.52 ms.
-//   SG_DELTA_GATHER the pattern bit planes of the window setup gathered by four bit-select LOP3 per plane and 16-base word, with
-//                   the shifted copies made on the fma pipe (multiplications by 2, 4, 16, 256 that arrive as kernel
-//                   parameters) and the halves joined by one PRMT: 36 alu-pipe + 36 fma-pipe instructions per window
-//                   instead of ~80 alu-pipe ones (the compiler's compress_even is LEA.HI + LOP3 per stage): 36.58 -> 36.84 ms.
-//                   2 = the same gathers with plain shifts (IMAD.SHL, the fma pipe's shift form) and one hand-placed
-//                   LOP3 per bit select: 36.64 -> 36.48 ms.  ON.
-//   SG_DELTA_OFFMUL the base code of a column brought to bits 31:30 by an IMAD (k_sel[column]) and to the mask table's
-//                   stride by one SHF + one IMAD, instead of four masked copies per text word + one PRMT per column
-//                   (16 instead of 23 alu-pipe instructions per 16 columns, 32 more IMADs, 72 registers): 36.58 -> 37.62 ms;
-//                   both together 37.51 ms.  Like SG_DELTA_FMA: a real multiplication is not a free ride on the fma pipe
-//                   (both pipes issue once per two cycles per scheduler; what is traded is issue slots, not pipe time).
-#ifndef SG_DELTA_GATHER
-#define SG_DELTA_GATHER 2
-#endif
-#ifndef SG_DELTA_OFFMUL
-#define SG_DELTA_OFFMUL 0
-#endif
-#ifndef SG_DELTA_PFPM
-#define SG_DELTA_PFPM 0
-#endif
-#ifndef SG_DELTA_FMA
-#define SG_DELTA_FMA 0
-#endif
-#ifndef SG_DELTA_EARLY
-#define SG_DELTA_EARLY 0
-#endif
-#ifndef SG_DELTA_TBFMA
-#define SG_DELTA_TBFMA 0
-#endif
-#ifndef SG_DELTA_RLE2
-#define SG_DELTA_RLE2 1
-#endif
-//   SG_DELTA_SHORTFAST  windows with fewer than W-O pattern characters take the unchecked walk too and have their op streams
-//                   cut where the pattern ran out (see the traceback).  ON.
-#ifndef SG_DELTA_SHORTFAST
-#define SG_DELTA_SHORTFAST 1
-#endif
+// What was tried on this kernel and measured on a B200 against the version below (1 M x 10 kbp pairs, alignment kernel alone,
+// +-0.01 ms run to run; profiles/r01_kernel_variants_ab.txt).  The code of the variants that lost is gone (git history has it):
+//   * pattern masks of column i-1 fetched from shared memory while column i is computed: 37.0 -> 37.8 ms (the short-scoreboard
+//     stalls the ncu source view shows at the first use of an LDS are already covered by the other warps of the scheduler, and
+//     two more registers are live);
+//   * the 64-bit addition and/or the two shifts of a column on the fma pipe (IMAD / IMAD.WIDE.U32 with run-time multipliers 1
+//     and 2 that ptxas cannot turn back into alu-pipe instructions; a column drops from 18 to 15 alu-pipe instructions): both
+//     39.8 ms, addition only 36.6 -> 39.8 ms, shifts only 36.6 -> 38.0 ms.  IMAD.WIDE costs about 6 issue cycles more than the
+//     IADD3 it replaces;
+//   * the next window's text and pattern words requested right after the traceback, so that their L2 latency is covered by the
+//     run-length encoding: 37.0 -> 37.9 ms (69 registers instead of 62);
+//   * fast traceback steps accumulating their stream bits (and the column address) with predicated IMADs instead of the 89
+//     VIADDs per window the compiler emits: no change at all (36.59 vs 36.59 ms) -- VIADD does not compete with LOP3/SHF for the
+//     alu pipe, and the traceback is not what that pipe waits for;
+//   * a leaner run-emission loop (op bits rotated into place, one output pointer): 36.90 -> 36.59 ms, KEPT; the same loop
+//     handling two runs per iteration: 36.46 -> 37.52 ms;
+//   * the pattern bit planes of the window setup gathered by four bit selects per plane and 16-base word with plain shifts
+//     (IMAD.SHL, the fma pipe's shift form) and one hand-placed LOP3 per select instead of the compiler's compress_even
+//     (LEA.HI + LOP3 per stage, ~80 alu-pipe instructions per window): 36.64 -> 36.48 ms, KEPT; the same with the shifts as
+//     multiplications by opaque constants: 36.58 -> 36.84 ms;
+//   * the base code of a column brought to bits 31:30 by an IMAD and to the mask table's stride by one SHF + one IMAD, instead
+//     of four masked copies per text word + one PRMT per column (16 instead of 23 alu-pipe instructions per 16 columns, 32 more
+//     IMADs, 72 registers): 36.58 -> 37.62 ms.  A real multiplication is not a free ride on the fma pipe: both pipes issue once
+//     per two cycles per scheduler; what is traded is issue slots, not pipe time;
+//   * windows with fewer than W-O pattern characters taking the unchecked walk too, their op streams cut where the pattern ran
+//     out (see the traceback): 150 bp reads 2.01 -> 2.04 G alignments/s at 64/33, 2.21 -> 2.25 at 32/17, KEPT;
+//   * runs stored as whole words instead of bytes (EMIT below): 11.87 -> 11.65 ms per 303 104 pairs, 18.04 -> 12.74 ms when most
+//     windows are mostly edits, KEPT as what the host API launches (profiles/r02_variant_ab.jsonl).
 
 namespace sg {
 
@@ -144,8 +118,8 @@ __device__ __forceinline__ void lds_pair(uint32_t addr, uint32_t &a, uint32_t &b
 
 // Odd bits of x (bit 2k+1, k = 0..15) gathered into bits 16+k of the result; its low half is garbage.  x1 = x << 1.
 // Each stage keeps the upper of two neighbouring groups where it is and takes the lower one from a shifted copy -- a
-// bit select, so the garbage never carries into the payload -- and the shifted copies are IMADs (k4, k16, k256 are the
-// opaque constants 4, 16, 256): 4 alu-pipe + 3 fma-pipe instructions.
+// bit select, so the garbage never carries into the payload -- and the shifted copies are plain shifts, which the compiler
+// emits as IMAD.SHL (the fma pipe's shift form): 4 alu-pipe + 3 fma-pipe instructions.
 __device__ __forceinline__ uint32_t bit_select(uint32_t a, uint32_t b, uint32_t m)   // (a & m) | (b & ~m) as ONE LOP3
 {
 #ifdef SG_SIM
@@ -156,9 +130,8 @@ __device__ __forceinline__ uint32_t bit_select(uint32_t a, uint32_t b, uint32_t 
     return d;
 #endif
 }
-__device__ __forceinline__ uint32_t gather_odd_hi(uint32_t x, uint32_t x1, uint32_t k4, uint32_t k16, uint32_t k256)
+__device__ __forceinline__ uint32_t gather_odd_hi(uint32_t x, uint32_t x1)
 {
-#if SG_DELTA_GATHER == 2
     // plain shifts (the compiler makes them IMAD.SHL, the shift form of the fma pipe) and hand-placed LOP3s (left to
     // itself it splits every select into two LOP3 with simplified masks)
     uint32_t y = bit_select(x, x1, 0x88888888u);
@@ -166,31 +139,19 @@ __device__ __forceinline__ uint32_t gather_odd_hi(uint32_t x, uint32_t x1, uint3
     y = bit_select(y, y << 4, 0xF000F000u);
     y = bit_select(y, y << 8, 0xFF000000u);
     return y;
-#else
-    uint32_t y = (x & 0x88888888u) | (x1 & 0x77777777u);      // pairs at bits 3:2 of every nibble
-    y = (y & 0xC0C0C0C0u) | ((y * k4) & 0x3F3F3F3Fu);         // four bits at 7:4 of every byte
-    y = (y & 0xF000F000u) | ((y * k16) & 0x0FFF0FFFu);        // eight at 15:8 of every half
-    y = (y & 0xFF000000u) | ((y * k256) & 0x00FFFFFFu);       // sixteen at 31:16
-    return y;
-#endif
 }
 
 // pattern_planes (sg_align.cuh) with gather_odd_hi: plane 1 = the odd bits of the 2-bit codes, plane 0 = the odd bits of
 // the word shifted left by one
 template <int NW>
-__device__ __forceinline__ void pattern_planes_fma(const uint32_t (&pw)[2 * NW], uint32_t (&p0)[NW], uint32_t (&p1)[NW],
-                                                   const uint32_t k2, const uint32_t k4, const uint32_t k16, const uint32_t k256)
+__device__ __forceinline__ void pattern_planes_gather(const uint32_t (&pw)[2 * NW], uint32_t (&p0)[NW], uint32_t (&p1)[NW])
 {
 #pragma unroll
     for (int k = 0; k < NW; k++) {
         const uint32_t a = pw[2 * k], b = pw[2 * k + 1];
-#if SG_DELTA_GATHER == 2
         const uint32_t a1 = a << 1, b1 = b << 1, a2 = a << 2, b2 = b << 2;
-#else
-        const uint32_t a1 = a * k2, b1 = b * k2, a2 = a * k4, b2 = b * k4;
-#endif
-        const uint32_t ha = gather_odd_hi(a, a1, k4, k16, k256), hb = gather_odd_hi(b, b1, k4, k16, k256);
-        const uint32_t la = gather_odd_hi(a1, a2, k4, k16, k256), lb = gather_odd_hi(b1, b2, k4, k16, k256);
+        const uint32_t ha = gather_odd_hi(a, a1), hb = gather_odd_hi(b, b1);
+        const uint32_t la = gather_odd_hi(a1, a2), lb = gather_odd_hi(b1, b2);
         // pattern positions 32k..32k+31 go to word NW-1-k, bit-reversed
         p0[NW - 1 - k] = __brev(__byte_perm(la, lb, 0x7632));
         p1[NW - 1 - k] = __brev(__byte_perm(ha, hb, 0x7632));
@@ -213,58 +174,6 @@ __device__ __forceinline__ void delta_column(uint32_t (&Pv)[NW], uint32_t (&Mv)[
     }
     shl1<NW>(Ph, Phs);   // carry-in 0: D(i,m) = 0 for every column
     shl1<NW>(Mh, Mhs);
-#pragma unroll
-    for (int k = 0; k < NW; k++) {
-        const uint32_t xv = ~pm[k] | Mv[k];
-        Pv[k] = Mhs[k] | ~(xv | Phs[k]);
-        Mv[k] = Phs[k] & xv;
-    }
-}
-
-// The same column with the addition and the shifts on the fma pipe: the kernel is bound by the alu pipe (LOP3, SHF, IADD3,
-// PRMT: 18 of a column's 23 instructions at W=64) while the fma pipe idles.  one == 1 and two == 2 arrive as kernel
-// parameters so that the multiplications stay IMADs:
-//   t + Pv      = IMAD.WIDE.U32(t.lo, one, Pv) ; hi += t.hi * one          (was IADD3 + IMAD.X)
-//   x << 1      = IMAD.WIDE.U32(x.lo, two, 0)  ; hi = x.hi * two + carry   (was IMAD.IADD + SHF.L.W.HI)
-template <int NW>
-__device__ __forceinline__ void delta_column_fma(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&pm)[NW], uint32_t (&Ph)[NW],
-                                                 const uint32_t one, const uint32_t two)
-{
-    uint32_t t[NW], s[NW], x[NW], Mh[NW], Phs[NW], Mhs[NW];
-#pragma unroll
-    for (int k = 0; k < NW; k++) t[k] = ~pm[k] & Pv[k];
-    if constexpr (NW == 2) {
-        if (SG_DELTA_FMA != 3) {
-            const uint64_t w = (uint64_t)t[0] * one + (((uint64_t)Pv[1] << 32) | Pv[0]);
-            s[0] = (uint32_t)w;
-            s[1] = t[1] * one + (uint32_t)(w >> 32);
-        } else {
-            add_vec<NW>(t, Pv, s);
-        }
-    } else {
-        s[0] = t[0] * one + Pv[0];
-    }
-#pragma unroll
-    for (int k = 0; k < NW; k++) {
-        x[k] = (s[k] ^ Pv[k]) | ~pm[k];
-        Ph[k] = Mv[k] | ~(x[k] | Pv[k]);
-        Mh[k] = Pv[k] & x[k];
-    }
-    if constexpr (NW == 2) {
-        if (SG_DELTA_FMA != 2) {
-            const uint64_t wp = (uint64_t)Ph[0] * two, wm = (uint64_t)Mh[0] * two;
-            Phs[0] = (uint32_t)wp;
-            Phs[1] = Ph[1] * two + (uint32_t)(wp >> 32);
-            Mhs[0] = (uint32_t)wm;
-            Mhs[1] = Mh[1] * two + (uint32_t)(wm >> 32);
-        } else {
-            shl1<NW>(Ph, Phs);
-            shl1<NW>(Mh, Mhs);
-        }
-    } else {
-        Phs[0] = Ph[0] * two;
-        Mhs[0] = Mh[0] * two;
-    }
 #pragma unroll
     for (int k = 0; k < NW; k++) {
         const uint32_t xv = ~pm[k] | Mv[k];
@@ -348,10 +257,6 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
                     out = P.slab + P.slab_off[idx];
                     out_end = P.slab + P.slab_off[idx + 1];
                 }
-#if SG_DELTA_EARLY
-                load_window<NWIN>(P.text, t_pos, tw);
-                load_window<NWIN>(P.query, q_pos, pw);
-#endif
                 have = true;
                 break;
             }
@@ -367,16 +272,10 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
             uint64_t tl = t_end - t_pos, ql = q_end - q_pos;
             n = tl < (uint64_t)W ? (int)tl : W;
             m = ql < (uint64_t)W ? (int)ql : W;
-#if !SG_DELTA_EARLY
             load_window<NWIN>(P.text, t_pos, tw);
             load_window<NWIN>(P.query, q_pos, pw);
-#endif
             uint32_t p0[NW], p1[NW], hm[NW];
-#if SG_DELTA_GATHER
-            pattern_planes_fma<NW>(pw, p0, p1, P.k_two, P.k_4, P.k_16, P.k_256);
-#else
-            pattern_planes<NW>(pw, p0, p1);
-#endif
+            pattern_planes_gather<NW>(pw, p0, p1);
             ones_shl<NW>(W - m, hm);
             // pm[c]: zero where pattern[J] == c (src/genasm_cpu.cpp:178-198) and in the W-m padding bits
             uint32_t m0[NW], m1[NW], m2[NW], m3[NW];
@@ -401,12 +300,8 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
         // steps beyond that point read whatever the planes hold below the pattern (in bounds: at most TB_LIMIT columns
         // and TB_LIMIT mask shifts) and are cut off afterwards, where the m-th pattern-consuming step is found in the
         // op streams.  (Before, one short window among a warp's 32 sent the whole warp through the checked loop: with
-        // 150 bp reads that was nearly every iteration -- SG_DELTA_SHORTFAST=0 restores it.)
-#if SG_DELTA_SHORTFAST
+        // 150 bp reads that was nearly every iteration.)
         const bool tb_fast = true;
-#else
-        const bool tb_fast = __all_sync(0xFFFFFFFFu, !have || m >= TBL);
-#endif
 #ifdef SG_STATS
         if (lane == 0) {
             atomicAdd(&g_delta_stats[uniform ? 0 : 1], 1ull);
@@ -425,16 +320,6 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
             constexpr uint32_t NONE = 4u * PMS * 4u;   // byte offset of the "matches nothing" masks
             static_assert(TBCOLS == HB * 16, "traceback columns = the lower half of the window");
             const char *pmb = reinterpret_cast<const char *>(pm_s);
-#if SG_DELTA_PFPM
-            // the masks of a column are requested one column ahead: an LDS issued right before its first use costs a
-            // third of the column's time in short-scoreboard stalls (ncu source view of the previous version)
-            uint32_t pmn[NW];
-            {
-                uint32_t off = (tw[NWIN - 1] >> 22) & 0x300u;   // column 15 of the last word: code * 256 B
-                if (!UNI) off = 15 < n - (NWIN - 1) * 16 ? off : NONE;
-                lds_vec<NW>(reinterpret_cast<const uint32_t *>(pmb + off), pmn);
-            }
-#endif
 #pragma unroll
             for (int half = 1; half >= 0; half--) {
 #pragma unroll 1
@@ -445,49 +330,18 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
                     uint32_t *tbp = tb_s + b * 16 * TBS;
                     // base codes as shared-memory offsets: four masked copies hold the codes of columns 4q+r in byte q,
                     // and one byte permute per column moves that byte to bits 15:8 (code * 256 B, the mask table's stride)
-#if !SG_DELTA_OFFMUL || SG_DELTA_PFPM
                     uint32_t cq[4];
                     cq[0] = cw & 0x03030303u;
                     cq[1] = (cw >> 2) & 0x03030303u;
                     cq[2] = (cw >> 4) & 0x03030303u;
                     cq[3] = (cw >> 6) & 0x03030303u;
-#endif
-#if SG_DELTA_PFPM
-                    // column 15 of the word that follows (none after the last word: any valid offset will do)
-                    uint32_t nwv = half == 1 ? tw[HB - 1] : 0u;
-                    if (HB == 2 && b == 1) nwv = tw[half * HB];
-                    uint32_t off15 = (nwv >> 22) & 0x300u;
-                    if (!UNI) off15 = nrel >= 0 ? off15 : NONE;      // 15 < nrel + 16
-#endif
 #pragma unroll
                     for (int ii = 15; ii >= 0; ii--) {
                         uint32_t pm[NW], Ph[NW];
-#if SG_DELTA_PFPM
-#pragma unroll
-                        for (int k = 0; k < NW; k++) pm[k] = pmn[k];
-                        {
-                            uint32_t off = off15;
-                            if (ii > 0) {
-                                off = __byte_perm(cq[(ii - 1) & 3], 0u, 0x4404u | ((uint32_t)((ii - 1) >> 2) << 4));
-                                if (!UNI) off = ii - 1 < nrel ? off : NONE;
-                            }
-                            lds_vec<NW>(reinterpret_cast<const uint32_t *>(pmb + off), pmn);
-                        }
-#elif SG_DELTA_OFFMUL
-                        // code -> bits 31:30 (IMAD, the lower codes fall off the top), -> bits 1:0 (SHF), x 256 B (IMAD)
-                        uint32_t off = (ii == 15 ? cw : cw * P.k_sel[ii]) >> 30;
-                        if (!UNI) off = ii < nrel ? off : 4u;
-                        lds_vec<NW>(reinterpret_cast<const uint32_t *>(pmb + off * P.k_256), pm);
-#else
                         uint32_t off = __byte_perm(cq[ii & 3], 0u, 0x4404u | ((uint32_t)(ii >> 2) << 4));
                         if (!UNI) off = ii < nrel ? off : NONE;
                         lds_vec<NW>(reinterpret_cast<const uint32_t *>(pmb + off), pm);
-#endif
-#if SG_DELTA_FMA
-                        delta_column_fma<NW>(Pv, Mv, pm, Ph, P.k_one, P.k_two);
-#else
                         delta_column<NW>(Pv, Mv, pm, Ph);
-#endif
                         if (half == 0) {
                             const uint32_t v = Pv[TOP], hh = Ph[TOP], e = pm[TOP];
                             *reinterpret_cast<uint2 *>(tbp + ii * TBS) = make_uint2(v | hh, ~v & (hh | e));
@@ -535,32 +389,6 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
                     if (!(hi && lo)) mask >>= 1;
                     lds_pair(tcol, ca, cb);
                 }
-#elif SG_DELTA_TBFMA
-                // the same step with the three accumulations (two stream bits, the column address) as predicated IMADs
-                // on the idle fma pipe: x += k_one * constant, k_one == 1 being a kernel parameter ptxas cannot fold
-                asm volatile(
-                    "{\n\t"
-                    ".reg .pred ph, pl, pi, pd;\n\t"
-                    ".reg .b32 t;\n\t"
-                    "and.b32 t, %2, %4;\n\t"
-                    "setp.ne.u32 ph, t, 0;\n\t"
-                    "and.b32 t, %3, %4;\n\t"
-                    "setp.ne.u32 pl, t, 0;\n\t"
-                    "@ph mad.lo.u32 %0, %8, %6, %0;\n\t"
-                    "@pl mad.lo.u32 %1, %8, %6, %1;\n\t"
-                    "and.pred pd, ph, pl;\n\t"
-                    "not.pred pi, pl;\n\t"
-                    "and.pred pi, pi, ph;\n\t"
-#if SG_DELTA_TBFMA == 2
-                    "@!pi add.u32 %5, %5, %7;\n\t"                 // the address stays on the alu pipe: it is on the load's critical path
-#else
-                    "@!pi mad.lo.u32 %5, %8, %7, %5;\n\t"
-#endif
-                    "@!pd shr.u32 %4, %4, 1;\n\t"
-                    "ld.shared.v2.u32 {%2, %3}, [%5];\n\t"
-                    "}"
-                    : "+r"(h0), "+r"(l0), "+r"(ca), "+r"(cb), "+r"(mask), "+r"(tcol)
-                    : "r"(1u << k), "n"(TBS * 4), "r"(P.k_one));
 #else
                 asm volatile(
                     "{\n\t"
@@ -584,7 +412,6 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
 #endif
             }
             bit0 = TBL < 32 ? 1u << (TBL & 31) : 0u;
-#if SG_DELTA_SHORTFAST
             if (m < TBL) {
                 constexpr uint32_t kWalked = TBL < 32 ? (1u << (TBL & 31)) - 1u : 0xFFFFFFFFu;
                 const uint32_t nd = ~(h0 & l0) & kWalked;          // steps that consumed a pattern character (all but 'D')
@@ -607,7 +434,6 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
                 // else: fewer than m pattern characters consumed so far (deletions): the state is that of a checked walk
                 // after TB_LIMIT steps, and the loop below goes on from it
             }
-#endif
         }
 #pragma unroll
         for (int w = 0; w < SW; w++) {
@@ -632,12 +458,6 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
         const int j = __clz(mask);
         t_pos += (uint64_t)i;
         q_pos += (uint64_t)j;
-#if SG_DELTA_EARLY
-        if (q_pos < q_end) {   // the next window's words travel while the runs are encoded and stored
-            load_window<NWIN>(P.text, t_pos, tw);
-            load_window<NWIN>(P.query, q_pos, pw);
-        }
-#endif
 
         // ---- RLE on the streams: per-window runs, flushed at window end, never merged across windows (quirk Q2) ----
         // a run ends at step k when op k+1 differs (the streams are zero beyond the last step) and at the last step
@@ -661,7 +481,6 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
         const bool fits = !want_cigar || (uint64_t)(out_end - out) >= (uint64_t)nb;
         if (!fits) overflow = true;
         if (want_cigar && fits) {
-#if SG_DELTA_RLE2
             // one byte per run, (op << 6) | length.  The op bits of step p are brought to bits 7 and 6 by one rotation each
             // (the streams are pre-rotated by 7 and 6 per word), merged by one LOP3 and joined with the length by another.
             uint8_t *o = out;
@@ -671,29 +490,6 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
             for (int w = 0; w < SW; w++) {
                 uint32_t ew = e[w];
                 const uint32_t h7 = __funnelshift_l(hs[w], hs[w], 7), l6 = __funnelshift_l(ls[w], ls[w], 6);
-#if SG_DELTA_RLE2 == 2
-                // two runs per iteration: half the loop overhead, and the two extractions overlap
-                while (ew) {
-                    const uint32_t ew2 = ew & (ew - 1u);
-                    const int p = __ffs((int)ew) - 1;
-                    const uint32_t rh = __funnelshift_r(h7, h7, p), rl = __funnelshift_r(l6, l6, p);
-                    const uint32_t t = (rh & 0x80u) | (rl & ~0x80u);
-                    o[0] = (uint8_t)((t & 0xC0u) | (uint32_t)(p - st));
-                    if (ew2) {
-                        const int p2 = __ffs((int)ew2) - 1;
-                        const uint32_t rh2 = __funnelshift_r(h7, h7, p2), rl2 = __funnelshift_r(l6, l6, p2);
-                        const uint32_t t2 = (rh2 & 0x80u) | (rl2 & ~0x80u);
-                        o[1] = (uint8_t)((t2 & 0xC0u) | (uint32_t)(p2 - p));
-                        o += 2;
-                        st = p2;
-                        ew = ew2 & (ew2 - 1u);
-                    } else {
-                        o += 1;
-                        st = p;
-                        ew = 0u;
-                    }
-                }
-#else
                 while (ew) {
                     const int p = __ffs((int)ew) - 1;
                     const uint32_t rh = __funnelshift_r(h7, h7, p), rl = __funnelshift_r(l6, l6, p);
@@ -722,23 +518,8 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
                     st = p;
                     ew &= ew - 1u;
                 }
-#endif
                 st -= 32;
             }
-#else
-            int start = -1;                              // step before the current run's first
-#pragma unroll
-            for (int w = 0; w < SW; w++) {
-                uint32_t ew = e[w];
-                while (ew) {
-                    const int p = __ffs((int)ew) - 1;
-                    const uint32_t o = ((hs[w] >> p) & 1u) * 2u + ((ls[w] >> p) & 1u);
-                    *out++ = (uint8_t)(o * 64u + (uint32_t)(32 * w + p - start));
-                    start = 32 * w + p;
-                    ew &= ew - 1u;
-                }
-            }
-#endif
         }
         nruns += nb;
         ed += edits;

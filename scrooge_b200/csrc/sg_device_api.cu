@@ -509,8 +509,6 @@ int sg_dev_align_ordered(int W, int O, const uint32_t *d_text, const uint64_t *d
     P.counter = (unsigned long long *)d_counter;
     P.edit = d_edit; P.ref_consumed = d_ref_consumed; P.nruns = d_nruns; P.status = d_status; P.dc_entries = d_dc_entries; P.windows = d_windows;
     P.order = d_order;
-    P.k_one = 1u; P.k_two = 2u; P.k_4 = 4u; P.k_16 = 16u; P.k_256 = 256u;
-    for (int c = 0; c < 16; c++) P.k_sel[c] = 1u << (30 - 2 * c);
     if (!tuned_config(W, O)) return launch_generic(*di, P, W, O, st);
     if (use_delta()) {
         // runs as whole words: only with CIGAR output, and only on the caller's promise of 4-byte aligned slots

@@ -65,8 +65,6 @@ int sim_generic_align(int W, int O, int gp, unsigned ctas, const uint32_t *text,
     P.n = n; P.flags = flags; P.slab = slab; P.slab_off = slab_off; P.counter = &counter;
     P.edit = edit; P.ref_consumed = ref_consumed; P.nruns = nruns; P.status = status; P.dc_entries = dc_entries; P.windows = windows;
     P.order = order;
-    P.k_one = 1u; P.k_two = 2u; P.k_4 = 4u; P.k_16 = 16u; P.k_256 = 256u;
-    for (int c = 0; c < 16; c++) P.k_sel[c] = 1u << (30 - 2 * c);
     const int NW = (W + 31) / 32, TBL = W - O;
     a.G.W = W; a.G.TBL = TBL; a.G.NWT = (TBL + 31) / 32; a.G.planes = nullptr;
     if ((size_t)sg::generic_smem_words(NW, W, TBL, gp != 0) * 4 > sizeof(sg::smem_all)) return -2;
@@ -132,8 +130,6 @@ int sim_delta_align(int W, int emit, unsigned ctas, const uint32_t *text, const 
     P.n = n; P.flags = flags; P.slab = slab; P.slab_off = slab_off; P.counter = &counter;
     P.edit = edit; P.ref_consumed = ref_consumed; P.nruns = nruns; P.status = status; P.dc_entries = dc_entries; P.windows = windows;
     P.order = order;
-    P.k_one = 1u; P.k_two = 2u; P.k_4 = 4u; P.k_16 = 16u; P.k_256 = 256u;
-    for (int c = 0; c < 16; c++) P.k_sel[c] = 1u << (30 - 2 * c);
     for (auto &c : sim::counters) c = 0;
     void (*fn)(void *) = nullptr;
     unsigned block = 0;
