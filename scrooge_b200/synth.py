@@ -76,3 +76,15 @@ def pairs_as_strings(text: np.ndarray, tlen: np.ndarray, reads: np.ndarray) -> T
     texts = [text[i, : int(tlen[i])].tobytes().decode() for i in range(len(tlen))]
     queries = [reads[i].tobytes().decode() for i in range(reads.shape[0])]
     return texts, queries
+
+
+def mapping_host(seed: int, genome_len: int, n_reads: int, read_len: int, err: float = 0.10, ratio: Tuple[int, int, int] = PACBIO):
+    """A small read-mapping case generated on the host (BASELINE.json configs[3] in miniature): returns (genome uint8
+    [genome_len], reads uint8 [n, L], true start uint64 [n])."""
+    genome = np.empty(genome_len, dtype=np.uint8)
+    bench_check(bench_lib().sg_synth_genome(seed, 0, genome_len, genome.ctypes.data, None, None))
+    reads = np.empty((n_reads, read_len), dtype=np.uint8)
+    pos = np.empty(n_reads, dtype=np.uint64)
+    bench_check(bench_lib().sg_synth_reads(seed + 1, 0, n_reads, read_len, float(err), ratio[0], ratio[1], ratio[2], genome.ctypes.data,
+                                           genome_len, reads.ctypes.data, pos.ctypes.data, 0, None))
+    return genome, reads, pos
