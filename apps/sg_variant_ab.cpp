@@ -1,4 +1,4 @@
-// sg_variant_ab -- A/B of the alignment kernel's run-emission variants (bytes / SG_FLAG_RUN_WORDS / 64-bit pairs) on device-resident
+// sg_variant_ab -- A/B of the alignment kernel's run-emission variants (bytes / SG_FLAG_RUN_WORDS / no run storage) on device-resident
 // synthetic workloads, in seconds and without Python: every variant must produce the same distances, consumed prefixes, run
 // counts and run bytes as the default, and its kernel time (CUDA events, best and mean of `reps` launches after a warm-up)
 // is printed beside the default's.  One JSON line per workload on stdout.
@@ -112,12 +112,8 @@ static bool same(const Outputs &a, const Outputs &b)
 static void ab(const char *name, const Batch &b, int reps, cudaStream_t st)
 {
     const uint64_t sample = std::min<uint64_t>(b.n, 32768);
-    unsetenv("SG_DELTA_EMIT");
     Outputs bytes = run_variant(b, 0u, reps, sample, st);
     Outputs words = run_variant(b, SG_FLAG_RUN_WORDS, reps, sample, st);
-    setenv("SG_DELTA_EMIT", "2", 1);
-    Outputs pairs = run_variant(b, SG_FLAG_RUN_WORDS, reps, sample, st);
-    unsetenv("SG_DELTA_EMIT");
     // no run storage at all (traceback and run counting still happen): what any emission scheme can save at most
     float dist_only_ms = 1e30f;
     {
@@ -147,13 +143,12 @@ static void ab(const char *name, const Batch &b, int reps, cudaStream_t st)
     double ed = 0;
     for (uint64_t k = 0; k < b.n; k++) { total_runs += bytes.nruns[k]; bad_status += bytes.status[k] != 0; ed += (double)bytes.edit[k]; }
     printf("{\"workload\": \"%s\", \"W\": %d, \"alignments\": %llu, \"read_len\": %llu, \"runs_per_alignment\": %.1f, \"mean_edit\": %.1f, \"status_nonzero\": %llu, "
-           "\"identical\": {\"words\": %s, \"pairs\": %s}, \"kernel_ms_best_mean\": {\"bytes\": [%.4f, %.4f], \"words\": [%.4f, %.4f], \"pairs\": [%.4f, %.4f]}, \"distance_only_ms\": %.4f, "
-           "\"alignments_per_s\": {\"bytes\": %.4g, \"words\": %.4g, \"pairs\": %.4g}, "
-           "\"speedup_over_bytes\": {\"words\": %.4f, \"pairs\": %.4f}, \"compared\": \"edit, ref_consumed, nruns, status of every alignment; run bytes of the first %llu\"}\n",
+           "\"identical\": {\"words\": %s}, \"kernel_ms_best_mean\": {\"bytes\": [%.4f, %.4f], \"words\": [%.4f, %.4f]}, \"distance_only_ms\": %.4f, "
+           "\"alignments_per_s\": {\"bytes\": %.4g, \"words\": %.4g}, "
+           "\"speedup_over_bytes\": {\"words\": %.4f}, \"compared\": \"edit, ref_consumed, nruns, status of every alignment; run bytes of the first %llu\"}\n",
            name, b.W, (unsigned long long)b.n, (unsigned long long)b.L, (double)total_runs / (double)b.n, ed / (double)b.n, (unsigned long long)bad_status,
-           same(bytes, words) ? "true" : "false", same(bytes, pairs) ? "true" : "false", bytes.best_ms, bytes.mean_ms, words.best_ms, words.mean_ms,
-           pairs.best_ms, pairs.mean_ms, dist_only_ms, b.n / (bytes.best_ms * 1e-3), b.n / (words.best_ms * 1e-3), b.n / (pairs.best_ms * 1e-3),
-           bytes.best_ms / words.best_ms, bytes.best_ms / pairs.best_ms, (unsigned long long)sample);
+           same(bytes, words) ? "true" : "false", bytes.best_ms, bytes.mean_ms, words.best_ms, words.mean_ms, dist_only_ms,
+           b.n / (bytes.best_ms * 1e-3), b.n / (words.best_ms * 1e-3), bytes.best_ms / words.best_ms, (unsigned long long)sample);
     fflush(stdout);
 }
 
@@ -162,7 +157,7 @@ static Batch make_pairs(int W, uint64_t n, uint32_t L, double err, uint32_t ws, 
 {
     Batch b;
     b.W = W; b.n = n; b.L = L;
-    b.cap = (2ull * L + 8ull + 7ull) & ~7ull;   // slots on 8-byte boundaries (SG_FLAG_RUN_WORDS needs 4, the 64-bit experiment 8)
+    b.cap = (2ull * L + 8ull + 3ull) & ~3ull;   // slots on 4-byte boundaries (SG_FLAG_RUN_WORDS)
     const uint64_t stride = sg_synth_text_stride(L, 64);
     char *text = dalloc<char>(n * stride), *reads = dalloc<char>(n * L);
     b.tlen = dalloc<uint64_t>(n);

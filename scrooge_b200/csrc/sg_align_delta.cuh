@@ -190,8 +190,9 @@ __device__ __forceinline__ void delta_column(uint32_t (&Pv)[NW], uint32_t (&Mv)[
 //      spurious candidate location of read mapping walks ~45 one-step runs per window -- the byte stores are what the
 //      kernel waits for: every lane's store is a separate 32-byte sector write in L1 and L2 (32 wavefronts per
 //      instruction), ~20 x 32 per window and warp against the ~1 000 cycles a window's arithmetic takes.
-//   2  the same with two registers and 64-bit stores (two PRMTs per run, one store per eight runs; slots on 8-byte
-//      boundaries).  Experiment knob of the A/B tool (SG_DELTA_EMIT=2 with SG_FLAG_RUN_WORDS), not used by the host API.
+//      (The same with two registers and 64-bit stores -- two PRMTs per run, one store per eight runs -- was measured too:
+//      11.60 ms where words take 11.65 on 10 kbp pairs, 1.630 against 1.613 ms on 150 bp reads at 32/17, no difference on
+//      spurious candidates; not kept.)
 template <int W, int EMIT = 0>
 __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_delta_kernel(const AlignParams P)
 {
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
     int64_t ed = 0;
     uint8_t *out = nullptr, *out_end = nullptr;
     uint32_t nruns = 0;
-    uint32_t acc = 0u, acc_lo = 0u;   // EMIT >= 1: the runs not yet stored, newest in the top byte of acc (EMIT == 2: {acc, acc_lo})
+    uint32_t acc = 0u;             // EMIT == 1: the runs not yet stored, newest in the top byte
     uint64_t entries = 0;
     bool overflow = false;
     int n = -1, m = 0;
@@ -503,14 +504,6 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
                             *reinterpret_cast<uint32_t *>(o - 4) = acc;
                             SG_SIM_COUNT(1, 1);
                         }
-                    } else if constexpr (EMIT == 2) {
-                        acc_lo = __byte_perm(acc_lo, acc, 0x4321);
-                        acc = __byte_perm(acc, (t & 0xC0u) | (uint32_t)(p - st), 0x4321);
-                        o++;
-                        if (((uint32_t)(uintptr_t)o & 7u) == 0u) {
-                            *reinterpret_cast<uint2 *>(o - 8) = make_uint2(acc_lo, acc);
-                            SG_SIM_COUNT(2, 1);
-                        }
                     } else {
                         *o++ = (uint8_t)((t & 0xC0u) | (uint32_t)(p - st));
                         SG_SIM_COUNT(0, 1);
@@ -524,14 +517,6 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
         nruns += nb;
         ed += edits;
         if (q_pos >= q_end) {
-            if constexpr (EMIT == 2) {
-                const uint32_t pend = (uint32_t)(uintptr_t)out & 7u;   // 1..7 pending runs: down to the low bytes of the pair
-                if (want_cigar && pend != 0u) {
-                    const uint64_t v = (((uint64_t)acc << 32) | acc_lo) >> (64u - 8u * pend);
-                    *reinterpret_cast<uint2 *>(out - pend) = make_uint2((uint32_t)v, (uint32_t)(v >> 32));
-                    SG_SIM_COUNT(2, 1);
-                }
-            }
             if constexpr (EMIT == 1) {
                 // the pending 1..3 runs: moved down to the low bytes and stored as a word that ends inside the slot (its end is
                 // 4-byte aligned); the bytes above them are padding nobody reads

@@ -35,7 +35,7 @@ int cuda_fail(cudaError_t e, const char *what)
 struct DeviceInfo {
     int sms = 0;
     int ctas_per_sm[2][2] = {{0, 0}, {0, 0}};  // row-wise kernel: [W=64 | W=32][smem forefront | TMEM forefront]
-    int delta_ctas_per_sm[2][3] = {{0, 0, 0}, {0, 0, 0}};   // delta kernel: [W=64 | W=32][runs stored as bytes | words | 64-bit pairs]
+    int delta_ctas_per_sm[2][2] = {{0, 0}, {0, 0}};   // delta kernel: [W=64 | W=32][runs stored as bytes | as words]
     bool ready = false;
 };
 static DeviceInfo g_dev_info[64];
@@ -157,8 +157,6 @@ static int device_info(DeviceInfo **out)
             if (!rc) rc = setup_delta_kernel<64, 1>(&di.delta_ctas_per_sm[0][1]);
             if (!rc) rc = setup_delta_kernel<32, 0>(&di.delta_ctas_per_sm[1][0]);
             if (!rc) rc = setup_delta_kernel<32, 1>(&di.delta_ctas_per_sm[1][1]);
-            if (!rc) rc = setup_delta_kernel<64, 2>(&di.delta_ctas_per_sm[0][2]);
-            if (!rc) rc = setup_delta_kernel<32, 2>(&di.delta_ctas_per_sm[1][2]);
             if (rc) return rc;
             di.ready = true;
             ready[dev].store(true, std::memory_order_release);
@@ -514,12 +512,6 @@ int sg_dev_align_ordered(int W, int O, const uint32_t *d_text, const uint64_t *d
         // runs as whole words: only with CIGAR output, and only on the caller's promise of 4-byte aligned slots
         const bool words = (flags & SG_FLAG_RUN_WORDS) && !(flags & SG_FLAG_DISTANCE_ONLY);
         if (words && ((uintptr_t)d_slab & 3u) != 0) return fail(SG_ERR_BAD_ARG, "sg_dev_align: SG_FLAG_RUN_WORDS needs a 4-byte aligned d_slab (and slab offsets)");
-        // experiment knob of apps/sg_variant_ab: SG_DELTA_EMIT=2 stores pairs of words (slots on 8-byte boundaries)
-        const char *knob = words ? std::getenv("SG_DELTA_EMIT") : nullptr;   // read per launch: the tool switches it between launches
-        if (knob && atoi(knob) == 2) {
-            if (((uintptr_t)d_slab & 7u) != 0) return fail(SG_ERR_BAD_ARG, "sg_dev_align: SG_DELTA_EMIT=2 needs an 8-byte aligned d_slab (and slab offsets)");
-            return W == 64 ? launch_delta<64, 2>(*di, P, st) : launch_delta<32, 2>(*di, P, st);
-        }
         if (words) return W == 64 ? launch_delta<64, 1>(*di, P, st) : launch_delta<32, 1>(*di, P, st);
         return W == 64 ? launch_delta<64, 0>(*di, P, st) : launch_delta<32, 0>(*di, P, st);
     }

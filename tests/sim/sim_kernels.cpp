@@ -117,7 +117,7 @@ int sim_gather_runs(int group, const uint8_t *slab, const uint64_t *slab_off, co
 
 // One launch of genasm_delta_kernel<W, EMIT> over n alignments on `ctas` CTAs; all pointers are host memory laid out as
 // sg_dev_align's device buffers (include/scrooge_b200.h).  counters_out[8]: SG_SIM_COUNT events (0 = byte stores of runs,
-// 1 = word stores, 2 = 64-bit stores of runs, per lane).  Returns 0, or -1 for an unknown variant.
+// 1 = word stores of runs, per lane).  Returns 0, or -1 for an unknown variant.
 int sim_delta_align(int W, int emit, unsigned ctas, const uint32_t *text, const uint64_t *text_start, const uint64_t *text_len,
                     const uint32_t *query, const uint64_t *query_start, const uint64_t *query_len, uint64_t n, uint32_t flags,
                     uint8_t *slab, const uint64_t *slab_off, int64_t *edit, uint64_t *ref_consumed, uint32_t *nruns, uint8_t *status,
@@ -133,10 +133,10 @@ int sim_delta_align(int W, int emit, unsigned ctas, const uint32_t *text, const 
     for (auto &c : sim::counters) c = 0;
     void (*fn)(void *) = nullptr;
     unsigned block = 0;
-    if (W == 64) { block = sg::DeltaLayout<64>::WARPS_PER_CTA * 32; fn = emit == 2 ? body<64, 2> : emit ? body<64, 1> : body<64, 0>; static_assert(sg::DeltaLayout<64>::BYTES_PER_CTA <= sizeof(sg::smem_all), ""); }
-    else if (W == 32) { block = sg::DeltaLayout<32>::WARPS_PER_CTA * 32; fn = emit == 2 ? body<32, 2> : emit ? body<32, 1> : body<32, 0>; }
+    if (W == 64) { block = sg::DeltaLayout<64>::WARPS_PER_CTA * 32; fn = emit ? body<64, 1> : body<64, 0>; static_assert(sg::DeltaLayout<64>::BYTES_PER_CTA <= sizeof(sg::smem_all), ""); }
+    else if (W == 32) { block = sg::DeltaLayout<32>::WARPS_PER_CTA * 32; fn = emit ? body<32, 1> : body<32, 0>; }
     else return -1;
-    if (emit < 0 || emit > 2) return -1;
+    if (emit != 0 && emit != 1) return -1;
     sim::launch(ctas, block, sg::smem_all, fn, &P);
     if (counters_out) for (int k = 0; k < 8; k++) counters_out[k] = sim::counters[k];
     return 0;

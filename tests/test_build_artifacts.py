@@ -36,7 +36,7 @@ def test_alignment_kernels_fit_their_occupancy(ptxas):
     """genasm_delta_kernel runs 6 CTAs x 4 warps per SM (DESIGN.md 4.1): 65 536 registers / 768 threads = 85 per thread at most;
     all run-emission variants included."""
     delta = {k: r for k, (r, _) in ptxas.items() if "genasm_delta_kernel" in k}
-    assert len(delta) == 6, sorted(delta)          # W = 64 / 32  x  bytes / words / 64-bit pairs
+    assert len(delta) == 4, sorted(delta)          # W = 64 / 32  x  runs stored as bytes / as words
     assert max(delta.values()) <= 80, delta
 
 
@@ -61,4 +61,4 @@ def test_sass_has_the_sm100_instructions_the_design_names():
     tmem = [v for k, v in seen.items() if "genasm_align_kernel" in k and {"LDTM", "STTM"} <= v]
     assert len(tmem) == 2, "the tensor-memory forefront variants (W = 64, 32) use tcgen05.ld/st"
     delta = [v for k, v in seen.items() if "genasm_delta_kernel" in k]
-    assert len(delta) == 6 and all({"LOP3", "SHF", "PRMT", "LDS", "STS"} <= v and not ({"LDL", "STL"} & v) for v in delta)
+    assert len(delta) == 4 and all({"LOP3", "SHF", "PRMT", "LDS", "STS"} <= v and not ({"LDL", "STL"} & v) for v in delta)

@@ -71,8 +71,7 @@ def run_sim(sim, W, emit, texts, queries, ctas=2, distance_only=False, order=Non
     qw, qs, ql = pack_blob(queries)
     cap = np.array([cap_of(len(q)) if cap_of else 2 * len(q) + 8 for q in queries], dtype=np.uint64)
     if emit:
-        al = np.uint64(4 * emit - 1)                         # SG_FLAG_RUN_WORDS: slots start and end on 4-byte (variant 2: 8-byte) boundaries
-        cap = (cap + al) & ~al
+        cap = (cap + np.uint64(3)) & ~np.uint64(3)          # SG_FLAG_RUN_WORDS: slots start and end on 4-byte boundaries
     slab_off = np.zeros(n + 1, dtype=np.uint64)
     slab_off[1:] = np.cumsum(cap)
     slab = np.full(int(slab_off[-1]) + 16, 0xEE, dtype=np.uint8)
@@ -123,7 +122,7 @@ def check(out, res, n, cigars=True):
             assert cigar_of(out, a) == res.cigars[a], a
 
 
-@pytest.mark.parametrize("emit", [0, 1, 2])
+@pytest.mark.parametrize("emit", [0, 1])
 @pytest.mark.parametrize("W", [64, 32])
 def test_sim_matches_oracle_mixed(sim, oracle, W, emit):
     """Mixed bag (empty / 1-base / W+-1 lengths, exhausted texts, unrelated pairs, up to 40-80 % error) over several warps
@@ -139,12 +138,11 @@ def test_sim_matches_oracle_mixed(sim, oracle, W, emit):
     if emit == 0:
         assert int(out["counters"][0]) == total and int(out["counters"][1]) == 0
     else:
-        g = 4 * emit
-        assert int(out["counters"][0]) == 0 and int(out["counters"][3 - emit]) == 0
-        assert int(out["counters"][emit]) == int(((out["nruns"].astype(np.int64) + g - 1) // g).sum())
+        assert int(out["counters"][0]) == 0
+        assert int(out["counters"][1]) == int(((out["nruns"].astype(np.int64) + 3) // 4).sum())
 
 
-@pytest.mark.parametrize("emit", [0, 1, 2])
+@pytest.mark.parametrize("emit", [0, 1])
 @pytest.mark.parametrize("W", [64, 32])
 def test_sim_golden_vectors(sim, golden, W, emit):
     for group, items in golden[W]["groups"].items():
@@ -155,7 +153,7 @@ def test_sim_golden_vectors(sim, golden, W, emit):
             assert int(out["edit"][a]) == x["edit"] and cigar_of(out, a) == x["cigar"], (group, a)
 
 
-@pytest.mark.parametrize("emit", [0, 1, 2])
+@pytest.mark.parametrize("emit", [0, 1])
 def test_sim_order_distance_only_and_overflow(sim, oracle, emit):
     T, Q = random_pairs(7, 150, [10, 100, 300, 700], [0.05, 0.3])
     res = oracle.align_pairs(T, Q, W=64)
@@ -183,11 +181,8 @@ def test_sim_unrelated_candidates_store_counts(sim, oracle):
     res = oracle.align_pairs(T, Q, W=64)
     a = run_sim(sim, 64, 0, T, Q, ctas=1)
     b = run_sim(sim, 64, 1, T, Q, ctas=1)
-    c = run_sim(sim, 64, 2, T, Q, ctas=1)
     check(a, res, len(T))
     check(b, res, len(T))
-    check(c, res, len(T))
-    assert int(c["counters"][2]) * 7.8 < int(a["counters"][0])
     runs_per_window = a["nruns"].sum() / a["windows"].sum()
     assert runs_per_window > 15          # 6.4 at 10 % error
     assert int(b["counters"][1]) * 3.9 < int(a["counters"][0])

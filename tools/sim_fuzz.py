@@ -31,7 +31,7 @@ def main():
         for W in (64, 32):
             T, Q = random_pairs(seed + W, per, [0, 1, 2, 3, W - 1, W, W + 1, 2 * W + 1, 100, 150, 400, 1500, 4000], [0, 0.02, 0.05, 0.1, 0.15, 0.3, 0.6, 0.8])
             want = oracle.align_pairs(T, Q, W=W, threads=8)
-            for emit in (0, 1, 2):
+            for emit in (0, 1):
                 out = tks.run_sim(sim, W, emit, T, Q, ctas=rng.choice([1, 2, 3]))
                 tks.check(out, want, len(T))
                 pairs += len(T)
