@@ -49,6 +49,9 @@ template <int GROUP> void gather_body(void *arg)
 
 extern "C" {
 
+// order in which the fibers of a CTA are scheduled: 0 = thread order, otherwise pseudo-random per sweep
+void sim_set_schedule_seed(uint64_t seed) { sim::schedule_seed = seed; }
+
 // genasm_generic_kernel for any window configuration the product accepts (2 <= W <= 256, 0 <= O < W, W - O <= 128), op planes
 // in shared memory (gp = 0) or in a per-CTA global scratch (gp = 1); one-warp CTAs as in the product's launch.
 int sim_generic_align(int W, int O, int gp, unsigned ctas, const uint32_t *text, const uint64_t *text_start, const uint64_t *text_len,

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <stdio.h>
 #include <vector>
+#include <utility>
 #include "sim_runtime.h"
 
 namespace sim {
@@ -14,6 +15,7 @@ ThreadCtx *cur = nullptr;
 uint3 block_idx, block_dim, grid_dim;
 unsigned char *smem_base = nullptr;
 uint64_t counters[8];
+uint64_t schedule_seed = 0;
 
 namespace {
 struct Fiber {
@@ -113,11 +115,21 @@ void launch(unsigned grid, unsigned block, void *smem, void (*body)(void *), voi
             f.ctx.uc_link = nullptr;
             makecontext(&f.ctx, trampoline, 0);
         }
+        // round-robin sweeps over the fibers; with schedule_seed != 0 every sweep visits them in a fresh pseudo-random order, so
+        // that lanes reach the work queue and the rendezvous in orders a GPU might produce as well
+        std::vector<unsigned> order(block);
+        for (unsigned t = 0; t < block; t++) order[t] = t;
+        uint64_t rs = schedule_seed * 0x9E3779B97F4A7C15ull + b + 1;
         unsigned left = block;
         while (left) {
             left = 0;
-            for (unsigned t = 0; t < block; t++) {
-                Fiber &f = fibers[t];
+            if (schedule_seed)
+                for (unsigned t = block - 1; t > 0; t--) {
+                    rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17;
+                    std::swap(order[t], order[rs % (t + 1)]);
+                }
+            for (unsigned k = 0; k < block; k++) {
+                Fiber &f = fibers[order[k]];
                 if (f.done) continue;
                 cur = &f.t;
                 swapcontext(&sched_ctx, &f.ctx);

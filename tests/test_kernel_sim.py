@@ -38,6 +38,7 @@ def sim():
     lib.sim_pack_2bit.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint]
     lib.sim_scan_runs.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.sim_gather_runs.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_uint64, C.c_void_p, C.c_uint]
+    lib.sim_set_schedule_seed.argtypes = [C.c_uint64]
     return lib
 
 
@@ -263,3 +264,32 @@ def test_sim_scan_and_gather_match_numpy(sim, group):
         want = np.concatenate([slab[int(slab_off[a]): int(slab_off[a]) + int(nruns[a])] for a in range(n)] + [np.zeros(0, np.uint8)])
         assert np.array_equal(runs[:total], want)
         assert (runs[total:] == 0x5A).all(), "wrote past the dense array"
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_sim_results_do_not_depend_on_the_schedule(sim, oracle, seed):
+    """The fibers of a CTA scheduled in a fresh pseudo-random order every sweep: lanes take other alignments from the queue and
+    reach the votes in other orders, the results are the same (tuned kernel with both emissions, general kernel, scan + gather)."""
+    T, Q = random_pairs(77 + seed, 300, [0, 1, 33, 64, 65, 150, 500, 1200], [0, 0.05, 0.15, 0.4])
+    res = oracle.align_pairs(T, Q, W=64)
+    sim.sim_set_schedule_seed(seed)
+    try:
+        for emit in (0, 1):
+            check(run_sim(sim, 64, emit, T, Q, ctas=2), res, len(T))
+        check(run_sim(sim, 64, 0, T, Q, ctas=3, generic=(33, 0)), res, len(T))
+        rng = np.random.default_rng(seed)
+        n = 3000
+        nruns = rng.integers(0, 30, n).astype(np.uint32)
+        slab_off = np.zeros(n + 1, dtype=np.uint64)
+        slab_off[1:] = np.cumsum(nruns.astype(np.uint64) + 3)
+        slab = rng.integers(0, 256, int(slab_off[-1]) + 16).astype(np.uint8)
+        run_off = np.zeros(n + 1, dtype=np.uint64)
+        tmp = np.zeros(8, dtype=np.uint64)
+        sim.sim_scan_runs(p(nruns), n, p(run_off), p(tmp))
+        assert int(run_off[-1]) == int(nruns.sum())
+        runs = np.zeros(int(run_off[-1]) + 16, dtype=np.uint8)
+        sim.sim_gather_runs(32, p(slab), p(slab_off), p(nruns), p(run_off), n, p(runs), 2)
+        want = np.concatenate([slab[int(slab_off[a]): int(slab_off[a]) + int(nruns[a])] for a in range(n)])
+        assert np.array_equal(runs[: len(want)], want)
+    finally:
+        sim.sim_set_schedule_seed(0)
