@@ -33,7 +33,7 @@
 // count and the run count happen after the walk, on the streams, with bit tricks (run boundaries = hs ^ hs >> 1 |
 // ls ^ ls >> 1, edits = popc(hs | ls)): one loop iteration per RUN instead of bookkeeping per step.
 //
-// Per-warp shared memory (W=64): pattern masks 5 x 256 B + traceback columns 32 x 256 B = 9.25 KB (22 warps per SM);
+// Per-warp shared memory (W=64): pattern masks 5 x 256 B + traceback columns 32 x 256 B = 9.25 KB (four-warp CTAs of 37 KB: 24 warps per SM);
 // every array [column][lane] so that all accesses are conflict free.
 #pragma once
 #include "sg_align.cuh"
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(DeltaLayout<W>::WARPS_PER_CTA * 32) genasm_del
 
         // ---- DC: columns W-1 .. 0, two delta vectors per lane ----------------------------------------------
         // lanes without work ride along on whatever their scratch holds; nothing of it is ever read
-        // Code size matters here: the SM's instruction cache holds 32 KB and 22 warps at different points of the loop
+        // Code size matters here: the SM's instruction cache holds 32 KB and 24 warps at different points of the loop
         // body share it, so the 64 columns are NOT fully unrolled: two loops (columns without / with a traceback
         // store) of NWIN/2 iterations over one 16-column text word each.
         auto columns = [&](auto uni) {
