@@ -491,6 +491,11 @@ def main():
         # where every byte the host packs still crosses PCIe at a quarter of its size.
         ceil_gbs = max(h2d_gbs, conc_h2d_gbs + 0.75 * conc_pack_gbs)
         ceiling = ceil_gbs * 1e9 / (ascii_bytes / ne)
+        # The same with the link shared: the packed chunks (a quarter of the bytes the packers consume) cross PCIe through the
+        # same copy engine as the ASCII chunks, so with the packers delivering p = 0.75 x their concurrent rate the copy engine
+        # has only (its concurrent rate - p / 4) left for ASCII.  The rule above ignores that and is the more demanding figure.
+        p_gbs = 0.75 * conc_pack_gbs
+        ceil_shared_gbs = max(h2d_gbs, max(0.0, conc_h2d_gbs - p_gbs / 4) + p_gbs)
 
         def gather(x):
             if world == 1:
@@ -515,6 +520,10 @@ def main():
                                    "ASCII bytes per pair; all rates measured in this run on this run's pinned input with all ranks at "
                                    "once (pinned ASCII -> device copies only; sg_host_pack_2bit only; both at the same time for 0.5 s)"},
                "frac_of_ceiling": value_e2e / ceiling,
+               "ceiling_link_shared": {"value": ceil_shared_gbs * 1e9 / (ascii_bytes / ne), "unit": "alignments/s", "ascii_gbs": ceil_shared_gbs,
+                                       "frac": value_e2e / (ceil_shared_gbs * 1e9 / (ascii_bytes / ne)),
+                                       "rule": "max(copy engines alone, (concurrent copy engines - p / 4) + p) with p = 0.75 x concurrent "
+                                               "packers: the packed chunks cross PCIe through the same copy engine as the ASCII chunks"},
                "breakdown_per_rank": per_rank,
                "api": "sg_align_pairs (C ABI, pinned host ASCII blobs in, distances + packed CIGAR runs out); adaptive ingest: a "
                       "persistent team of packer threads per GPU (bound to the GPU's CPUs) packs chunks to 2 bit/base (AVX-512) from "
