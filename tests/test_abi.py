@@ -139,3 +139,19 @@ def test_streaming_renderer_is_exact_at_every_alignment(sglib):
             assert end == dst + len(want)
             assert bytes(out[o0:o0 + len(want)]) == want, (cnt, mis)
             assert (out[:o0] == 0x7E).all() and (out[o0 + len(want):] == 0x7E).all(), ("wrote outside the text", cnt, mis)
+
+
+def test_headers_are_plain_c(tmp_path, sglib):
+    """The boundary is a C ABI: both public headers compile as C99 (-pedantic -Werror) and a C program links against the
+    libraries and calls them."""
+    import subprocess
+    src = tmp_path / "c_abi.c"
+    src.write_text('#include "scrooge_b200.h"\n#include "scrooge_b200_bench.h"\n#include <stdio.h>\n'
+                   'int main(void) { sg_call_stats s; (void)s; printf("v%d devices=%d overlap=%d\\n", sg_version(), sg_device_count(), '
+                   'sg_default_overlap(64)); return 0; }\n')
+    libdir = os.path.join(ROOT, "scrooge_b200", "lib")
+    exe = str(tmp_path / "c_abi")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), str(src), "-L" + libdir,
+                    "-lscrooge_b200", "-lscrooge_b200_bench", "-Wl,-rpath," + libdir, "-o", exe], check=True, capture_output=True, text=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and out.stdout.startswith("v1 devices=") and "overlap=33" in out.stdout, out.stdout + out.stderr
