@@ -140,3 +140,20 @@ def test_mapping_point_on_the_simulated_device(fake_device, stress):
         assert m["mean_edit_distance_first_2048"] > 3000 > m["true_start_mean_edit"]
     else:
         assert m["mean_edit_distance_first_2048"] < 1500
+
+
+@pytest.mark.parametrize("W,L,err", [(64, 1000, 0.10), (32, 150, 0.05), (64, 777, 0.45)])
+def test_gpu_variant_test_body_on_the_simulated_device(fake_device, monkeypatch, oracle, W, L, err):
+    """tests/test_gpu_variants.py's device-API case, the very function the GPU box runs, on the simulated device with fewer
+    pairs: its Python is exercised here first (device.check_runs, a device kernel of the bench library, is stubbed)."""
+    import test_gpu_variants as tgv
+    from scrooge_b200 import device
+    monkeypatch.setattr(tgv, "N_PAIRS", 1100)
+    monkeypatch.setattr(device, "check_runs", lambda *a, **k: 0)
+    monkeypatch.setattr(torch, "device", lambda *a, **k: "cpu")
+    tgv.test_device_api_run_words_equals_bytes_and_oracle(oracle, None, W, L, err)
+
+
+def test_gpu_variant_child_program_compiles():
+    import test_gpu_variants as tgv
+    compile(tgv._CHILD, "child", "exec")

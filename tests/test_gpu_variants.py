@@ -12,6 +12,7 @@ import pytest
 from conftest import ROOT, mapping_case, random_pairs
 
 pytestmark = pytest.mark.gpu
+N_PAIRS = 8192   # per device-API case (tests/test_bench_logic_sim.py runs the same test body on the simulated device with fewer)
 
 
 def _cigars(runs, run_off, idxs):
@@ -26,7 +27,7 @@ def test_device_api_run_words_equals_bytes_and_oracle(oracle, sglib, W, L, err):
     import torch
     from scrooge_b200 import device, synth
     wl = synth.Workload("t", L, err, synth.PACBIO, W, 777 + L)
-    n = 8192
+    n = N_PAIRS
     dev = torch.device("cuda:0")
     text, tlen, reads = device.synth_pairs_device(wl.seed, 0, n, wl.read_len, wl.err, wl.ratio, wl.slack, dev)
     stride = text.shape[1]
