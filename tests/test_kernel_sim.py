@@ -64,7 +64,7 @@ def p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def run_sim(sim, W, emit, texts, queries, ctas=2, distance_only=False, order=None, cap_of=None, want_stats=True, generic=None):
+def run_sim(sim, W, emit, texts, queries, ctas=2, distance_only=False, order=None, cap_of=None, want_stats=True, generic=None, slab_off=None):
     """One simulated launch.  generic = None: genasm_delta_kernel<W, emit>; generic = (O, gp): genasm_generic_kernel at window
     configuration (W, O), op planes in shared (gp = 0) or global (gp = 1) memory."""
     n = len(texts)
@@ -73,8 +73,9 @@ def run_sim(sim, W, emit, texts, queries, ctas=2, distance_only=False, order=Non
     cap = np.array([cap_of(len(q)) if cap_of else 2 * len(q) + 8 for q in queries], dtype=np.uint64)
     if emit:
         cap = (cap + np.uint64(3)) & ~np.uint64(3)          # SG_FLAG_RUN_WORDS: slots start and end on 4-byte boundaries
-    slab_off = np.zeros(n + 1, dtype=np.uint64)
-    slab_off[1:] = np.cumsum(cap)
+    if slab_off is None:
+        slab_off = np.zeros(n + 1, dtype=np.uint64)
+        slab_off[1:] = np.cumsum(cap)
     slab = np.full(int(slab_off[-1]) + 16, 0xEE, dtype=np.uint8)
     assert slab.ctypes.data % 16 == 0
     edit = np.full(n, -7, dtype=np.int64)
@@ -293,3 +294,19 @@ def test_sim_results_do_not_depend_on_the_schedule(sim, oracle, seed):
         assert np.array_equal(runs[: len(want)], want)
     finally:
         sim.sim_set_schedule_seed(0)
+
+
+def test_sim_host_api_slab_layout(sim, oracle):
+    """The slab layout the host API hands the kernel for blob inputs (sg_host_threads.h: slab_offset_blob, every offset rounded
+    up to a multiple of 4 on its own) with the word-storing kernel: every alignment intact, nothing outside its slot."""
+    T, Q = random_pairs(4242, 300, [0, 1, 2, 3, 5, 17, 33, 64, 150, 151, 999], [0, 0.1, 0.5])
+    res = oracle.align_pairs(T, Q, W=64)
+    qpre = np.concatenate([[0], np.cumsum([len(q) for q in Q])]).astype(np.uint64)
+    k = np.arange(len(Q) + 1, dtype=np.uint64)
+    off = (np.uint64(2) * qpre + np.uint64(12) * k + np.uint64(3)) & ~np.uint64(3)          # slab_offset_blob(q_prefix, k, words = true)
+    assert (off % 4 == 0).all() and ((off[1:] - off[:-1]) >= 2 * np.array([len(q) for q in Q], dtype=np.uint64) + 8).all()
+    out = run_sim(sim, 64, 1, T, Q, ctas=2, slab_off=off)
+    check(out, res, len(T))
+    for a in range(len(T)):   # the bytes of a slot beyond its runs and their padding word are untouched
+        used = (int(out["nruns"][a]) + 3) & ~3
+        assert (out["slab"][int(off[a]) + used: int(off[a + 1])] == 0xEE).all(), a
