@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(128) synth_reads_kernel(SgSynthParams p, uint6
 // Independent chains of the DC recurrence's own instructions.  kind 0: LOP3 only; 1: SHF (funnel shift) only;
 // 2: two LOP3 per SHF (the DC mix); 3: LOP3 + IMAD alternating (alu pipe + fma pipe); 4-6: one DC entry
 // (4 LOP3 + a 64-bit shift left by one) with the shift done as IMAD+SHF, IMAD.SHL+IMAD.WIDE, or IMAD.HI+IMAD+SHL.
+#ifndef SG_SIM   // the peak probe is chains of inline PTX: nothing for the host simulation (tests/sim) to check
 template <int KIND>
 __global__ void __launch_bounds__(256) int32_peak_kernel(uint32_t *__restrict__ sink, int iters, uint32_t seed)
 {
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(256) int32_peak_kernel(uint32_t *__restrict__ 
     for (int k = 0; k < CH; k++) acc ^= a[k] ^ b[k] ^ c[k];
     if (acc == 0x12345678u) sink[0] = acc;  // keep the chains alive
 }
+#endif  // !SG_SIM
 // ops per loop iteration; kinds 4-6 count one "DC entry" (4 LOP3 + a 64-bit shift) as 6 ops
 constexpr int kPeakOpsPerIter[7] = {8 * 4 * 3, 8 * 4 * 3, 8 * 4 * 3, 8 * 4 * 4, 8 * 4 * 6, 8 * 4 * 6, 8 * 4 * 6};
 

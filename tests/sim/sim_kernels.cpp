@@ -10,6 +10,7 @@
 #undef __shared__
 #define __shared__ static
 #include "../../scrooge_b200/csrc/sg_aux.cuh"
+#include "../../scrooge_b200/csrc/sg_bench_aux.cuh"
 
 namespace sg {
 __attribute__((aligned(16))) uint32_t smem_all[(227 * 1024) / 4];   // what `extern __shared__ uint32_t smem_all[]` in the kernels resolves to
@@ -45,9 +46,25 @@ template <int GROUP> void gather_body(void *arg)
     const GatherArgs *a = static_cast<const GatherArgs *>(arg);
     sg::gather_runs_kernel<GROUP>(a->slab, a->slab_off, a->nruns, a->run_off, a->n, a->runs);
 }
+struct CheckArgs { const uint8_t *runs; const uint64_t *run_off; uint64_t n; const uint64_t *query_len; const int64_t *edit;
+                   const uint64_t *ref_consumed; uint32_t max_count; unsigned long long *n_bad; };
+void check_body(void *arg)
+{
+    const CheckArgs *a = static_cast<const CheckArgs *>(arg);
+    sg::check_runs_kernel(a->runs, a->run_off, a->n, a->query_len, a->edit, a->ref_consumed, a->max_count, a->n_bad);
+}
 }  // namespace
 
 extern "C" {
+
+// check_runs_kernel of the bench library (sg_dev_check_runs): *n_bad += alignments whose runs contradict their other results
+int sim_check_runs(const uint8_t *runs, const uint64_t *run_off, uint64_t n, const uint64_t *query_len, const int64_t *edit,
+                   const uint64_t *ref_consumed, uint32_t max_count, uint64_t *n_bad, unsigned blocks)
+{
+    CheckArgs a{runs, run_off, n, query_len, edit, ref_consumed, max_count, (unsigned long long *)n_bad};
+    sim::launch(blocks, 256, sg::smem_all, check_body, &a);
+    return 0;
+}
 
 // order in which the fibers of a CTA are scheduled: 0 = thread order, otherwise pseudo-random per sweep
 void sim_set_schedule_seed(uint64_t seed) { sim::schedule_seed = seed; }

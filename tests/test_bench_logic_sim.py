@@ -145,11 +145,18 @@ def test_mapping_point_on_the_simulated_device(fake_device, stress):
 @pytest.mark.parametrize("W,L,err", [(64, 1000, 0.10), (32, 150, 0.05), (64, 777, 0.45)])
 def test_gpu_variant_test_body_on_the_simulated_device(fake_device, monkeypatch, oracle, W, L, err):
     """tests/test_gpu_variants.py's device-API case, the very function the GPU box runs, on the simulated device with fewer
-    pairs: its Python is exercised here first (device.check_runs, a device kernel of the bench library, is stubbed)."""
+    pairs: its Python is exercised here first (device.check_runs runs the bench library's checking kernel in the simulation)."""
     import test_gpu_variants as tgv
     from scrooge_b200 import device
     monkeypatch.setattr(tgv, "N_PAIRS", 1100)
-    monkeypatch.setattr(device, "check_runs", lambda *a, **k: 0)
+
+    def check_runs(runs, run_off, query_len, out, W, O=None):
+        bad = torch.zeros(1, dtype=torch.int64)
+        tks.sim.__wrapped__().sim_check_runs(C.c_void_p(runs.data_ptr()), C.c_void_p(run_off.data_ptr()), query_len.numel(), C.c_void_p(query_len.data_ptr()),
+                                             C.c_void_p(out.edit.data_ptr()), C.c_void_p(out.ref_consumed.data_ptr()),
+                                             W - (min(W // 2 + 1, W - 1) if O is None else O), C.c_void_p(bad.data_ptr()), 2)
+        return int(bad[0])
+    monkeypatch.setattr(device, "check_runs", check_runs)
     monkeypatch.setattr(torch, "device", lambda *a, **k: "cpu")
     tgv.test_device_api_run_words_equals_bytes_and_oracle(oracle, None, W, L, err)
 

@@ -17,7 +17,7 @@ SIM_DIR = os.path.join(ROOT, "tests", "sim")
 SIM_LIB = os.path.join(SIM_DIR, "_build", "libsgsim.so")
 SIM_SRC = [os.path.join(SIM_DIR, "sim_kernels.cpp"), os.path.join(SIM_DIR, "sim_runtime.cpp")]
 SIM_DEPS = SIM_SRC + [os.path.join(SIM_DIR, "sim_runtime.h"), os.path.join(SIM_DIR, "shim", "cuda_runtime.h")] + [
-    os.path.join(ROOT, "scrooge_b200", "csrc", f) for f in ("sg_align.cuh", "sg_align_delta.cuh", "sg_align_generic.cuh", "sg_aux.cuh")]
+    os.path.join(ROOT, "scrooge_b200", "csrc", f) for f in ("sg_align.cuh", "sg_align_delta.cuh", "sg_align_generic.cuh", "sg_aux.cuh", "sg_bench_aux.cuh", "sg_synth.h")]
 CODE = np.full(256, 255, dtype=np.uint8)
 for _k, _c in enumerate("ACGT"):
     CODE[ord(_c)] = _k
@@ -39,6 +39,7 @@ def sim():
     lib.sim_scan_runs.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.sim_gather_runs.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_uint64, C.c_void_p, C.c_uint]
     lib.sim_set_schedule_seed.argtypes = [C.c_uint64]
+    lib.sim_check_runs.argtypes = [C.c_void_p] * 2 + [C.c_uint64] + [C.c_void_p] * 3 + [C.c_uint32, C.c_void_p, C.c_uint]
     return lib
 
 
@@ -310,3 +311,38 @@ def test_sim_host_api_slab_layout(sim, oracle):
     for a in range(len(T)):   # the bytes of a slot beyond its runs and their padding word are untouched
         used = (int(out["nruns"][a]) + 3) & ~3
         assert (out["slab"][int(off[a]) + used: int(off[a + 1])] == 0xEE).all(), a
+
+
+def test_sim_batch_checker_catches_every_kind_of_inconsistency(sim, oracle):
+    """check_runs_kernel (what bench.py runs over the whole timed batch): clean on real results, and each kind of damage to a
+    run byte, a distance, a consumed prefix or a query length is counted once per damaged alignment."""
+    T, Q = random_pairs(31, 200, [1, 33, 64, 150, 700], [0, 0.1, 0.4], short_text=0.0)
+    T, Q = zip(*[(t, q) for t, q in zip(T, Q) if len(q)])
+    out = run_sim(sim, 64, 1, list(T), list(Q), ctas=2)
+    n = len(T)
+    run_off = np.zeros(n + 1, dtype=np.uint64)
+    run_off[1:] = np.cumsum(out["nruns"].astype(np.uint64))
+    runs = np.concatenate([out["slab"][int(out["slab_off"][a]): int(out["slab_off"][a]) + int(out["nruns"][a])] for a in range(n)])
+    qlen = np.array([len(q) for q in Q], dtype=np.uint64)
+
+    def count_bad(runs=runs, qlen=qlen, edit=out["edit"], rc=out["rc"], max_count=31):
+        bad = np.zeros(1, dtype=np.uint64)
+        sim.sim_check_runs(p(np.ascontiguousarray(runs)), p(run_off), n, p(qlen), p(edit), p(rc), max_count, p(bad), 2)
+        return int(bad[0])
+
+    assert count_bad() == 0
+    r = runs.copy(); r[int(run_off[3])] ^= 1                      # a count off by one
+    assert count_bad(runs=r) == 1
+    r = runs.copy(); r[int(run_off[5])] &= 0xC0                   # a zero-length run
+    assert count_bad(runs=r) == 1
+    r = runs.copy(); r[int(run_off[7])] = (r[int(run_off[7])] & 0xC0) | 40   # longer than a window's walk
+    assert count_bad(runs=r) == 1
+    r = runs.copy(); r[int(run_off[9])] ^= 0x40                   # '=' <-> 'X' (or 'I' <-> 'D'): the edit count (or the lengths) change
+    assert count_bad(runs=r) == 1
+    e = out["edit"].copy(); e[11] += 1; e[12] -= 1
+    assert count_bad(edit=e) == 2
+    c = out["rc"].copy(); c[13] += 1
+    assert count_bad(rc=c) == 1
+    q = qlen.copy(); q[0] += 1; q[n - 1] += 1
+    assert count_bad(qlen=q) == 2
+    assert count_bad(max_count=15) > 0                            # the 32/17 limit on 64/33 results
